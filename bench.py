@@ -1,0 +1,353 @@
+#!/usr/bin/env python
+"""bench.py -- BPR triples/sec at d=64 on the synthetic 1M x 100K x 50M set (BASELINE.json
+configs[1]), one process per GPU.
+
+A "step" is one epoch of the hot path over the rank's shard of the 50M interactions:
+  K0  device Philox negative sampling for every (u,i) pair      (qrec_sample_neg_philox)
+  K1  fused gather -> dots -> sigmoid -> SGD step -> scatter-add (qrec_bpr_sgd_batch_f32)
+  +   regU*|P|^2 + regI*|Q|^2 for the epoch loss                (qrec_sumsq_f32, BPR.py:40)
+with the (u,i) pairs, the rated-item CSR and both tables already resident in HBM.  `e2e` is the
+same epoch entered through the host-buffer C-ABI call (qrec_bpr_epoch_host): the step's
+(u,i,j) index arrays start in pinned HOST memory and are copied to the device inside the timed
+region, the loss comes back to the host.
+
+Multi-GPU (strong scaling of the fixed 50M set): users are range-partitioned, so P rows and each
+user's triples live on one rank; Q (25.6 MB) is replicated and its per-rank deltas are summed
+with an NCCL all-reduce `--q-syncs` times per step.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NUM_USERS, NUM_ITEMS, DEGREE, D = 1_000_000, 100_000, 50, 64
+LR, REG_U, REG_I = 0.01, 0.001, 0.001
+ALGO_BYTES_PER_TRIPLE = 24 * D + 12          # 3 rows read + 3 rows written + 3 int32
+METRIC = 'BPR triples/sec at d=64'
+WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, shuffled triples'
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(p) as f:
+            return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def recorded_traffic():
+    """dram bytes per K1 launch from the committed ncu --set full capture, if one exists."""
+    p = os.path.join(ROOT, 'profiles', 'k1_traffic.json')
+    try:
+        with open(p) as f:
+            return json.load(f)
+    except Exception:
+        return None
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['no samples']}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's numpy loop on host cores
+# ---------------------------------------------------------------------------------------------
+def host_workload(n_triples, seed=7):
+    rng = np.random.default_rng(seed)
+    P = rng.random((NUM_USERS, D)) / 3            # float64, like base/iterativeRecommender.py:37-38
+    Q = rng.random((NUM_ITEMS, D)) / 3
+    u = rng.integers(0, NUM_USERS, n_triples).astype(np.int32)
+    i = rng.integers(0, NUM_ITEMS, n_triples).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, NUM_ITEMS - 1, n_triples)) % NUM_ITEMS).astype(np.int32)
+    return P, Q, u, i, j
+
+
+def cpu_baseline(sample_triples):
+    """Times oracle/bpr_ref.c (float64 restatement of model/ranking/BPR.py:45-53) on one host core."""
+    from oracle import c_oracle
+    P, Q, u, i, j = host_workload(sample_triples)
+    c_oracle.bpr_sgd_sequential(P, Q, u[:100000], i[:100000], j[:100000], LR, REG_U, REG_I)  # warm
+    t0 = time.perf_counter()
+    c_oracle.bpr_sgd_sequential(P, Q, u, i, j, LR, REG_U, REG_I)
+    dt = time.perf_counter() - t0
+    return {'value': sample_triples / dt, 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d shuffled triples of the same 1M x 100K d=64 workload, float64 C port of the '
+                      'reference numpy loop (oracle/bpr_ref.c); the loop is a serial dependency chain, '
+                      'so 1 thread (host has %d cores)' % (sample_triples, os.cpu_count() or 0),
+            'seconds': dt}
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle import c_oracle
+    sample = args.ref_sample
+    P, Q, u, i, j = host_workload(sample * (args.steps + args.warmup))
+    for w in range(args.warmup):
+        s = slice(w * sample, (w + 1) * sample)
+        c_oracle.bpr_sgd_sequential(P, Q, u[s], i[s], j[s], LR, REG_U, REG_I)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        s = slice((args.warmup + k) * sample, (args.warmup + k + 1) * sample)
+        c_oracle.bpr_sgd_sequential(P, Q, u[s], i[s], j[s], LR, REG_U, REG_I)
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    desc = ('%d shuffled triples per step of the same workload; float64 C port (oracle/bpr_ref.c) of '
+            'model/ranking/BPR.py:45-53; the Python reference itself cannot travel to the GPU box '
+            '(measured here: ~95 K triples/s); serial dependency chain => 1 thread of %d' % (sample, os.cpu_count() or 0))
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'triples/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+        'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'sample_triples_per_step': sample},
+        'cpu_baseline': {'value': value, 'unit': 'triples/s', 'cores': 1, 'kind': 'port', 'sample': desc},
+        'e2e': {'value': value, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from qrec_b200 import engine as E
+    from qrec_b200 import synthetic
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+
+    users_local = NUM_USERS // world
+    n_local = users_local * DEGREE
+    data = synthetic.make_interactions(users_local, NUM_ITEMS, DEGREE, device=dev,
+                                       user_offset=rank * users_local)
+    P, Q = synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + rank, device=dev)
+    if world > 1:
+        dist.broadcast(Q, 0)
+    g = torch.Generator(device=dev); g.manual_seed(99 + rank)
+    perm = torch.randperm(n_local, device=dev, generator=g)
+    u = data['u'][perm].contiguous()
+    i = data['i'][perm].contiguous()
+    del perm
+    j = torch.empty(n_local, dtype=torch.int32, device=dev)
+    rowptr, cols = data['sorted_rowptr'], data['sorted_cols']
+    loss = torch.zeros(3, dtype=torch.float64, device=dev)
+    q_syncs = max(1, args.q_syncs) if world > 1 else 1
+    Qbase = Q.clone() if world > 1 else None
+    delta = torch.empty_like(Q) if world > 1 else None
+    bounds = [n_local * s // q_syncs for s in range(q_syncs + 1)]
+    k1_events = []
+
+    def step(epoch, timed):
+        loss.zero_()
+        E.sample_neg_philox(u, rowptr, cols, NUM_ITEMS, 2024, epoch, out=j)
+        for s in range(q_syncs):
+            a, b = bounds[s], bounds[s + 1]
+            if timed:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+            E.bpr_sgd_batch(P, Q, u[a:b], i[a:b], j[a:b], LR, REG_U, REG_I, loss[0:1])
+            if timed:
+                e1.record()
+                k1_events.append((e0, e1, b - a))
+            if world > 1:
+                E.axpby(delta, Q, Qbase, 1.0, -1.0)           # this rank's item-row deltas
+                dist.all_reduce(delta)                         # NCCL sum over NVLink
+                E.axpby(Qbase, Qbase, delta, 1.0, 1.0)
+                Q.copy_(Qbase)
+        E.sumsq(P, loss[1:2])
+        E.sumsq(Q, loss[2:3])
+
+    launches_before = None
+    for w in range(args.warmup):
+        step(w, False)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches_before = E.launch_count()
+    t_beg, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_beg.record()
+    for k in range(args.steps):
+        step(args.warmup + k, True)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches = E.launch_count() - launches_before
+    clocks = sampler.stop() if sampler else None
+    elapsed_ms = t_beg.elapsed_time(t_end)
+    k1_ms = sum(a.elapsed_time(b) for a, b, _ in k1_events)
+    k1_triples = sum(c for _, _, c in k1_events)
+    final = loss.cpu().numpy()
+    t = torch.tensor([elapsed_ms, k1_ms], dtype=torch.float64, device=dev)
+    lsum = torch.tensor([float(final[0] + REG_U * final[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lsum)
+    elapsed_ms, k1_ms = float(t[0].item()), float(t[1].item())
+    epoch_loss = float(lsum.item()) + REG_I * float(final[2])
+    assert np.isfinite(epoch_loss), 'loss is not finite'
+    total_triples = n_local * world * args.steps
+    value = total_triples / (elapsed_ms * 1e-3)
+
+    # ------------------------------------------------------------------ e2e: host buffers
+    hu, hi = u.cpu().pin_memory(), i.cpu().pin_memory()
+    hj = j.cpu().pin_memory()
+    pipe = E.HostPipeline(local, chunk_triples=1 << 22)
+
+    def e2e_step():
+        l = pipe.bpr_epoch(P, Q, hu, hi, hj, LR, REG_U, REG_I)
+        if world > 1:
+            E.axpby(delta, Q, Qbase, 1.0, -1.0)
+            dist.all_reduce(delta)
+            E.axpby(Qbase, Qbase, delta, 1.0, 1.0)
+            Q.copy_(Qbase)
+            torch.cuda.synchronize()
+        return l
+
+    for w in range(max(1, args.warmup // 2)):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        e2e_loss = e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_s = float(te.item())
+    assert np.isfinite(e2e_loss)
+    pipe.close()
+    e2e_value = total_triples / e2e_s
+
+    if rank == 0:
+        peak, peak_src = measured_hbm_peak()
+        per_launch_triples = k1_triples / max(1, len(k1_events))
+        per_launch_ms = k1_ms / max(1, len(k1_events))
+        achieved = per_launch_triples * ALGO_BYTES_PER_TRIPLE / (per_launch_ms * 1e-3) / 1e9
+        tr = recorded_traffic()
+        out = {
+            'metric': METRIC, 'value': value, 'unit': 'triples/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {
+                'workload': WORKLOAD, 'users': NUM_USERS, 'items': NUM_ITEMS, 'interactions': NUM_USERS * DEGREE,
+                'd': D, 'lr': LR, 'reg': REG_U, 'triples_per_step': n_local * world,
+                'order': 'positives shuffled once, negatives re-sampled on device every step (Philox)',
+                'l2_policy': 'inputs larger than L2: P 256 MB + 600 MB of indices per step vs 126 MB L2',
+                'parallelism': ('users range-partitioned over %d ranks, Q replicated, %d delta all-reduces/step'
+                                % (world, q_syncs)) if world > 1 else 'single GPU',
+                'epoch_loss': epoch_loss,
+            },
+            'roofline': {
+                'bound': 'hbm', 'kernel': 'bpr_sgd_batch_kernel<16,1,4>', 'achieved': achieved, 'peak': peak,
+                'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
+                'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
+                'launch_ms': per_launch_ms, 'launch_triples': per_launch_triples,
+                'traffic': (tr or {}).get('dram_bytes_per_launch'),
+                'traffic_note': (tr or {}).get('note', 'no ncu --set full capture recorded yet'),
+            },
+            'e2e': {'value': e2e_value, 'unit': 'triples/s', 'h2d_bytes_per_step': 12 * n_local * world,
+                    'd2h_bytes_per_step': 8 * world, 'ms_per_step': 1e3 * e2e_s / args.steps,
+                    'api': 'qrec_bpr_epoch_host: pinned host (u,i,j) -> chunked H2D overlapped with K1 -> loss D2H'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out['cpu_baseline'] = cpu_baseline(args.cpu_sample)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--q-syncs', type=int, default=4, help='item-table all-reduces per step when N>1')
+    ap.add_argument('--cpu-sample', type=int, default=20_000_000)
+    ap.add_argument('--ref-sample', type=int, default=4_000_000)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    assert args.warmup >= 0 and args.steps >= 1
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

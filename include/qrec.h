@@ -1,0 +1,206 @@
+/*
+ * qrec.h -- C ABI of libqrec.so, the B200 (sm_100a) engine behind QRec's
+ * embedding-training hot path.
+ *
+ * The reference (Coder-Yu/QRec) is pure Python and defines no FFI; its plugin
+ * interface is the Recommender class surface.  Every entry point below replaces
+ * one reference function on the hot path (cited as file:line relative to the
+ * reference checkout) and is what the Python layer (qrec_b200/engine.py, via
+ * ctypes) binds.  INTEGRATION.md shows the stub a QRec maintainer would add.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes, no torch / Python types.
+ *   - every function returns int: 0 = QREC_OK, <0 = error; the message is
+ *     available from qrec_last_error() (thread-local).  Nothing throws.
+ *   - "dev" pointers are CUDA device pointers owned by the caller (in the Python
+ *     layer: torch CUDA tensors -> data_ptr()).  The library allocates device
+ *     memory only inside an opaque qrec_ctx (pipelined host path workspaces).
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream);
+ *     all device entry points are asynchronous on that stream.
+ *   - ids are int32 (U + I < 2^31 in every configuration); offsets/counts int64.
+ *   - tables are row-major [rows, d], rows contiguous, 16-byte aligned.
+ */
+#ifndef QREC_H_
+#define QREC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QREC_OK 0
+#define QREC_ERR_ARG (-1)    /* bad argument (null pointer, unsupported d, ...) */
+#define QREC_ERR_CUDA (-2)   /* a CUDA runtime call failed; see qrec_last_error */
+#define QREC_ERR_STATE (-3)  /* object used in the wrong state */
+#define QREC_ERR_NOMEM (-4)
+
+const char* qrec_last_error(void);
+/* "qrec-b200 <semver> sm_100a" */
+const char* qrec_version(void);
+/* number of kernels this library has launched in this process (bench `gpu_launches`) */
+int64_t qrec_launch_count(void);
+
+/* =====================================================================================
+ * K0 (compat) -- CPython `random` (MT19937) clone, host side, bit exact.
+ * Replaces the `random.choice / shuffle / randint / random` calls on the path:
+ *   model/ranking/BPR.py:28,35-38   base/deepRecommender.py:30,47-49,69-71
+ *   base/iterativeRecommender.py:101   util/dataSplit.py:15
+ * State is caller-owned: 624 words + index, the layout of random.getstate()[1].
+ * ===================================================================================== */
+typedef struct qrec_mt19937 {
+  uint32_t mt[624];
+  uint32_t index;
+} qrec_mt19937;
+
+/* random.seed(int) -- init_by_array over the 32-bit little-endian words of |seed| */
+int qrec_mt_seed(qrec_mt19937* st, uint64_t seed);
+/* random.setstate / getstate: state625 = 624 words followed by the index */
+int qrec_mt_set_state(qrec_mt19937* st, const uint32_t* state625);
+int qrec_mt_get_state(const qrec_mt19937* st, uint32_t* state625);
+uint32_t qrec_mt_next_u32(qrec_mt19937* st);           /* genrand_uint32            */
+double qrec_mt_random(qrec_mt19937* st);               /* random.random()           */
+uint32_t qrec_mt_randbelow(qrec_mt19937* st, uint32_t n); /* Random._randbelow(n), n>=1 */
+/* random.shuffle applied to perm[0..n) in place (perm holds any int32 payload) */
+int qrec_mt_shuffle_i32(qrec_mt19937* st, int64_t n, int32_t* perm);
+/* the same swap sequence applied to two parallel arrays (the (user,item) columns of
+ * trainingData): base/deepRecommender.py:30, base/iterativeRecommender.py:101 */
+int qrec_mt_shuffle_pairs_i32(qrec_mt19937* st, int64_t n, int32_t* a, int32_t* b);
+/* util/dataSplit.py:9-26: keep[k] = 0 if random() < test_ratio (goes to test) else 1 */
+int qrec_mt_data_split(qrec_mt19937* st, int64_t n, double test_ratio, uint8_t* keep);
+
+/* A user's rated-item set for rejection: CSR over users, column ids SORTED ascending
+ * inside each row (membership = binary search).  rowptr has n_users+1 entries. */
+
+/* model/ranking/BPR.py:31-38 -- one epoch of the numpy path's sampler.
+ * Iterates users 0..n_users-1 and, per user, its positives in `pos_cols` order (the
+ * reference's insertion order, CSR rowptr `pos_rowptr`); draws j = randbelow(num_items)
+ * until j is not in the user's sorted positive set.  Emits n = pos_rowptr[n_users]
+ * triples.  Users with an empty positive row are skipped (BPR.py:22-25). */
+int qrec_sample_bpr_epoch(qrec_mt19937* st, int32_t n_users, int32_t num_items,
+                          const int64_t* pos_rowptr, const int32_t* pos_cols,
+                          const int64_t* sorted_rowptr, const int32_t* sorted_cols,
+                          int32_t* out_u, int32_t* out_i, int32_t* out_j);
+
+/* base/deepRecommender.py:44-50 (and model/ranking/BPR.py:67-74): for each row k of a
+ * batch, j[k] = randbelow(num_items) until j not rated by u[k]. */
+int qrec_sample_pairwise(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,
+                         const int64_t* sorted_rowptr, const int32_t* sorted_cols,
+                         int32_t* out_j);
+
+/* base/deepRecommender.py:65-76: per interaction emit (u,i,1) then 4 x (u, randint(0,I-1)
+ * until unrated, 0).  Outputs have 5*n entries. */
+int qrec_sample_pointwise(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,
+                          const int32_t* i, const int64_t* sorted_rowptr,
+                          const int32_t* sorted_cols, int32_t* out_u, int32_t* out_i,
+                          int32_t* out_y);
+
+/* =====================================================================================
+ * K0 (fast) -- device sampler: Philox4x32-10 counter RNG + binary-search rejection.
+ * Same role as base/deepRecommender.py:47-49 for throughput runs (the MT19937 stream is
+ * serial by construction).  j[k] = (philox(seed; k, attempt, epoch).x * num_items) >> 32,
+ * attempt = 0,1,... until j is not rated by u[k].  Deterministic in (seed, epoch, k).
+ * ===================================================================================== */
+int qrec_sample_neg_philox(int64_t n, int32_t num_items, const int32_t* dev_u,
+                           const int64_t* dev_sorted_rowptr, const int32_t* dev_sorted_cols,
+                           uint64_t seed, uint32_t epoch, int32_t* dev_out_j, void* stream);
+
+/* =====================================================================================
+ * K1 -- BPR.optimization(u,i,j), model/ranking/BPR.py:45-53 (statement order as there).
+ * ===================================================================================== */
+
+/* Host prepass for the dependency-ordered kernel: for triple k, wait_x[k] = number of
+ * earlier triples (k' < k) that touch the same table row (P[u_k]; Q[i_k]; Q[j_k], where a
+ * Q row counts touches both as i and as j). */
+int qrec_bpr_order_prepare(int64_t n, const int32_t* u, const int32_t* i, const int32_t* j,
+                           int32_t num_users, int32_t num_items, int32_t* wait_u,
+                           int32_t* wait_i, int32_t* wait_j);
+
+/* Parity mode: results identical to running BPR.optimization over the triples in array
+ * order (Gauss-Seidel SGD, BPR.py:31-39), executed as a dataflow over the per-row
+ * dependency chains.  dev_ver_p / dev_ver_q: int32[num_users] / int32[num_items] row
+ * version counters, dev_ticket: uint64[1]; all three must be ZERO on entry.
+ * dev_loss: double[1], the kernel ADDS sum_k -ln(s_k) (BPR.py:53).  Any d >= 1. */
+int qrec_bpr_sgd_ordered_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                             const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                             const int32_t* dev_wait_u, const int32_t* dev_wait_i,
+                             const int32_t* dev_wait_j, int32_t* dev_ver_p, int32_t* dev_ver_q,
+                             unsigned long long* dev_ticket, float lr, float reg_u, float reg_i,
+                             double* dev_loss, void* stream);
+int qrec_bpr_sgd_ordered_f64(double* dev_P, double* dev_Q, int32_t d, int64_t n,
+                             const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                             const int32_t* dev_wait_u, const int32_t* dev_wait_i,
+                             const int32_t* dev_wait_j, int32_t* dev_ver_p, int32_t* dev_ver_q,
+                             unsigned long long* dev_ticket, double lr, double reg_u,
+                             double reg_i, double* dev_loss, void* stream);
+
+/* Throughput mode: one fused gather -> 2 dots -> sigmoid -> BPR step -> scatter-add kernel.
+ * Every triple reads its three rows, applies BPR.py:45-52 to its private copy and adds the
+ * row deltas back with 128-bit vector reductions (red.global.add.v4.f32).  Triples that
+ * share no row with another in-flight triple get exactly the reference update; rows shared
+ * inside a launch receive the SUM of their deltas (atomic, order-free).
+ * d must be a multiple of 4, 4 <= d <= 256.  dev_loss: double[1], accumulated. */
+int qrec_bpr_sgd_batch_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                           const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                           float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
+
+/* regU*sum(P*P) + regI*sum(Q*Q) building block (BPR.py:40): dev_out[0] += sum(x[k]^2). */
+int qrec_sumsq_f32(const float* dev_x, int64_t n, double* dev_out, void* stream);
+int qrec_sumsq_f64(const double* dev_x, int64_t n, double* dev_out, void* stream);
+
+/* =====================================================================================
+ * Pipelined host entry (what trainModel calls when the triples live in HOST memory):
+ * chunks the index arrays, overlaps H2D copies (copy stream) with the K1 kernel (compute
+ * stream) through a ring of device staging buffers owned by the ctx, returns the loss.
+ * ===================================================================================== */
+typedef struct qrec_ctx qrec_ctx;
+int qrec_ctx_create(int device, int64_t chunk_triples, qrec_ctx** out);
+int qrec_ctx_destroy(qrec_ctx* ctx);
+/* host u/i/j: pinned memory gives true overlap; pageable memory works but serialises.
+ * *host_loss receives sum_k -ln(s_k) of this call.  Synchronous on return. */
+int qrec_bpr_epoch_host(qrec_ctx* ctx, float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                        const int32_t* host_u, const int32_t* host_i, const int32_t* host_j,
+                        float lr, float reg_u, float reg_i, double* host_loss);
+
+/* =====================================================================================
+ * K2 -- Y = A * X for the normalised joint adjacency, CSR, fp32 values, int32 columns.
+ * Replaces tf.sparse_tensor_dense_matmul(norm_adj, E): model/ranking/LightGCN.py:17,
+ * model/ranking/NGCF.py:28, model/ranking/SimGCL.py:25,33.  A is symmetric, so the same
+ * call is the backward pass.  Optional fused layer accumulation (LightGCN.py:19):
+ * if dev_acc != NULL, acc[r,:] += acc_scale * Y[r,:].  d multiple of 4, <= 256.
+ * ===================================================================================== */
+int qrec_spmm_csr_f32(int32_t n_rows, const int64_t* dev_rowptr, const int32_t* dev_cols,
+                      const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
+                      float* dev_acc, float acc_scale, void* stream);
+
+/* =====================================================================================
+ * K3 -- gather rows of the propagated tables, bpr_loss + batch L2 and its gradient,
+ * scatter-added into dense gradient buffers.  util/loss.py:3-6, LightGCN.py:22-24,28-30.
+ *   y = u.p - u.n ; s = sigmoid(y) ; loss += -ln(s + eps) + reg*0.5*(|u|^2+|p|^2+|n|^2)
+ *   dL/dy = -s(1-s)/(s+eps)
+ *   gU[u] += dL/dy*(p-n) + reg*u ; gV[i] += dL/dy*u + reg*p ; gV[j] += -dL/dy*u + reg*n
+ * dev_gU/dev_gV must be zeroed by the caller.  dev_loss: double[1], accumulated.
+ * ===================================================================================== */
+int qrec_bpr_grad_scatter_f32(const float* dev_U, const float* dev_V, int32_t d, int64_t n,
+                              const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                              float eps, float reg, float* dev_gU, float* dev_gV,
+                              double* dev_loss, void* stream);
+
+/* =====================================================================================
+ * K4 -- tf.train.AdamOptimizer (TF 1.14) dense update over a whole variable:
+ * LightGCN.py:31-32, NGCF.py:54, SimGCL.py:99, BPR.py:84.
+ *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
+ *   var -= lr_t * m / (sqrt(v) + eps)            (t = 1-based step count)
+ * ===================================================================================== */
+int qrec_adam_dense_tf1_f32(float* dev_var, float* dev_m, float* dev_v, const float* dev_g,
+                            int64_t n, float lr, float beta1, float beta2, float eps,
+                            int64_t t, void* stream);
+
+/* Layer mean helper (LightGCN.py:19): dst[k] = scale * (a[k] + b[k]); dst may alias a. */
+int qrec_axpby_f32(float* dev_dst, const float* dev_a, const float* dev_b, float alpha,
+                   float beta, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QREC_H_ */

@@ -1,0 +1,100 @@
+"""ctypes binding of libqrec.so (the C ABI declared in include/qrec.h).
+
+The library is built in-tree by `__graft_entry__.build()` (qrec_b200/csrc/Makefile).  There is
+no fallback: if the shared object is missing or a symbol cannot be resolved, importing the
+engine raises.  Nothing here imports or executes anything under oracle/.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libqrec.so')
+
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u32p = C.POINTER(C.c_uint32)
+c_u8p = C.POINTER(C.c_uint8)
+c_f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+
+class MTState(C.Structure):
+    """qrec_mt19937: 624 state words + index (random.getstate()[1] layout)."""
+    _fields_ = [('mt', C.c_uint32 * 624), ('index', C.c_uint32)]
+
+
+MTp = C.POINTER(MTState)
+
+# name -> (restype, argtypes).  Device pointers travel as c_void_p (tensor.data_ptr()).
+SIGNATURES = {
+    'qrec_last_error': (C.c_char_p, []),
+    'qrec_version': (C.c_char_p, []),
+    'qrec_launch_count': (C.c_int64, []),
+    'qrec_mt_seed': (C.c_int, [MTp, C.c_uint64]),
+    'qrec_mt_set_state': (C.c_int, [MTp, c_u32p]),
+    'qrec_mt_get_state': (C.c_int, [MTp, c_u32p]),
+    'qrec_mt_next_u32': (C.c_uint32, [MTp]),
+    'qrec_mt_random': (C.c_double, [MTp]),
+    'qrec_mt_randbelow': (C.c_uint32, [MTp, C.c_uint32]),
+    'qrec_mt_shuffle_i32': (C.c_int, [MTp, C.c_int64, c_i32p]),
+    'qrec_mt_shuffle_pairs_i32': (C.c_int, [MTp, C.c_int64, c_i32p, c_i32p]),
+    'qrec_mt_data_split': (C.c_int, [MTp, C.c_int64, C.c_double, c_u8p]),
+    'qrec_sample_bpr_epoch': (C.c_int, [MTp, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i64p, c_i32p,
+                                        c_i32p, c_i32p, c_i32p]),
+    'qrec_sample_pairwise': (C.c_int, [MTp, C.c_int64, C.c_int32, c_i32p, c_i64p, c_i32p, c_i32p]),
+    'qrec_sample_pointwise': (C.c_int, [MTp, C.c_int64, C.c_int32, c_i32p, c_i32p, c_i64p, c_i32p,
+                                        c_i32p, c_i32p, c_i32p]),
+    'qrec_sample_neg_philox': (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, C.c_uint64, C.c_uint32,
+                                         vp, vp]),
+    'qrec_bpr_order_prepare': (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32,
+                                         c_i32p, c_i32p, c_i32p]),
+    'qrec_bpr_sgd_ordered_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, vp, vp,
+                                           vp, vp, C.c_float, C.c_float, C.c_float, vp, vp]),
+    'qrec_bpr_sgd_ordered_f64': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, vp, vp,
+                                           vp, vp, C.c_double, C.c_double, C.c_double, vp, vp]),
+    'qrec_bpr_sgd_batch_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
+                                         C.c_float, C.c_float, vp, vp]),
+    'qrec_sumsq_f32': (C.c_int, [vp, C.c_int64, vp, vp]),
+    'qrec_sumsq_f64': (C.c_int, [vp, C.c_int64, vp, vp]),
+    'qrec_ctx_create': (C.c_int, [C.c_int, C.c_int64, C.POINTER(vp)]),
+    'qrec_ctx_destroy': (C.c_int, [vp]),
+    'qrec_bpr_epoch_host': (C.c_int, [vp, vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
+                                      C.c_float, C.c_float, c_f64p]),
+    'qrec_spmm_csr_f32': (C.c_int, [C.c_int32, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
+    'qrec_bpr_grad_scatter_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
+                                            C.c_float, vp, vp, vp, vp]),
+    'qrec_adam_dense_tf1_f32': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,
+                                          C.c_float, C.c_float, C.c_int64, vp]),
+    'qrec_axpby_f32': (C.c_int, [vp, vp, vp, C.c_float, C.c_float, C.c_int64, vp]),
+}
+
+
+class QRecError(RuntimeError):
+    pass
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            'qrec_b200: %s not found -- build it with `python -c "import __graft_entry__ as g; '
+            'g.build()"` (or `make -C qrec_b200/csrc`).  There is no CPU fallback.' % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError('qrec_b200: libqrec.so does not export %s' % name) from e
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def check(rc, what=''):
+    """Turn a negative return code into an exception carrying qrec_last_error()."""
+    if rc != 0:
+        msg = lib.qrec_last_error()
+        raise QRecError('%s failed (rc=%d): %s' % (what or 'libqrec call', rc,
+                                                   msg.decode() if msg else ''))

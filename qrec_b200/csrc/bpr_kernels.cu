@@ -1,0 +1,401 @@
+// K1: BPR.optimization(u,i,j) on the GPU (reference: model/ranking/BPR.py:45-53).
+//
+//   x = P[u].Q[i] - P[u].Q[j];  s = 1/(1+exp(-x));  g = lr*(1-s)
+//   P[u] += g*(Q[i]-Q[j]);  Q[i] += g*P[u](new);  Q[j] -= g*P[u](new)
+//   P[u] -= lr*regU*P[u];   Q[i] -= lr*regI*Q[i];  Q[j] -= lr*regI*Q[j];   loss += -ln(s)
+//
+// Two kernels:
+//   * bpr_sgd_ordered_kernel  -- parity mode.  The reference loop is Gauss-Seidel: triple k
+//     must see every earlier update of its three rows.  Instead of level-by-level launches
+//     the kernel runs the epoch as a dataflow: warps claim triples in array order from a
+//     ticket counter and spin until each of their three rows has reached the version
+//     (= number of earlier touches) computed by qrec_bpr_order_prepare.  Because tickets are
+//     handed out in order to running warps, the oldest unfinished triple always has its
+//     dependencies satisfied, so the scheme cannot deadlock whatever the grid size.
+//   * bpr_sgd_batch_kernel    -- throughput mode.  LPR lanes own one triple (d=64: a half
+//     warp, one float4 per lane = one 128-bit LDG per row), the dot products are reduced with
+//     xor-shuffles inside the lane group and the three row deltas go back with
+//     REDG.E.ADD.F32x4 (red.global.add.v4.f32).  UNROLL triples per lane group are in flight
+//     before the first use so each warp keeps 2*UNROLL*3 row loads outstanding.
+#include <cmath>
+
+#include "common.h"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// Round-to-nearest mul/add/sub that ptxas never contracts into an FMA: numpy evaluates
+// `P[u] += g*(Q[i]-Q[j])` as separate multiply and add, and parity mode follows it.
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ float sigmoid_full(float x) { return 1.0f / (1.0f + expf(-x)); }
+__device__ __forceinline__ double sigmoid_full(double x) { return 1.0 / (1.0 + exp(-x)); }
+__device__ __forceinline__ double neg_log(float s) { return -(double)logf(s); }
+__device__ __forceinline__ double neg_log(double s) { return -log(s); }
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// parity mode
+// ------------------------------------------------------------------------------------------
+template <typename T, int E>  // E = ceil(d/32) elements per lane, element index e*32+lane
+__global__ void __launch_bounds__(256)
+bpr_sgd_ordered_kernel(T* __restrict__ P, T* __restrict__ Q, int d, long long n,
+                       const int* __restrict__ u, const int* __restrict__ i,
+                       const int* __restrict__ j, const int* __restrict__ wu,
+                       const int* __restrict__ wi, const int* __restrict__ wj, int* ver_p,
+                       int* ver_q, unsigned long long* ticket, T lr, T reg_u, T reg_i,
+                       double* loss) {
+  const int lane = threadIdx.x & 31;
+  double local_loss = 0.0;
+  const T a_u = mul_rn(lr, reg_u), a_i = mul_rn(lr, reg_i);
+  while (true) {
+    unsigned long long k = 0;
+    if (lane == 0) k = atomicAdd(ticket, 1ULL);
+    k = __shfl_sync(0xffffffffu, k, 0);
+    if (k >= (unsigned long long)n) break;
+    const int uu = u[k], ii = i[k], jj = j[k];
+    // lanes 0..2 each watch one row version
+    const int* vp = lane == 0 ? ver_p + uu : (lane == 1 ? ver_q + ii : ver_q + jj);
+    const int need = lane == 0 ? wu[k] : (lane == 1 ? wi[k] : wj[k]);
+    unsigned backoff = 8;
+    while (true) {
+      const int have = lane < 3 ? ld_acquire_gpu(vp) : need;
+      if (__all_sync(0xffffffffu, have == need)) break;
+      __nanosleep(backoff);
+      if (backoff < 64) backoff <<= 1;
+    }
+    T* pr = P + (size_t)uu * d;
+    T* qir = Q + (size_t)ii * d;
+    T* qjr = Q + (size_t)jj * d;
+    T p[E], qi[E], qj[E];
+    T di = 0, dj = 0;
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int c = e * 32 + lane;
+      if (c < d) {
+        p[e] = __ldcg(pr + c);  // L2-coherent: the row was last written by another SM
+        qi[e] = __ldcg(qir + c);
+        qj[e] = __ldcg(qjr + c);
+        di += p[e] * qi[e];
+        dj += p[e] * qj[e];
+      } else {
+        p[e] = qi[e] = qj[e] = 0;
+      }
+    }
+    di = warp_sum(di);
+    dj = warp_sum(dj);
+    const T s = sigmoid_full(sub_rn(di, dj));
+    const T g = mul_rn(lr, sub_rn((T)1, s));
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int c = e * 32 + lane;
+      if (c < d) {
+        T pn = add_rn(p[e], mul_rn(g, sub_rn(qi[e], qj[e])));
+        T qin = add_rn(qi[e], mul_rn(g, pn));
+        T qjn = sub_rn(qj[e], mul_rn(g, pn));
+        pn = sub_rn(pn, mul_rn(a_u, pn));
+        qin = sub_rn(qin, mul_rn(a_i, qin));
+        qjn = sub_rn(qjn, mul_rn(a_i, qjn));
+        __stcg(pr + c, pn);
+        __stcg(qir + c, qin);
+        __stcg(qjr + c, qjn);
+      }
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane < 3) red_release_gpu_add(const_cast<int*>(vp), 1);
+    if (lane == 0) local_loss += neg_log(s);
+  }
+  if (lane == 0 && local_loss != 0.0) atomicAdd(loss, local_loss);
+}
+
+// ------------------------------------------------------------------------------------------
+// throughput mode
+// ------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+
+// One BPR step on a 4-wide slice; returns the three deltas.
+__device__ __forceinline__ void bpr_step4(float4 p, float4 qi, float4 qj, float g, float a_u,
+                                          float a_i, float4& dp, float4& dqi, float4& dqj) {
+#define QREC_STEP(c)                                  \
+  {                                                   \
+    float pn = p.c + g * (qi.c - qj.c);               \
+    float qin = qi.c + g * pn;                        \
+    float qjn = qj.c - g * pn;                        \
+    dp.c = (pn - a_u * pn) - p.c;                     \
+    dqi.c = (qin - a_i * qin) - qi.c;                 \
+    dqj.c = (qjn - a_i * qjn) - qj.c;                 \
+  }
+  QREC_STEP(x) QREC_STEP(y) QREC_STEP(z) QREC_STEP(w)
+#undef QREC_STEP
+}
+
+template <int LPR, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256)
+bpr_sgd_batch_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, long long n,
+                     const int* __restrict__ u, const int* __restrict__ i,
+                     const int* __restrict__ j, float lr, float reg_u, float reg_i,
+                     double* loss) {
+  constexpr int TPW = 32 / LPR;  // triples processed side by side in one warp
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = nvec * 4;
+  const float a_u = lr * reg_u, a_i = lr * reg_i;
+  float lsum = 0.f;
+
+  for (long long base = warp * 32; base < n; base += nwarps * 32) {
+    const long long k = base + lane;
+    int mu = 0, mi = 0, mj = 0;
+    if (k < n) {
+      mu = __ldg(u + k);
+      mi = __ldg(i + k);
+      mj = __ldg(j + k);
+    }
+    const int cnt = (n - base) < 32 ? (int)(n - base) : 32;
+    for (int s0 = 0; s0 < cnt; s0 += TPW * UNROLL) {
+      float4 p[UNROLL][VPL], qi[UNROLL][VPL], qj[UNROLL][VPL];
+      float* pr[UNROLL];
+      float* qir[UNROLL];
+      float* qjr[UNROLL];
+      bool ok[UNROLL];
+#pragma unroll
+      for (int r = 0; r < UNROLL; ++r) {
+        const int t = s0 + r * TPW + sub;
+        const int uu = __shfl_sync(0xffffffffu, mu, t & 31);
+        const int ii = __shfl_sync(0xffffffffu, mi, t & 31);
+        const int jj = __shfl_sync(0xffffffffu, mj, t & 31);
+        ok[r] = t < cnt;
+        pr[r] = P + (size_t)uu * d + l * 4;
+        qir[r] = Q + (size_t)ii * d + l * 4;
+        qjr[r] = Q + (size_t)jj * d + l * 4;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          if (ok[r] && (l + v * LPR) < nvec) {
+            p[r][v] = *reinterpret_cast<const float4*>(pr[r] + v * LPR * 4);
+            qi[r][v] = *reinterpret_cast<const float4*>(qir[r] + v * LPR * 4);
+            qj[r][v] = *reinterpret_cast<const float4*>(qjr[r] + v * LPR * 4);
+          } else {
+            p[r][v] = qi[r][v] = qj[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < UNROLL; ++r) {
+        float x = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) x += dot4(p[r][v], qi[r][v]) - dot4(p[r][v], qj[r][v]);
+        x = group_sum<LPR>(x);
+        const float s = 1.0f / (1.0f + expf(-x));
+        const float g = lr * (1.0f - s);
+        if (ok[r]) {
+          if (l == 0) lsum += -logf(s);
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if ((l + v * LPR) < nvec) {
+              float4 dp, dqi, dqj;
+              bpr_step4(p[r][v], qi[r][v], qj[r][v], g, a_u, a_i, dp, dqi, dqj);
+              red_add_v4(pr[r] + v * LPR * 4, dp);
+              red_add_v4(qir[r] + v * LPR * 4, dqi);
+              red_add_v4(qjr[r] + v * LPR * 4, dqj);
+            }
+          }
+        }
+      }
+    }
+  }
+  // block reduction of the loss: one double atomic per block
+  __shared__ float wsum[8];
+  lsum = warp_sum(lsum);
+  if (lane == 0) wsum[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w];
+    if (t != 0.0) atomicAdd(loss, t);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+sumsq_kernel(const T* __restrict__ x, long long n, double* out) {
+  double acc = 0.0;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if constexpr (sizeof(T) == 4) {
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (long long k = tid; k < n4; k += stride) {
+      const float4 v = __ldg(x4 + k);
+      acc += (double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z + (double)v.w * v.w;
+    }
+    for (long long k = (n4 << 2) + tid; k < n; k += stride) acc += (double)x[k] * x[k];
+  } else {
+    for (long long k = tid; k < n; k += stride) acc += (double)x[k] * (double)x[k];
+  }
+  acc = warp_sum(acc);
+  __shared__ double wsum[8];
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += wsum[w];
+    atomicAdd(out, t);
+  }
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
+}
+
+template <typename T>
+int launch_ordered(T* P, T* Q, int d, long long n, const int* u, const int* i, const int* j,
+                   const int* wu, const int* wi, const int* wj, int* ver_p, int* ver_q,
+                   unsigned long long* ticket, T lr, T reg_u, T reg_i, double* loss,
+                   cudaStream_t st) {
+  QREC_REQUIRE(P && Q && loss && ticket && ver_p && ver_q, "bpr_sgd_ordered: null pointer");
+  QREC_REQUIRE(d >= 1 && d <= 256, "bpr_sgd_ordered: d=%d unsupported (1..256)", d);
+  QREC_REQUIRE(n >= 0, "bpr_sgd_ordered: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(u && i && j && wu && wi && wj, "bpr_sgd_ordered: null index pointer");
+  const int e = (d + 31) / 32;
+  // 2 CTAs of 8 warps per SM: enough warps to cover the dependency DAG's width at the
+  // synthetic scale (~25 independent triples per level in user-major order) without
+  // drowning the LSU in pollers.
+  const int grid = sm_count() * 2;
+#define QREC_ORD(E)                                                                              \
+  bpr_sgd_ordered_kernel<T, E><<<grid, 256, 0, st>>>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p,     \
+                                                     ver_q, ticket, lr, reg_u, reg_i, loss)
+  if (e <= 1) QREC_ORD(1);
+  else if (e <= 2) QREC_ORD(2);
+  else if (e <= 4) QREC_ORD(4);
+  else QREC_ORD(8);
+#undef QREC_ORD
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+}  // namespace
+
+namespace qrec {
+// shared with runtime.cu (pipelined host path)
+int launch_bpr_batch(float* P, float* Q, int d, long long n, const int* u, const int* i,
+                     const int* j, float lr, float reg_u, float reg_i, double* loss,
+                     cudaStream_t st) {
+  QREC_REQUIRE(P && Q && loss, "bpr_sgd_batch: null pointer");
+  QREC_REQUIRE(d >= 4 && d <= 256 && (d % 4) == 0, "bpr_sgd_batch: d=%d unsupported (multiple of 4, 4..256)", d);
+  QREC_REQUIRE(n >= 0, "bpr_sgd_batch: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(u && i && j, "bpr_sgd_batch: null index pointer");
+  const int nvec = d / 4;
+  const long long warps_needed = (n + 31) / 32;
+  const long long blocks_needed = (warps_needed + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;  // 8 CTAs x 8 warps per SM, grid-stride beyond
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+#define QREC_BATCH(LPR, VPL, UN)                                                                \
+  bpr_sgd_batch_kernel<LPR, VPL, UN><<<grid, 256, 0, st>>>(P, Q, nvec, n, u, i, j, lr, reg_u,   \
+                                                           reg_i, loss)
+  if (nvec <= 4) QREC_BATCH(4, 1, 2);
+  else if (nvec <= 8) QREC_BATCH(8, 1, 4);
+  else if (nvec <= 16) QREC_BATCH(16, 1, 4);
+  else if (nvec <= 32) QREC_BATCH(32, 1, 4);
+  else QREC_BATCH(32, 2, 2);
+#undef QREC_BATCH
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+}  // namespace qrec
+
+extern "C" {
+
+int qrec_bpr_sgd_ordered_f32(float* P, float* Q, int32_t d, int64_t n, const int32_t* u,
+                             const int32_t* i, const int32_t* j, const int32_t* wu,
+                             const int32_t* wi, const int32_t* wj, int32_t* ver_p,
+                             int32_t* ver_q, unsigned long long* ticket, float lr, float reg_u,
+                             float reg_i, double* loss, void* stream) {
+  return launch_ordered<float>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p, ver_q, ticket, lr, reg_u,
+                               reg_i, loss, (cudaStream_t)stream);
+}
+
+int qrec_bpr_sgd_ordered_f64(double* P, double* Q, int32_t d, int64_t n, const int32_t* u,
+                             const int32_t* i, const int32_t* j, const int32_t* wu,
+                             const int32_t* wi, const int32_t* wj, int32_t* ver_p,
+                             int32_t* ver_q, unsigned long long* ticket, double lr,
+                             double reg_u, double reg_i, double* loss, void* stream) {
+  return launch_ordered<double>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p, ver_q, ticket, lr, reg_u,
+                                reg_i, loss, (cudaStream_t)stream);
+}
+
+int qrec_bpr_sgd_batch_f32(float* P, float* Q, int32_t d, int64_t n, const int32_t* u,
+                           const int32_t* i, const int32_t* j, float lr, float reg_u,
+                           float reg_i, double* loss, void* stream) {
+  return qrec::launch_bpr_batch(P, Q, d, n, u, i, j, lr, reg_u, reg_i, loss, (cudaStream_t)stream);
+}
+
+int qrec_sumsq_f32(const float* x, int64_t n, double* out, void* stream) {
+  QREC_REQUIRE(out && (x || n == 0) && n >= 0, "qrec_sumsq_f32: bad argument");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0, "qrec_sumsq_f32: x not 16-byte aligned");
+  const long long blocks = (n / 4 + 255) / 256 + 1;
+  const long long cap = (long long)sm_count() * 8;
+  sumsq_kernel<float><<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_sumsq_f64(const double* x, int64_t n, double* out, void* stream) {
+  QREC_REQUIRE(out && (x || n == 0) && n >= 0, "qrec_sumsq_f64: bad argument");
+  if (n == 0) return QREC_OK;
+  const long long blocks = (n + 255) / 256;
+  const long long cap = (long long)sm_count() * 8;
+  sumsq_kernel<double><<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+}  // extern "C"

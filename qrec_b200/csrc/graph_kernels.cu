@@ -1,0 +1,352 @@
+// K2/K3/K4: the kernels behind the graph models' training step
+// (reference: model/ranking/LightGCN.py:11-41, util/loss.py:3-6, base/graphRecommender.py:10-39).
+//
+//   K2  spmm_csr_kernel          Y = A X (+ fused layer accumulation), CSR row partitioned:
+//                                LPR lanes own one row of Y (d=64: a half warp, float4 per lane);
+//                                the lane group streams the row's (col,val) pairs coalesced,
+//                                broadcasts them with group-masked shuffles and keeps 4 gathered
+//                                X rows in flight per lane.
+//   K3  bpr_grad_scatter_kernel  gather 3 rows of the propagated tables, -ln(sigmoid(y)+eps)
+//                                + batch L2, gradient scatter-added (REDG.ADD.F32x4) into the
+//                                dense gradient buffers.
+//   K4  adam_dense_tf1_kernel    TF1 AdamOptimizer dense update (every row moves every step).
+#include <cmath>
+
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+template <int LPR>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float dot4(float4 a, float4 b) {
+  return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+}
+__device__ __forceinline__ void fma4(float4& acc, float s, float4 x) {
+  acc.x = fmaf(s, x.x, acc.x); acc.y = fmaf(s, x.y, acc.y);
+  acc.z = fmaf(s, x.z, acc.z); acc.w = fmaf(s, x.w, acc.w);
+}
+
+int sm_count() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------ K2
+template <int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+spmm_csr_kernel(int n_rows, const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                const float* __restrict__ vals, const float* __restrict__ X,
+                float* __restrict__ Y, int nvec, float* __restrict__ acc, float acc_scale) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int d = nvec * 4;
+  const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + sub;
+  const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * GPW;
+  for (long long r = group; r < n_rows; r += ngroups) {
+    const long long start = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    float4 a[VPL];
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) a[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long base = start; base < end; base += LPR) {
+      const long long idx = base + l;
+      int c = 0;
+      float w = 0.f;
+      if (idx < end) {
+        c = __ldg(cols + idx);
+        w = __ldg(vals + idx);
+      }
+      const int m = (end - base) < LPR ? (int)(end - base) : LPR;
+      for (int t = 0; t < m; t += 4) {
+        int cc[4];
+        float ww[4];
+        float4 x[4][VPL];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          // lanes beyond m carry c=0,w=0: the (valid) row 0 is fetched and multiplied by 0
+          cc[q] = __shfl_sync(gmask, c, sub * LPR + ((t + q) & (LPR - 1)));
+          ww[q] = __shfl_sync(gmask, w, sub * LPR + ((t + q) & (LPR - 1)));
+          if (t + q >= m) ww[q] = 0.f;
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if ((t + q) < m && (l + v * LPR) < nvec)
+              x[q][v] = __ldg(reinterpret_cast<const float4*>(X + (size_t)cc[q] * d) + l + v * LPR);
+            else
+              x[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) fma4(a[v], ww[q], x[q][v]);
+      }
+    }
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      if ((l + v * LPR) < nvec) {
+        float4* yp = reinterpret_cast<float4*>(Y + (size_t)r * d) + l + v * LPR;
+        *yp = a[v];
+        if (acc != nullptr) {
+          float4* ap = reinterpret_cast<float4*>(acc + (size_t)r * d) + l + v * LPR;
+          float4 o = *ap;
+          fma4(o, acc_scale, a[v]);
+          *ap = o;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K3
+template <int LPR, int VPL, int UNROLL>
+__global__ void __launch_bounds__(256)
+bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V, int nvec,
+                        long long n, const int* __restrict__ u, const int* __restrict__ i,
+                        const int* __restrict__ j, float eps, float reg, float* __restrict__ gU,
+                        float* __restrict__ gV, double* loss) {
+  constexpr int TPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const int d = nvec * 4;
+  float lsum = 0.f;
+  for (long long base = warp * 32; base < n; base += nwarps * 32) {
+    const long long k = base + lane;
+    int mu = 0, mi = 0, mj = 0;
+    if (k < n) { mu = __ldg(u + k); mi = __ldg(i + k); mj = __ldg(j + k); }
+    const int cnt = (n - base) < 32 ? (int)(n - base) : 32;
+    for (int s0 = 0; s0 < cnt; s0 += TPW * UNROLL) {
+      float4 p[UNROLL][VPL], qi[UNROLL][VPL], qj[UNROLL][VPL];
+      size_t ou[UNROLL], oi[UNROLL], oj[UNROLL];
+      bool ok[UNROLL];
+#pragma unroll
+      for (int r = 0; r < UNROLL; ++r) {
+        const int t = s0 + r * TPW + sub;
+        const int uu = __shfl_sync(0xffffffffu, mu, t & 31);
+        const int ii = __shfl_sync(0xffffffffu, mi, t & 31);
+        const int jj = __shfl_sync(0xffffffffu, mj, t & 31);
+        ok[r] = t < cnt;
+        ou[r] = (size_t)uu * d + l * 4;
+        oi[r] = (size_t)ii * d + l * 4;
+        oj[r] = (size_t)jj * d + l * 4;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          if (ok[r] && (l + v * LPR) < nvec) {
+            p[r][v] = __ldg(reinterpret_cast<const float4*>(U + ou[r] + v * LPR * 4));
+            qi[r][v] = __ldg(reinterpret_cast<const float4*>(V + oi[r] + v * LPR * 4));
+            qj[r][v] = __ldg(reinterpret_cast<const float4*>(V + oj[r] + v * LPR * 4));
+          } else {
+            p[r][v] = qi[r][v] = qj[r][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < UNROLL; ++r) {
+        float y = 0.f, sq = 0.f;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) {
+          y += dot4(p[r][v], qi[r][v]) - dot4(p[r][v], qj[r][v]);
+          sq += dot4(p[r][v], p[r][v]) + dot4(qi[r][v], qi[r][v]) + dot4(qj[r][v], qj[r][v]);
+        }
+        y = group_sum<LPR>(y);
+        sq = group_sum<LPR>(sq);
+        const float s = 1.0f / (1.0f + expf(-y));
+        // d/dy of -ln(s+eps) = -s(1-s)/(s+eps)      
+        const float gy = -s * (1.0f - s) / (s + eps);
+        if (ok[r]) {
+          if (l == 0) lsum += -logf(s + eps) + reg * 0.5f * sq;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) {
+            if ((l + v * LPR) < nvec) {
+              const float4 P4 = p[r][v], I4 = qi[r][v], J4 = qj[r][v];
+              float4 gu, gi, gj;
+              gu.x = gy * (I4.x - J4.x) + reg * P4.x; gu.y = gy * (I4.y - J4.y) + reg * P4.y;
+              gu.z = gy * (I4.z - J4.z) + reg * P4.z; gu.w = gy * (I4.w - J4.w) + reg * P4.w;
+              gi.x = gy * P4.x + reg * I4.x; gi.y = gy * P4.y + reg * I4.y;
+              gi.z = gy * P4.z + reg * I4.z; gi.w = gy * P4.w + reg * I4.w;
+              gj.x = -gy * P4.x + reg * J4.x; gj.y = -gy * P4.y + reg * J4.y;
+              gj.z = -gy * P4.z + reg * J4.z; gj.w = -gy * P4.w + reg * J4.w;
+              red_add_v4(gU + ou[r] + v * LPR * 4, gu);
+              red_add_v4(gV + oi[r] + v * LPR * 4, gi);
+              red_add_v4(gV + oj[r] + v * LPR * 4, gj);
+            }
+          }
+        }
+      }
+    }
+  }
+  __shared__ float wsum[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+  if (lane == 0) wsum[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w];
+    if (t != 0.0) atomicAdd(loss, t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ K4
+__global__ void __launch_bounds__(256)
+adam_dense_tf1_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
+                      const float* __restrict__ g, long long n, float lr_t, float b1, float b2,
+                      float eps) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  const float ob1 = 1.0f - b1, ob2 = 1.0f - b2;
+  for (long long k = tid; k < n4; k += stride) {
+    float4 G = __ldg(reinterpret_cast<const float4*>(g) + k);
+    float4 M = reinterpret_cast<float4*>(m)[k];
+    float4 Vv = reinterpret_cast<float4*>(v)[k];
+    float4 W = reinterpret_cast<float4*>(var)[k];
+#define QREC_ADAM(c)                              \
+  M.c = b1 * M.c + ob1 * G.c;                     \
+  Vv.c = b2 * Vv.c + ob2 * (G.c * G.c);           \
+  W.c = W.c - lr_t * M.c / (sqrtf(Vv.c) + eps);
+    QREC_ADAM(x) QREC_ADAM(y) QREC_ADAM(z) QREC_ADAM(w)
+    reinterpret_cast<float4*>(m)[k] = M;
+    reinterpret_cast<float4*>(v)[k] = Vv;
+    reinterpret_cast<float4*>(var)[k] = W;
+  }
+  for (long long k = (n4 << 2) + tid; k < n; k += stride) {
+    float G = g[k], M = m[k], Vv = v[k], W = var[k];
+    M = b1 * M + ob1 * G;
+    Vv = b2 * Vv + ob2 * (G * G);
+    W = W - lr_t * M / (sqrtf(Vv) + eps);
+    m[k] = M; v[k] = Vv; var[k] = W;
+  }
+#undef QREC_ADAM
+}
+
+__global__ void __launch_bounds__(256)
+axpby_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b,
+             float alpha, float beta, long long n) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = n >> 2;
+  for (long long k = tid; k < n4; k += stride) {
+    const float4 A = reinterpret_cast<const float4*>(a)[k];
+    const float4 B = reinterpret_cast<const float4*>(b)[k];
+    float4 o;
+    o.x = alpha * A.x + beta * B.x; o.y = alpha * A.y + beta * B.y;
+    o.z = alpha * A.z + beta * B.z; o.w = alpha * A.w + beta * B.w;
+    reinterpret_cast<float4*>(dst)[k] = o;
+  }
+  for (long long k = (n4 << 2) + tid; k < n; k += stride) dst[k] = alpha * a[k] + beta * b[k];
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+
+extern "C" {
+
+int qrec_spmm_csr_f32(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
+                      const float* vals, const float* X, float* Y, int32_t d, float* acc,
+                      float acc_scale, void* stream) {
+  QREC_REQUIRE(n_rows >= 0, "qrec_spmm_csr_f32: n_rows < 0");
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_spmm_csr_f32: d=%d unsupported (multiple of 4, 4..256)", d);
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && X && Y, "qrec_spmm_csr_f32: null pointer");
+  QREC_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(acc), "qrec_spmm_csr_f32: tables must be 16-byte aligned");
+  QREC_REQUIRE(X != Y, "qrec_spmm_csr_f32: X and Y must not alias");
+  const int nvec = d / 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long cap = (long long)sm_count() * 8;
+#define QREC_SPMM(LPR, VPL)                                                                      \
+  {                                                                                              \
+    const long long groups_per_block = 8 * (32 / LPR);                                           \
+    long long blocks = (n_rows + groups_per_block - 1) / groups_per_block;                       \
+    if (blocks > cap) blocks = cap;                                                              \
+    spmm_csr_kernel<LPR, VPL><<<(int)blocks, 256, 0, st>>>(                                      \
+        n_rows, reinterpret_cast<const long long*>(rowptr), cols, vals, X, Y, nvec, acc, acc_scale); \
+  }
+  if (nvec <= 4) QREC_SPMM(4, 1)
+  else if (nvec <= 8) QREC_SPMM(8, 1)
+  else if (nvec <= 16) QREC_SPMM(16, 1)
+  else if (nvec <= 32) QREC_SPMM(32, 1)
+  else QREC_SPMM(32, 2)
+#undef QREC_SPMM
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_grad_scatter_f32(const float* U, const float* V, int32_t d, int64_t n,
+                              const int32_t* u, const int32_t* i, const int32_t* j, float eps,
+                              float reg, float* gU, float* gV, double* loss, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_bpr_grad_scatter_f32: d=%d unsupported", d);
+  QREC_REQUIRE(n >= 0, "qrec_bpr_grad_scatter_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(U && V && u && i && j && gU && gV && loss, "qrec_bpr_grad_scatter_f32: null pointer");
+  QREC_REQUIRE(aligned16(U) && aligned16(V) && aligned16(gU) && aligned16(gV),
+               "qrec_bpr_grad_scatter_f32: tables must be 16-byte aligned");
+  const int nvec = d / 4;
+  const long long blocks_needed = ((n + 31) / 32 + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_K3(LPR, VPL, UN)                                                                    \
+  bpr_grad_scatter_kernel<LPR, VPL, UN><<<grid, 256, 0, st>>>(U, V, nvec, n, u, i, j, eps, reg,  \
+                                                              gU, gV, loss)
+  if (nvec <= 4) QREC_K3(4, 1, 2);
+  else if (nvec <= 8) QREC_K3(8, 1, 4);
+  else if (nvec <= 16) QREC_K3(16, 1, 4);
+  else if (nvec <= 32) QREC_K3(32, 1, 4);
+  else QREC_K3(32, 2, 2);
+#undef QREC_K3
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_adam_dense_tf1_f32(float* var, float* m, float* v, const float* g, int64_t n, float lr,
+                            float beta1, float beta2, float eps, int64_t t, void* stream) {
+  QREC_REQUIRE(n >= 0 && t >= 1, "qrec_adam_dense_tf1_f32: bad n or t");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(var && m && v && g, "qrec_adam_dense_tf1_f32: null pointer");
+  QREC_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(g),
+               "qrec_adam_dense_tf1_f32: buffers must be 16-byte aligned");
+  // TF1 computes lr_t in the variable dtype (fp32) from fp32 beta powers
+  const float b1p = powf(beta1, (float)t), b2p = powf(beta2, (float)t);
+  const float lr_t = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
+  const long long blocks = (n / 4 + 255) / 256 + 1;
+  const long long cap = (long long)sm_count() * 8;
+  adam_dense_tf1_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      var, m, v, g, n, lr_t, beta1, beta2, eps);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_axpby_f32(float* dst, const float* a, const float* b, float alpha, float beta, int64_t n,
+                   void* stream) {
+  QREC_REQUIRE(n >= 0, "qrec_axpby_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(dst && a && b, "qrec_axpby_f32: null pointer");
+  QREC_REQUIRE(aligned16(dst) && aligned16(a) && aligned16(b), "qrec_axpby_f32: buffers must be 16-byte aligned");
+  const long long blocks = (n / 4 + 255) / 256 + 1;
+  const long long cap = (long long)sm_count() * 8;
+  axpby_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(dst, a, b, alpha, beta, n);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,340 @@
+"""Python face of libqrec.so: thin, typed wrappers over the C ABI (include/qrec.h).
+
+Tables and index arrays on the device are torch CUDA tensors (torch is plumbing: allocation,
+streams, torch.distributed); every compute call below goes through ctypes into the hand-written
+sm_100a kernels.  There is no CPU path here: device entry points raise if a tensor is not on a
+CUDA device.
+"""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import lib, check, MTState, QRecError  # noqa: F401  (QRecError re-exported)
+
+
+def _i32p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _i64p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+def version():
+    return lib.qrec_version().decode()
+
+
+def launch_count():
+    return int(lib.qrec_launch_count())
+
+
+# =============================================================================================
+# K0 (compat): CPython `random` clone + the reference samplers (host)
+# =============================================================================================
+class RatedCSR(object):
+    """Per-user item sets of the id-mapped training matrix, in the two orders the reference uses.
+
+    `pos_*`   : insertion order of trainSet_u[user] restricted to rating >= 1 -- the iteration
+                order of BPR.trainModel (model/ranking/BPR.py:22-25, 31-33).
+    `sorted_*`: every rated item of the user, ascending ids -- the rejection set
+                (`item_j in self.PositiveSet[user]`, BPR.py:36; `neg_item in trainSet_u[user]`,
+                base/deepRecommender.py:48).  Duplicate (user,item) lines collapse, as in the
+                reference's dict-of-dicts (data/rating.py:55).
+    """
+
+    def __init__(self, num_users, num_items, u_ids, i_ids, ratings=None, positive_threshold=1.0):
+        u_ids = np.ascontiguousarray(u_ids, dtype=np.int64)
+        i_ids = np.ascontiguousarray(i_ids, dtype=np.int64)
+        n = u_ids.shape[0]
+        if ratings is None:
+            ratings = np.ones(n, dtype=np.float64)
+        ratings = np.asarray(ratings, dtype=np.float64)
+        self.num_users, self.num_items = int(num_users), int(num_items)
+        key = u_ids * self.num_items + i_ids
+        # dict semantics: position of the FIRST occurrence, value of the LAST one
+        order = np.argsort(key, kind='stable')
+        ks = key[order]
+        first = np.ones(n, dtype=bool)
+        first[1:] = ks[1:] != ks[:-1]
+        last = np.ones(n, dtype=bool)
+        last[:-1] = ks[1:] != ks[:-1]
+        first_pos = order[first]                 # original index of first occurrence per pair
+        last_rating = ratings[order[last]]       # rating of last occurrence per pair
+        uniq_u = u_ids[first_pos]
+        uniq_i = i_ids[first_pos]
+        # sorted rows: pairs are already ordered by (u, i)
+        self.sorted_rowptr = np.zeros(self.num_users + 1, dtype=np.int64)
+        np.add.at(self.sorted_rowptr, uniq_u + 1, 1)
+        np.cumsum(self.sorted_rowptr, out=self.sorted_rowptr)
+        self.sorted_cols = np.ascontiguousarray(uniq_i, dtype=np.int32)
+        # positive rows in insertion order
+        keep = last_rating >= positive_threshold
+        pu, pi, ppos = uniq_u[keep], uniq_i[keep], first_pos[keep]
+        o2 = np.lexsort((ppos, pu))
+        self.pos_rowptr = np.zeros(self.num_users + 1, dtype=np.int64)
+        np.add.at(self.pos_rowptr, pu + 1, 1)
+        np.cumsum(self.pos_rowptr, out=self.pos_rowptr)
+        self.pos_cols = np.ascontiguousarray(pi[o2], dtype=np.int32)
+
+    @property
+    def num_positives(self):
+        return int(self.pos_rowptr[-1])
+
+
+class MT19937(object):
+    """Bit-exact clone of CPython's `random.Random` for the calls the reference makes."""
+
+    def __init__(self, seed=None):
+        self._st = MTState()
+        if seed is not None:
+            self.seed(seed)
+
+    def seed(self, s):
+        check(lib.qrec_mt_seed(C.byref(self._st), abs(int(s))), 'qrec_mt_seed')
+
+    def setstate(self, state):
+        """Accepts random.getstate() or a uint32[625] array (624 words + index)."""
+        if isinstance(state, tuple):
+            assert state[0] == 3
+            state = state[1]
+        a = np.ascontiguousarray(state, dtype=np.uint32)
+        assert a.shape == (625,)
+        check(lib.qrec_mt_set_state(C.byref(self._st), a.ctypes.data_as(C.POINTER(C.c_uint32))),
+              'qrec_mt_set_state')
+
+    def getstate_array(self):
+        a = np.empty(625, dtype=np.uint32)
+        check(lib.qrec_mt_get_state(C.byref(self._st), a.ctypes.data_as(C.POINTER(C.c_uint32))),
+              'qrec_mt_get_state')
+        return a
+
+    def getstate(self):
+        return (3, tuple(int(x) for x in self.getstate_array()), None)
+
+    def random(self):
+        return float(lib.qrec_mt_random(C.byref(self._st)))
+
+    def randbelow(self, n):
+        return int(lib.qrec_mt_randbelow(C.byref(self._st), int(n)))
+
+    def getrandbits32(self):
+        return int(lib.qrec_mt_next_u32(C.byref(self._st)))
+
+    def shuffle(self, x):
+        assert x.dtype == np.int32 and x.flags.c_contiguous
+        check(lib.qrec_mt_shuffle_i32(C.byref(self._st), x.shape[0], _i32p(x)), 'qrec_mt_shuffle_i32')
+
+    def shuffle_pairs(self, a, b):
+        assert a.dtype == np.int32 and b.dtype == np.int32 and a.shape == b.shape
+        assert a.flags.c_contiguous and b.flags.c_contiguous
+        check(lib.qrec_mt_shuffle_pairs_i32(C.byref(self._st), a.shape[0], _i32p(a), _i32p(b)),
+              'qrec_mt_shuffle_pairs_i32')
+
+    def data_split(self, n, test_ratio):
+        keep = np.empty(n, dtype=np.uint8)
+        check(lib.qrec_mt_data_split(C.byref(self._st), n, float(test_ratio),
+                                     keep.ctypes.data_as(C.POINTER(C.c_uint8))), 'qrec_mt_data_split')
+        return keep.astype(bool)
+
+    def sample_bpr_epoch(self, csr, out=None):
+        """One epoch of model/ranking/BPR.py:31-38 -> (u, i, j) int32 arrays."""
+        n = csr.num_positives
+        if out is None:
+            out = (np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int32))
+        u, i, j = out
+        check(lib.qrec_sample_bpr_epoch(C.byref(self._st), csr.num_users, csr.num_items,
+                                        _i64p(csr.pos_rowptr), _i32p(csr.pos_cols),
+                                        _i64p(csr.sorted_rowptr), _i32p(csr.sorted_cols),
+                                        _i32p(u), _i32p(i), _i32p(j)), 'qrec_sample_bpr_epoch')
+        return u, i, j
+
+    def sample_pairwise(self, csr, u, out=None):
+        """Negatives for a batch of users: base/deepRecommender.py:44-50."""
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        j = np.empty(u.shape[0], np.int32) if out is None else out
+        check(lib.qrec_sample_pairwise(C.byref(self._st), u.shape[0], csr.num_items, _i32p(u),
+                                       _i64p(csr.sorted_rowptr), _i32p(csr.sorted_cols), _i32p(j)),
+              'qrec_sample_pairwise')
+        return j
+
+    def sample_pointwise(self, csr, u, i):
+        """1 positive + 4 negatives per interaction: base/deepRecommender.py:65-76."""
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        i = np.ascontiguousarray(i, dtype=np.int32)
+        n = u.shape[0]
+        ou, oi, oy = (np.empty(5 * n, np.int32) for _ in range(3))
+        check(lib.qrec_sample_pointwise(C.byref(self._st), n, csr.num_items, _i32p(u), _i32p(i),
+                                        _i64p(csr.sorted_rowptr), _i32p(csr.sorted_cols),
+                                        _i32p(ou), _i32p(oi), _i32p(oy)), 'qrec_sample_pointwise')
+        return ou, oi, oy
+
+
+def bpr_order_prepare(u, i, j, num_users, num_items):
+    """Row-version numbers for the dependency-ordered kernel (host, O(n))."""
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    j = np.ascontiguousarray(j, dtype=np.int32)
+    n = u.shape[0]
+    wu, wi, wj = (np.empty(n, np.int32) for _ in range(3))
+    check(lib.qrec_bpr_order_prepare(n, _i32p(u), _i32p(i), _i32p(j), int(num_users), int(num_items),
+                                     _i32p(wu), _i32p(wi), _i32p(wj)), 'qrec_bpr_order_prepare')
+    return wu, wi, wj
+
+
+# =============================================================================================
+# device entry points
+# =============================================================================================
+def _torch():
+    import torch
+    return torch
+
+
+def _dev(t, dtype, name):
+    torch = _torch()
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise QRecError('%s must be a CUDA tensor (the engine has no CPU path)' % name)
+    if t.dtype != dtype:
+        raise QRecError('%s must be %s, got %s' % (name, dtype, t.dtype))
+    if not t.is_contiguous():
+        raise QRecError('%s must be contiguous' % name)
+    return t.data_ptr()
+
+
+def _stream():
+    return _torch().cuda.current_stream().cuda_stream
+
+
+def sample_neg_philox(u, sorted_rowptr, sorted_cols, num_items, seed, epoch, out=None):
+    torch = _torch()
+    n = u.shape[0]
+    if out is None:
+        out = torch.empty(n, dtype=torch.int32, device=u.device)
+    check(lib.qrec_sample_neg_philox(n, int(num_items), _dev(u, torch.int32, 'u'),
+                                     _dev(sorted_rowptr, torch.int64, 'sorted_rowptr'),
+                                     _dev(sorted_cols, torch.int32, 'sorted_cols'),
+                                     int(seed), int(epoch), _dev(out, torch.int32, 'out'), _stream()),
+          'qrec_sample_neg_philox')
+    return out
+
+
+def bpr_sgd_ordered(P, Q, u, i, j, wu, wi, wj, lr, reg_u, reg_i, loss):
+    """Parity mode: sequential-equivalent BPR.optimization over the triples in array order."""
+    torch = _torch()
+    f64 = P.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    n = u.shape[0]
+    d = P.shape[1]
+    assert Q.shape[1] == d
+    ver_p = torch.zeros(P.shape[0], dtype=torch.int32, device=P.device)
+    ver_q = torch.zeros(Q.shape[0], dtype=torch.int32, device=P.device)
+    ticket = torch.zeros(1, dtype=torch.int64, device=P.device)
+    fn = lib.qrec_bpr_sgd_ordered_f64 if f64 else lib.qrec_bpr_sgd_ordered_f32
+    check(fn(_dev(P, dt, 'P'), _dev(Q, dt, 'Q'), d, n, _dev(u, torch.int32, 'u'),
+             _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'), _dev(wu, torch.int32, 'wu'),
+             _dev(wi, torch.int32, 'wi'), _dev(wj, torch.int32, 'wj'), ver_p.data_ptr(),
+             ver_q.data_ptr(), ticket.data_ptr(), float(lr), float(reg_u), float(reg_i),
+             _dev(loss, torch.float64, 'loss'), _stream()), 'qrec_bpr_sgd_ordered')
+    return loss
+
+
+def bpr_sgd_batch(P, Q, u, i, j, lr, reg_u, reg_i, loss):
+    """Throughput mode: fused gather-dot-sigmoid-update-scatter-add over device triples."""
+    torch = _torch()
+    n = u.shape[0]
+    d = P.shape[1]
+    assert Q.shape[1] == d and i.shape[0] == n and j.shape[0] == n
+    check(lib.qrec_bpr_sgd_batch_f32(_dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), d, n,
+                                     _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'),
+                                     _dev(j, torch.int32, 'j'), float(lr), float(reg_u),
+                                     float(reg_i), _dev(loss, torch.float64, 'loss'), _stream()),
+          'qrec_bpr_sgd_batch_f32')
+    return loss
+
+
+def sumsq(x, out):
+    torch = _torch()
+    fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32
+    check(fn(_dev(x, x.dtype, 'x'), x.numel(), _dev(out, torch.float64, 'out'), _stream()), 'qrec_sumsq')
+    return out
+
+
+class HostPipeline(object):
+    """qrec_ctx: copy/compute pipeline for epochs whose triples live in host memory."""
+
+    def __init__(self, device=0, chunk_triples=1 << 22):
+        self._ctx = C.c_void_p()
+        check(lib.qrec_ctx_create(int(device), int(chunk_triples), C.byref(self._ctx)), 'qrec_ctx_create')
+
+    def close(self):
+        if self._ctx:
+            check(lib.qrec_ctx_destroy(self._ctx), 'qrec_ctx_destroy')
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def bpr_epoch(self, P, Q, u, i, j, lr, reg_u, reg_i):
+        """u,i,j: host int32 (numpy arrays or CPU torch tensors; pinned gives overlap)."""
+        torch = _torch()
+
+        def hp(a, name):
+            if isinstance(a, np.ndarray):
+                assert a.dtype == np.int32 and a.flags.c_contiguous, name
+                return a.ctypes.data, a.shape[0]
+            assert (not a.is_cuda) and a.dtype == torch.int32 and a.is_contiguous(), name
+            return a.data_ptr(), a.shape[0]
+
+        pu, n = hp(u, 'u')
+        pi, ni = hp(i, 'i')
+        pj, nj = hp(j, 'j')
+        assert n == ni == nj
+        torch.cuda.current_stream().synchronize()   # tables may have pending work on torch's stream
+        loss = C.c_double(0.0)
+        check(lib.qrec_bpr_epoch_host(self._ctx, _dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'),
+                                      P.shape[1], n, pu, pi, pj, float(lr), float(reg_u), float(reg_i),
+                                      C.byref(loss)), 'qrec_bpr_epoch_host')
+        return loss.value
+
+
+def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0):
+    """Y = A @ X (CSR fp32); optional fused acc += acc_scale * Y."""
+    torch = _torch()
+    n_rows = rowptr.shape[0] - 1
+    d = X.shape[1]
+    check(lib.qrec_spmm_csr_f32(n_rows, _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
+                                _dev(vals, torch.float32, 'vals'), _dev(X, torch.float32, 'X'),
+                                _dev(Y, torch.float32, 'Y'), d,
+                                _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                float(acc_scale), _stream()), 'qrec_spmm_csr_f32')
+    return Y
+
+
+def bpr_grad_scatter(U, V, u, i, j, eps, reg, gU, gV, loss):
+    torch = _torch()
+    check(lib.qrec_bpr_grad_scatter_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'),
+                                        U.shape[1], u.shape[0], _dev(u, torch.int32, 'u'),
+                                        _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'),
+                                        float(eps), float(reg), _dev(gU, torch.float32, 'gU'),
+                                        _dev(gV, torch.float32, 'gV'), _dev(loss, torch.float64, 'loss'),
+                                        _stream()), 'qrec_bpr_grad_scatter_f32')
+    return loss
+
+
+def adam_dense_tf1(var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
+    torch = _torch()
+    check(lib.qrec_adam_dense_tf1_f32(_dev(var, torch.float32, 'var'), _dev(m, torch.float32, 'm'),
+                                      _dev(v, torch.float32, 'v'), _dev(g, torch.float32, 'g'),
+                                      var.numel(), float(lr), float(beta1), float(beta2), float(eps),
+                                      int(t), _stream()), 'qrec_adam_dense_tf1_f32')
+    return var
+
+
+def axpby(dst, a, b, alpha, beta):
+    torch = _torch()
+    check(lib.qrec_axpby_f32(_dev(dst, torch.float32, 'dst'), _dev(a, torch.float32, 'a'),
+                             _dev(b, torch.float32, 'b'), float(alpha), float(beta), dst.numel(),
+                             _stream()), 'qrec_axpby_f32')
+    return dst

@@ -1,0 +1,54 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line('markers', 'gpu: needs a CUDA device (run on the B200 box)')
+
+
+@pytest.fixture(scope='session')
+def golden_bpr():
+    return np.load(os.path.join(GOLDEN, 'bpr_filmtrust_seed0.npz'))
+
+
+@pytest.fixture(scope='session')
+def golden_graph():
+    return np.load(os.path.join(GOLDEN, 'sampler_graph_filmtrust_seed1234.npz'))
+
+
+def ids_from_names(names, vocab):
+    lut = {n: k for k, n in enumerate(vocab.tolist())}
+    return np.array([lut[n] for n in names.tolist()], dtype=np.int32)
+
+
+@pytest.fixture(scope='session')
+def bpr_ids(golden_bpr):
+    """(u_ids, i_ids, num_users, num_items) of the FilmTrust training list in reference order."""
+    g = golden_bpr
+    u = ids_from_names(g['train_users'], g['user_names'])
+    i = ids_from_names(g['train_items'], g['item_names'])
+    return u, i, len(g['user_names']), len(g['item_names'])
+
+
+@pytest.fixture(scope='session')
+def graph_ids(golden_graph):
+    g = golden_graph
+    u = ids_from_names(g['train_users'], g['user_names'])
+    i = ids_from_names(g['train_items'], g['item_names'])
+    return u, i, len(g['user_names']), len(g['item_names'])
+
+
+def rows_and_sets(u, i, num_users):
+    """dict-of-dict view of the training list: per-user item lists (insertion order, dedup) + sets."""
+    rows = [dict() for _ in range(num_users)]
+    for uu, ii in zip(u.tolist(), i.tolist()):
+        rows[uu][ii] = 1
+    return [list(r.keys()) for r in rows], [set(r.keys()) for r in rows]

@@ -1,0 +1,279 @@
+"""Parity tests proper for K0(fast)/K1: the CUDA path (through the C ABI) against the oracle and
+the golden vectors recorded from the reference.  Needs a GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+LR, REG = 0.01, 0.001
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope='module')
+def E():
+    from qrec_b200 import engine
+    return engine
+
+
+def _init_tables(nu, ni, d=64):
+    np.random.seed(0)
+    P = np.random.rand(nu, d) / 3
+    Q = np.random.rand(ni, d) / 3
+    return P, Q
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _run_ordered(torch, E, P, Q, t, nu, ni, lr=LR, reg=REG):
+    wu, wi, wj = E.bpr_order_prepare(t[:, 0], t[:, 1], t[:, 2], nu, ni)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_ordered(P, Q, _dev(torch, t[:, 0]), _dev(torch, t[:, 1]), _dev(torch, t[:, 2]),
+                      _dev(torch, wu), _dev(torch, wi), _dev(torch, wj), lr, reg, reg, loss)
+    torch.cuda.synchronize()
+    return float(loss.item())
+
+
+def test_ordered_f64_matches_reference_three_epochs(torch, E, golden_bpr, bpr_ids):
+    """float64 parity mode == the reference's numpy path (model/ranking/BPR.py:19-53), incl. the
+    epoch loss (BPR.py:40) and the adaptive learning rate (iterativeRecommender.py:56-63)."""
+    from oracle import bpr_oracle as O
+    _, _, nu, ni = bpr_ids
+    P0, Q0 = _init_tables(nu, ni)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    lr, last = LR, 0.0
+    for ep in range(3):
+        t = golden_bpr['triples_epoch'][ep]
+        loss = _run_ordered(torch, E, P, Q, t, nu, ni, lr=lr)
+        reg = torch.zeros(2, dtype=torch.float64, device='cuda')
+        E.sumsq(P, reg[0:1]); E.sumsq(Q, reg[1:2])
+        loss += REG * float(reg[0].item()) + REG * float(reg[1].item())
+        assert abs(loss - golden_bpr['loss'][ep]) <= 1e-9 * golden_bpr['loss'][ep]
+        if ep == 0:
+            np.testing.assert_allclose(P.cpu().numpy(), golden_bpr['P_epoch1'], rtol=1e-10, atol=1e-13)
+            np.testing.assert_allclose(Q.cpu().numpy(), golden_bpr['Q_epoch1'], rtol=1e-10, atol=1e-13)
+        lr = O.update_learning_rate(lr, 1.0, ep + 1, last, loss)
+        assert lr == golden_bpr['lrate'][ep][1]
+        last = loss
+    np.testing.assert_allclose(P.cpu().numpy(), golden_bpr['P_epoch3'], rtol=2e-7, atol=1e-8)
+    np.testing.assert_allclose(Q.cpu().numpy(), golden_bpr['Q_epoch3'], rtol=2e-7, atol=1e-8)
+
+
+def test_ordered_f32_within_1e5_relative_after_one_epoch(torch, E, golden_bpr, bpr_ids):
+    """north_star tolerance: fp32 embeddings within 1e-5 relative after one epoch (max-norm
+    relative, i.e. |got-ref|_inf <= 1e-5*|ref|_inf) against the float64 reference."""
+    from oracle import c_oracle
+    _, _, nu, ni = bpr_ids
+    P0, Q0 = _init_tables(nu, ni)
+    P, Q = _dev(torch, P0.astype(np.float32)), _dev(torch, Q0.astype(np.float32))
+    t = golden_bpr['triples_epoch'][0]
+    loss = _run_ordered(torch, E, P, Q, t, nu, ni)
+    for got, ref in ((P.cpu().numpy(), golden_bpr['P_epoch1']), (Q.cpu().numpy(), golden_bpr['Q_epoch1'])):
+        assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()
+        np.testing.assert_allclose(got, ref, rtol=1e-5, atol=2e-6)
+    # and against the fp32 sequential oracle it is tighter still (same arithmetic, only the dot
+    # product summation order differs)
+    Pc, Qc = P0.astype(np.float32), Q0.astype(np.float32)
+    closs = c_oracle.bpr_sgd_sequential(Pc, Qc, t[:, 0], t[:, 1], t[:, 2], LR, REG, REG)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=2e-5, atol=2e-6)
+    assert abs(loss - closs) <= 1e-5 * closs
+
+
+@pytest.mark.parametrize('d', [1, 7, 50, 64, 100, 200])
+def test_ordered_generic_d_heavy_conflicts(torch, E, d):
+    """Few rows, many triples: almost every triple depends on its predecessor."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(d)
+    nu, ni, n = 5, 9, 3000
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = rng.integers(0, ni, n).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, ni - 1, n)) % ni).astype(np.int32)
+    P0 = rng.random((nu, d)) / 3
+    Q0 = rng.random((ni, d)) / 3
+    t = np.stack([u, i, j], 1)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = _run_ordered(torch, E, P, Q, t, nu, ni, lr=0.05, reg=0.01)
+    Pc, Qc = P0.copy(), Q0.copy()
+    closs = c_oracle.bpr_sgd_sequential(Pc, Qc, u, i, j, 0.05, 0.01, 0.01)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qc, rtol=1e-9, atol=1e-12)
+    assert abs(loss - closs) <= 1e-9 * abs(closs)
+
+
+def test_ordered_empty_input(torch, E):
+    P = torch.ones(3, 8, device='cuda', dtype=torch.float64)
+    Q = torch.ones(4, 8, device='cuda', dtype=torch.float64)
+    z = torch.zeros(0, dtype=torch.int32, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_ordered(P, Q, z, z, z, z, z, z, 0.1, 0.1, 0.1, loss)
+    torch.cuda.synchronize()
+    assert float(loss.item()) == 0.0 and bool((P == 1).all())
+
+
+def _conflict_free_triples(rng, nu, ni, n):
+    assert n <= nu and 2 * n <= ni
+    u = rng.permutation(nu)[:n].astype(np.int32)
+    items = rng.permutation(ni)[:2 * n].astype(np.int32)
+    return u, items[:n].copy(), items[n:].copy()
+
+
+@pytest.mark.parametrize('d,n', [(64, 1), (64, 31), (64, 1000), (64, 4097), (16, 333), (32, 500),
+                                 (48, 257), (128, 700), (256, 300), (200, 123), (8, 64)])
+def test_batch_conflict_free_equals_reference_step(torch, E, d, n):
+    """Triples that share no row: the fused kernel must give exactly BPR.optimization per triple
+    (up to one fp32 rounding of `row + delta`)."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(1000 * d + n)
+    nu, ni = max(n, 8), max(2 * n, 16)
+    u, i, j = _conflict_free_triples(rng, nu, ni, n)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(P, Q, _dev(torch, u), _dev(torch, i), _dev(torch, j), 0.05, 0.01, 0.02, loss)
+    torch.cuda.synchronize()
+    Pc, Qc = P0.copy(), Q0.copy()
+    closs = c_oracle.bpr_sgd_sequential(Pc, Qc, u, i, j, 0.05, 0.01, 0.02)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qc, rtol=1e-6, atol=1e-7)
+    assert abs(float(loss.item()) - closs) <= 1e-5 * abs(closs) + 1e-6
+
+
+def test_batch_with_shared_rows_sums_deltas(torch, E):
+    """Rows shared inside a launch get the SUM of per-triple deltas (scatter-add).  Reads may see
+    a neighbour's delta already applied (the kernel is fused, not two-phase), which perturbs each
+    delta by O(lr * |delta|); the tolerance below is that second-order term."""
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(5)
+    nu, ni, n, d = 50, 40, 4000, 64
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = rng.integers(0, ni, n).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, ni - 1, n)) % ni).astype(np.int32)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    lr = 1e-4
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(P, Q, _dev(torch, u), _dev(torch, i), _dev(torch, j), lr, REG, REG, loss)
+    torch.cuda.synchronize()
+    dP, dQ, jl = O.bpr_sgd_jacobi(P0, Q0, np.stack([u, i, j], 1), lr, REG, REG)
+    gotP = P.cpu().numpy().astype(np.float64) - P0
+    gotQ = Q.cpu().numpy().astype(np.float64) - Q0
+    assert np.abs(gotP - dP).max() <= 0.03 * np.abs(dP).max()
+    assert np.abs(gotQ - dQ).max() <= 0.03 * np.abs(dQ).max()
+    assert abs(float(loss.item()) - jl) <= 1e-3 * jl
+
+
+def test_batch_bad_arguments(torch, E):
+    P = torch.zeros(4, 6, device='cuda')      # d=6 not a multiple of 4
+    Q = torch.zeros(4, 6, device='cuda')
+    z = torch.zeros(1, dtype=torch.int32, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    with pytest.raises(E.QRecError):
+        E.bpr_sgd_batch(P, Q, z, z, z, 0.1, 0, 0, loss)
+    with pytest.raises(E.QRecError):          # CPU tensors are rejected: there is no CPU path
+        E.bpr_sgd_batch(P.cpu(), Q, z, z, z, 0.1, 0, 0, loss)
+
+
+def test_batch_training_tracks_sequential_loss_curve(torch, E, golden_bpr, bpr_ids):
+    """Throughput mode on the reference's own FilmTrust triples: the epoch losses follow the
+    reference's (Hogwild vs Gauss-Seidel differ in second order only)."""
+    _, _, nu, ni = bpr_ids
+    P0, Q0 = _init_tables(nu, ni)
+    P, Q = _dev(torch, P0.astype(np.float32)), _dev(torch, Q0.astype(np.float32))
+    rng = np.random.default_rng(0)
+    for ep in range(3):
+        t = golden_bpr['triples_epoch'][ep][rng.permutation(golden_bpr['triples_epoch'].shape[1])]
+        lr = float(golden_bpr['lrate'][ep][0])
+        loss = torch.zeros(3, dtype=torch.float64, device='cuda')
+        E.bpr_sgd_batch(P, Q, _dev(torch, t[:, 0]), _dev(torch, t[:, 1]), _dev(torch, t[:, 2]), lr, REG, REG, loss[0:1])
+        E.sumsq(P, loss[1:2]); E.sumsq(Q, loss[2:3])
+        l = loss.cpu().numpy()
+        total = l[0] + REG * l[1] + REG * l[2]
+        assert abs(total - golden_bpr['loss'][ep]) <= 0.05 * golden_bpr['loss'][ep]
+
+
+def test_host_pipeline_equals_device_call(torch, E):
+    rng = np.random.default_rng(11)
+    nu, ni, n, d = 5000, 9000, 3000, 64
+    u, i, j = _conflict_free_triples(rng, nu, ni, n)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    Pa, Qa, Pb, Qb = _dev(torch, P0), _dev(torch, Q0), _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(Pa, Qa, _dev(torch, u), _dev(torch, i), _dev(torch, j), 0.05, 0.01, 0.01, loss)
+    pipe = E.HostPipeline(0, chunk_triples=700)       # 5 chunks, last one short
+    hu, hi, hj = (torch.from_numpy(x).pin_memory() for x in (u, i, j))
+    hl = pipe.bpr_epoch(Pb, Qb, hu, hi, hj, 0.05, 0.01, 0.01)
+    torch.cuda.synchronize()
+    assert torch.equal(Pa, Pb) and torch.equal(Qa, Qb)
+    assert abs(hl - float(loss.item())) <= 1e-9 * abs(hl)
+    # pageable numpy input and an empty epoch
+    assert pipe.bpr_epoch(Pb, Qb, u[:0].copy(), i[:0].copy(), j[:0].copy(), 0.05, 0.01, 0.01) == 0.0
+    pipe.close()
+
+
+def test_philox_sampler_bit_exact_and_valid(torch, E, bpr_ids):
+    from oracle import bpr_oracle as O
+    from conftest import rows_and_sets
+    u, i, nu, ni = bpr_ids
+    csr = E.RatedCSR(nu, ni, u, i)
+    _, sets = rows_and_sets(u, i, nu)
+    rp, cols = _dev(torch, csr.sorted_rowptr), _dev(torch, csr.sorted_cols)
+    for seed, epoch in ((0, 0), (0x1234567890abcdef, 3)):
+        j = E.sample_neg_philox(_dev(torch, u), rp, cols, ni, seed, epoch).cpu().numpy()
+        ref = O.sample_neg_philox(u.tolist(), sets, ni, seed, epoch)
+        assert np.array_equal(j, ref)
+        assert all(jj not in sets[uu] for uu, jj in zip(u.tolist(), j.tolist()))
+        assert j.min() >= 0 and j.max() < ni
+    # dense user: 1890 of 1891 items rated -> many rejections, still terminates and is exact
+    dense_items = np.arange(ni - 1)
+    csr2 = E.RatedCSR(1, ni, np.zeros(ni - 1, np.int64), dense_items)
+    uu = torch.zeros(257, dtype=torch.int32, device='cuda')
+    j2 = E.sample_neg_philox(uu, _dev(torch, csr2.sorted_rowptr), _dev(torch, csr2.sorted_cols), ni, 9, 1)
+    assert bool((j2 == ni - 1).all())
+
+
+def test_sumsq(torch, E):
+    rng = np.random.default_rng(2)
+    for n in (1, 3, 4, 1027, 1 << 20):
+        x = rng.standard_normal(n)
+        for dt in (np.float32, np.float64):
+            xs = x.astype(dt)
+            out = torch.zeros(1, dtype=torch.float64, device='cuda')
+            E.sumsq(_dev(torch, xs), out)
+            ref = float((xs.astype(np.float64) ** 2).sum())
+            assert abs(float(out.item()) - ref) <= 1e-12 * ref + 1e-300
+
+
+def test_full_size_properties_synthetic(torch, E):
+    """BASELINE-size tables (1M x 100K, d=64), 4M shuffled triples: size-independent properties.
+    (1) lr=0 with reg=0 is the identity; (2) rows not named by any triple are untouched;
+    (3) the loss equals sum softplus(-x) computed by an independent torch expression."""
+    g = torch.Generator(device='cuda'); g.manual_seed(1)
+    nu, ni, d, n = 1_000_000, 100_000, 64, 1 << 22
+    P = torch.rand(nu, d, device='cuda', generator=g) / 3
+    Q = torch.rand(ni, d, device='cuda', generator=g) / 3
+    u = torch.randint(0, nu // 2, (n,), device='cuda', generator=g, dtype=torch.int32)   # upper half never touched
+    i = torch.randint(0, ni // 2, (n,), device='cuda', generator=g, dtype=torch.int32)
+    j = torch.randint(ni // 2, ni - 1000, (n,), device='cuda', generator=g, dtype=torch.int32)
+    P0, Q0 = P.clone(), Q.clone()
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(P, Q, u, i, j, 0.0, 0.0, 0.0, loss)
+    assert torch.equal(P, P0) and torch.equal(Q, Q0)
+    ul, il, jl = u.long(), i.long(), j.long()
+    x = (P0[ul] * (Q0[il] - Q0[jl])).sum(1).double()
+    ref = torch.nn.functional.softplus(-x).sum().item()
+    assert abs(loss.item() - ref) <= 1e-5 * ref
+    E.bpr_sgd_batch(P, Q, u, i, j, 0.01, 0.001, 0.001, loss)
+    torch.cuda.synchronize()
+    assert torch.equal(P[nu // 2:], P0[nu // 2:]) and torch.equal(Q[ni - 1000:], Q0[ni - 1000:])
+    assert not torch.equal(P[:nu // 2], P0[:nu // 2])
+    assert bool(torch.isfinite(P).all()) and bool(torch.isfinite(Q).all())

@@ -1,0 +1,133 @@
+"""Parity tests for K2 (SpMM), K3 (BPR gradient scatter), K4 (TF1 Adam) and the composed
+LightGCN step, against the oracle restatements and the reference's own adjacency.  Needs a GPU."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.fixture(scope='module')
+def E():
+    from qrec_b200 import engine
+    return engine
+
+
+def _dev(torch, a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _golden_adj(g):
+    import scipy.sparse as sp
+    return sp.csr_matrix((g['adj_data'], g['adj_indices'], g['adj_indptr']), shape=tuple(g['adj_shape']))
+
+
+@pytest.mark.parametrize('d', [64, 16, 32, 48, 128, 256, 8])
+def test_spmm_reference_adjacency(torch, E, golden_graph, d):
+    adj = _golden_adj(golden_graph)
+    rng = np.random.default_rng(d)
+    X = rng.standard_normal((adj.shape[0], d)).astype(np.float32)
+    Y = torch.empty(adj.shape[0], d, device='cuda')
+    acc0 = rng.standard_normal((adj.shape[0], d)).astype(np.float32)
+    acc = _dev(torch, acc0)
+    E.spmm_csr(_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data),
+               _dev(torch, X), Y, acc=acc, acc_scale=0.25)
+    ref = (adj.astype(np.float64) @ X.astype(np.float64))
+    np.testing.assert_allclose(Y.cpu().numpy(), ref, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(acc.cpu().numpy(), acc0 + 0.25 * ref, rtol=2e-5, atol=2e-6)
+
+
+def test_spmm_ragged_rows(torch, E):
+    """Empty rows, a single huge row, and rows longer than one lane-group chunk."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(3)
+    n, d = 300, 64
+    rows, cols = [], []
+    for r in range(n):
+        deg = 0 if r % 7 == 0 else (n if r == 5 else int(rng.integers(1, 40)))
+        c = rng.choice(n, size=deg, replace=False)
+        rows += [r] * deg; cols += c.tolist()
+    A = sp.csr_matrix((rng.standard_normal(len(rows)).astype(np.float32), (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Y = torch.full((n, d), 7.0, device='cuda')
+    E.spmm_csr(_dev(torch, A.indptr.astype(np.int64)), _dev(torch, A.indices), _dev(torch, A.data), _dev(torch, X), Y)
+    np.testing.assert_allclose(Y.cpu().numpy(), A.astype(np.float64) @ X, rtol=1e-4, atol=1e-5)
+    assert bool((Y[0] == 0).all())       # empty row is written as zeros, not left stale
+
+
+def test_spmm_symmetric_linear(torch, E, golden_graph):
+    """Properties the backward pass relies on: A is symmetric, so <A x, y> = <x, A y>; linearity."""
+    adj = _golden_adj(golden_graph)
+    rp, ci, va = _dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data)
+    g = torch.Generator(device='cuda'); g.manual_seed(0)
+    x = torch.randn(adj.shape[0], 64, device='cuda', generator=g)
+    y = torch.randn(adj.shape[0], 64, device='cuda', generator=g)
+    Ax, Ay, Axy = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    E.spmm_csr(rp, ci, va, x, Ax); E.spmm_csr(rp, ci, va, y, Ay); E.spmm_csr(rp, ci, va, 2 * x - 3 * y, Axy)
+    a, b = (Ax.double() * y.double()).sum().item(), (x.double() * Ay.double()).sum().item()
+    assert abs(a - b) <= 1e-5 * max(abs(a), 1.0)
+    torch.testing.assert_close(Axy, 2 * Ax - 3 * Ay, rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('d,n', [(64, 2048), (64, 1), (64, 1669), (32, 300), (128, 500), (256, 100)])
+def test_bpr_grad_scatter(torch, E, d, n):
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(d + n)
+    nu, ni = 200, 150                     # small tables -> many duplicate indices inside the batch
+    U = (rng.standard_normal((nu, d)) * 0.1).astype(np.float32)
+    V = (rng.standard_normal((ni, d)) * 0.1).astype(np.float32)
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = rng.integers(0, ni, n).astype(np.int32)
+    j = rng.integers(0, ni, n).astype(np.int32)
+    gU, gV = torch.zeros(nu, d, device='cuda'), torch.zeros(ni, d, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_grad_scatter(_dev(torch, U), _dev(torch, V), _dev(torch, u), _dev(torch, i), _dev(torch, j),
+                       1e-7, 0.001, gU, gV, loss)
+    rl, rU, rV = O.bpr_loss_grad(U, V, u, i, j, 1e-7, 0.001)
+    np.testing.assert_allclose(gU.cpu().numpy(), rU, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(gV.cpu().numpy(), rV, rtol=1e-4, atol=1e-6)
+    assert abs(loss.item() - rl) <= 1e-5 * abs(rl)
+
+
+def test_bpr_grad_matches_torch_autograd(torch, E):
+    """Independent check of the hand-derived gradient (util/loss.py:3-6 + batch L2)."""
+    g = torch.Generator(device='cuda'); g.manual_seed(4)
+    nu, ni, d, n = 64, 80, 64, 512
+    U = (torch.randn(nu, d, device='cuda', generator=g) * 0.2).requires_grad_()
+    V = (torch.randn(ni, d, device='cuda', generator=g) * 0.2).requires_grad_()
+    u = torch.randint(0, nu, (n,), device='cuda', generator=g)
+    i = torch.randint(0, ni, (n,), device='cuda', generator=g)
+    j = torch.randint(0, ni, (n,), device='cuda', generator=g)
+    ue, pe, ne = U[u], V[i], V[j]
+    score = (ue * pe).sum(1) - (ue * ne).sum(1)
+    l = -torch.log(torch.sigmoid(score) + 10e-8).sum() + 0.001 * 0.5 * ((ue ** 2).sum() + (pe ** 2).sum() + (ne ** 2).sum())
+    l.backward()
+    gU, gV = torch.zeros(nu, d, device='cuda'), torch.zeros(ni, d, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_grad_scatter(U.detach(), V.detach(), u.int(), i.int(), j.int(), 10e-8, 0.001, gU, gV, loss)
+    torch.testing.assert_close(gU, U.grad, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(gV, V.grad, rtol=1e-4, atol=1e-6)
+    assert abs(loss.item() - l.item()) <= 1e-5 * abs(l.item())
+
+
+def test_adam_tf1(torch, E):
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(8)
+    for n in (5, 4096, 64 * 1001 + 3):
+        var = rng.standard_normal(n).astype(np.float32)
+        m = np.zeros(n, np.float32); v = np.zeros(n, np.float32)
+        dv, dm, dvv = _dev(torch, var), _dev(torch, m), _dev(torch, v)
+        for t in range(1, 6):
+            g = (rng.standard_normal(n) * (t % 2)).astype(np.float32)   # zero grads still move var (dense Adam)
+            O.adam_tf1(var, m, v, g, 0.001, t)
+            E.adam_dense_tf1(dv, dm, dvv, _dev(torch, g), 0.001, t)
+        np.testing.assert_allclose(dv.cpu().numpy(), var, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(dm.cpu().numpy(), m, rtol=1e-5, atol=1e-8)
+        np.testing.assert_allclose(dvv.cpu().numpy(), v, rtol=1e-5, atol=1e-10)

@@ -1,0 +1,134 @@
+"""K0 compat: the C MT19937 clone in libqrec.so against CPython's `random` (the reference's RNG)
+and against the sampler streams recorded from the reference.  CPU only (host code)."""
+import random
+
+import numpy as np
+import pytest
+
+from qrec_b200 import engine as E
+from conftest import rows_and_sets
+
+
+@pytest.mark.parametrize('seed', [0, 1, 1234, 2**31 - 1, 2**32 + 5, 2**63 + 11])
+def test_seed_and_raw_stream(seed):
+    r = random.Random(seed)
+    m = E.MT19937(seed)
+    assert m.getstate() == r.getstate()
+    assert [m.getrandbits32() for _ in range(2000)] == [r.getrandbits(32) for _ in range(2000)]
+    assert [m.random() for _ in range(500)] == [r.random() for _ in range(500)]
+    assert m.getstate() == r.getstate()
+
+
+def test_randbelow_choice_randint():
+    r = random.Random(7)
+    m = E.MT19937(7)
+    for n in [1, 2, 3, 5, 7, 8, 1891, 2044, 65536, 100000, 2**31 - 1, 2**32 - 1]:
+        assert [m.randbelow(n) for _ in range(300)] == [r._randbelow(n) for _ in range(300)]
+    seq = list(range(1891))
+    assert [m.randbelow(1891) for _ in range(1000)] == [r.choice(seq) for _ in range(1000)]
+    assert [m.randbelow(50) for _ in range(1000)] == [r.randint(0, 49) for _ in range(1000)]
+
+
+@pytest.mark.parametrize('n', [0, 1, 2, 3, 1000, 34437])
+def test_shuffle(n):
+    r = random.Random(99)
+    m = E.MT19937(99)
+    x = list(range(n))
+    r.shuffle(x)
+    a = np.arange(n, dtype=np.int32)
+    m.shuffle(a)
+    assert a.tolist() == x
+    assert m.getstate() == r.getstate()
+
+
+def test_data_split_matches_python():
+    r = random.Random(0)
+    m = E.MT19937(0)
+    keep = m.data_split(5000, 0.2)
+    ref = np.array([not (r.random() < 0.2) for _ in range(5000)])
+    assert np.array_equal(keep, ref)
+    # out-of-range ratio is reset to 0.3 (util/dataSplit.py:10-11)
+    r2, m2 = random.Random(3), E.MT19937(3)
+    assert np.array_equal(m2.data_split(100, 1.5), np.array([not (r2.random() < 0.3) for _ in range(100)]))
+
+
+def test_bpr_epoch_stream_golden(golden_bpr, bpr_ids):
+    """Bit-exact (u,i,j) for 3 epochs incl. the end-of-epoch shuffle, from the reference's state."""
+    u, i, nu, ni = bpr_ids
+    csr = E.RatedCSR(nu, ni, u, i)
+    assert csr.num_positives == golden_bpr['triples_epoch'].shape[1]
+    m = E.MT19937()
+    m.setstate(golden_bpr['mt_state_after_split'])
+    su, si = u.copy(), i.copy()
+    for ep in range(3):
+        tu, ti, tj = m.sample_bpr_epoch(csr)
+        assert np.array_equal(np.stack([tu, ti, tj], 1), golden_bpr['triples_epoch'][ep])
+        m.shuffle_pairs(su, si)
+        assert np.array_equal(m.getstate_array(), golden_bpr['mt_state_after_epoch'][ep])
+
+
+def test_rated_csr_dict_semantics():
+    # duplicates collapse; first-insertion order; rating threshold uses the LAST value
+    u = np.array([0, 0, 1, 0, 1, 0])
+    i = np.array([3, 1, 2, 3, 0, 2])
+    r = np.array([1, 1, 1, 0.5, 1, 1.0])
+    c = E.RatedCSR(2, 4, u, i, r)
+    assert c.sorted_rowptr.tolist() == [0, 3, 5] and c.sorted_cols.tolist() == [1, 2, 3, 0, 2]
+    # (0,3) was overwritten with 0.5 -> not positive; order of the rest = first appearance
+    assert c.pos_rowptr.tolist() == [0, 2, 4] and c.pos_cols.tolist() == [1, 2, 2, 0]
+    rows, sets = rows_and_sets(u, i, 2)
+    assert rows[0] == [3, 1, 2] and sets[1] == {0, 2}
+
+
+def test_pairwise_and_pointwise_golden(golden_graph, graph_ids):
+    g = golden_graph
+    u, i, nu, ni = graph_ids
+    csr = E.RatedCSR(nu, ni, u, i)
+    m = E.MT19937()
+    m.setstate(g['mt_state_before_pairwise'])
+    su, si = u.copy(), i.copy()
+    m.shuffle_pairs(su, si)
+    assert np.array_equal(su, g['shuffled_u']) and np.array_equal(si, g['shuffled_i'])
+    js = [m.sample_pairwise(csr, su[b:b + 2048]) for b in range(0, len(su), 2048)]
+    assert len(js) == int(g['pair_num_batches']) and len(js[-1]) == g['pair_last'].shape[1]
+    assert np.array_equal(np.concatenate(js), g['pair_all_j'])
+    assert np.array_equal(m.getstate_array(), g['mt_state_after_pairwise'])
+    m.setstate(g['mt_state_before_pointwise'])
+    for b, key in ((0, 'point_b0'), (1, 'point_b1')):
+        sl = slice(b * 2048, (b + 1) * 2048)
+        ou, oi, oy = m.sample_pointwise(csr, su[sl], si[sl])
+        assert np.array_equal(np.stack([ou, oi, oy]), g[key])
+    assert np.array_equal(m.getstate_array(), g['mt_state_after_pointwise'])
+
+
+def test_sampler_edge_cases():
+    m = E.MT19937(5)
+    empty = E.RatedCSR(3, 10, np.array([], np.int64), np.array([], np.int64))
+    tu, ti, tj = m.sample_bpr_epoch(empty)
+    assert len(tu) == 0
+    assert len(m.sample_pairwise(empty, np.array([], np.int32))) == 0
+    # a user that rated every item cannot be given a negative: error, not an endless loop
+    full = E.RatedCSR(1, 3, np.array([0, 0, 0]), np.array([0, 1, 2]))
+    with pytest.raises(E.QRecError):
+        m.sample_bpr_epoch(full)
+    with pytest.raises(E.QRecError):
+        m.sample_pairwise(full, np.array([0], np.int32))
+    # ragged: users without interactions are skipped
+    rag = E.RatedCSR(4, 6, np.array([1, 3, 3]), np.array([2, 0, 5]))
+    tu, ti, tj = m.sample_bpr_epoch(rag)
+    assert tu.tolist() == [1, 3, 3] and ti.tolist() == [2, 0, 5]
+    assert all(j not in s for j, s in zip(tj.tolist(), [{2}, {0, 5}, {0, 5}]))
+
+
+def test_order_prepare():
+    u = np.array([0, 0, 1, 0], np.int32)
+    i = np.array([1, 2, 1, 3], np.int32)
+    j = np.array([2, 3, 0, 1], np.int32)
+    wu, wi, wj = E.bpr_order_prepare(u, i, j, 2, 4)
+    assert wu.tolist() == [0, 1, 0, 2]
+    assert wi.tolist() == [0, 1, 1, 1]      # Q[1]:0, Q[2]: touched by k=0 as j -> 1, Q[1] again ->1, Q[3]: 1
+    assert wj.tolist() == [0, 0, 0, 2]
+    with pytest.raises(E.QRecError):
+        E.bpr_order_prepare(np.array([0], np.int32), np.array([1], np.int32), np.array([1], np.int32), 1, 2)
+    with pytest.raises(E.QRecError):
+        E.bpr_order_prepare(np.array([5], np.int32), np.array([1], np.int32), np.array([0], np.int32), 1, 2)
