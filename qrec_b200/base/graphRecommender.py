@@ -1,0 +1,63 @@
+"""`GraphRecommender`: the adjacency builders of the graph models
+(reference: base/graphRecommender.py:10-61).
+
+`create_joint_sparse_adjaceny` returns the same scipy CSR (float32, D^-1/2 (R (+) R^T) D^-1/2 of
+the (U+I)x(U+I) bipartite graph, duplicate interactions summed before normalisation);
+`create_joint_sparse_adj_tensor` hands it to the device as a `DeviceCSR` (int64 rowptr, int32
+cols, fp32 vals) -- the operand of the K2 SpMM kernel -- instead of building a tf.SparseTensor
+from a Python list of (row, col) pairs.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from .deepRecommender import DeepRecommender
+
+
+class DeviceCSR(object):
+    """CSR operand resident in HBM; `matmul` is qrec_spmm_csr_f32."""
+
+    def __init__(self, mat, device):
+        import torch
+        mat = mat.tocsr()
+        mat.sort_indices()
+        self.shape = mat.shape
+        self.nnz = mat.nnz
+        self.rowptr = torch.from_numpy(mat.indptr.astype(np.int64)).to(device)
+        self.cols = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
+        self.vals = torch.from_numpy(mat.data.astype(np.float32)).to(device)
+
+    def matmul(self, X, out, acc=None, acc_scale=0.0):
+        from .. import engine
+        return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale)
+
+
+class GraphRecommender(DeepRecommender):
+    def __init__(self, conf, trainingSet, testSet, fold='[1]'):
+        super(GraphRecommender, self).__init__(conf, trainingSet, testSet, fold)
+
+    def create_joint_sparse_adjaceny(self):
+        n_nodes = self.num_users + self.num_items
+        u, i, _ = self.data.training_ids()
+        ones = np.ones(u.shape[0], dtype=np.float32)
+        upper = sp.csr_matrix((ones, (u, i.astype(np.int64) + self.num_users)), shape=(n_nodes, n_nodes))
+        adj = upper + upper.T
+        deg = np.asarray(adj.sum(1)).ravel()
+        with np.errstate(divide='ignore'):
+            d_inv_sqrt = np.power(deg, -0.5)
+        d_inv_sqrt[np.isinf(d_inv_sqrt)] = 0.
+        scale = sp.diags(d_inv_sqrt)
+        return scale.dot(adj).dot(scale)
+
+    def create_joint_sparse_adj_tensor(self):
+        return DeviceCSR(self.create_joint_sparse_adjaceny(), self._device())
+
+    def create_sparse_rating_matrix(self):
+        """(U x I) COO float32, entry = 1/|items rated by the user| (graphRecommender.py:41-51)."""
+        u, i, _ = self.data.training_ids()
+        per_user = np.array([len(self.data.trainSet_u[self.data.id2user[k]]) for k in range(self.num_users)],
+                            dtype=np.float64)
+        vals = 1.0 / per_user[u]
+        return sp.coo_matrix((vals, (u, i)), shape=(self.num_users, self.num_items), dtype=np.float32)
+
+    def create_sparse_adj_tensor(self):
+        return DeviceCSR(self.create_sparse_rating_matrix(), self._device())

@@ -75,6 +75,13 @@ class RatedCSR(object):
         np.add.at(self.pos_rowptr, pu + 1, 1)
         np.cumsum(self.pos_rowptr, out=self.pos_rowptr)
         self.pos_cols = np.ascontiguousarray(pi[o2], dtype=np.int32)
+        # the positives again, ascending ids: BPR.trainModel rejects against PositiveSet only
+        # (model/ranking/BPR.py:36); identical to sorted_* when every rating is >= threshold
+        if bool(keep.all()):
+            self.possorted_rowptr, self.possorted_cols = self.sorted_rowptr, self.sorted_cols
+        else:
+            self.possorted_rowptr = self.pos_rowptr
+            self.possorted_cols = np.ascontiguousarray(pi, dtype=np.int32)   # (u,i)-sorted already
 
     @property
     def num_positives(self):
@@ -144,7 +151,7 @@ class MT19937(object):
         u, i, j = out
         check(lib.qrec_sample_bpr_epoch(C.byref(self._st), csr.num_users, csr.num_items,
                                         _i64p(csr.pos_rowptr), _i32p(csr.pos_cols),
-                                        _i64p(csr.sorted_rowptr), _i32p(csr.sorted_cols),
+                                        _i64p(csr.possorted_rowptr), _i32p(csr.possorted_cols),
                                         _i32p(u), _i32p(i), _i32p(j)), 'qrec_sample_bpr_epoch')
         return u, i, j
 

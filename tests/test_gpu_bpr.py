@@ -183,17 +183,20 @@ def test_batch_bad_arguments(torch, E):
 
 
 def test_batch_training_tracks_sequential_loss_curve(torch, E, golden_bpr, bpr_ids):
-    """Throughput mode on the reference's own FilmTrust triples: the epoch losses follow the
-    reference's (Hogwild vs Gauss-Seidel differ in second order only)."""
+    """Throughput mode on the reference's own FilmTrust triples, launched in minibatches of 1024
+    (on a table this small a single launch would hold the whole epoch in flight at once, i.e. be
+    a Jacobi step over the epoch): the epoch losses follow the reference's Gauss-Seidel curve."""
     _, _, nu, ni = bpr_ids
     P0, Q0 = _init_tables(nu, ni)
     P, Q = _dev(torch, P0.astype(np.float32)), _dev(torch, Q0.astype(np.float32))
     rng = np.random.default_rng(0)
     for ep in range(3):
         t = golden_bpr['triples_epoch'][ep][rng.permutation(golden_bpr['triples_epoch'].shape[1])]
+        tu, ti, tj = (_dev(torch, t[:, c]) for c in range(3))
         lr = float(golden_bpr['lrate'][ep][0])
         loss = torch.zeros(3, dtype=torch.float64, device='cuda')
-        E.bpr_sgd_batch(P, Q, _dev(torch, t[:, 0]), _dev(torch, t[:, 1]), _dev(torch, t[:, 2]), lr, REG, REG, loss[0:1])
+        for b in range(0, len(t), 1024):
+            E.bpr_sgd_batch(P, Q, tu[b:b + 1024], ti[b:b + 1024], tj[b:b + 1024], lr, REG, REG, loss[0:1])
         E.sumsq(P, loss[1:2]); E.sumsq(Q, loss[2:3])
         l = loss.cpu().numpy()
         total = l[0] + REG * l[1] + REG * l[2]
