@@ -189,8 +189,8 @@ int qrec_bpr_grad_scatter_f32(const float* dev_U, const float* dev_V, int32_t d,
 /* =====================================================================================
  * K4 -- tf.train.AdamOptimizer (TF 1.14) dense update over a whole variable:
  * LightGCN.py:31-32, NGCF.py:54, SimGCL.py:99, BPR.py:84.
- *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m = b1 m + (1-b1) g; v = b2 v + (1-b2) g^2;
- *   var -= lr_t * m / (sqrt(v) + eps)            (t = 1-based step count)
+ *   lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m += (g-m)(1-b1); v += (g*g-v)(1-b2);
+ *   var -= (m*lr_t) / (sqrt(v) + eps)            (t = 1-based step count; fp32 throughout)
  * ===================================================================================== */
 int qrec_adam_dense_tf1_f32(float* dev_var, float* dev_m, float* dev_v, const float* dev_g,
                             int64_t n, float lr, float beta1, float beta2, float eps,

@@ -250,12 +250,17 @@ def bpr_loss_grad(Ue, Ve, u, i, j, eps, reg):
 
 
 def adam_tf1(var, m, v, g, lr, t, b1=0.9, b2=0.999, eps=1e-8):
-    """tf.train.AdamOptimizer dense update, TF 1.14.  In place, fp32."""
+    """tf.train.AdamOptimizer dense update as TF 1.14's ApplyAdam functor evaluates it
+    (tensorflow/core/kernels/training_ops.cc, un-vendored third party), all fp32:
+        alpha = lr*sqrt(1-b2^t)/(1-b1^t);  m += (g-m)*(1-b1);  v += (g*g-v)*(1-b2);
+        var -= (m*alpha)/(sqrt(v)+eps)
+    In place."""
     f = np.float32
-    lr_t = f(lr) * np.sqrt(f(1) - f(b2) ** f(t)) / (f(1) - f(b1) ** f(t))
-    m[...] = f(b1) * m + f(1 - b1) * g
-    v[...] = f(b2) * v + f(1 - b2) * (g * g)
-    var[...] = var - lr_t * m / (np.sqrt(v) + f(eps))
+    b1, b2 = f(b1), f(b2)
+    alpha = f(lr) * np.sqrt(f(1) - f(float(b2) ** t)) / (f(1) - f(float(b1) ** t))
+    m += (g - m) * (f(1) - b1)
+    v += (g * g - v) * (f(1) - b2)
+    var -= (m * alpha) / (np.sqrt(v) + f(eps))
     return var
 
 

@@ -9,7 +9,9 @@
 //   K3  bpr_grad_scatter_kernel  gather 3 rows of the propagated tables, -ln(sigmoid(y)+eps)
 //                                + batch L2, gradient scatter-added (REDG.ADD.F32x4) into the
 //                                dense gradient buffers.
-//   K4  adam_dense_tf1_kernel    TF1 AdamOptimizer dense update (every row moves every step).
+//   K4  adam_dense_tf1_kernel    TF1 AdamOptimizer dense update (every row moves every step), in
+//                                the ApplyAdam form  m += (g-m)(1-b1); v += (g*g-v)(1-b2);
+//                                var -= m*alpha/(sqrt(v)+eps).
 #include <cmath>
 
 #include "common.h"
@@ -220,9 +222,9 @@ adam_dense_tf1_kernel(float* __restrict__ var, float* __restrict__ m, float* __r
     float4 Vv = reinterpret_cast<float4*>(v)[k];
     float4 W = reinterpret_cast<float4*>(var)[k];
 #define QREC_ADAM(c)                              \
-  M.c = b1 * M.c + ob1 * G.c;                     \
-  Vv.c = b2 * Vv.c + ob2 * (G.c * G.c);           \
-  W.c = W.c - lr_t * M.c / (sqrtf(Vv.c) + eps);
+  M.c = M.c + (G.c - M.c) * ob1;                  \
+  Vv.c = Vv.c + (G.c * G.c - Vv.c) * ob2;         \
+  W.c = W.c - (M.c * lr_t) / (sqrtf(Vv.c) + eps);
     QREC_ADAM(x) QREC_ADAM(y) QREC_ADAM(z) QREC_ADAM(w)
     reinterpret_cast<float4*>(m)[k] = M;
     reinterpret_cast<float4*>(v)[k] = Vv;
@@ -230,9 +232,9 @@ adam_dense_tf1_kernel(float* __restrict__ var, float* __restrict__ m, float* __r
   }
   for (long long k = (n4 << 2) + tid; k < n; k += stride) {
     float G = g[k], M = m[k], Vv = v[k], W = var[k];
-    M = b1 * M + ob1 * G;
-    Vv = b2 * Vv + ob2 * (G * G);
-    W = W - lr_t * M / (sqrtf(Vv) + eps);
+    M = M + (G - M) * ob1;
+    Vv = Vv + (G * G - Vv) * ob2;
+    W = W - (M * lr_t) / (sqrtf(Vv) + eps);
     m[k] = M; v[k] = Vv; var[k] = W;
   }
 #undef QREC_ADAM
@@ -325,8 +327,9 @@ int qrec_adam_dense_tf1_f32(float* var, float* m, float* v, const float* g, int6
   QREC_REQUIRE(var && m && v && g, "qrec_adam_dense_tf1_f32: null pointer");
   QREC_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(g),
                "qrec_adam_dense_tf1_f32: buffers must be 16-byte aligned");
-  // TF1 computes lr_t in the variable dtype (fp32) from fp32 beta powers
-  const float b1p = powf(beta1, (float)t), b2p = powf(beta2, (float)t);
+  // TF1 evaluates alpha in the variable dtype (fp32); beta^t is rounded to fp32 once here (TF keeps
+  // a running fp32 product, which differs in the last bits only)
+  const float b1p = (float)pow((double)beta1, (double)t), b2p = (float)pow((double)beta2, (double)t);
   const float lr_t = lr * sqrtf(1.0f - b2p) / (1.0f - b1p);
   const long long blocks = (n / 4 + 255) / 256 + 1;
   const long long cap = (long long)sm_count() * 8;

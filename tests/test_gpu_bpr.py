@@ -217,7 +217,7 @@ def test_host_pipeline_equals_device_call(torch, E):
     hl = pipe.bpr_epoch(Pb, Qb, hu, hi, hj, 0.05, 0.01, 0.01)
     torch.cuda.synchronize()
     assert torch.equal(Pa, Pb) and torch.equal(Qa, Qb)
-    assert abs(hl - float(loss.item())) <= 1e-9 * abs(hl)
+    assert abs(hl - float(loss.item())) <= 1e-6 * abs(hl)      # fp32 partial sums regroup per chunk
     # pageable numpy input and an empty epoch
     assert pipe.bpr_epoch(Pb, Qb, u[:0].copy(), i[:0].copy(), j[:0].copy(), 0.05, 0.01, 0.01) == 0.0
     pipe.close()
