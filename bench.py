@@ -169,7 +169,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from qrec_b200 import engine as E
-    from qrec_b200 import synthetic
+    from qrec_b200 import synthetic, parallel
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -196,9 +196,8 @@ def run_ours(args):
     rowptr, cols = data['sorted_rowptr'], data['sorted_cols']
     loss = torch.zeros(3, dtype=torch.float64, device=dev)
     q_syncs = max(1, args.q_syncs) if world > 1 else 1
-    Qbase = Q.clone() if world > 1 else None
-    delta = torch.empty_like(Q) if world > 1 else None
-    bounds = [n_local * s // q_syncs for s in range(q_syncs + 1)]
+    qsync = parallel.ReplicatedTableSync(Q)
+    bounds = parallel.sync_points(n_local, q_syncs)
     k1_events = []
 
     def step(epoch, timed):
@@ -213,11 +212,7 @@ def run_ours(args):
             if timed:
                 e1.record()
                 k1_events.append((e0, e1, b - a))
-            if world > 1:
-                E.axpby(delta, Q, Qbase, 1.0, -1.0)           # this rank's item-row deltas
-                dist.all_reduce(delta)                         # NCCL sum over NVLink
-                E.axpby(Qbase, Qbase, delta, 1.0, 1.0)
-                Q.copy_(Qbase)
+            qsync.sync()          # N>1: NCCL all-reduce of this rank's item-row deltas (no-op at N=1)
         E.sumsq(P, loss[1:2])
         E.sumsq(Q, loss[2:3])
 
@@ -265,12 +260,8 @@ def run_ours(args):
 
     def e2e_step():
         l = pipe.bpr_epoch(P, Q, hu, hi, hj, LR, REG_U, REG_I)
-        if world > 1:
-            E.axpby(delta, Q, Qbase, 1.0, -1.0)
-            dist.all_reduce(delta)
-            E.axpby(Qbase, Qbase, delta, 1.0, 1.0)
-            Q.copy_(Qbase)
-            torch.cuda.synchronize()
+        qsync.sync()
+        torch.cuda.synchronize()
         return l
 
     for w in range(max(1, args.warmup // 2)):
