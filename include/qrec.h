@@ -168,10 +168,16 @@ int qrec_bpr_epoch_host(qrec_ctx* ctx, float* dev_P, float* dev_Q, int32_t d, in
  * model/ranking/NGCF.py:28, model/ranking/SimGCL.py:25,33.  A is symmetric, so the same
  * call is the backward pass.  Optional fused layer accumulation (LightGCN.py:19):
  * if dev_acc != NULL, acc[r,:] += acc_scale * Y[r,:].  d multiple of 4, <= 256.
+ * nnz = rowptr[n_rows] (passed by value so the launch needs no device read-back).
  * ===================================================================================== */
-int qrec_spmm_csr_f32(int32_t n_rows, const int64_t* dev_rowptr, const int32_t* dev_cols,
+int qrec_spmm_csr_f32(int32_t n_rows, int64_t nnz, const int64_t* dev_rowptr, const int32_t* dev_cols,
                       const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
                       float* dev_acc, float acc_scale, void* stream);
+/* Same product with plain row partitioning (one lane group per row, no atomics, bit-reproducible
+ * summation order).  qrec_spmm_csr_f32 balances by non-zeros instead and is the default. */
+int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* dev_rowptr, const int32_t* dev_cols,
+                               const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
+                               float* dev_acc, float acc_scale, void* stream);
 
 /* =====================================================================================
  * K3 -- gather rows of the propagated tables, bpr_loss + batch L2 and its gradient,

@@ -22,13 +22,18 @@ class DeviceCSR(object):
         mat.sort_indices()
         self.shape = mat.shape
         self.nnz = mat.nnz
+        # short, even rows: one lane group per row is fastest (no atomics); a long-tailed degree
+        # distribution needs the nnz-balanced kernel or the hot rows serialise the launch
+        lengths = np.diff(mat.indptr)
+        self.rowsplit = bool(lengths.size == 0 or lengths.max() <= 4096)
         self.rowptr = torch.from_numpy(mat.indptr.astype(np.int64)).to(device)
         self.cols = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
         self.vals = torch.from_numpy(mat.data.astype(np.float32)).to(device)
 
     def matmul(self, X, out, acc=None, acc_scale=0.0):
         from .. import engine
-        return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale)
+        return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale,
+                               rowsplit=self.rowsplit)
 
 
 class GraphRecommender(DeepRecommender):

@@ -1,7 +1,8 @@
 // K2/K3/K4: the kernels behind the graph models' training step
 // (reference: model/ranking/LightGCN.py:11-41, util/loss.py:3-6, base/graphRecommender.py:10-39).
 //
-//   K2  spmm_csr_kernel          Y = A X (+ fused layer accumulation), CSR row partitioned:
+//   K2  spmm_csr_balanced_kernel Y = A X (+ fused layer accumulation), CSR, nnz-balanced chunks
+//       spmm_csr_kernel          the plain row-partitioned variant (kept for comparison):
 //                                LPR lanes own one row of Y (d=64: a half warp, float4 per lane);
 //                                the lane group streams the row's (col,val) pairs coalesced,
 //                                broadcasts them with group-masked shuffles and keeps 4 gathered
@@ -112,6 +113,120 @@ spmm_csr_kernel(int n_rows, const long long* __restrict__ rowptr, const int* __r
           *ap = o;
         }
       }
+    }
+  }
+}
+
+// nnz-balanced variant: every lane group owns QN consecutive non-zeros instead of whole rows, so a
+// 150 K-entry row of a power-law graph is spread over ~300 lane groups.  The group finds the row
+// of its first non-zero by binary search in rowptr, walks the row segments inside its chunk, stores
+// rows that lie completely inside the chunk and RED-adds the partial sums of rows that straddle a
+// chunk boundary (Y is zero-filled beforehand; the fused `acc += s*Y` epilogue is linear, so
+// partial rows add s*partial to acc).
+template <int LPR, int VPL, int QN>
+__global__ void __launch_bounds__(256)
+spmm_csr_balanced_kernel(int n_rows, long long nnz, const long long* __restrict__ rowptr,
+                         const int* __restrict__ cols, const float* __restrict__ vals,
+                         const float* __restrict__ X, float* __restrict__ Y, int nvec,
+                         float* __restrict__ acc, float acc_scale) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int d = nvec * 4;
+  const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + sub;
+  const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * GPW;
+  const long long nchunks = (nnz + QN - 1) / QN;
+  for (long long ch = group; ch < nchunks; ch += ngroups) {
+    const long long lo = ch * QN;
+    const long long hi = (lo + QN) < nnz ? (lo + QN) : nnz;
+    // first row whose end lies beyond lo: smallest r with rowptr[r+1] > lo.  LPR-ary search: the
+    // lanes of the group probe LPR segment ends at once (ballot), 16x shrink per round at d=64.
+    int a = 0, b = n_rows - 1;
+    while (a < b) {
+      const int len = b - a + 1;
+      const int step = (len + LPR - 1) / LPR;
+      int p = a + (l + 1) * step - 1;
+      if (p > b) p = b;
+      const bool pred = __ldg(rowptr + p + 1) > lo;
+      const unsigned bal = (__ballot_sync(gmask, pred) & gmask) >> (sub * LPR);
+      const int f = __ffs(bal) - 1;            // pred(b) is true, so some lane fires
+      int pf = a + (f + 1) * step - 1;
+      if (pf > b) pf = b;
+      a = a + f * step;
+      b = pf;
+    }
+    int r = a;
+    long long rs = __ldg(rowptr + r), re = __ldg(rowptr + r + 1);
+    while (true) {
+      const long long start = rs > lo ? rs : lo;
+      const long long end = re < hi ? re : hi;
+      float4 acc4[VPL];
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) acc4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long base = start; base < end; base += LPR) {
+        const long long idx = base + l;
+        int c = 0;
+        float w = 0.f;
+        if (idx < end) { c = __ldg(cols + idx); w = __ldg(vals + idx); }
+        const int m = (end - base) < LPR ? (int)(end - base) : LPR;
+        for (int t = 0; t < m; t += 4) {
+          int cc[4];
+          float ww[4];
+          float4 x[4][VPL];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            cc[q] = __shfl_sync(gmask, c, sub * LPR + ((t + q) & (LPR - 1)));
+            ww[q] = __shfl_sync(gmask, w, sub * LPR + ((t + q) & (LPR - 1)));
+            if (t + q >= m) ww[q] = 0.f;
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) {
+              if ((t + q) < m && (l + v * LPR) < nvec)
+                x[q][v] = __ldg(reinterpret_cast<const float4*>(X + (size_t)cc[q] * d) + l + v * LPR);
+              else
+                x[q][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int v = 0; v < VPL; ++v) fma4(acc4[v], ww[q], x[q][v]);
+        }
+      }
+      const bool whole = (rs >= lo) && (re <= hi);
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) {
+        if ((l + v * LPR) < nvec && end > start) {
+          float* yp = Y + (size_t)r * d + (l + v * LPR) * 4;
+          if (whole) {
+            *reinterpret_cast<float4*>(yp) = acc4[v];
+            if (acc != nullptr) {
+              float4* ap = reinterpret_cast<float4*>(acc + (size_t)r * d) + l + v * LPR;
+              float4 o = *ap;
+              fma4(o, acc_scale, acc4[v]);
+              *ap = o;
+            }
+          } else {
+            red_add_v4(yp, acc4[v]);
+            if (acc != nullptr) {
+              float4 sc = make_float4(acc_scale * acc4[v].x, acc_scale * acc4[v].y,
+                                      acc_scale * acc4[v].z, acc_scale * acc4[v].w);
+              red_add_v4(acc + (size_t)r * d + (l + v * LPR) * 4, sc);
+            }
+          }
+        }
+      }
+      if (re >= hi) break;
+      // next non-empty row
+      do {
+        ++r;
+        rs = re;
+        re = __ldg(rowptr + r + 1);
+      } while (re == rs && r < n_rows - 1);
+      if (rs >= hi) break;
     }
   }
 }
@@ -263,15 +378,49 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 extern "C" {
 
-int qrec_spmm_csr_f32(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
+int qrec_spmm_csr_f32(int32_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* cols,
                       const float* vals, const float* X, float* Y, int32_t d, float* acc,
                       float acc_scale, void* stream) {
-  QREC_REQUIRE(n_rows >= 0, "qrec_spmm_csr_f32: n_rows < 0");
+  QREC_REQUIRE(n_rows >= 0 && nnz >= 0, "qrec_spmm_csr_f32: n_rows or nnz < 0");
   QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_spmm_csr_f32: d=%d unsupported (multiple of 4, 4..256)", d);
   if (n_rows == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && X && Y, "qrec_spmm_csr_f32: null pointer");
   QREC_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(acc), "qrec_spmm_csr_f32: tables must be 16-byte aligned");
   QREC_REQUIRE(X != Y, "qrec_spmm_csr_f32: X and Y must not alias");
+  cudaStream_t st = (cudaStream_t)stream;
+  QREC_CUDA(cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)n_rows * d, st));
+  if (nnz == 0) return QREC_OK;
+  QREC_REQUIRE(cols && vals, "qrec_spmm_csr_f32: null cols/vals");
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+  constexpr int QN = 1024;
+#define QREC_SPMMB(LPR, VPL)                                                                     \
+  {                                                                                              \
+    const long long groups_per_block = 8 * (32 / LPR);                                           \
+    long long blocks = ((nnz + QN - 1) / QN + groups_per_block - 1) / groups_per_block;          \
+    if (blocks > cap) blocks = cap;                                                              \
+    spmm_csr_balanced_kernel<LPR, VPL, QN><<<(int)blocks, 256, 0, st>>>(                         \
+        n_rows, nnz, reinterpret_cast<const long long*>(rowptr), cols, vals, X, Y, nvec, acc, acc_scale); \
+  }
+  if (nvec <= 4) QREC_SPMMB(4, 1)
+  else if (nvec <= 8) QREC_SPMMB(8, 1)
+  else if (nvec <= 16) QREC_SPMMB(16, 1)
+  else if (nvec <= 32) QREC_SPMMB(32, 1)
+  else QREC_SPMMB(32, 2)
+#undef QREC_SPMMB
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* rowptr, const int32_t* cols,
+                      const float* vals, const float* X, float* Y, int32_t d, float* acc,
+                      float acc_scale, void* stream) {
+  QREC_REQUIRE(n_rows >= 0, "qrec_spmm_csr_rowsplit_f32: n_rows < 0");
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_spmm_csr_rowsplit_f32: d=%d unsupported (multiple of 4, 4..256)", d);
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && X && Y, "qrec_spmm_csr_rowsplit_f32: null pointer");
+  QREC_REQUIRE(aligned16(X) && aligned16(Y) && aligned16(acc), "qrec_spmm_csr_rowsplit_f32: tables must be 16-byte aligned");
+  QREC_REQUIRE(X != Y, "qrec_spmm_csr_rowsplit_f32: X and Y must not alias");
   const int nvec = d / 4;
   cudaStream_t st = (cudaStream_t)stream;
   const long long cap = (long long)sm_count() * 8;

@@ -306,12 +306,14 @@ class HostPipeline(object):
         return loss.value
 
 
-def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0):
-    """Y = A @ X (CSR fp32); optional fused acc += acc_scale * Y."""
+def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
+    """Y = A @ X (CSR fp32); optional fused acc += acc_scale * Y.  `rowsplit` selects the plain
+    row-partitioned kernel instead of the nnz-balanced default."""
     torch = _torch()
     n_rows = rowptr.shape[0] - 1
     d = X.shape[1]
-    check(lib.qrec_spmm_csr_f32(n_rows, _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
+    fn = lib.qrec_spmm_csr_rowsplit_f32 if rowsplit else lib.qrec_spmm_csr_f32
+    check(fn(n_rows, int(cols.shape[0]), _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
                                 _dev(vals, torch.float32, 'vals'), _dev(X, torch.float32, 'X'),
                                 _dev(Y, torch.float32, 'Y'), d,
                                 _dev(acc, torch.float32, 'acc') if acc is not None else None,

@@ -28,8 +28,9 @@ def _golden_adj(g):
     return sp.csr_matrix((g['adj_data'], g['adj_indices'], g['adj_indptr']), shape=tuple(g['adj_shape']))
 
 
+@pytest.mark.parametrize('rowsplit', [False, True])
 @pytest.mark.parametrize('d', [64, 16, 32, 48, 128, 256, 8])
-def test_spmm_reference_adjacency(torch, E, golden_graph, d):
+def test_spmm_reference_adjacency(torch, E, golden_graph, d, rowsplit):
     adj = _golden_adj(golden_graph)
     rng = np.random.default_rng(d)
     X = rng.standard_normal((adj.shape[0], d)).astype(np.float32)
@@ -37,13 +38,14 @@ def test_spmm_reference_adjacency(torch, E, golden_graph, d):
     acc0 = rng.standard_normal((adj.shape[0], d)).astype(np.float32)
     acc = _dev(torch, acc0)
     E.spmm_csr(_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data),
-               _dev(torch, X), Y, acc=acc, acc_scale=0.25)
+               _dev(torch, X), Y, acc=acc, acc_scale=0.25, rowsplit=rowsplit)
     ref = (adj.astype(np.float64) @ X.astype(np.float64))
     np.testing.assert_allclose(Y.cpu().numpy(), ref, rtol=2e-5, atol=2e-6)
     np.testing.assert_allclose(acc.cpu().numpy(), acc0 + 0.25 * ref, rtol=2e-5, atol=2e-6)
 
 
-def test_spmm_ragged_rows(torch, E):
+@pytest.mark.parametrize('rowsplit', [False, True])
+def test_spmm_ragged_rows(torch, E, rowsplit):
     """Empty rows, a single huge row, and rows longer than one lane-group chunk."""
     import scipy.sparse as sp
     rng = np.random.default_rng(3)
@@ -57,9 +59,41 @@ def test_spmm_ragged_rows(torch, E):
     A.sort_indices()
     X = rng.standard_normal((n, d)).astype(np.float32)
     Y = torch.full((n, d), 7.0, device='cuda')
-    E.spmm_csr(_dev(torch, A.indptr.astype(np.int64)), _dev(torch, A.indices), _dev(torch, A.data), _dev(torch, X), Y)
+    E.spmm_csr(_dev(torch, A.indptr.astype(np.int64)), _dev(torch, A.indices), _dev(torch, A.data), _dev(torch, X), Y,
+               rowsplit=rowsplit)
     np.testing.assert_allclose(Y.cpu().numpy(), A.astype(np.float64) @ X, rtol=1e-4, atol=1e-5)
     assert bool((Y[0] == 0).all())       # empty row is written as zeros, not left stale
+
+
+def test_spmm_power_law_rows_split_across_chunks(torch, E):
+    """A few rows far longer than the 1024-nnz chunk (hot items), many empty rows at both ends, and
+    the fused accumulate on rows that straddle chunk boundaries."""
+    import scipy.sparse as sp
+    rng = np.random.default_rng(9)
+    n, d = 4000, 64
+    deg = np.minimum((n * rng.random(n) ** 6).astype(int), n)
+    deg[:5] = 0; deg[-7:] = 0; deg[10] = 3000; deg[11] = 1; deg[12] = 2500
+    rows = np.repeat(np.arange(n), deg)
+    cols = np.concatenate([rng.choice(n, k, replace=False) for k in deg if k > 0])
+    A = sp.csr_matrix((rng.standard_normal(len(rows)).astype(np.float32), (rows, cols)), shape=(n, n))
+    A.sort_indices()
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    acc0 = rng.standard_normal((n, d)).astype(np.float32)
+    ref = A.astype(np.float64) @ X.astype(np.float64)
+    for rowsplit in (False, True):
+        Y = torch.full((n, d), 3.0, device='cuda')
+        acc = _dev(torch, acc0)
+        E.spmm_csr(_dev(torch, A.indptr.astype(np.int64)), _dev(torch, A.indices), _dev(torch, A.data),
+                   _dev(torch, X), Y, acc=acc, acc_scale=-0.5, rowsplit=rowsplit)
+        # rows of up to 3000 unit-variance terms: fp32 accumulation error ~ 1e-4 absolute
+        np.testing.assert_allclose(Y.cpu().numpy(), ref, rtol=1e-3, atol=1e-3)
+        np.testing.assert_allclose(acc.cpu().numpy(), acc0 - 0.5 * ref, rtol=1e-3, atol=1e-3)
+    # all-empty matrix
+    Z = sp.csr_matrix((n, n), dtype=np.float32)
+    Y = torch.full((n, d), 3.0, device='cuda')
+    E.spmm_csr(_dev(torch, Z.indptr.astype(np.int64)), _dev(torch, Z.indices.astype(np.int32)),
+               _dev(torch, Z.data), _dev(torch, X), Y)
+    assert bool((Y == 0).all())
 
 
 def test_spmm_symmetric_linear(torch, E, golden_graph):

@@ -79,12 +79,14 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / steps
 
-    ms = timed(lambda: E.spmm_csr(rowptr, cols, vals, X, Y, acc=acc, acc_scale=0.25), args.steps, args.warmup)
     algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)            # no-reuse gather model
     floor = nnz * 8 + N * (4 + 8 * D)
-    print(json.dumps({'kernel': 'spmm_csr_f32(+acc)', 'rows': N, 'nnz': nnz, 'd': D, 'ms': ms,
-                      'algorithmic_GB': algo / 1e9, 'achieved_GBs': algo / ms / 1e6, 'frac_of_measured_hbm': algo / ms / 1e6 / peak,
-                      'compulsory_GB': floor / 1e9, 'zipf': args.zipf}))
+    for rowsplit in (False, True):
+        ms = timed(lambda: E.spmm_csr(rowptr, cols, vals, X, Y, acc=acc, acc_scale=0.25, rowsplit=rowsplit), args.steps, args.warmup)
+        print(json.dumps({'kernel': 'spmm_csr_rowsplit_f32(+acc)' if rowsplit else 'spmm_csr_f32(+acc, nnz-balanced)',
+                          'rows': N, 'nnz': nnz, 'd': D, 'ms': ms, 'algorithmic_GB': algo / 1e9,
+                          'achieved_GBs': algo / ms / 1e6, 'frac_of_measured_hbm': algo / ms / 1e6 / peak,
+                          'compulsory_GB': floor / 1e9, 'zipf': args.zipf}))
     if args.spmm_only:
         return
     # full LightGCN steps through the drop-in class's step function
