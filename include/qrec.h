@@ -206,6 +206,57 @@ int qrec_adam_dense_tf1_f32(float* dev_var, float* dev_m, float* dev_v, const fl
 int qrec_axpby_f32(float* dev_dst, const float* dev_a, const float* dev_b, float alpha,
                    float beta, int64_t n, void* stream);
 
+/* =====================================================================================
+ * K6 -- SimGCL pieces (model/ranking/SimGCL.py:30-38,60-78) and the small dense helpers of
+ * NGCF (model/ranking/NGCF.py:27-41).  All fp32, row-major, d multiple of 4 where noted.
+ * ===================================================================================== */
+
+/* SimGCL.py:33-35: E += sign(E) * l2_normalize(U[0,1)^d, axis=1) * eps, in place.  The uniform
+ * noise of element (row r, column c) is word (c & 3) of Philox4x32-10(key = seed;
+ * counter = (r, c >> 2, tag, step)), mapped to [0,1) as (w >> 8) * 2^-24 -- `tag` separates
+ * encoders/layers, `step` minibatches (tf.random.uniform draws fresh noise per sess.run).
+ * Optional fused layer mean: acc[r,:] += acc_scale * E_new[r,:].  d multiple of 4. */
+int qrec_simgcl_perturb_f32(float* dev_E, int64_t n_rows, int32_t d, float eps, uint64_t seed,
+                            uint32_t tag, uint32_t step, float* dev_acc, float acc_scale,
+                            void* stream);
+
+/* Z[r,:] = l2_normalize(T[idx[r],:]) (tf.nn.l2_normalize, epsilon 1e-12 on the squared norm);
+ * norms[r] = the divisor.  SimGCL.py:61-69. */
+int qrec_gather_normalize_f32(const float* dev_T, const int32_t* dev_idx, int32_t n, int32_t d,
+                              float* dev_Z, float* dev_norms, void* stream);
+
+/* InfoNCE over an n x n matrix of raw dots S_ij = z1_i . z2_j (SimGCL.py:70-78):
+ * loss[0] += sum_i (log sum_j exp(S_ij/tau) - S_ii/tau);  S_ij <- dLoss/dS_ij. */
+int qrec_infonce_rows_f32(float* dev_S, int32_t n, float tau, double* dev_loss, void* stream);
+
+/* Gradient through the row normalisation, added into the dense gradient buffer:
+ * G[idx[r],:] += scale * (dZ_r - Z_r (Z_r . dZ_r)) / norms[r]. */
+int qrec_normalize_bwd_scatter_f32(const float* dev_dZ, const float* dev_Z, const float* dev_norms,
+                                   const int32_t* dev_idx, int32_t n, int32_t d, float scale,
+                                   float* dev_G, void* stream);
+
+/* C[M,N] = alpha * op(A) * op(B) + beta * C, row-major fp32 (op = transpose when the flag is
+ * non-zero).  tf.matmul at NGCF.py:29,31 and SimGCL.py:70-71 -- bandwidth-sized products. */
+int qrec_sgemm_f32(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32_t K, float alpha,
+                   const float* dev_A, int32_t lda, const float* dev_B, int32_t ldb, float beta,
+                   float* dev_C, int32_t ldc, void* stream);
+
+/* NGCF.py:32-40 forward: H = dropout(leaky_relu(Z, 0.2), keep) (training only; Philox mask,
+ * counter (r, c>>2, tag, step)), out = l2_normalize(H) written with row stride ld_out (a column
+ * block of the concatenated [N, 3d] table, NGCF.py:42), norms = divisor. */
+int qrec_ngcf_act_fwd_f32(const float* dev_Z, int64_t n_rows, int32_t d, float keep,
+                          int32_t training, uint64_t seed, uint32_t tag, uint32_t step,
+                          float* dev_H, float* dev_out, int32_t ld_out, float* dev_norms,
+                          void* stream);
+/* ... and its backward: dZ from dOut (w.r.t. the normalised output) and the optional dH_extra
+ * (w.r.t. H through the next layer). */
+int qrec_ngcf_act_bwd_f32(const float* dev_dOut, int32_t ld_dout, const float* dev_dH_extra, const float* dev_H,
+                          const float* dev_Z, const float* dev_norms, int64_t n_rows, int32_t d,
+                          float keep, int32_t training, uint64_t seed, uint32_t tag, uint32_t step,
+                          float* dev_dZ, void* stream);
+/* dst = a * b elementwise (the bi-interaction term ego (.) side, NGCF.py:30). */
+int qrec_mul_f32(float* dev_dst, const float* dev_a, const float* dev_b, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

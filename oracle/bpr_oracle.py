@@ -159,8 +159,8 @@ _M0, _M1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57)
 _W0, _W1 = 0x9E3779B9, 0xBB67AE85
 
 
-def philox4x32_10_x(c0, c1, c2, c3, k0, k1):
-    """Vectorised over uint32 arrays c0..c3; scalar keys.  Returns the first output word."""
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised over uint32 arrays c0..c3; scalar keys.  Returns the four output words."""
     c0 = c0.astype(np.uint64); c1 = c1.astype(np.uint64)
     c2 = c2.astype(np.uint64); c3 = c3.astype(np.uint64)
     mask = np.uint64(0xFFFFFFFF)
@@ -175,7 +175,12 @@ def philox4x32_10_x(c0, c1, c2, c3, k0, k1):
         c0, c1, c2, c3 = n0, lo1, n2, lo0
         k0 = (k0 + _W0) & 0xFFFFFFFF
         k1 = (k1 + _W1) & 0xFFFFFFFF
-    return c0.astype(np.uint32)
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def philox4x32_10_x(c0, c1, c2, c3, k0, k1):
+    """First output word only (the negative sampler uses just this one)."""
+    return philox4x32_10(c0, c1, c2, c3, k0, k1)[0]
 
 
 def sample_neg_philox(users, rated_sets, num_items, seed, epoch):

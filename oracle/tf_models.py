@@ -1,0 +1,93 @@
+"""Restatements of the reference's TensorFlow-1.14 graphs in torch (CPU, float64, autograd).
+TEST INFRASTRUCTURE ONLY.  "Parity unpinned": TensorFlow is absent from this image, so these follow
+the cited reference lines and TF1 op semantics instead of recorded TF outputs;
+using autograd here makes them an independent check of the engine's hand-derived backward passes.
+"""
+import numpy as np
+import torch
+
+from . import bpr_oracle as O
+
+
+def philox_uniform(n_rows, d, seed, tag, step):
+    """The engine's noise definition (include/qrec.h, qrec_simgcl_perturb_f32): element (r, c) is
+    word (c & 3) of Philox4x32-10(key=seed; ctr=(r, c>>2, tag, step)), u = (w >> 8) * 2^-24."""
+    nvec = d // 4
+    r = np.repeat(np.arange(n_rows, dtype=np.uint32), nvec)
+    v = np.tile(np.arange(nvec, dtype=np.uint32), n_rows)
+    words = O.philox4x32_10(r, v, np.full(r.shape, tag, np.uint32), np.full(r.shape, step, np.uint32),
+                            seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    w = np.stack(words, axis=1).reshape(n_rows, d)
+    return (w >> np.uint32(8)).astype(np.float64) * (1.0 / 16777216.0)
+
+
+def _sp(adj):
+    adj = adj.tocoo()
+    return torch.sparse_coo_tensor(np.stack([adj.row, adj.col]), adj.data.astype(np.float64), adj.shape).coalesce()
+
+
+def _bpr_loss(ue, pe, ne, eps):
+    score = (ue * pe).sum(1) - (ue * ne).sum(1)                       # util/loss.py:4
+    return -torch.log(torch.sigmoid(score) + eps).sum()               # util/loss.py:5
+
+
+def _l2n(x):
+    return x * torch.rsqrt(torch.clamp((x * x).sum(1, keepdim=True), min=1e-12))   # tf.nn.l2_normalize
+
+
+def simgcl_loss_and_grad(adj, ego, num_users, u, i, j, n_layers, eps, cl_rate, reg, noise, tau=0.2):
+    """model/ranking/SimGCL.py:22-38,60-98.  ego: float64 array [N,d]; noise[e][k]: uniform [N,d]
+    arrays for perturbed encoder e (0/1), layer k.  Returns (rec, cl, d total / d ego)."""
+    A = _sp(adj)
+    E0 = torch.tensor(ego, dtype=torch.float64, requires_grad=True)
+
+    def encoder(pert):
+        emb, outs = E0, []
+        for k in range(n_layers):
+            emb = torch.sparse.mm(A, emb)
+            if pert is not None:
+                nz = torch.tensor(noise[pert][k], dtype=torch.float64)
+                emb = emb + torch.sign(emb) * _l2n(nz) * eps          # SimGCL.py:34-35
+            outs.append(emb)
+        m = torch.stack(outs).mean(0)                                  # SimGCL.py:27,37
+        return m[:num_users], m[num_users:]
+    mU, mV = encoder(None)
+    p1U, p1V = encoder(0)
+    p2U, p2V = encoder(1)
+    ut, it, jt = (torch.as_tensor(np.asarray(x), dtype=torch.long) for x in (u, i, j))
+    ue, pe, ne = mU[ut], mV[it], mV[jt]
+    rec = _bpr_loss(ue, pe, ne, 10e-8) + reg * 0.5 * ((ue ** 2).sum() + (pe ** 2).sum() + (ne ** 2).sum())
+    cl = 0
+    for t1, t2, idx in ((p1U, p2U, torch.unique(ut)), (p1V, p2V, torch.unique(it))):
+        z1, z2 = _l2n(t1[idx]), _l2n(t2[idx])
+        pos = torch.exp((z1 * z2).sum(1) / tau)
+        ttl = torch.exp(z1 @ z2.t() / tau).sum(1)
+        cl = cl - torch.log(pos / ttl).sum()
+    total = rec + cl_rate * cl
+    total.backward()
+    return float(rec), float(cl_rate * cl), E0.grad.numpy()
+
+
+def ngcf_loss_and_grad(adj, ego, W1, W2, num_users, u, i, j, reg, masks=None, keep=0.9):
+    """model/ranking/NGCF.py:19-53.  masks[k]: 0/1 dropout keep masks [N,d] (None = inference).
+    Returns (loss, grad_ego, [grad_W1_k], [grad_W2_k], final [N,3d] embeddings)."""
+    A = _sp(adj)
+    E0 = torch.tensor(ego, dtype=torch.float64, requires_grad=True)
+    W1t = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in W1]
+    W2t = [torch.tensor(w, dtype=torch.float64, requires_grad=True) for w in W2]
+    e, outs = E0, [E0]
+    for k in range(len(W1)):
+        side = torch.sparse.mm(A, e)
+        z = (side + e) @ W1t[k] + (e * side) @ W2t[k]
+        e = torch.nn.functional.leaky_relu(z, 0.2)
+        if masks is not None:
+            e = e * torch.tensor(masks[k], dtype=torch.float64) / keep
+        outs.append(_l2n(e))
+    allE = torch.cat(outs, 1)
+    Ue, Ve = allE[:num_users], allE[num_users:]
+    ut, it, jt = (torch.as_tensor(np.asarray(x), dtype=torch.long) for x in (u, i, j))
+    ue, pe, ne = Ue[ut], Ve[it], Ve[jt]
+    loss = _bpr_loss(ue, pe, ne, 10e-8) + reg * 0.5 * ((ue ** 2).sum() + (pe ** 2).sum() + (ne ** 2).sum())
+    loss.backward()
+    return (float(loss), E0.grad.numpy(), [w.grad.numpy() for w in W1t], [w.grad.numpy() for w in W2t],
+            allE.detach().numpy())

@@ -1,0 +1,428 @@
+// K6 and the small dense helpers of the graph models:
+//   * simgcl_perturb_kernel      E += sign(E) * l2_normalize(U[0,1)^d) * eps   (SimGCL.py:33-35),
+//                                Philox noise generated in registers, optional fused layer mean
+//   * gather_normalize_kernel    Z = l2_normalize(T[idx])                      (SimGCL.py:61-69)
+//   * infonce_rows_kernel        row log-sum-exp of S/tau, loss, dS in place   (SimGCL.py:70-78)
+//   * normalize_bwd_scatter      gradient through l2_normalize, added to the dense grad rows
+//   * sgemm_f32                  C = alpha*op(A)*op(B) + beta*C, fp32 SIMT tiles -- the B' x B' x d
+//                                similarity products and NGCF's [N,d]x[d,d] layer transforms are
+//                                bandwidth-sized, not tensor-core-sized (tensor
+//                                cores only for NeuMF's MLP)
+//   * leaky_relu / dropout / row l2-normalise forward+backward for NGCF (NGCF.py:29-40)
+#include <cmath>
+
+#include "common.h"
+
+namespace {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += W0; k1 += W1;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t w) { return (float)(w >> 8) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
+
+int sm_count() {
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+  return v;
+}
+
+// one warp per row, lanes stride over float4 slices (d multiple of 4, any size)
+__global__ void __launch_bounds__(256)
+simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, float eps, uint32_t k0,
+                      uint32_t k1, uint32_t tag, uint32_t step, float* __restrict__ acc,
+                      float acc_scale) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += nwarps) {
+    float4* row = reinterpret_cast<float4*>(E) + r * nvec;
+    float ss = 0.f;
+    // first pass: squared norm of the row's noise (regenerated below; Philox is cheaper than HBM)
+    for (int v = lane; v < nvec; v += 32) {
+      uint32_t w[4];
+      philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
+      const float a = u01(w[0]), b = u01(w[1]), c = u01(w[2]), d4 = u01(w[3]);
+      ss += a * a + b * b + c * c + d4 * d4;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float inv = eps * rsqrtf(fmaxf(ss, 1e-12f));       // tf.nn.l2_normalize epsilon
+    for (int v = lane; v < nvec; v += 32) {
+      uint32_t w[4];
+      philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
+      float4 e = row[v];
+      e.x += sgn(e.x) * u01(w[0]) * inv;
+      e.y += sgn(e.y) * u01(w[1]) * inv;
+      e.z += sgn(e.z) * u01(w[2]) * inv;
+      e.w += sgn(e.w) * u01(w[3]) * inv;
+      row[v] = e;
+      if (acc != nullptr) {
+        float4* ap = reinterpret_cast<float4*>(acc) + r * nvec + v;
+        float4 o = *ap;
+        o.x += acc_scale * e.x; o.y += acc_scale * e.y; o.z += acc_scale * e.z; o.w += acc_scale * e.w;
+        *ap = o;
+      }
+    }
+  }
+}
+
+// Z[r,:] = T[idx[r],:] / max(|T[idx[r]]|, 1e-6); norms[r] = that denominator.  warp per row.
+__global__ void __launch_bounds__(256)
+gather_normalize_kernel(const float* __restrict__ T, const int* __restrict__ idx, int n, int d,
+                        float* __restrict__ Z, float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n; r += nwarps) {
+    const float* src = T + (size_t)idx[r] * d;
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) { const float x = src[c]; ss += x * x; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(fmaxf(ss, 1e-12f));
+    for (int c = lane; c < d; c += 32) Z[(size_t)r * d + c] = src[c] / nrm;
+    if (lane == 0) norms[r] = nrm;
+  }
+}
+
+// S holds raw dots z1_i . z2_j (n x n, row-major).  Per row i: lse_i = log sum_j exp(S_ij/tau);
+// loss += lse_i - S_ii/tau;  S_ij <- (exp(S_ij/tau - lse_i) - [i==j]) / tau   (= dLoss/dS_ij raw).
+__global__ void __launch_bounds__(256)
+infonce_rows_kernel(float* __restrict__ S, int n, float inv_tau, double* loss) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    float* row = S + (size_t)i * n;
+    float m = -INFINITY;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) m = fmaxf(m, row[j] * inv_tau);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = red[0];
+      for (int w = 1; w < (int)(blockDim.x >> 5); ++w) t = fmaxf(t, red[w]);
+      bcast = t;
+    }
+    __syncthreads();
+    const float mx = bcast;
+    float s = 0.f;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) s += expf(row[j] * inv_tau - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t = 0.f;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+      const float lse = mx + logf(t);
+      atomicAdd(loss, (double)(lse - row[i] * inv_tau));
+      bcast = lse;
+    }
+    __syncthreads();
+    const float lse = bcast;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const float p = expf(row[j] * inv_tau - lse);
+      row[j] = (p - (j == i ? 1.f : 0.f)) * inv_tau;
+    }
+    __syncthreads();
+  }
+}
+
+// G[idx[r],:] += scale * (dZ_r - Z_r * (Z_r . dZ_r)) / norm_r        (idx unique within a call)
+__global__ void __launch_bounds__(256)
+normalize_bwd_scatter_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
+                             const float* __restrict__ norms, const int* __restrict__ idx, int n,
+                             int d, float scale, float* __restrict__ G) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = warp; r < n; r += nwarps) {
+    const float* z = Z + (size_t)r * d;
+    const float* g = dZ + (size_t)r * d;
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) dot += z[c] * g[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float k = scale / norms[r];
+    float* dst = G + (size_t)idx[r] * d;
+    for (int c = lane; c < d; c += 32) atomicAdd(dst + c, k * (g[c] - z[c] * dot));
+  }
+}
+
+// C[M,N] = alpha * op(A) * op(B) + beta * C, row-major, 64x64 tile, 16x16 threads, 4x4 micro-tile.
+// ksplit > 1: the K range is cut into `ksplit` slabs (work item = tile x slab) and partial products
+// are atomically added into C, which the host has pre-scaled by beta (the [d,N]x[N,d] weight
+// gradients of NGCF have one output tile and K = #nodes).
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+             const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
+             int ksplit) {
+  constexpr int BM = 64, BN = 64, BK = 16;
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const long long ntiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int kslab = ((K + ksplit - 1) / ksplit + BK - 1) / BK * BK;
+  for (long long work = blockIdx.x; work < ntiles * ksplit; work += gridDim.x) {
+    const long long tile = work / ksplit;
+    const int slab = (int)(work % ksplit);
+    const int kbeg = slab * kslab, kend = (kbeg + kslab) < K ? (kbeg + kslab) : K;
+    const int tn = (N + BN - 1) / BN;
+    const int m0 = (int)(tile / tn) * BM, n0 = (int)(tile % tn) * BN;
+    float acc[4][4] = {};
+    for (int k0 = kbeg; k0 < kend; k0 += BK) {
+      for (int e = threadIdx.x; e < BM * BK; e += 256) {
+        int m, k;
+        if (TA) { m = e % BM; k = e / BM; } else { k = e % BK; m = e / BK; }
+        const int gm = m0 + m, gk = k0 + k;
+        float v = 0.f;
+        if (gm < M && gk < kend) v = TA ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+        As[k][m] = v;
+      }
+      for (int e = threadIdx.x; e < BN * BK; e += 256) {
+        int n, k;
+        if (TB) { k = e % BK; n = e / BK; } else { n = e % BN; k = e / BN; }
+        const int gn = n0 + n, gk = k0 + k;
+        float v = 0.f;
+        if (gn < N && gk < kend) v = TB ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+        Bs[k][n] = v;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        float a[4], b[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int p = 0; p < 4; ++p) acc[q][p] = fmaf(a[q], b[p], acc[q][p]);
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int gm = m0 + ty * 4 + q;
+      if (gm >= M) continue;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int gn = n0 + tx * 4 + p;
+        if (gn < N) {
+          float* c = C + (size_t)gm * ldc + gn;
+          if (ksplit > 1) atomicAdd(c, alpha * acc[q][p]);
+          else *c = alpha * acc[q][p] + (beta != 0.f ? beta * *c : 0.f);
+        }
+      }
+    }
+  }
+}
+
+// ---- NGCF elementwise pieces (NGCF.py:29-40) ------------------------------------------------------
+// forward: H = leaky_relu(Z, 0.2); H *= mask/keep (mask from Philox, keep prob); Nrm = |H| row norm;
+// out = H / max(|H|, 1e-6).  Stores H (post-dropout) for the backward pass.  warp per row.
+__global__ void __launch_bounds__(256)
+ngcf_act_fwd_kernel(const float* __restrict__ Zin, long long n_rows, int d, float keep, int training,
+                    uint32_t k0, uint32_t k1, uint32_t tag, uint32_t step, float* __restrict__ H,
+                    float* __restrict__ out, int ld_out, float* __restrict__ norms) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += nwarps) {
+    float ss = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      float z = Zin[r * d + c];
+      float h = z > 0.f ? z : 0.2f * z;
+      if (training) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)(c >> 2), tag, step, k0, k1, w);
+        h = (u01(w[c & 3]) < keep) ? h / keep : 0.f;
+      }
+      H[r * d + c] = h;
+      ss += h * h;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float nrm = sqrtf(fmaxf(ss, 1e-12f));
+    for (int c = lane; c < d; c += 32) out[r * ld_out + c] = H[r * d + c] / nrm;
+    if (lane == 0) norms[r] = nrm;
+  }
+}
+
+// backward: given dOut (grad wrt normalised output) and dH_extra (grad wrt H from the next layer's
+// use of the un-normalised ego embedding), produce dZ (grad wrt the pre-activation).
+__global__ void __launch_bounds__(256)
+ngcf_act_bwd_kernel(const float* __restrict__ dOut, int ld_dout, const float* __restrict__ dH_extra,
+                    const float* __restrict__ H, const float* __restrict__ Zin,
+                    const float* __restrict__ norms, long long n_rows, int d, float keep,
+                    int training, uint32_t k0, uint32_t k1, uint32_t tag, uint32_t step,
+                    float* __restrict__ dZ) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long r = warp; r < n_rows; r += nwarps) {
+    const float nrm = norms[r];
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32) dot += (H[r * d + c] / nrm) * dOut[r * ld_dout + c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    for (int c = lane; c < d; c += 32) {
+      const float o = H[r * d + c] / nrm;
+      float g = (dOut[r * ld_dout + c] - o * dot) / nrm;
+      if (dH_extra != nullptr) g += dH_extra[r * d + c];
+      if (training) {
+        uint32_t w[4];
+        philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)(c >> 2), tag, step, k0, k1, w);
+        g = (u01(w[c & 3]) < keep) ? g / keep : 0.f;
+      }
+      const float z = Zin[r * d + c];
+      dZ[r * d + c] = z > 0.f ? g : 0.2f * g;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+scale_matrix_kernel(float* __restrict__ C, int M, int N, int ldc, float beta) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < (long long)M * N; k += stride) {
+    float* c = C + (k / N) * ldc + (k % N);
+    *c = beta != 0.f ? beta * *c : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mul_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __restrict__ b, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = a[k] * b[k];
+}
+
+inline int grid_for(long long work_items, int per_block) {
+  long long blocks = (work_items + per_block - 1) / per_block;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+extern "C" {
+
+int qrec_simgcl_perturb_f32(float* E, int64_t n_rows, int32_t d, float eps, uint64_t seed,
+                            uint32_t tag, uint32_t step, float* acc, float acc_scale, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && d >= 4 && d % 4 == 0, "qrec_simgcl_perturb_f32: bad shape (d multiple of 4)");
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(E != nullptr, "qrec_simgcl_perturb_f32: null table");
+  simgcl_perturb_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      E, n_rows, d / 4, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc, acc_scale);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_gather_normalize_f32(const float* T, const int32_t* idx, int32_t n, int32_t d, float* Z,
+                              float* norms, void* stream) {
+  QREC_REQUIRE(n >= 0 && d >= 1, "qrec_gather_normalize_f32: bad shape");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(T && idx && Z && norms, "qrec_gather_normalize_f32: null pointer");
+  gather_normalize_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(T, idx, n, d, Z, norms);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_infonce_rows_f32(float* S, int32_t n, float tau, double* loss, void* stream) {
+  QREC_REQUIRE(n >= 0 && tau > 0.f, "qrec_infonce_rows_f32: bad argument");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(S && loss, "qrec_infonce_rows_f32: null pointer");
+  infonce_rows_kernel<<<grid_for(n, 1), 256, 0, (cudaStream_t)stream>>>(S, n, 1.0f / tau, loss);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_normalize_bwd_scatter_f32(const float* dZ, const float* Z, const float* norms,
+                                   const int32_t* idx, int32_t n, int32_t d, float scale, float* G,
+                                   void* stream) {
+  QREC_REQUIRE(n >= 0 && d >= 1, "qrec_normalize_bwd_scatter_f32: bad shape");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(dZ && Z && norms && idx && G, "qrec_normalize_bwd_scatter_f32: null pointer");
+  normalize_bwd_scatter_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(dZ, Z, norms, idx, n, d, scale, G);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_sgemm_f32(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32_t K, float alpha,
+                   const float* A, int32_t lda, const float* B, int32_t ldb, float beta, float* C,
+                   int32_t ldc, void* stream) {
+  QREC_REQUIRE(M >= 0 && N >= 0 && K >= 0, "qrec_sgemm_f32: negative dimension");
+  if (M == 0 || N == 0) return QREC_OK;
+  QREC_REQUIRE(A && B && C, "qrec_sgemm_f32: null pointer");
+  const long long tiles = (long long)((M + 63) / 64) * ((N + 63) / 64);
+  cudaStream_t st = (cudaStream_t)stream;
+  int ksplit = 1;
+  const long long target = (long long)sm_count() * 4;
+  if (tiles < target / 2 && K >= 4096) {
+    ksplit = (int)((target + tiles - 1) / tiles);
+    if (ksplit > (K + 1023) / 1024) ksplit = (K + 1023) / 1024;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1) {
+    scale_matrix_kernel<<<grid_for((long long)M * N, 1024), 256, 0, st>>>(C, M, N, ldc, beta);
+    QREC_LAUNCH_CHECK();
+  }
+  const int grid = grid_for(tiles * ksplit, 1);
+  if (!trans_a && !trans_b) sgemm_kernel<false, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ksplit);
+  else if (trans_a && !trans_b) sgemm_kernel<true, false><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ksplit);
+  else if (!trans_a && trans_b) sgemm_kernel<false, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ksplit);
+  else sgemm_kernel<true, true><<<grid, 256, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, ksplit);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_ngcf_act_fwd_f32(const float* Zin, int64_t n_rows, int32_t d, float keep, int32_t training,
+                          uint64_t seed, uint32_t tag, uint32_t step, float* H, float* out,
+                          int32_t ld_out, float* norms, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && d >= 1 && keep > 0.f && keep <= 1.f, "qrec_ngcf_act_fwd_f32: bad argument");
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(Zin && H && out && norms, "qrec_ngcf_act_fwd_f32: null pointer");
+  ngcf_act_fwd_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      Zin, n_rows, d, keep, training, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, H, out, ld_out, norms);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_ngcf_act_bwd_f32(const float* dOut, int32_t ld_dout, const float* dH_extra, const float* H, const float* Zin,
+                          const float* norms, int64_t n_rows, int32_t d, float keep, int32_t training,
+                          uint64_t seed, uint32_t tag, uint32_t step, float* dZ, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && d >= 1 && keep > 0.f && keep <= 1.f, "qrec_ngcf_act_bwd_f32: bad argument");
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(dOut && H && Zin && norms && dZ, "qrec_ngcf_act_bwd_f32: null pointer");
+  ngcf_act_bwd_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
+      dOut, ld_dout, dH_extra, H, Zin, norms, n_rows, d, keep, training, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, dZ);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_mul_f32(float* dst, const float* a, const float* b, int64_t n, void* stream) {
+  QREC_REQUIRE(n >= 0, "qrec_mul_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(dst && a && b, "qrec_mul_f32: null pointer");
+  mul_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(dst, a, b, n);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+}  // extern "C"

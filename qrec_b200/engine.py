@@ -347,3 +347,87 @@ def axpby(dst, a, b, alpha, beta):
                              _dev(b, torch.float32, 'b'), float(alpha), float(beta), dst.numel(),
                              _stream()), 'qrec_axpby_f32')
     return dst
+
+
+# ---------------------------------------------------------------------------------------------
+# K6 / dense helpers (SimGCL, NGCF)
+# ---------------------------------------------------------------------------------------------
+def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0):
+    torch = _torch()
+    check(lib.qrec_simgcl_perturb_f32(_dev(Emb, torch.float32, 'E'), Emb.shape[0], Emb.shape[1], float(eps),
+                                      int(seed), int(tag), int(step),
+                                      _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                      float(acc_scale), _stream()), 'qrec_simgcl_perturb_f32')
+    return Emb
+
+
+def gather_normalize(T, idx, Z, norms):
+    torch = _torch()
+    check(lib.qrec_gather_normalize_f32(_dev(T, torch.float32, 'T'), _dev(idx, torch.int32, 'idx'), idx.shape[0],
+                                        T.shape[1], _dev(Z, torch.float32, 'Z'), _dev(norms, torch.float32, 'norms'),
+                                        _stream()), 'qrec_gather_normalize_f32')
+    return Z
+
+
+def infonce_rows(S, tau, loss):
+    torch = _torch()
+    assert S.shape[0] == S.shape[1]
+    check(lib.qrec_infonce_rows_f32(_dev(S, torch.float32, 'S'), S.shape[0], float(tau),
+                                    _dev(loss, torch.float64, 'loss'), _stream()), 'qrec_infonce_rows_f32')
+    return loss
+
+
+def normalize_bwd_scatter(dZ, Z, norms, idx, scale, G):
+    torch = _torch()
+    check(lib.qrec_normalize_bwd_scatter_f32(_dev(dZ, torch.float32, 'dZ'), _dev(Z, torch.float32, 'Z'),
+                                             _dev(norms, torch.float32, 'norms'), _dev(idx, torch.int32, 'idx'),
+                                             idx.shape[0], Z.shape[1], float(scale), _dev(G, torch.float32, 'G'),
+                                             _stream()), 'qrec_normalize_bwd_scatter_f32')
+    return G
+
+
+def sgemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
+    """C = alpha * op(A) @ op(B) + beta * C for contiguous row-major fp32 matrices."""
+    torch = _torch()
+    M = A.shape[1] if trans_a else A.shape[0]
+    K = A.shape[0] if trans_a else A.shape[1]
+    N = B.shape[0] if trans_b else B.shape[1]
+    assert (B.shape[1] if trans_b else B.shape[0]) == K and tuple(C.shape) == (M, N)
+    check(lib.qrec_sgemm_f32(int(trans_a), int(trans_b), M, N, K, float(alpha), _dev(A, torch.float32, 'A'),
+                             A.shape[1], _dev(B, torch.float32, 'B'), B.shape[1], float(beta),
+                             _dev(C, torch.float32, 'C'), C.shape[1], _stream()), 'qrec_sgemm_f32')
+    return C
+
+
+def _strided_rows(t, name):
+    """[rows, d] fp32 view whose rows are contiguous but may sit ld apart (a column block)."""
+    torch = _torch()
+    if not (isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1):
+        raise QRecError('%s must be a 2-D fp32 CUDA tensor with unit column stride' % name)
+    return t.data_ptr(), t.stride(0)
+
+
+def ngcf_act_fwd(Z, keep, training, seed, tag, step, H, out, norms):
+    torch = _torch()
+    po, ldo = _strided_rows(out, 'out')
+    check(lib.qrec_ngcf_act_fwd_f32(_dev(Z, torch.float32, 'Z'), Z.shape[0], Z.shape[1], float(keep), int(training),
+                                    int(seed), int(tag), int(step), _dev(H, torch.float32, 'H'), po, ldo,
+                                    _dev(norms, torch.float32, 'norms'), _stream()), 'qrec_ngcf_act_fwd_f32')
+
+
+def ngcf_act_bwd(dOut, dH_extra, H, Z, norms, keep, training, seed, tag, step, dZ):
+    torch = _torch()
+    pd, ldd = _strided_rows(dOut, 'dOut')
+    check(lib.qrec_ngcf_act_bwd_f32(pd, ldd,
+                                    _dev(dH_extra, torch.float32, 'dH_extra') if dH_extra is not None else None,
+                                    _dev(H, torch.float32, 'H'), _dev(Z, torch.float32, 'Z'),
+                                    _dev(norms, torch.float32, 'norms'), Z.shape[0], Z.shape[1], float(keep),
+                                    int(training), int(seed), int(tag), int(step), _dev(dZ, torch.float32, 'dZ'),
+                                    _stream()), 'qrec_ngcf_act_bwd_f32')
+
+
+def mul(dst, a, b):
+    torch = _torch()
+    check(lib.qrec_mul_f32(_dev(dst, torch.float32, 'dst'), _dev(a, torch.float32, 'a'), _dev(b, torch.float32, 'b'),
+                           dst.numel(), _stream()), 'qrec_mul_f32')
+    return dst
