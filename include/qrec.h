@@ -257,6 +257,19 @@ int qrec_ngcf_act_bwd_f32(const float* dev_dOut, int32_t ld_dout, const float* d
 /* dst = a * b elementwise (the bi-interaction term ego (.) side, NGCF.py:30). */
 int qrec_mul_f32(float* dev_dst, const float* dev_a, const float* dev_b, int64_t n, void* stream);
 
+/* =====================================================================================
+ * K5 building block -- tensor-core GEMM for NeuMF's MLP (model/ranking/NeuMF.py:39-50):
+ *   C[M,N] = epilogue(A[M,K] * B), fp32 storage, TF32 tcgen05.mma with fp32 accumulation in TMEM.
+ * b_is_nk = 0: B is [K,N] row-major (a weight matrix, forward pass);
+ * b_is_nk = 1: B is [N,K] row-major (dX = dY * W^T uses W as stored).
+ * epilogue: 0 none | 1 relu(x + bias[n]) | 2 x * (mask[m,n] > 0) (ReLU backward) | 3 x + bias[n].
+ * A 16-byte aligned, K % 4 == 0, lda % 4 == 0.
+ * ===================================================================================== */
+int qrec_tc_gemm_tf32(int32_t b_is_nk, int32_t M, int32_t N, int32_t K, const float* dev_A,
+                      int32_t lda, const float* dev_B, int32_t ldb, float* dev_C, int32_t ldc,
+                      int32_t epilogue, const float* dev_bias, const float* dev_mask,
+                      int32_t ldmask, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -431,3 +431,21 @@ def mul(dst, a, b):
     check(lib.qrec_mul_f32(_dev(dst, torch.float32, 'dst'), _dev(a, torch.float32, 'a'), _dev(b, torch.float32, 'b'),
                            dst.numel(), _stream()), 'qrec_mul_f32')
     return dst
+
+
+EPI_NONE, EPI_BIAS_RELU, EPI_RELU_MASK, EPI_BIAS = 0, 1, 2, 3
+
+
+def tc_gemm(A, B, C, b_is_nk=False, epilogue=EPI_NONE, bias=None, mask=None):
+    """C = epilogue(A @ B) (b_is_nk=False, B [K,N]) or epilogue(A @ B.T) (b_is_nk=True, B [N,K]) on the
+    tcgen05 TF32 tensor-core path."""
+    torch = _torch()
+    M, K = A.shape
+    N = B.shape[0] if b_is_nk else B.shape[1]
+    assert (B.shape[1] if b_is_nk else B.shape[0]) == K and tuple(C.shape) == (M, N)
+    check(lib.qrec_tc_gemm_tf32(int(b_is_nk), M, N, K, _dev(A, torch.float32, 'A'), A.stride(0),
+                                _dev(B, torch.float32, 'B'), B.stride(0), _dev(C, torch.float32, 'C'), C.stride(0),
+                                int(epilogue), _dev(bias, torch.float32, 'bias') if bias is not None else None,
+                                _dev(mask, torch.float32, 'mask') if mask is not None else None,
+                                mask.stride(0) if mask is not None else 0, _stream()), 'qrec_tc_gemm_tf32')
+    return C
