@@ -270,6 +270,27 @@ int qrec_tc_gemm_tf32(int32_t b_is_nk, int32_t M, int32_t N, int32_t K, const fl
                       int32_t epilogue, const float* dev_bias, const float* dev_mask,
                       int32_t ldmask, void* stream);
 
+/* =====================================================================================
+ * K5 -- NeuMF (model/ranking/NeuMF.py:12-123): row gather / scatter-add around the tensor-core
+ * MLP and the three prediction heads with their BCE losses.
+ * ===================================================================================== */
+/* out[b, 0:d] = T[idx[b], :], output rows ld_out apart (tf.nn.embedding_lookup + tf.concat,
+ * NeuMF.py:27-30,41). */
+int qrec_gather_rows_f32(const float* dev_T, const int32_t* dev_idx, int64_t n, int32_t d,
+                         float* dev_out, int32_t ld_out, void* stream);
+/* G[idx[b], :] += scale * src[b, 0:d] (IndexedSlices gradient, duplicates summed). */
+int qrec_scatter_add_rows_f32(float* dev_G, const int32_t* dev_idx, int64_t n, int32_t d,
+                              const float* dev_src, int32_t ld_src, float scale, void* stream);
+/* mode 0 GMF | 1 MLP | 2 NeuMF head: y = sigmoid(wg*(UG*IG).h_mf + wm*H3.h_mlp); when training,
+ * loss += BCE(r, y; +1e-9) [+ reg*l2_loss(UG)+reg*l2_loss(IG), modes 0/2], dz = dLoss/dz, and the
+ * per-sample gradients GMF=UG*IG, dUG, dIG (incl. reg), dH3 (ReLU-masked).  The h-vector terms of
+ * the regulariser and all weight gradients are assembled by the caller from dz/GMF/dH3. */
+int qrec_neumf_head_f32(int32_t mode, int32_t training, const float* dev_UG, const float* dev_IG,
+                        const float* dev_H3, const float* dev_h_mf, const float* dev_h_mlp,
+                        const float* dev_r, int64_t n, int32_t d, float reg, double* dev_loss,
+                        float* dev_y, float* dev_dz, float* dev_GMF, float* dev_dUG, float* dev_dIG,
+                        float* dev_dH3, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

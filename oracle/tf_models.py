@@ -91,3 +91,35 @@ def ngcf_loss_and_grad(adj, ego, W1, W2, num_users, u, i, j, reg, masks=None, ke
     loss.backward()
     return (float(loss), E0.grad.numpy(), [w.grad.numpy() for w in W1t], [w.grad.numpy() for w in W2t],
             allE.detach().numpy())
+
+
+def neumf_loss_and_grad(params, mode, u, i, r, reg):
+    """model/ranking/NeuMF.py:27-75.  params: dict of float64 arrays (PG,QG,PM,QM,h_mf,h_mlp,W1..b3).
+    mode 0 = mf_loss, 1 = mlp_loss, 2 = neu_loss.  Returns (loss, {name: grad}, y)."""
+    P = {k: torch.tensor(np.asarray(v, dtype=np.float64), requires_grad=True) for k, v in params.items()}
+    ut, it = (torch.as_tensor(np.asarray(x), dtype=torch.long) for x in (u, i))
+    rt = torch.tensor(np.asarray(r, dtype=np.float64))
+    UG, IG = P['PG'][ut], P['QG'][it]
+    gmf = UG * IG
+    x = torch.cat([P['PM'][ut], P['QM'][it]], 1)
+    h = torch.relu(x @ P['W1'] + P['b1'])
+    h = torch.relu(h @ P['W2'] + P['b2'])
+    mlp = torch.relu(h @ P['W3'] + P['b3'])
+    l2 = lambda t: (t ** 2).sum() / 2                                   # noqa: E731  tf.nn.l2_loss
+    mf_reg = reg * (l2(UG) + l2(IG) + l2(P['h_mf']))
+    e = 10e-10
+
+    def bce(y):
+        return -(rt * torch.log(y + e) + (1 - rt) * torch.log(1 - y + e)).sum()
+    if mode == 0:
+        y = torch.sigmoid((gmf * P['h_mf']).sum(1))
+        loss = bce(y) + mf_reg
+    elif mode == 1:
+        y = torch.sigmoid((mlp * P['h_mlp']).sum(1))
+        loss = bce(y)
+    else:
+        hn = torch.cat([0.5 * P['h_mf'], 0.5 * P['h_mlp']])
+        y = torch.sigmoid((torch.cat([gmf, mlp], 1) * hn).sum(1))
+        loss = bce(y) + mf_reg + reg * l2(hn)
+    loss.backward()
+    return float(loss), {k: (v.grad.numpy() if v.grad is not None else None) for k, v in P.items()}, y.detach().numpy()

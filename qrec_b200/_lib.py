@@ -79,6 +79,10 @@ SIGNATURES = {
     'qrec_ngcf_act_bwd_f32': (C.c_int, [vp, C.c_int32, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_float, C.c_int32,
                                         C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]),
     'qrec_mul_f32': (C.c_int, [vp, vp, vp, C.c_int64, vp]),
+    'qrec_gather_rows_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int32, vp]),
+    'qrec_scatter_add_rows_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int32, C.c_float, vp]),
+    'qrec_neumf_head_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_float,
+                                      vp, vp, vp, vp, vp, vp, vp, vp]),
     'qrec_tc_gemm_tf32': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp,
                                     C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]),
 }

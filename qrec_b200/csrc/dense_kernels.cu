@@ -311,6 +311,94 @@ mul_kernel(float* __restrict__ dst, const float* __restrict__ a, const float* __
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) dst[k] = a[k] * b[k];
 }
 
+
+// ---- NeuMF pieces (model/ranking/NeuMF.py:27-75) ------------------------------------------------
+// out[b, 0:d] = T[idx[b], :]   (row stride ld_out: writes one half of the concatenated MLP input)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const float* __restrict__ T, const int* __restrict__ idx, long long n, int nvec,
+                   float* __restrict__ out, int ld_out) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n * nvec; k += stride) {
+    const long long b = k / nvec;
+    const int v = (int)(k % nvec);
+    const float4 x = __ldg(reinterpret_cast<const float4*>(T + (size_t)__ldg(idx + b) * nvec * 4) + v);
+    *reinterpret_cast<float4*>(out + (size_t)b * ld_out + v * 4) = x;
+  }
+}
+
+// G[idx[b], :] += scale * src[b, 0:d]   (duplicates in idx accumulate: REDG.ADD.F32x4)
+__global__ void __launch_bounds__(256)
+scatter_add_rows_kernel(float* __restrict__ G, const int* __restrict__ idx, long long n, int nvec,
+                        const float* __restrict__ src, int ld_src, float scale) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n * nvec; k += stride) {
+    const long long b = k / nvec;
+    const int v = (int)(k % nvec);
+    float4 x = *reinterpret_cast<const float4*>(src + (size_t)b * ld_src + v * 4);
+    x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
+    float* dst = G + (size_t)__ldg(idx + b) * nvec * 4 + v * 4;
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+  }
+}
+
+// Prediction heads and their gradients.  mode 0 = GMF (NeuMF.py:52-58), 1 = MLP (:60-65),
+// 2 = fused NeuMF (:67-73).  One warp per sample.
+//   z = wg * (UG*IG).h_mf + wm * H3.h_mlp,  (wg, wm) = (1,0) | (0,1) | (.5,.5);  y = sigmoid(z)
+//   loss += -(r ln(y+1e-9) + (1-r) ln(1-y+1e-9)) [+ reg*0.5(|UG|^2+|IG|^2) unless mode 1]
+//   dz = dLoss/dz;  GMF = UG*IG;  dUG = wg*dz*h_mf*IG + reg*UG;  dIG likewise;
+//   dH3 = wm*dz*h_mlp masked by H3 > 0 (ReLU);  training = 0: only y is written.
+__global__ void __launch_bounds__(256)
+neumf_head_kernel(int mode, int training, const float* __restrict__ UG, const float* __restrict__ IG,
+                  const float* __restrict__ H3, const float* __restrict__ h_mf,
+                  const float* __restrict__ h_mlp, const float* __restrict__ r, long long n, int d,
+                  float reg, double* loss, float* __restrict__ y_out, float* __restrict__ dz_out,
+                  float* __restrict__ GMF, float* __restrict__ dUG, float* __restrict__ dIG,
+                  float* __restrict__ dH3) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const float wg = mode == 0 ? 1.f : (mode == 1 ? 0.f : 0.5f);
+  const float wm = mode == 1 ? 1.f : (mode == 0 ? 0.f : 0.5f);
+  double lsum = 0.0;
+  for (long long b = warp; b < n; b += nwarps) {
+    float z = 0.f, sq = 0.f;
+    for (int c = lane; c < d; c += 32) {
+      if (mode != 1) {
+        const float ug = UG[b * d + c], ig = IG[b * d + c];
+        z += wg * ug * ig * h_mf[c];
+        sq += ug * ug + ig * ig;
+      }
+      if (mode != 0) z += wm * H3[b * d + c] * h_mlp[c];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      z += __shfl_xor_sync(0xffffffffu, z, o);
+      sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    }
+    const float y = 1.0f / (1.0f + expf(-z));
+    if (lane == 0 && y_out != nullptr) y_out[b] = y;
+    if (!training) continue;
+    const float rb = r[b];
+    const float e = 10e-10f;                                   // the literal in NeuMF.py:55
+    const float dy = -rb / (y + e) + (1.f - rb) / (1.f - y + e);
+    const float dz = dy * y * (1.f - y);
+    if (lane == 0) {
+      lsum += -(double)(rb * logf(y + e) + (1.f - rb) * logf(1.f - y + e)) + (mode != 1 ? 0.5 * reg * sq : 0.0);
+      dz_out[b] = dz;
+    }
+    for (int c = lane; c < d; c += 32) {
+      if (mode != 1) {
+        const float ug = UG[b * d + c], ig = IG[b * d + c];
+        GMF[b * d + c] = ug * ig;
+        dUG[b * d + c] = wg * dz * h_mf[c] * ig + reg * ug;
+        dIG[b * d + c] = wg * dz * h_mf[c] * ug + reg * ig;
+      }
+      if (mode != 0) dH3[b * d + c] = H3[b * d + c] > 0.f ? wm * dz * h_mlp[c] : 0.f;
+    }
+  }
+  if (training && lane == 0 && lsum != 0.0) atomicAdd(loss, lsum);
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)sm_count() * 8;
@@ -421,6 +509,43 @@ int qrec_mul_f32(float* dst, const float* a, const float* b, int64_t n, void* st
   if (n == 0) return QREC_OK;
   QREC_REQUIRE(dst && a && b, "qrec_mul_f32: null pointer");
   mul_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(dst, a, b, n);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_gather_rows_f32(const float* T, const int32_t* idx, int64_t n, int32_t d, float* out,
+                         int32_t ld_out, void* stream) {
+  QREC_REQUIRE(n >= 0 && d >= 4 && d % 4 == 0 && ld_out % 4 == 0, "qrec_gather_rows_f32: bad shape (d, ld multiples of 4)");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(T && idx && out, "qrec_gather_rows_f32: null pointer");
+  gather_rows_kernel<<<grid_for(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(T, idx, n, d / 4, out, ld_out);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_scatter_add_rows_f32(float* G, const int32_t* idx, int64_t n, int32_t d, const float* src,
+                              int32_t ld_src, float scale, void* stream) {
+  QREC_REQUIRE(n >= 0 && d >= 4 && d % 4 == 0 && ld_src % 4 == 0, "qrec_scatter_add_rows_f32: bad shape");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(G && idx && src, "qrec_scatter_add_rows_f32: null pointer");
+  scatter_add_rows_kernel<<<grid_for(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(G, idx, n, d / 4, src, ld_src, scale);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_neumf_head_f32(int32_t mode, int32_t training, const float* UG, const float* IG,
+                        const float* H3, const float* h_mf, const float* h_mlp, const float* r,
+                        int64_t n, int32_t d, float reg, double* loss, float* y_out, float* dz_out,
+                        float* GMF, float* dUG, float* dIG, float* dH3, void* stream) {
+  QREC_REQUIRE(mode >= 0 && mode <= 2 && n >= 0 && d >= 1, "qrec_neumf_head_f32: bad argument");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(mode == 1 || (UG && IG && h_mf), "qrec_neumf_head_f32: GMF inputs missing");
+  QREC_REQUIRE(mode == 0 || (H3 && h_mlp), "qrec_neumf_head_f32: MLP inputs missing");
+  QREC_REQUIRE(!training || (r && loss && dz_out), "qrec_neumf_head_f32: training outputs missing");
+  QREC_REQUIRE(!training || mode == 1 || (GMF && dUG && dIG), "qrec_neumf_head_f32: GMF gradient buffers missing");
+  QREC_REQUIRE(!training || mode == 0 || dH3, "qrec_neumf_head_f32: dH3 missing");
+  neumf_head_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(mode, training, UG, IG, H3, h_mf, h_mlp, r, n, d, reg,
+                                                                      loss, y_out, dz_out, GMF, dUG, dIG, dH3);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

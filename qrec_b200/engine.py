@@ -449,3 +449,32 @@ def tc_gemm(A, B, C, b_is_nk=False, epilogue=EPI_NONE, bias=None, mask=None):
                                 _dev(mask, torch.float32, 'mask') if mask is not None else None,
                                 mask.stride(0) if mask is not None else 0, _stream()), 'qrec_tc_gemm_tf32')
     return C
+
+
+def gather_rows(T, idx, out):
+    """out[b, :d] = T[idx[b]]; `out` may be a column block of a wider matrix."""
+    torch = _torch()
+    po, ldo = _strided_rows(out, 'out')
+    check(lib.qrec_gather_rows_f32(_dev(T, torch.float32, 'T'), _dev(idx, torch.int32, 'idx'), idx.shape[0],
+                                   T.shape[1], po, ldo, _stream()), 'qrec_gather_rows_f32')
+    return out
+
+
+def scatter_add_rows(G, idx, src, scale=1.0):
+    torch = _torch()
+    ps, lds = _strided_rows(src, 'src')
+    check(lib.qrec_scatter_add_rows_f32(_dev(G, torch.float32, 'G'), _dev(idx, torch.int32, 'idx'), idx.shape[0],
+                                        G.shape[1], ps, lds, float(scale), _stream()), 'qrec_scatter_add_rows_f32')
+    return G
+
+
+def neumf_head(mode, training, UG, IG, H3, h_mf, h_mlp, r, reg, loss, y, dz, GMF, dUG, dIG, dH3):
+    torch = _torch()
+    f = lambda t, n: _dev(t, torch.float32, n) if t is not None else None      # noqa: E731
+    n = (UG if UG is not None else H3).shape[0]
+    d = (UG if UG is not None else H3).shape[1]
+    check(lib.qrec_neumf_head_f32(int(mode), int(training), f(UG, 'UG'), f(IG, 'IG'), f(H3, 'H3'), f(h_mf, 'h_mf'),
+                                  f(h_mlp, 'h_mlp'), f(r, 'r'), n, d, float(reg),
+                                  _dev(loss, torch.float64, 'loss') if loss is not None else None,
+                                  f(y, 'y'), f(dz, 'dz'), f(GMF, 'GMF'), f(dUG, 'dUG'), f(dIG, 'dIG'), f(dH3, 'dH3'),
+                                  _stream()), 'qrec_neumf_head_f32')

@@ -184,3 +184,58 @@ def test_graph_models_full_lifecycle(golden_bpr, tmp_path, name, extra):
     got = {m.split(':')[0]: float(m.split(':')[1]) for m in measure[1:]}
     # popularity-level ranking on this split is P@10 ~ 0.05; a few epochs must be far above it
     assert got['Precision'] > 0.12 and got['Recall'] > 0.25
+
+
+@pytest.mark.parametrize('mode', [0, 1, 2])
+def test_neumf_step_vs_autograd(torch, golden_graph, tmp_path, mode):
+    """Loss, predictions and every parameter gradient of one NeuMF minibatch (reference pointwise
+    batch: 1 positive + 4 negatives) against the float64 autograd restatement.  The MLP runs on the
+    TF32 tensor-core path, hence the 1e-2-of-max tolerance on gradients."""
+    from oracle import tf_models
+    from qrec_b200.model.ranking.NeuMF import NeuMF
+    g = golden_graph
+    m = _graph_model(NeuMF, g, tmp_path, '')
+    # make the MLP do something visible: scale the embedding tables up from xavier-on-rows
+    for k in ('PG', 'QG', 'PM', 'QM'):
+        m.params[k].mul_(8.0)
+    m.params['b1'].normal_(0, 0.05); m.params['b2'].normal_(0, 0.05); m.params['b3'].normal_(0, 0.05)
+    before = {k: v.cpu().numpy().astype(np.float64) for k, v in m.params.items()}
+    u, i, y = g['point_b0']
+    r = y.astype(np.float32)
+    loss = m.train_step(mode, _dev(torch, u), _dev(torch, i), _dev(torch, r))
+    ref_loss, ref_g, ref_y = tf_models.neumf_loss_and_grad(before, mode, u, i, r, m.regU)
+    # loss reported by the kernel excludes the h-vector regularisers; loss_value() adds them, but
+    # uses the post-update parameters -> compare against the restatement minus those terms
+    hreg = 0.0
+    if mode != 1:
+        hreg += m.regU * 0.5 * (before['h_mf'] ** 2).sum()
+    if mode == 2:
+        hreg += m.regU * 0.5 * 0.25 * ((before['h_mf'] ** 2).sum() + (before['h_mlp'] ** 2).sum())
+    assert abs(loss.item() - (ref_loss - hreg)) <= 2e-3 * abs(ref_loss)
+    np.testing.assert_allclose(m._y[:len(u)].cpu().numpy(), ref_y, rtol=5e-3, atol=2e-3)
+    for k in m.opt_vars[mode]:
+        got = m.grads[k].cpu().numpy()
+        assert np.abs(got - ref_g[k]).max() <= 1e-2 * np.abs(ref_g[k]).max() + 1e-7, k
+    # variables outside this phase's optimiser did not move
+    for k in set(m.params) - set(m.opt_vars[mode]):
+        assert np.array_equal(m.params[k].cpu().numpy().astype(np.float64), before[k]), k
+    # prediction path (all items of one user) agrees with the training-time forward
+    pred = {0: m.predict_mf, 1: m.predict_mlp, 2: m.predict_neu}[mode](3)
+    assert pred.shape == (m.num_items,) and np.all((pred > 0) & (pred < 1))
+
+
+def test_neumf_full_lifecycle(golden_bpr, tmp_path):
+    import random
+    from qrec_b200.util.config import ModelConf
+    from qrec_b200.model.ranking.NeuMF import NeuMF
+    g = golden_bpr
+    os.chdir(tmp_path)
+    conf = (str(g['conf']).replace('model.name=BPR', 'model.name=NeuMF').replace('num.max.epoch=3', 'num.max.epoch=10')
+            .replace('learnRate=-init 0.01', 'learnRate=-init 0.002'))
+    train = [[u, i, r] for u, i, r in zip(g['train_users'].tolist(), g['train_items'].tolist(), g['train_rating'].tolist())]
+    test = [[u, i, r] for u, i, r in zip(g['test_users'].tolist(), g['test_items'].tolist(), g['test_rating'].tolist())]
+    random.seed(4); np.random.seed(4)
+    with contextlib.redirect_stdout(io.StringIO()):
+        measure = NeuMF(ModelConf.from_string(conf), train, test).execute()
+    got = {m.split(':')[0]: float(m.split(':')[1]) for m in measure[1:]}
+    assert got['Precision'] > 0.12 and got['Recall'] > 0.25
