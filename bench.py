@@ -71,7 +71,7 @@ class ClockSampler(object):
             fd, self.path = tempfile.mkstemp(suffix='.csv')
             os.close(fd)
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -160,6 +160,75 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }))
+
+
+# ---------------------------------------------------------------------------------------------
+# second half of the headline metric: LightGCN epoch time on the same synthetic graph
+# ---------------------------------------------------------------------------------------------
+def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, warmup=2):
+    """LightGCN (3 layers, d=64) minibatch steps with the reference's semantics -- the whole
+    propagation, its backward pass and a dense Adam update for EVERY minibatch
+    (model/ranking/LightGCN.py:35-39) -- on the 1M x 100K x 50M-edge graph.  Step time does not
+    depend on the batch size B (SpMM bound), so the epoch time is step x ceil(50M / B); both the
+    reference-style B=2048 and a large batch are reported, extrapolated from `steps` timed steps."""
+    from qrec_b200.model.ranking.LightGCN import LightGCN
+    U, I, N = NUM_USERS, NUM_ITEMS, NUM_USERS + NUM_ITEMS
+    rowptr, cols, vals = synthetic.build_norm_adj(data, U, I, dev)
+    nnz = int(cols.numel())
+
+    class Shell(LightGCN):
+        def __init__(self):
+            pass
+
+    class Adj(object):
+        def matmul(self, X, out, acc=None, acc_scale=0.0):
+            return E.spmm_csr(rowptr, cols, vals, X, out, acc=acc, acc_scale=acc_scale, rowsplit=True)
+    m = Shell()
+    m.num_users, m.num_items, m.emb_size, m.n_layers = U, I, D, layers
+    m.lRate, m.regU, m.device, m.norm_adj = 0.001, 0.001, dev, Adj()
+    g = torch.Generator(device=dev); g.manual_seed(5)
+    m.ego = torch.randn(N, D, device=dev, generator=g) * 0.005
+    m.user_embeddings, m.item_embeddings = m.ego[:U], m.ego[U:]
+    m._buf = [torch.empty(N, D, device=dev) for _ in range(2)]
+    m._mean, m._grad, m._total = (torch.zeros(N, D, device=dev) for _ in range(3))
+    m._adam_m, m._adam_v = torch.zeros(N, D, device=dev), torch.zeros(N, D, device=dev)
+    m._loss, m._step = torch.zeros(1, dtype=torch.float64, device=dev), 0
+    spmm_algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)                 # SURVEY 8(d) no-reuse gather model
+    res = {'layers': layers, 'rows': N, 'nnz': nnz, 'semantics': 'full propagation + backward + dense Adam per minibatch'}
+    perm = torch.randperm(U * DEGREE, device=dev, generator=g)
+    for B in (2048, 65536):
+        idx = perm[:B]
+        bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
+        bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
+        for _ in range(warmup):
+            m.train_step(bu, bi, bj)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            m.train_step(bu, bi, bj)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        n_steps = -(-U * DEGREE // B)
+        step_bytes = 2 * layers * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
+        res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
+                               'epoch_extrapolated_from_steps': steps, 'algorithmic_GB_per_step': step_bytes / 1e9,
+                               'frac_of_hbm_peak': step_bytes / ms / 1e6 / peak, 'loss': float(m._loss.item())}
+    X, Y = m.ego, m._buf[0]
+    for _ in range(warmup):
+        E.spmm_csr(rowptr, cols, vals, X, Y, rowsplit=True)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        E.spmm_csr(rowptr, cols, vals, X, Y, rowsplit=True)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    res['spmm'] = {'kernel': 'spmm_csr_kernel<16,1>', 'ms': ms, 'algorithmic_GB': spmm_algo / 1e9,
+                   'achieved_GBs': spmm_algo / ms / 1e6, 'frac_of_hbm_peak': spmm_algo / ms / 1e6 / peak}
+    return res
 
 
 # ---------------------------------------------------------------------------------------------
@@ -306,7 +375,8 @@ def run_ours(args):
                 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
                 'launch_ms': per_launch_ms, 'launch_triples': per_launch_triples,
-                'traffic': (tr or {}).get('dram_bytes_per_launch'),
+                'traffic': (int(tr['dram_bytes_per_launch'] * per_launch_triples / tr['launch_triples'])
+                            if tr and tr.get('launch_triples') else None),
                 'traffic_note': (tr or {}).get('note', 'no ncu --set full capture recorded yet'),
             },
             'e2e': {'value': e2e_value, 'unit': 'triples/s', 'h2d_bytes_per_step': 12 * n_local * world,
@@ -315,6 +385,10 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        if world == 1 and not args.no_lightgcn:
+            del u, i, j, hu, hi, hj
+            torch.cuda.empty_cache()
+            out['lightgcn'] = lightgcn_section(torch, E, synthetic, data, dev, peak)
         if world == 1 and not args.no_cpu_baseline:
             out['cpu_baseline'] = cpu_baseline(args.cpu_sample)
         print(json.dumps(out))
@@ -325,13 +399,14 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--q-syncs', type=int, default=4, help='item-table all-reduces per step when N>1')
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
     ap.add_argument('--ref-sample', type=int, default=4_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-lightgcn', action='store_true')
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     if args.impl == 'reference':

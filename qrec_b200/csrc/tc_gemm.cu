@@ -65,6 +65,18 @@ __device__ __forceinline__ uint32_t sw_off(int row, int k) {
   return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (k & 3) * 4);
 }
 
+// tcgen05 kind::tf32 reads the top 19 bits of each fp32 operand, i.e. truncates.  Rounding to
+// nearest-away while staging removes the systematic toward-zero bias (2^-11 unbiased instead of up
+// to 2^-10 one-sided per operand), which matters over the 6-GEMM forward/backward chain of the MLP.
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float4 to_tf32(float4 v) {
+  return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+}
+
 enum Epilogue { EPI_NONE = 0, EPI_BIAS_RELU = 1, EPI_RELU_MASK = 2, EPI_BIAS = 3 };
 
 // B_IS_NK: B is stored [N,K] row-major (already K-major); otherwise [K,N] row-major.
@@ -110,7 +122,7 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
       const int gm = m0 + row, gk = k0 + c * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk);
-      *reinterpret_cast<float4*>(sA[s] + sw_off(row, c * 4)) = v;
+      *reinterpret_cast<float4*>(sA[s] + sw_off(row, c * 4)) = to_tf32(v);
     }
     // ---- B tile: 64 n-rows x 32 k
     if (B_IS_NK) {
@@ -120,7 +132,7 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
         const int gn = n0 + row, gk = k0 + c * 4;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gn * ldb + gk);
-        *reinterpret_cast<float4*>(sB[s] + sw_off(row, c * 4)) = v;
+        *reinterpret_cast<float4*>(sB[s] + sw_off(row, c * 4)) = to_tf32(v);
       }
     } else {
 #pragma unroll
@@ -129,7 +141,7 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
         const int gn = n0 + n, gk = k0 + k;
         float v = 0.f;
         if (gn < N && gk < K) v = B[(size_t)gk * ldb + gn];          // coalesced along n
-        *reinterpret_cast<float*>(sB[s] + sw_off(n, k)) = v;          // transposed into K-major
+        *reinterpret_cast<float*>(sB[s] + sw_off(n, k)) = to_tf32(v);  // transposed into K-major
       }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)

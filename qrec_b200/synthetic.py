@@ -51,3 +51,28 @@ def init_tables(num_users, num_items, d, seed=1, device='cuda'):
     P = torch.rand(num_users, d, device=device, generator=g) / 3
     Q = torch.rand(num_items, d, device=device, generator=g) / 3
     return P, Q
+
+
+def build_norm_adj(data, num_users, num_items, device):
+    """D^-1/2 (R (+) R^T) D^-1/2 as device CSR (base/graphRecommender.py:10-29), from the
+    synthetic user-major pairs.  Setup code (torch ops), not the measured path."""
+    u = data['u'].long()
+    i_sorted = data['sorted_cols'].long()            # per-user ascending
+    n = num_users + num_items
+    deg_u = torch.bincount(u, minlength=num_users).double()
+    deg_i = torch.bincount(i_sorted, minlength=num_items).double()
+    # user rows: already CSR, columns offset by num_users
+    vals_u = (1.0 / torch.sqrt(deg_u[u] * deg_i[i_sorted])).float()
+    # item rows: sort pairs by (item, user)
+    key = i_sorted * num_users + u
+    order = torch.argsort(key)
+    it, us = i_sorted[order], u[order]
+    vals_i = vals_u[order]
+    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
+    rowptr[1:num_users + 1] = torch.cumsum(deg_u.long(), 0)
+    rowptr[num_users + 1:] = rowptr[num_users] + torch.cumsum(deg_i.long(), 0)
+    cols = torch.cat([(i_sorted + num_users).int(), us.int()]).contiguous()
+    vals = torch.cat([vals_u, vals_i]).contiguous()
+    return rowptr, cols, vals
+
+

@@ -190,7 +190,7 @@ def test_graph_models_full_lifecycle(golden_bpr, tmp_path, name, extra):
 def test_neumf_step_vs_autograd(torch, golden_graph, tmp_path, mode):
     """Loss, predictions and every parameter gradient of one NeuMF minibatch (reference pointwise
     batch: 1 positive + 4 negatives) against the float64 autograd restatement.  The MLP runs on the
-    TF32 tensor-core path, hence the 1e-2-of-max tolerance on gradients."""
+    TF32 tensor-core path (6 chained TF32 products), hence the 2e-2-of-max tolerance on gradients."""
     from oracle import tf_models
     from qrec_b200.model.ranking.NeuMF import NeuMF
     g = golden_graph
@@ -215,7 +215,7 @@ def test_neumf_step_vs_autograd(torch, golden_graph, tmp_path, mode):
     np.testing.assert_allclose(m._y[:len(u)].cpu().numpy(), ref_y, rtol=5e-3, atol=2e-3)
     for k in m.opt_vars[mode]:
         got = m.grads[k].cpu().numpy()
-        assert np.abs(got - ref_g[k]).max() <= 1e-2 * np.abs(ref_g[k]).max() + 1e-7, k
+        assert np.abs(got - ref_g[k]).max() <= 2e-2 * np.abs(ref_g[k]).max() + 1e-7, k
     # variables outside this phase's optimiser did not move
     for k in set(m.params) - set(m.opt_vars[mode]):
         assert np.array_equal(m.params[k].cpu().numpy().astype(np.float64), before[k]), k

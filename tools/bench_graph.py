@@ -15,30 +15,6 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def build_norm_adj(data, num_users, num_items, device):
-    """D^-1/2 (R (+) R^T) D^-1/2 as device CSR (base/graphRecommender.py:10-29), from the
-    synthetic user-major pairs.  Setup code (torch ops), not the measured path."""
-    import torch
-    u = data['u'].long()
-    i_sorted = data['sorted_cols'].long()            # per-user ascending
-    n = num_users + num_items
-    deg_u = torch.bincount(u, minlength=num_users).double()
-    deg_i = torch.bincount(i_sorted, minlength=num_items).double()
-    # user rows: already CSR, columns offset by num_users
-    vals_u = (1.0 / torch.sqrt(deg_u[u] * deg_i[i_sorted])).float()
-    # item rows: sort pairs by (item, user)
-    key = i_sorted * num_users + u
-    order = torch.argsort(key)
-    it, us = i_sorted[order], u[order]
-    vals_i = vals_u[order]
-    rowptr = torch.zeros(n + 1, dtype=torch.int64, device=device)
-    rowptr[1:num_users + 1] = torch.cumsum(deg_u.long(), 0)
-    rowptr[num_users + 1:] = rowptr[num_users] + torch.cumsum(deg_i.long(), 0)
-    cols = torch.cat([(i_sorted + num_users).int(), us.int()]).contiguous()
-    vals = torch.cat([vals_u, vals_i]).contiguous()
-    return rowptr, cols, vals
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--layers', type=int, default=3)
@@ -55,7 +31,7 @@ def main():
     torch.cuda.set_device(dev)
     U, I, DEG, D = int(1_000_000 * args.scale), int(100_000 * args.scale), 50, 64
     data = synthetic.make_interactions(U, I, DEG, device=dev, zipf=args.zipf)
-    rowptr, cols, vals = build_norm_adj(data, U, I, dev)
+    rowptr, cols, vals = synthetic.build_norm_adj(data, U, I, dev)
     N, nnz = U + I, int(cols.numel())
     peak = 6540.5
     try:
