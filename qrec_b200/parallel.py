@@ -55,3 +55,132 @@ def sync_points(n, pieces):
     """Boundaries that cut n triples into `pieces` nearly equal launches: [0, ..., n]."""
     pieces = max(1, int(pieces))
     return [n * s // pieces for s in range(pieces + 1)]
+
+
+# =============================================================================================
+# LightGCN / SimGCL propagation over row-sharded tables (SURVEY.md section 8e, config 3)
+# =============================================================================================
+class NodePartition(object):
+    """1-D partition of the joint (U + I) node space: rank r owns users [r*bu, (r+1)*bu) and items
+    [r*bi, (r+1)*bi), stored locally as [its users; its items].  An all-gather of the local blocks
+    therefore yields the table in "gathered order" [u_0; i_0; u_1; i_1; ...]; `to_gathered` maps a
+    global node id to its row there.  Users and items are split separately so that every rank holds
+    the same share of both degree populations (balanced nnz)."""
+
+    def __init__(self, num_users, num_items, world):
+        if num_users % world or num_items % world:
+            raise ValueError('NodePartition: num_users and num_items must be multiples of the world size '
+                             '(pad the tables)')
+        self.num_users, self.num_items, self.world = num_users, num_items, world
+        self.bu, self.bi = num_users // world, num_items // world
+        self.block = self.bu + self.bi
+
+    def to_gathered(self, node):
+        """node: int64 tensor of global ids (users < U <= items) -> rows in gathered order."""
+        is_item = node >= self.num_users
+        it = node - self.num_users
+        pos_u = (node // self.bu) * self.block + node % self.bu
+        pos_i = (it // self.bi) * self.block + self.bu + it % self.bi
+        return torch.where(is_item, pos_i, pos_u)
+
+    def local_nodes(self, rank):
+        """Global ids of the rows rank `rank` owns, in local order."""
+        u = torch.arange(rank * self.bu, (rank + 1) * self.bu)
+        i = torch.arange(rank * self.bi, (rank + 1) * self.bi) + self.num_users
+        return torch.cat([u, i])
+
+
+def shard_adjacency(rowptr, cols, vals, part, rank):
+    """Rows of the global CSR owned by `rank`, column ids rewritten to gathered order.
+    Inputs are tensors on any device (setup code, torch ops)."""
+    dev = rowptr.device
+    rows = part.local_nodes(rank).to(dev)
+    start, end = rowptr[rows], rowptr[rows + 1]
+    lens = end - start
+    lrowptr = torch.zeros(rows.numel() + 1, dtype=torch.int64, device=dev)
+    lrowptr[1:] = torch.cumsum(lens, 0)
+    total = int(lrowptr[-1].item())
+    # flat gather indices: for each local row, the contiguous span [start, end)
+    row_of = torch.repeat_interleave(torch.arange(rows.numel(), device=dev), lens)
+    offs = torch.arange(total, device=dev) - lrowptr[row_of]
+    src = start[row_of] + offs
+    lcols = part.to_gathered(cols[src].long()).int().contiguous()
+    lvals = vals[src].contiguous()
+    # keep column ids ascending inside a row (the remap is monotone inside a rank block only)
+    key = row_of * (part.world * part.block) + lcols.long()
+    order = torch.argsort(key)
+    return lrowptr, lcols[order].contiguous(), lvals[order].contiguous()
+
+
+def all_gather_rows(local, out, group=None):
+    """out[[rank blocks]] <- local blocks of every rank (equal sizes)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out.copy_(local)
+        return out
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
+class ShardedLightGCN(object):
+    """LightGCN training step over a row-sharded ego table (reference semantics per minibatch:
+    model/ranking/LightGCN.py:13-39).  Per layer: all-gather E_k (NCCL over NVLink), local K2 SpMM
+    over the owned rows.  The minibatch is replicated: after one more all-gather of the layer mean
+    every rank evaluates K3 on the whole batch and keeps the gradient rows it owns, so no
+    gradient collective is needed; backward = the same gather + SpMM; Adam is purely local."""
+
+    def __init__(self, part, rank, lrowptr, lcols, lvals, ego_local, n_layers, lr, reg,
+                 spmm=None, grad=None, adam=None, scale=None, group=None):
+        from . import engine as E
+        self.part, self.rank, self.group = part, rank, group
+        self.rowptr, self.cols, self.vals = lrowptr, lcols, lvals
+        self.ego = ego_local                              # [block, d], this rank's rows
+        self.n_layers, self.lr, self.reg = n_layers, lr, reg
+        dev, d = ego_local.device, ego_local.shape[1]
+        n_full = part.world * part.block
+        new = lambda *s: torch.zeros(*s, device=dev)      # noqa: E731
+        self.full = new(n_full, d)                        # gather target
+        self.buf = [new(part.block, d) for _ in range(2)]
+        self.mean, self.total = new(part.block, d), new(part.block, d)
+        self.grad_full = new(n_full, d)
+        self.m, self.v = new(part.block, d), new(part.block, d)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.step = 0
+        # kernels (injectable so that the gloo CPU test can exercise the collective logic)
+        self._spmm = spmm or (lambda X, Y, acc, s: E.spmm_csr(self.rowptr, self.cols, self.vals, X, Y, acc=acc, acc_scale=s))
+        self._grad = grad or (lambda Ue, Ve, u, i, j, gU, gV, loss: E.bpr_grad_scatter(Ue, Ve, u, i, j, 10e-8, self.reg, gU, gV, loss))
+        self._adam = adam or (lambda var, m, v, g, t: E.adam_dense_tf1(var, m, v, g, self.lr, t))
+        self._scale = scale or (lambda dst, src, s: E.axpby(dst, src, src, s, 0.0))
+
+    def _propagate(self, src_local, acc):
+        """acc <- s*src + s*sum_{k=1..n} A^k src (local rows); s = 1/(n+1)."""
+        s = 1.0 / (self.n_layers + 1)
+        self._scale(acc, src_local, s)
+        cur = src_local
+        for k in range(self.n_layers):
+            all_gather_rows(cur, self.full, self.group)
+            nxt = self.buf[k % 2]
+            self._spmm(self.full, nxt, acc, s)
+            cur = nxt
+        return acc
+
+    def gathered_batch_ids(self, u, i, j):
+        """(u, i, j) global ids -> rows of the gathered user/item views used by K3."""
+        nu = self.part.num_users
+        return (self.part.to_gathered(u.long()).int(), self.part.to_gathered(i.long() + nu).int(),
+                self.part.to_gathered(j.long() + nu).int())
+
+    def train_step(self, u, i, j):
+        """u, i, j: the WHOLE minibatch (global ids, int32) on every rank."""
+        self._propagate(self.ego, self.mean)
+        all_gather_rows(self.mean, self.full, self.group)
+        gu, gi, gj = self.gathered_batch_ids(u, i, j)
+        self.grad_full.zero_()
+        self.loss.zero_()
+        # users and items index the same gathered table: K3 takes it as both "tables"
+        self._grad(self.full, self.full, gu, gi, gj, self.grad_full, self.grad_full, self.loss)
+        lo = self.rank * self.part.block
+        g_local = self.grad_full[lo:lo + self.part.block]
+        self._propagate(g_local, self.total)
+        self.step += 1
+        self._adam(self.ego, self.m, self.v, self.total, self.step)
+        return self.loss

@@ -71,3 +71,97 @@ def test_single_process_sync_is_identity():
     s = parallel.ReplicatedTableSync(Q)
     Q += 1
     assert s.sync() is Q and bool((Q == 2).all()) and s.world == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded LightGCN: partition / remap logic and the collective schedule, gloo world_size 2.
+# The kernels are replaced by CPU stand-ins INSIDE THIS TEST (the product default is the CUDA path).
+# ---------------------------------------------------------------------------------------------
+def _toy_graph(U, I, seed=0):
+    import numpy as np
+    import scipy.sparse as sp
+    rng = np.random.default_rng(seed)
+    n = U + I
+    rows, cols = [], []
+    for u in range(U):
+        for it in rng.choice(I, size=3, replace=False):
+            rows += [u, U + it]; cols += [U + it, u]
+    A = sp.csr_matrix((np.ones(len(rows), np.float32), (rows, cols)), shape=(n, n))
+    d = np.asarray(A.sum(1)).ravel(); d[d == 0] = 1
+    A = sp.diags(d ** -0.5) @ A @ sp.diags(d ** -0.5)
+    A = A.tocsr(); A.sort_indices()
+    return A.astype(np.float32)
+
+
+def _cpu_kernels(lrowptr, lcols, lvals, reg, lr):
+    import numpy as np
+    from oracle import bpr_oracle as O
+
+    def spmm(X, Y, acc, s):
+        A = torch.sparse_csr_tensor(lrowptr, lcols.long(), lvals, size=(lrowptr.numel() - 1, X.shape[0]))
+        Y.copy_(A @ X)
+        if acc is not None:
+            acc.add_(Y, alpha=s)
+
+    def grad(Ue, Ve, u, i, j, gU, gV, loss):
+        l, a, b = O.bpr_loss_grad(Ue.numpy(), Ve.numpy(), u.numpy(), i.numpy(), j.numpy(), 10e-8, reg)
+        gU.add_(torch.from_numpy(a).float()); gV.add_(torch.from_numpy(b).float())   # same buffer: both add
+        loss += l
+
+    def adam(var, m, v, g, t):
+        O.adam_tf1(var.numpy(), m.numpy(), v.numpy(), g.numpy(), lr, t)
+
+    def scale(dst, src, s):
+        dst.copy_(src * s)
+    return spmm, grad, adam, scale
+
+
+def _lgcn_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import bpr_oracle as O
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        U, I, d, L, lr, reg = 8, 6, 4, 2, 0.01, 0.001
+        A = _toy_graph(U, I)
+        part = parallel.NodePartition(U, I, world)
+        rp, co, va = (torch.from_numpy(x) for x in (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data))
+        lrp, lco, lva = parallel.shard_adjacency(rp, co, va, part, rank)
+        rng = np.random.default_rng(1)
+        ego = (rng.standard_normal((U + I, d)) * 0.1).astype(np.float32)
+        mine = part.local_nodes(rank)
+        spmm, grad, adam, scale = _cpu_kernels(lrp, lco, lva, reg, lr)
+        m = parallel.ShardedLightGCN(part, rank, lrp, lco, lva, torch.from_numpy(ego[mine.numpy()].copy()), L, lr, reg,
+                                     spmm=spmm, grad=grad, adam=adam, scale=scale)
+        # single-process reference: oracle.lightgcn_step on the whole graph
+        Ur, Vr = ego[:U].copy(), ego[U:].copy()
+        mU, vU, mV, vV = (np.zeros_like(x) for x in (Ur, Ur, Vr, Vr))
+        for step in range(3):
+            u = rng.integers(0, U, 5).astype(np.int32); i = rng.integers(0, I, 5).astype(np.int32)
+            j = rng.integers(0, I, 5).astype(np.int32)
+            ref_loss = O.lightgcn_step(A, Ur, Vr, mU, vU, mV, vV, u, i, j, L, lr, reg, step + 1)
+            loss = m.train_step(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
+            full_ref = np.concatenate([Ur, Vr])
+            assert np.allclose(m.ego.numpy(), full_ref[mine.numpy()], rtol=1e-3, atol=1e-6), (rank, step)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_lightgcn_matches_single_process_world2():
+    port = 31500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_lgcn_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+def test_node_partition_roundtrip():
+    part = parallel.NodePartition(8, 4, 2)
+    g = part.to_gathered(torch.arange(12))
+    assert sorted(g.tolist()) == list(range(12))
+    assert g[:8].tolist() == [0, 1, 2, 3, 6, 7, 8, 9] and g[8:].tolist() == [4, 5, 10, 11]
+    assert part.local_nodes(1).tolist() == [4, 5, 6, 7, 10, 11]
+    with pytest.raises(ValueError):
+        parallel.NodePartition(7, 4, 2)

@@ -1,0 +1,108 @@
+#!/usr/bin/env python
+"""Sharded LightGCN step under torchrun (one rank per GPU, NCCL): (1) parity against the single-GPU
+step on a down-scaled graph, (2) step time on the synthetic 1M x 100K x 50M-edge graph.
+
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/dist_lightgcn.py
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--layers', type=int, default=3)
+    ap.add_argument('--batch', type=int, default=2048)
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from qrec_b200 import engine as E, synthetic, parallel
+    rank, world, local = (int(os.environ.get(k, d)) for k, d in (('RANK', 0), ('WORLD_SIZE', 1), ('LOCAL_RANK', 0)))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    D, DEG = 64, 50
+
+    def build(U, I):
+        data = synthetic.make_interactions(U, I, DEG, device=dev)           # same seed on every rank
+        rp, co, va = synthetic.build_norm_adj(data, U, I, dev)
+        part = parallel.NodePartition(U, I, world)
+        lrp, lco, lva = parallel.shard_adjacency(rp, co, va, part, rank)
+        g = torch.Generator(device=dev); g.manual_seed(3)
+        ego = torch.randn(U + I, D, device=dev, generator=g) * 0.005
+        mine = part.local_nodes(rank).to(dev)
+        m = parallel.ShardedLightGCN(part, rank, lrp, lco, lva, ego[mine].contiguous(), args.layers, 0.001, 0.001)
+        return data, (rp, co, va), ego, part, mine, m
+
+    # ---------------- parity on a small graph (every rank also runs the 1-GPU step)
+    U, I = 16000, 1600
+    data, (rp, co, va), ego, part, mine, m = build(U, I)
+    from qrec_b200.model.ranking.LightGCN import LightGCN
+
+    class Shell(LightGCN):
+        def __init__(self):
+            pass
+
+    class Adj(object):
+        def matmul(self, X, out, acc=None, acc_scale=0.0):
+            return E.spmm_csr(rp, co, va, X, out, acc=acc, acc_scale=acc_scale)
+    ref = Shell()
+    ref.num_users, ref.num_items, ref.emb_size, ref.n_layers, ref.lRate, ref.regU, ref.device = U, I, D, args.layers, 0.001, 0.001, dev
+    ref.norm_adj, ref.ego = Adj(), ego.clone()
+    N = U + I
+    ref._buf = [torch.empty(N, D, device=dev) for _ in range(2)]
+    ref._mean, ref._grad, ref._total = (torch.zeros(N, D, device=dev) for _ in range(3))
+    ref._adam_m, ref._adam_v = torch.zeros(N, D, device=dev), torch.zeros(N, D, device=dev)
+    ref._loss, ref._step = torch.zeros(1, dtype=torch.float64, device=dev), 0
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    for step in range(3):
+        idx = torch.randint(0, U * DEG, (args.batch,), device=dev, generator=g)
+        bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
+        bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, step)
+        l_ref = ref.train_step(bu, bi, bj).item()
+        l = m.train_step(bu, bi, bj).item()
+        assert abs(l - l_ref) <= 1e-5 * abs(l_ref), (l, l_ref)
+        torch.testing.assert_close(m.ego, ref.ego[mine], rtol=2e-3, atol=2e-6)
+    if rank == 0:
+        print(json.dumps({'parity': 'sharded == single-GPU LightGCN step', 'world': world, 'graph': [U, I, U * DEG]}))
+    del data, rp, co, va, ego, m, ref
+    torch.cuda.empty_cache()
+
+    # ---------------- timing at the benchmark scale
+    U, I = 1_000_000, 100_000
+    data, (rp, co, va), ego, part, mine, m = build(U, I)
+    del rp, co, va, ego
+    torch.cuda.empty_cache()
+    idx = torch.randint(0, U * DEG, (args.batch,), device=dev, generator=g)
+    bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
+    bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
+    for _ in range(2):
+        m.train_step(bu, bi, bj)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(args.steps):
+        m.train_step(bu, bi, bj)
+    b.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(t.item())
+        print(json.dumps({'lightgcn_sharded_step_ms': ms, 'world': world, 'layers': args.layers, 'batch': args.batch,
+                          'epoch_s_at_batch': ms * (-(-U * DEG // args.batch)) / 1e3, 'local_nnz': int(m.cols.numel())}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()
