@@ -144,6 +144,15 @@ int qrec_bpr_sgd_batch_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
                            const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
                            float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* K1 for a row-sharded item table: the Q rows of the batch were fetched from their
+ * owner ranks into dev_R (row pos_i[k] / pos_j[k] holds Q[i_k] / Q[j_k]).  Applies BPR.py:45-52,
+ * updates P in place and writes the item-row deltas to dev_D at the same positions, ready to be
+ * returned to the owners and scatter-added (qrec_scatter_add_rows_f32).  d multiple of 4, <= 128. */
+int qrec_bpr_sgd_staged_f32(float* dev_P, int32_t d, int64_t n, const int32_t* dev_u,
+                            const int32_t* dev_pos_i, const int32_t* dev_pos_j, const float* dev_R,
+                            float* dev_D, float lr, float reg_u, float reg_i, double* dev_loss,
+                            void* stream);
+
 /* regU*sum(P*P) + regI*sum(Q*Q) building block (BPR.py:40): dev_out[0] += sum(x[k]^2). */
 int qrec_sumsq_f32(const float* dev_x, int64_t n, double* dev_out, void* stream);
 int qrec_sumsq_f64(const double* dev_x, int64_t n, double* dev_out, void* stream);

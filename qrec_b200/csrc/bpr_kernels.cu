@@ -253,6 +253,66 @@ bpr_sgd_batch_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, lon
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// K1 on staged item rows (row-sharded Q): the rows of i and j were fetched from their
+// owner ranks into R[pos]; the step is the same, P is updated in place (REDG.ADD.F32x4) and the item
+// deltas are written next to the fetched rows (D[pos]) to be sent back and scatter-added by the
+// owner.  LPR = d/4 lanes per triple like the batch kernel; one triple per lane group per step.
+// ------------------------------------------------------------------------------------------
+template <int LPR>
+__global__ void __launch_bounds__(256)
+bpr_sgd_staged_kernel(float* __restrict__ P, int nvec, long long n, const int* __restrict__ u,
+                      const int* __restrict__ pos_i, const int* __restrict__ pos_j,
+                      const float* __restrict__ R, float* __restrict__ D, float lr, float reg_u,
+                      float reg_i, double* loss) {
+  constexpr int TPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * TPW + sub;
+  const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * TPW;
+  const int d = nvec * 4;
+  const float a_u = lr * reg_u, a_i = lr * reg_i;
+  float lsum = 0.f;
+  const long long rounds = (n + ngroups - 1) / ngroups;
+  for (long long it = 0; it < rounds; ++it) {
+    const long long k = it * ngroups + group;
+    const bool ok = k < n && l < nvec;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), qi = p, qj = p;
+    float* pr = nullptr;
+    size_t oi = 0, oj = 0;
+    if (ok) {
+      pr = P + (size_t)__ldg(u + k) * d + l * 4;
+      oi = (size_t)__ldg(pos_i + k) * d + l * 4;
+      oj = (size_t)__ldg(pos_j + k) * d + l * 4;
+      p = *reinterpret_cast<const float4*>(pr);
+      qi = __ldg(reinterpret_cast<const float4*>(R + oi));
+      qj = __ldg(reinterpret_cast<const float4*>(R + oj));
+    }
+    float x = dot4(p, qi) - dot4(p, qj);
+    x = group_sum<LPR>(x);
+    const float s = 1.0f / (1.0f + expf(-x));
+    const float g = lr * (1.0f - s);
+    if (ok) {
+      if (l == 0) lsum += -logf(s);
+      float4 dp, dqi, dqj;
+      bpr_step4(p, qi, qj, g, a_u, a_i, dp, dqi, dqj);
+      red_add_v4(pr, dp);
+      *reinterpret_cast<float4*>(D + oi) = dqi;
+      *reinterpret_cast<float4*>(D + oj) = dqj;
+    }
+  }
+  __shared__ float wsum[8];
+  lsum = warp_sum(lsum);
+  if (lane == 0) wsum[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w];
+    if (t != 0.0) atomicAdd(loss, t);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const T* __restrict__ x, long long n, double* out) {
@@ -375,6 +435,33 @@ int qrec_bpr_sgd_batch_f32(float* P, float* Q, int32_t d, int64_t n, const int32
                            const int32_t* i, const int32_t* j, float lr, float reg_u,
                            float reg_i, double* loss, void* stream) {
   return qrec::launch_bpr_batch(P, Q, d, n, u, i, j, lr, reg_u, reg_i, loss, (cudaStream_t)stream);
+}
+
+int qrec_bpr_sgd_staged_f32(float* P, int32_t d, int64_t n, const int32_t* u, const int32_t* pos_i,
+                            const int32_t* pos_j, const float* R, float* D, float lr, float reg_u,
+                            float reg_i, double* loss, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 128 && (d % 4) == 0, "qrec_bpr_sgd_staged_f32: d=%d unsupported (multiple of 4, 4..128)", d);
+  QREC_REQUIRE(n >= 0, "qrec_bpr_sgd_staged_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(P && u && pos_i && pos_j && R && D && loss, "qrec_bpr_sgd_staged_f32: null pointer");
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_STAGED(LPR)                                                                        \
+  {                                                                                             \
+    const long long per_block = 8 * (32 / LPR);                                                 \
+    long long blocks = (n + per_block - 1) / per_block;                                         \
+    if (blocks > cap) blocks = cap;                                                             \
+    bpr_sgd_staged_kernel<LPR><<<(int)blocks, 256, 0, st>>>(P, nvec, n, u, pos_i, pos_j, R, D,  \
+                                                            lr, reg_u, reg_i, loss);            \
+  }
+  if (nvec <= 4) QREC_STAGED(4)
+  else if (nvec <= 8) QREC_STAGED(8)
+  else if (nvec <= 16) QREC_STAGED(16)
+  else QREC_STAGED(32)
+#undef QREC_STAGED
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
 }
 
 int qrec_sumsq_f32(const float* x, int64_t n, double* out, void* stream) {

@@ -258,6 +258,17 @@ def bpr_sgd_batch(P, Q, u, i, j, lr, reg_u, reg_i, loss):
     return loss
 
 
+def bpr_sgd_staged(P, u, pos_i, pos_j, R, D, lr, reg_u, reg_i, loss):
+    """K1 against item rows staged in R (row-sharded Q); item deltas come back in D."""
+    torch = _torch()
+    check(lib.qrec_bpr_sgd_staged_f32(_dev(P, torch.float32, 'P'), P.shape[1], u.shape[0], _dev(u, torch.int32, 'u'),
+                                      _dev(pos_i, torch.int32, 'pos_i'), _dev(pos_j, torch.int32, 'pos_j'),
+                                      _dev(R, torch.float32, 'R'), _dev(D, torch.float32, 'D'), float(lr),
+                                      float(reg_u), float(reg_i), _dev(loss, torch.float64, 'loss'), _stream()),
+          'qrec_bpr_sgd_staged_f32')
+    return loss
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

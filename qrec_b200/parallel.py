@@ -146,7 +146,11 @@ class ShardedLightGCN(object):
         self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
         self.step = 0
         # kernels (injectable so that the gloo CPU test can exercise the collective logic)
-        self._spmm = spmm or (lambda X, Y, acc, s: E.spmm_csr(self.rowptr, self.cols, self.vals, X, Y, acc=acc, acc_scale=s))
+        # short, even rows -> plain row partitioning; a long-tailed local degree distribution -> nnz-balanced
+        max_row = int((lrowptr[1:] - lrowptr[:-1]).max().item()) if lrowptr.numel() > 1 else 0
+        self.rowsplit = max_row <= 4096
+        self._spmm = spmm or (lambda X, Y, acc, s: E.spmm_csr(self.rowptr, self.cols, self.vals, X, Y, acc=acc, acc_scale=s,
+                                                              rowsplit=self.rowsplit))
         self._grad = grad or (lambda Ue, Ve, u, i, j, gU, gV, loss: E.bpr_grad_scatter(Ue, Ve, u, i, j, 10e-8, self.reg, gU, gV, loss))
         self._adam = adam or (lambda var, m, v, g, t: E.adam_dense_tf1(var, m, v, g, self.lr, t))
         self._scale = scale or (lambda dst, src, s: E.axpby(dst, src, src, s, 0.0))
@@ -183,4 +187,78 @@ class ShardedLightGCN(object):
         self._propagate(g_local, self.total)
         self.step += 1
         self._adam(self.ego, self.m, self.v, self.total, self.step)
+        return self.loss
+
+
+# =============================================================================================
+# K7: BPR with a ROW-SHARDED item table (a table that does not fit one GPU)
+# =============================================================================================
+def _all_to_all(out, inp, out_splits, in_splits, group=None):
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        out.copy_(inp)
+        return out
+    dist.all_to_all_single(out, inp, output_split_sizes=out_splits, input_split_sizes=in_splits, group=group)
+    return out
+
+
+class ShardedItemTableBPR(object):
+    """Throughput-mode BPR where rank r owns users [lo_u, hi_u) (P rows + their triples) and the item
+    block [r*bi, (r+1)*bi) of Q.  Per minibatch of LOCAL triples (three exchanges):
+
+      ids    the 2n item ids (i then j) are bucketed by owner and exchanged      all-to-all (4 B/id)
+      rows   owners gather the requested rows (qrec_gather_rows_f32) and return   all-to-all (4d B/row)
+      step   qrec_bpr_sgd_staged_f32: BPR.py:45-52 on P (in place) and the staged rows -> item deltas
+      grads  deltas travel back the same way and are scatter-added by the owner   all-to-all + REDG
+
+    A rank's own item block takes the same path (the self-exchange never leaves the GPU).
+    Duplicate requests are not merged: every occurrence fetches its own copy and returns its own
+    delta, the owner's scatter-add sums them -- the same sum-of-deltas semantics as the single-GPU
+    kernel.  Collectives: torch.distributed all_to_all_single (NCCL over NVLink / gloo in tests)."""
+
+    def __init__(self, P_local, Q_local, num_items, rank, world, lr, reg_u, reg_i, group=None,
+                 gather=None, staged=None, scatter=None):
+        from . import engine as E
+        if num_items % world:
+            raise ValueError('ShardedItemTableBPR: num_items must be a multiple of the world size')
+        self.P, self.Q = P_local, Q_local
+        self.rank, self.world, self.group = rank, world, group
+        self.bi = num_items // world
+        self.lr, self.reg_u, self.reg_i = lr, reg_u, reg_i
+        self.loss = torch.zeros(1, dtype=torch.float64, device=P_local.device)
+        self._gather = gather or (lambda T, idx, out: E.gather_rows(T, idx, out))
+        self._staged = staged or (lambda P, u, pi, pj, R, D, loss: E.bpr_sgd_staged(P, u, pi, pj, R, D, self.lr, self.reg_u,
+                                                                                 self.reg_i, loss))
+        self._scatter = scatter or (lambda G, idx, src: E.scatter_add_rows(G, idx, src))
+        self.bytes_sent = 0
+
+    def step(self, u_local, i_glob, j_glob):
+        """u_local: int32 local user ids; i_glob/j_glob: int32 global item ids (device tensors)."""
+        dev, d, n = self.P.device, self.P.shape[1], u_local.shape[0]
+        ids = torch.cat([i_glob, j_glob]).long()                       # request k -> item id
+        owner = torch.div(ids, self.bi, rounding_mode='floor')
+        order = torch.argsort(owner, stable=True)                      # requests grouped by owner
+        send_ids = ids[order].int().contiguous()
+        send_counts = torch.bincount(owner, minlength=self.world)
+        recv_counts = torch.empty_like(send_counts)
+        _all_to_all(recv_counts, send_counts, None, None, self.group)  # one count per peer
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        n_recv = int(sum(rc))
+        recv_ids = torch.empty(n_recv, dtype=torch.int32, device=dev)
+        _all_to_all(recv_ids, send_ids, rc, sc, self.group)
+        # ---- owner side: gather the requested rows and send them back
+        local_rows = (recv_ids - self.rank * self.bi).contiguous()
+        rows_out = torch.empty(n_recv, d, device=dev)
+        self._gather(self.Q, local_rows, rows_out)
+        R = torch.empty(2 * n, d, device=dev)
+        _all_to_all(R, rows_out, sc, rc, self.group)
+        # ---- requester side: position of request k inside R is the inverse of `order`
+        pos = torch.empty(2 * n, dtype=torch.int32, device=dev)
+        pos[order] = torch.arange(2 * n, dtype=torch.int32, device=dev)
+        D = torch.zeros(2 * n, d, device=dev)
+        self._staged(self.P, u_local, pos[:n].contiguous(), pos[n:].contiguous(), R, D, self.loss)
+        # ---- deltas travel back; the owner scatter-adds them
+        back = torch.empty(n_recv, d, device=dev)
+        _all_to_all(back, D, rc, sc, self.group)
+        self._scatter(self.Q, local_rows, back)
+        self.bytes_sent += 4 * 2 * n + 2 * 4 * d * (2 * n - sc[self.rank])
         return self.loss

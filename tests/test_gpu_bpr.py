@@ -280,3 +280,31 @@ def test_full_size_properties_synthetic(torch, E):
     assert torch.equal(P[nu // 2:], P0[nu // 2:]) and torch.equal(Q[ni - 1000:], Q0[ni - 1000:])
     assert not torch.equal(P[:nu // 2], P0[:nu // 2])
     assert bool(torch.isfinite(P).all()) and bool(torch.isfinite(Q).all())
+
+
+def test_sharded_item_table_path_single_rank_equals_batch_kernel(torch, E):
+    """K7 with world=1: ids -> owner gather -> staged K1 -> delta scatter-add must reproduce the
+    fused batch kernel (conflict-free batch, so both equal the reference step)."""
+    from qrec_b200 import parallel
+    rng = np.random.default_rng(21)
+    nu, ni, n, d = 3000, 5000, 2500, 64
+    u, i, j = _conflict_free_triples(rng, nu, ni, n)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    Pa, Qa, Pb, Qb = _dev(torch, P0), _dev(torch, Q0), _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(Pa, Qa, _dev(torch, u), _dev(torch, i), _dev(torch, j), 0.05, 0.01, 0.02, loss)
+    m = parallel.ShardedItemTableBPR(Pb, Qb, ni, 0, 1, 0.05, 0.01, 0.02)
+    l2 = m.step(_dev(torch, u), _dev(torch, i), _dev(torch, j))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(Pb, Pa, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(Qb, Qa, rtol=1e-6, atol=1e-7)
+    assert abs(l2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    # duplicates: the same item requested many times -> deltas sum at the owner
+    u2 = np.arange(64, dtype=np.int32); i2 = np.full(64, 7, np.int32); j2 = np.full(64, 9, np.int32)
+    Pc, Qc = _dev(torch, P0), _dev(torch, Q0)
+    m2 = parallel.ShardedItemTableBPR(Pc, Qc, ni, 0, 1, 1e-3, 0.0, 0.0)
+    m2.step(_dev(torch, u2), _dev(torch, i2), _dev(torch, j2))
+    from oracle import bpr_oracle as O
+    dP, dQ, _ = O.bpr_sgd_jacobi(P0, Q0, np.stack([u2, i2, j2], 1), 1e-3, 0.0, 0.0)
+    np.testing.assert_allclose(Qc.cpu().numpy()[[7, 9]] - Q0[[7, 9]], dQ[[7, 9]], rtol=1e-3, atol=1e-7)

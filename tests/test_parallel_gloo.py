@@ -165,3 +165,66 @@ def test_node_partition_roundtrip():
     assert part.local_nodes(1).tolist() == [4, 5, 6, 7, 10, 11]
     with pytest.raises(ValueError):
         parallel.NodePartition(7, 4, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# K7: row-sharded item table, all-to-all row fetch / gradient return (gloo, CPU stand-in kernels)
+# ---------------------------------------------------------------------------------------------
+def _sharded_bpr_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import c_oracle
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        U, I, d, lr, reg = 40, 60, 8, 0.05, 0.01
+        rng = np.random.default_rng(0)
+        P0 = (rng.random((U, d)) / 3).astype(np.float32)
+        Q0 = (rng.random((I, d)) / 3).astype(np.float32)
+        # a conflict-free global batch (every user and item once) so that the result equals the
+        # sequential oracle exactly, split by user range
+        u = rng.permutation(U)[:24].astype(np.int32)
+        items = rng.permutation(I)[:48].astype(np.int32)
+        i, j = items[:24].copy(), items[24:].copy()
+        lo, hi = parallel.user_range(rank, world, U)
+        bi = I // world
+        lu, li, lj = parallel.shard_triples_by_user(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j), rank, world, U)
+
+        def gather(T, idx, o):
+            o.copy_(T[idx.long()])
+
+        def staged(P, uu, pi, pj, R, D, loss):
+            # the same arithmetic as the kernel, via the oracle's sequential step on private copies
+            for k in range(uu.numel()):
+                Pk = P[uu[k].long()].numpy()[None].copy()
+                Qk = np.stack([R[pi[k].long()].numpy(), R[pj[k].long()].numpy()]).copy()
+                q0 = Qk.copy()
+                l = c_oracle.bpr_sgd_sequential(Pk, Qk, np.array([0], np.int32), np.array([0], np.int32),
+                                                np.array([1], np.int32), lr, reg, reg)
+                P[uu[k].long()] = torch.from_numpy(Pk[0])
+                D[pi[k].long()] = torch.from_numpy(Qk[0] - q0[0])
+                D[pj[k].long()] = torch.from_numpy(Qk[1] - q0[1])
+                loss += l
+
+        def scatter(G, idx, src):
+            G.index_add_(0, idx.long(), src)
+        m = parallel.ShardedItemTableBPR(torch.from_numpy(P0[lo:hi].copy()), torch.from_numpy(Q0[rank * bi:(rank + 1) * bi].copy()),
+                                         I, rank, world, lr, reg, reg, gather=gather, staged=staged, scatter=scatter)
+        loss = m.step(lu, li, lj)
+        Pr, Qr = P0.copy(), Q0.copy()
+        ref_loss = c_oracle.bpr_sgd_sequential(Pr, Qr, u, i, j, lr, reg, reg)
+        tot = loss.clone()
+        dist.all_reduce(tot)
+        assert abs(float(tot) - ref_loss) < 1e-5 * ref_loss
+        assert np.allclose(m.P.numpy(), Pr[lo:hi], rtol=1e-6, atol=1e-7)
+        assert np.allclose(m.Q.numpy(), Qr[rank * bi:(rank + 1) * bi], rtol=1e-6, atol=1e-7)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_item_table_bpr_world2():
+    port = 33500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_sharded_bpr_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}

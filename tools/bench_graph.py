@@ -77,7 +77,7 @@ def main():
 
     class Adj(object):
         def matmul(self, Xin, out, acc=None, acc_scale=0.0):
-            return E.spmm_csr(rowptr, cols, vals, Xin, out, acc=acc, acc_scale=acc_scale)
+            return E.spmm_csr(rowptr, cols, vals, Xin, out, acc=acc, acc_scale=acc_scale, rowsplit=not args.zipf)
     m.norm_adj = Adj()
     m.ego = X.clone()
     m.user_embeddings, m.item_embeddings = m.ego[:U], m.ego[U:]
