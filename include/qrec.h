@@ -224,8 +224,9 @@ int qrec_axpby_f32(float* dev_dst, const float* dev_a, const float* dev_b, float
  * noise of element (row r, column c) is word (c & 3) of Philox4x32-10(key = seed;
  * counter = (r, c >> 2, tag, step)), mapped to [0,1) as (w >> 8) * 2^-24 -- `tag` separates
  * encoders/layers, `step` minibatches (tf.random.uniform draws fresh noise per sess.run).
- * Optional fused layer mean: acc[r,:] += acc_scale * E_new[r,:].  d multiple of 4. */
-int qrec_simgcl_perturb_f32(float* dev_E, int64_t n_rows, int32_t d, float eps, uint64_t seed,
+ * Optional fused layer mean: acc[r,:] += acc_scale * E_new[r,:].  d multiple of 4; columns
+ * >= d_valid (zero padding of a table whose logical width is not a multiple of 4) get no noise. */
+int qrec_simgcl_perturb_f32(float* dev_E, int64_t n_rows, int32_t d, int32_t d_valid, float eps, uint64_t seed,
                             uint32_t tag, uint32_t step, float* dev_acc, float acc_scale,
                             void* stream);
 

@@ -47,8 +47,20 @@ class DeepRecommender(IterativeRecommender):
         gen = torch.Generator(device=dev)
         gen.manual_seed(self.engine_seed)      # TF's own RNG stream is not reproducible; ours is
         self.device = dev
-        self.user_embeddings = self.truncated_normal((self.num_users, self.emb_size), 0.005, dev, gen)
-        self.item_embeddings = self.truncated_normal((self.num_items, self.emb_size), 0.005, dev, gen)
+        # device tables are `emb_pad` wide: the row kernels move 16-byte slices, so num.factors=50
+        # (the shipped confs) is stored as 52 columns with two zero columns that never change
+        # (zero gradient -> zero Adam update); exported tables are cut back to emb_size
+        self.emb_pad = self.emb_size + (-self.emb_size) % 4
+        self.user_embeddings = self.pad_columns(self.truncated_normal((self.num_users, self.emb_size), 0.005, dev, gen))
+        self.item_embeddings = self.pad_columns(self.truncated_normal((self.num_items, self.emb_size), 0.005, dev, gen))
+
+    def pad_columns(self, t):
+        import torch
+        if t.shape[1] == self.emb_pad:
+            return t.contiguous()
+        out = torch.zeros(t.shape[0], self.emb_pad, device=t.device, dtype=t.dtype)
+        out[:, :t.shape[1]] = t
+        return out
 
     # ------------------------------------------------------------------ samplers
     def _mt(self):

@@ -41,7 +41,7 @@ int sm_count() {
 
 // one warp per row, lanes stride over float4 slices (d multiple of 4, any size)
 __global__ void __launch_bounds__(256)
-simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, float eps, uint32_t k0,
+simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, int d_valid, float eps, uint32_t k0,
                       uint32_t k1, uint32_t tag, uint32_t step, float* __restrict__ acc,
                       float acc_scale) {
   const int lane = threadIdx.x & 31;
@@ -54,7 +54,9 @@ simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, float e
     for (int v = lane; v < nvec; v += 32) {
       uint32_t w[4];
       philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
-      const float a = u01(w[0]), b = u01(w[1]), c = u01(w[2]), d4 = u01(w[3]);
+      // columns >= d_valid are zero padding of the table: they carry no noise
+      const float a = (v * 4 + 0 < d_valid) ? u01(w[0]) : 0.f, b = (v * 4 + 1 < d_valid) ? u01(w[1]) : 0.f;
+      const float c = (v * 4 + 2 < d_valid) ? u01(w[2]) : 0.f, d4 = (v * 4 + 3 < d_valid) ? u01(w[3]) : 0.f;
       ss += a * a + b * b + c * c + d4 * d4;
     }
 #pragma unroll
@@ -411,13 +413,13 @@ inline int grid_for(long long work_items, int per_block) {
 
 extern "C" {
 
-int qrec_simgcl_perturb_f32(float* E, int64_t n_rows, int32_t d, float eps, uint64_t seed,
+int qrec_simgcl_perturb_f32(float* E, int64_t n_rows, int32_t d, int32_t d_valid, float eps, uint64_t seed,
                             uint32_t tag, uint32_t step, float* acc, float acc_scale, void* stream) {
   QREC_REQUIRE(n_rows >= 0 && d >= 4 && d % 4 == 0, "qrec_simgcl_perturb_f32: bad shape (d multiple of 4)");
   if (n_rows == 0) return QREC_OK;
   QREC_REQUIRE(E != nullptr, "qrec_simgcl_perturb_f32: null table");
   simgcl_perturb_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
-      E, n_rows, d / 4, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc, acc_scale);
+      E, n_rows, d / 4, (d_valid > 0 && d_valid < d) ? d_valid : d, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc, acc_scale);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

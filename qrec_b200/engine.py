@@ -363,9 +363,9 @@ def axpby(dst, a, b, alpha, beta):
 # ---------------------------------------------------------------------------------------------
 # K6 / dense helpers (SimGCL, NGCF)
 # ---------------------------------------------------------------------------------------------
-def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0):
+def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0):
     torch = _torch()
-    check(lib.qrec_simgcl_perturb_f32(_dev(Emb, torch.float32, 'E'), Emb.shape[0], Emb.shape[1], float(eps),
+    check(lib.qrec_simgcl_perturb_f32(_dev(Emb, torch.float32, 'E'), Emb.shape[0], Emb.shape[1], int(d_valid), float(eps),
                                       int(seed), int(tag), int(step),
                                       _dev(acc, torch.float32, 'acc') if acc is not None else None,
                                       float(acc_scale), _stream()), 'qrec_simgcl_perturb_f32')

@@ -31,8 +31,16 @@ class BPR(IterativeRecommender):
         torch.cuda.set_device(dev)
         fast = self.engine_mode == 'fast'
         dtype = torch.float32 if (fast or self.engine_precision == 'f32') else torch.float64
-        P = torch.from_numpy(self.P).to(device=dev, dtype=dtype).contiguous()
-        Q = torch.from_numpy(self.Q).to(device=dev, dtype=dtype).contiguous()
+        d = self.emb_size
+        # the fused kernel moves rows as 16-byte slices: pad d to a multiple of 4 with zero columns
+        # (they stay exactly zero under BPR.py:45-52, so the first d columns are unaffected)
+        dpad = d if (not fast or d % 4 == 0) else d + (4 - d % 4)
+
+        def upload(a):
+            t = torch.zeros(a.shape[0], dpad, device=dev, dtype=dtype)
+            t[:, :d] = torch.from_numpy(a).to(device=dev, dtype=dtype)
+            return t.contiguous()
+        P, Q = upload(self.P), upload(self.Q)
         acc = torch.zeros(3, dtype=torch.float64, device=dev)
         mt = E.MT19937()
         print('training...')
@@ -56,8 +64,8 @@ class BPR(IterativeRecommender):
             epoch += 1
             if self.isConverged(epoch):
                 break
-        self.P = P.cpu().numpy()
-        self.Q = Q.cpu().numpy()
+        self.P = np.ascontiguousarray(P[:, :d].cpu().numpy())
+        self.Q = np.ascontiguousarray(Q[:, :d].cpu().numpy())
 
     buildModel = trainModel
 

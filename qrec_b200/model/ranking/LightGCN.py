@@ -30,7 +30,7 @@ class LightGCN(GraphRecommender):
         self.ego = torch.cat([self.user_embeddings, self.item_embeddings], dim=0).contiguous()
         self.user_embeddings = self.ego[:self.num_users]
         self.item_embeddings = self.ego[self.num_users:]
-        dev, d = self.device, self.emb_size
+        dev, d = self.device, self.emb_pad
         self._buf = [torch.empty(n, d, device=dev) for _ in range(2)]
         self._mean = torch.empty(n, d, device=dev)
         self._grad = torch.zeros(n, d, device=dev)
@@ -80,7 +80,8 @@ class LightGCN(GraphRecommender):
                 if n % 20 == 0:      # the reference prints every batch; rate-limited here
                     print(self.foldInfo, 'training:', epoch + 1, 'batch', n, 'loss:', float(loss.item()))
         Ue, Ve = self.propagate()
-        self.U, self.V = Ue.cpu().numpy(), Ve.cpu().numpy()
+        d = self.emb_size
+        self.U, self.V = Ue[:, :d].cpu().numpy(), Ve[:, :d].cpu().numpy()
 
     buildModel = trainModel
 

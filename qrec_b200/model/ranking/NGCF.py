@@ -26,6 +26,8 @@ class NGCF(GraphRecommender):
     def initModel(self):
         super(NGCF, self).initModel()
         import torch
+        if self.emb_size % 4:
+            raise ValueError('NGCF on the B200 engine needs num.factors to be a multiple of 4 (got %d)' % self.emb_size)
         dev, d = self.device, self.emb_size
         self.n_layers = 2
         n = self.num_users + self.num_items

@@ -29,6 +29,8 @@ class NeuMF(DeepRecommender):
     def initModel(self):
         super(NeuMF, self).initModel()
         import torch
+        if self.emb_size % 4:
+            raise ValueError('NeuMF on the B200 engine needs num.factors to be a multiple of 4 (got %d)' % self.emb_size)
         dev, d = self.device, self.emb_size
         gen = torch.Generator(device=dev)
         gen.manual_seed(self.engine_seed + 3)

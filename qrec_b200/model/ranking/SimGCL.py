@@ -45,12 +45,12 @@ class SimGCL(GraphRecommender):
     def initModel(self):
         super(SimGCL, self).initModel()
         import torch
-        dev, d = self.device, self.emb_size
+        dev, d = self.device, self.emb_pad
         gen = torch.Generator(device=dev)
         gen.manual_seed(self.engine_seed + 1)
         n = self.num_users + self.num_items
-        self.ego = torch.cat([self.xavier_uniform(self.num_users, d, dev, gen),
-                              self.xavier_uniform(self.num_items, d, dev, gen)], dim=0).contiguous()
+        self.ego = torch.cat([self.pad_columns(self.xavier_uniform(self.num_users, self.emb_size, dev, gen)),
+                              self.pad_columns(self.xavier_uniform(self.num_items, self.emb_size, dev, gen))], dim=0).contiguous()
         self.user_embeddings = self.ego[:self.num_users]       # SimGCL.py:43-44 replaces the base tables
         self.item_embeddings = self.ego[self.num_users:]
         self.norm_adj = self.create_joint_sparse_adj_tensor()
@@ -76,7 +76,8 @@ class SimGCL(GraphRecommender):
             nxt = self._buf[k % 2]
             if perturbed:
                 self.norm_adj.matmul(cur, nxt)
-                E.simgcl_perturb(nxt, self.eps, self.noise_seed, perturbed * 16 + k, self._step, acc=out, acc_scale=s)
+                E.simgcl_perturb(nxt, self.eps, self.noise_seed, perturbed * 16 + k, self._step, acc=out, acc_scale=s,
+                                 d_valid=self.emb_size)
             else:
                 self.norm_adj.matmul(cur, nxt, acc=out, acc_scale=s)
             cur = nxt
@@ -85,7 +86,7 @@ class SimGCL(GraphRecommender):
     def _infonce(self, tab1, tab2, idx, grad_rows):
         import torch
         from ... import engine as E
-        b, d = idx.shape[0], self.emb_size
+        b, d = idx.shape[0], self.emb_pad
         dev = self.device
         Z1, Z2 = torch.empty(b, d, device=dev), torch.empty(b, d, device=dev)
         n1, n2 = torch.empty(b, device=dev), torch.empty(b, device=dev)
@@ -134,7 +135,8 @@ class SimGCL(GraphRecommender):
 
     def saveModel(self):
         mU, mV = self.encode(self._main, 0)
-        self.bestU, self.bestV = mU.cpu().numpy(), mV.cpu().numpy()
+        d = self.emb_size
+        self.bestU, self.bestV = mU[:, :d].cpu().numpy(), mV[:, :d].cpu().numpy()
 
     def trainModel(self):
         import torch
@@ -145,7 +147,7 @@ class SimGCL(GraphRecommender):
                     total, rec, cl = self.losses()
                     print('training:', epoch + 1, 'batch', n, 'total_loss:', total, 'rec_loss:', rec, 'cl_loss', cl)
             mU, mV = self.encode(self._main, 0)
-            self.U, self.V = mU.cpu().numpy(), mV.cpu().numpy()
+            self.U, self.V = mU[:, :self.emb_size].cpu().numpy(), mV[:, :self.emb_size].cpu().numpy()
             self.ranking_performance(epoch)
         self.U, self.V = self.bestU, self.bestV
 

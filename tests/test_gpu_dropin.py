@@ -142,3 +142,29 @@ def test_lightgcn_dropin_trains_and_ranks(golden_bpr, tmp_path):
         measure = LightGCN(ModelConf.from_string(conf), train, test).execute()
     got = {m.split(':')[0]: float(m.split(':')[1]) for m in measure[1:]}
     assert got['Precision'] > 0.25 and got['Recall'] > 0.4
+
+
+@pytest.mark.parametrize('model,extra', [('BPR', 'engine=-mode fast\n'), ('BPR', ''), ('LightGCN', 'LightGCN=-n_layer 2\n'),
+                                         ('SimGCL', 'SimGCL=-n_layer 2 -lambda 0.5 -eps 0.1\n')])
+def test_shipped_width_num_factors_50(golden_bpr, tmp_path, model, extra):
+    """The reference's shipped confs use num.factors=50 (config/BPR.conf:6, LightGCN.conf:6): rows of
+    200 bytes.  Parity mode takes any d; the 16-byte row kernels run on tables padded to 52 columns
+    whose two extra columns must stay exactly zero and never leak into the exported tables."""
+    import importlib
+    from qrec_b200.util.config import ModelConf
+    g = golden_bpr
+    os.chdir(tmp_path)
+    cls = getattr(importlib.import_module('qrec_b200.model.ranking.' + model), model)
+    conf = (str(g['conf']).replace('model.name=BPR', 'model.name=' + model).replace('num.factors=64', 'num.factors=50')
+            .replace('num.max.epoch=3', 'num.max.epoch=2') + extra)
+    train, test = _lists(g)
+    random.seed(6); np.random.seed(6)
+    m = cls(ModelConf.from_string(conf), train, test)
+    with contextlib.redirect_stdout(io.StringIO()):
+        measure = m.execute()
+    U, V = (m.P, m.Q) if model == 'BPR' else (m.U, m.V)
+    assert U.shape == (m.num_users, 50) and V.shape == (m.num_items, 50)
+    assert np.isfinite(U).all() and np.isfinite(V).all()
+    if model != 'BPR':
+        assert m.ego.shape[1] == 52 and float(m.ego[:, 50:].abs().max()) == 0.0
+    assert len(measure) == 5 and measure[0].startswith('Top 10')
