@@ -301,6 +301,16 @@ int qrec_neumf_head_f32(int32_t mode, int32_t training, const float* dev_UG, con
                         float* dev_y, float* dev_dz, float* dev_GMF, float* dev_dUG, float* dev_dIG,
                         float* dev_dH3, void* stream);
 
+/* =====================================================================================
+ * K8 (next row f-1) -- batched evaluation helpers: scores = P[users] * Q^T comes from
+ * qrec_sgemm_f32 (fp32, so the ranking matches the reference's GEMV to rounding), then the rated
+ * positions are overwritten with `value` (0 in the reference: base/recommender.py:147-149,
+ * base/iterativeRecommender.py:126-128).  rowptr/cols: the users' rated-item CSR.
+ * ===================================================================================== */
+int qrec_mask_rated_f32(float* dev_scores, int32_t n_rows, int64_t ld, const int32_t* dev_users,
+                        const int64_t* dev_rowptr, const int32_t* dev_cols, float value,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,7 @@ SIGNATURES = {
     'qrec_scatter_add_rows_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int32, C.c_float, vp]),
     'qrec_neumf_head_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_float,
                                       vp, vp, vp, vp, vp, vp, vp, vp]),
+    'qrec_mask_rated_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float, vp]),
     'qrec_tc_gemm_tf32': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp,
                                     C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]),
 }

@@ -136,13 +136,31 @@ class Recommender(object):
         ids, vals = find_k_largest(N, scores)
         return [(self.data.id2item[k], v) for k, v in zip(ids, vals)]
 
+    def device_tables(self):
+        """(U, V) fp32 CUDA tensors such that score(u, i) = U[u] . V[i], or None if the model ranks
+        some other way (then evaluation stays on the host, one user at a time)."""
+        return None
+
+    def _recommend_all_on_device(self, N):
+        """`engine=... -eval gpu`: top-N lists of every known test user in a few large launches."""
+        if not self.config.contains('engine') or OptionConf(self.config['engine']).options.get('-eval') != 'gpu':
+            return None
+        tables = self.device_tables()
+        if tables is None:
+            return None
+        from ..evaluate import batched_top_n
+        users = [u for u in self.data.testSet_u if self.data.containsUser(u)]
+        ids, vals = batched_top_n(tables[0], tables[1], [self.data.user[u] for u in users], self.data.rated_csr(), N)
+        return {u: [(self.data.id2item[int(k)], float(v)) for k, v in zip(ids[r], vals[r])] for r, u in enumerate(users)}
+
     def evalRanking(self):
         top, N = self._top_n_setting()
         self.recOutput.append('userId: recommendations in (itemId, ranking score) pairs, * means the item matches.\n')
         recList = {}
         n_test = len(self.data.testSet_u)
+        batched = self._recommend_all_on_device(N)
         for pos, user in enumerate(self.data.testSet_u):
-            recList[user] = self._recommend(user, N)
+            recList[user] = batched[user] if batched is not None and user in batched else self._recommend(user, N)
             if pos % 100 == 0:
                 print(self.modelName, self.foldInfo, 'progress:' + str(pos) + '/' + str(n_test))
             truth = self.data.testSet_u[user]

@@ -401,6 +401,22 @@ neumf_head_kernel(int mode, int training, const float* __restrict__ UG, const fl
   if (training && lane == 0 && lsum != 0.0) atomicAdd(loss, lsum);
 }
 
+
+// K8 helper (base/recommender.py:147-149): scores[b, item] = value for every item user_ids[b] rated
+// in the training set -- the reference overwrites rated positions with 0, it does not remove them.
+__global__ void __launch_bounds__(256)
+mask_rated_kernel(float* __restrict__ scores, int n_rows, long long ld, const int* __restrict__ users,
+                  const long long* __restrict__ rowptr, const int* __restrict__ cols, float value) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int b = warp; b < n_rows; b += nwarps) {
+    const int u = users[b];
+    const long long lo = rowptr[u], hi = rowptr[u + 1];
+    for (long long e = lo + lane; e < hi; e += 32) scores[(size_t)b * ld + cols[e]] = value;
+  }
+}
+
 inline int grid_for(long long work_items, int per_block) {
   long long blocks = (work_items + per_block - 1) / per_block;
   const long long cap = (long long)sm_count() * 8;
@@ -548,6 +564,17 @@ int qrec_neumf_head_f32(int32_t mode, int32_t training, const float* UG, const f
   QREC_REQUIRE(!training || mode == 0 || dH3, "qrec_neumf_head_f32: dH3 missing");
   neumf_head_kernel<<<grid_for(n, 8), 256, 0, (cudaStream_t)stream>>>(mode, training, UG, IG, H3, h_mf, h_mlp, r, n, d, reg,
                                                                       loss, y_out, dz_out, GMF, dUG, dIG, dH3);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_mask_rated_f32(float* scores, int32_t n_rows, int64_t ld, const int32_t* users,
+                        const int64_t* rowptr, const int32_t* cols, float value, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && ld >= 0, "qrec_mask_rated_f32: bad shape");
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(scores && users && rowptr, "qrec_mask_rated_f32: null pointer");
+  mask_rated_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(scores, n_rows, ld, users,
+                                                                         reinterpret_cast<const long long*>(rowptr), cols, value);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

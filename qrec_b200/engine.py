@@ -489,3 +489,11 @@ def neumf_head(mode, training, UG, IG, H3, h_mf, h_mlp, r, reg, loss, y, dz, GMF
                                   _dev(loss, torch.float64, 'loss') if loss is not None else None,
                                   f(y, 'y'), f(dz, 'dz'), f(GMF, 'GMF'), f(dUG, 'dUG'), f(dIG, 'dIG'), f(dH3, 'dH3'),
                                   _stream()), 'qrec_neumf_head_f32')
+
+
+def mask_rated(scores, users, rowptr, cols, value=0.0):
+    torch = _torch()
+    check(lib.qrec_mask_rated_f32(_dev(scores, torch.float32, 'scores'), scores.shape[0], scores.stride(0),
+                                  _dev(users, torch.int32, 'users'), _dev(rowptr, torch.int64, 'rowptr'),
+                                  _dev(cols, torch.int32, 'cols'), float(value), _stream()), 'qrec_mask_rated_f32')
+    return scores

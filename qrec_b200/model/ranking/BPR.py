@@ -117,6 +117,12 @@ class BPR(IterativeRecommender):
                     print('training:', epoch + 1, 'batch', n, 'loss:', l[0] + self.regU * 0.5 * (l[1] + l[2]))
         self.P, self.Q = U.cpu().numpy(), V.cpu().numpy()
 
+    def device_tables(self):
+        import torch
+        dev = torch.device('cuda', self.engine_device)
+        return (torch.from_numpy(np.ascontiguousarray(self.P, dtype=np.float32)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(self.Q, dtype=np.float32)).to(dev))
+
     def predictForRanking(self, u):
         if self.data.containsUser(u):
             return self.Q.dot(self.P[self.data.getUserId(u)])

@@ -153,6 +153,12 @@ class SimGCL(GraphRecommender):
 
     buildModel = trainModel
 
+    def device_tables(self):
+        import torch
+        dev = torch.device('cuda', self.engine_device)
+        return (torch.from_numpy(np.ascontiguousarray(self.U, dtype=np.float32)).to(dev),
+                torch.from_numpy(np.ascontiguousarray(self.V, dtype=np.float32)).to(dev))
+
     def predictForRanking(self, u):
         if self.data.containsUser(u):
             return self.V.dot(self.U[self.data.getUserId(u)])

@@ -168,3 +168,24 @@ def test_shipped_width_num_factors_50(golden_bpr, tmp_path, model, extra):
     if model != 'BPR':
         assert m.ego.shape[1] == 52 and float(m.ego[:, 50:].abs().max()) == 0.0
     assert len(measure) == 5 and measure[0].startswith('Top 10')
+
+
+def test_batched_device_evaluation_equals_host_flow(golden_bpr, tmp_path):
+    """`-eval gpu` (scores = sgemm, rated -> 0, top-N) gives the reference's metrics and the same
+    top-10 lists as the per-user host flow on the reference's own 3-epoch FilmTrust model."""
+    g = golden_bpr
+    model, measure, _, _, _ = _run_bpr(g, tmp_path, 'engine=-mode parity -precision f64 -eval gpu\n')
+    assert [m.strip() for m in measure] == g['measure'].tolist()
+    for mine, ref in zip(model.recOutput[1:65], g['rec_lines'].tolist()):
+        strip = lambda line: [(p.split(',')[0], p.endswith('*')) for p in line.strip().split(' (')[1:]]  # noqa: E731
+        assert strip(mine) == strip(ref)
+    # the helper on its own: rated items score exactly 0, order is descending
+    import torch
+    from qrec_b200.evaluate import batched_top_n
+    U, V = model.device_tables()
+    ids, vals = batched_top_n(U, V, np.arange(50), model.data.rated_csr(), 10, block=16)
+    assert np.all(np.diff(vals, axis=1) <= 0)
+    csr = model.data.rated_csr()
+    for r in range(50):
+        rated = set(csr.sorted_cols[csr.sorted_rowptr[r]:csr.sorted_rowptr[r + 1]].tolist())
+        assert all((k not in rated) or v == 0.0 for k, v in zip(ids[r].tolist(), vals[r].tolist()))
