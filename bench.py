@@ -228,7 +228,40 @@ def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, wa
     ms = a.elapsed_time(b) / steps
     res['spmm'] = {'kernel': 'spmm_csr_kernel<16,1>', 'ms': ms, 'algorithmic_GB': spmm_algo / 1e9,
                    'achieved_GBs': spmm_algo / ms / 1e6, 'frac_of_hbm_peak': spmm_algo / ms / 1e6 / peak}
+    res['cpu_baseline'] = lightgcn_cpu_baseline(torch, synthetic, dev, layers, res['batch_2048']['steps_per_epoch'])
+    res['cpu_baseline']['gpu_speedup_epoch_batch_2048'] = res['cpu_baseline']['epoch_s_batch_2048_best'] / res['batch_2048']['epoch_s']
     return res
+
+
+def lightgcn_cpu_baseline(torch, synthetic, dev, layers, steps_per_epoch, scale=10):
+    """CPU restatement of the reference's TF step cost (TensorFlow 1.14 is not installed): one SpMM
+    of the normalised adjacency on a 1/`scale` graph of the same degree structure -- the C port
+    (oracle/bpr_ref.c, index-order accumulation like TF's CPU kernel, 1 thread) and torch's CPU CSR
+    SpMM on all host cores -- scaled by `scale` (SpMM cost is linear in nnz) and by the 2*layers
+    products per minibatch (forward + backward); dense Adam and the O(B) terms are left out (they
+    only make the CPU slower)."""
+    from oracle import c_oracle
+    U, I = NUM_USERS // scale, NUM_ITEMS // scale
+    small = synthetic.make_interactions(U, I, DEGREE, device=dev, seed=777)
+    rp, co, va = (t.cpu() for t in synthetic.build_norm_adj(small, U, I, dev))
+    X = (torch.randn(U + I, D) * 0.005).contiguous()
+    t0 = time.perf_counter()
+    c_oracle.spmm_csr(rp.numpy(), co.numpy(), va.numpy(), X.numpy())
+    t_c = time.perf_counter() - t0
+    A = torch.sparse_csr_tensor(rp, co.long(), va, size=(U + I, U + I))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    A @ X
+    t0 = time.perf_counter()
+    for _ in range(3):
+        A @ X
+    t_t = (time.perf_counter() - t0) / 3
+    per_step = lambda t: t * scale * 2 * layers                           # noqa: E731
+    best = min(t_c, t_t)
+    return {'kind': 'port', 'sample': '1/%d-scale graph (%d x %d, %d nnz), one SpMM, extrapolated x%d and x%d products/step'
+            % (scale, U, I, int(co.numel()), scale, 2 * layers),
+            'spmm_s_c_port_1_thread': t_c, 'spmm_s_torch_cpu_all_cores': t_t, 'cores': os.cpu_count(),
+            'step_s_c_port': per_step(t_c), 'step_s_torch_cpu': per_step(t_t),
+            'epoch_s_batch_2048_best': per_step(best) * steps_per_epoch}
 
 
 # ---------------------------------------------------------------------------------------------

@@ -65,28 +65,36 @@ spmm_csr_kernel(int n_rows, const long long* __restrict__ rowptr, const int* __r
     float4 a[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) a[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // software pipeline: the (col,val) pairs of the next LPR non-zeros are fetched while the current
+    // ones are gathered; G gathered X rows are in flight per lane at any time.
+    constexpr int G = (VPL == 1) ? 8 : 4;
+    int c = 0;
+    float w = 0.f;
+    if (start + l < end) {
+      c = __ldg(cols + start + l);
+      w = __ldg(vals + start + l);
+    }
     for (long long base = start; base < end; base += LPR) {
-      const long long idx = base + l;
-      int c = 0;
-      float w = 0.f;
-      if (idx < end) {
-        c = __ldg(cols + idx);
-        w = __ldg(vals + idx);
-      }
       const int m = (end - base) < LPR ? (int)(end - base) : LPR;
-      for (int t = 0; t < m; t += 4) {
-        int cc[4];
-        float ww[4];
-        float4 x[4][VPL];
+      int cn = 0;
+      float wn = 0.f;
+      if (base + LPR + l < end) {
+        cn = __ldg(cols + base + LPR + l);
+        wn = __ldg(vals + base + LPR + l);
+      }
+      for (int t = 0; t < m; t += G) {
+        int cc[G];
+        float ww[G];
+        float4 x[G][VPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          // lanes beyond m carry c=0,w=0: the (valid) row 0 is fetched and multiplied by 0
+        for (int q = 0; q < G; ++q) {
+          // lanes beyond m carry c=0,w=0: masked below
           cc[q] = __shfl_sync(gmask, c, sub * LPR + ((t + q) & (LPR - 1)));
           ww[q] = __shfl_sync(gmask, w, sub * LPR + ((t + q) & (LPR - 1)));
           if (t + q >= m) ww[q] = 0.f;
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < G; ++q) {
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             if ((t + q) < m && (l + v * LPR) < nvec)
@@ -96,10 +104,12 @@ spmm_csr_kernel(int n_rows, const long long* __restrict__ rowptr, const int* __r
           }
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
+        for (int q = 0; q < G; ++q)
 #pragma unroll
           for (int v = 0; v < VPL; ++v) fma4(a[v], ww[q], x[q][v]);
       }
+      c = cn;
+      w = wn;
     }
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
