@@ -10,6 +10,8 @@
 //   * stages are recycled through mbarriers signalled by tcgen05.commit (2-stage ring), the
 //     epilogue reads the accumulator with tcgen05.ld.32x32b.x16 (warp w owns TMEM lanes 32w..32w+31),
 //     applies bias / ReLU / ReLU-mask and writes fp32 rows.
+//   * global loads are register-staged one k-block ahead (their latency overlaps the MMAs), the
+//     epilogue is parked in shared memory and written as whole 256-byte rows.
 // Tile: 128 x 64 per CTA, 128 threads.
 #include "common.h"
 
@@ -111,39 +113,60 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
   const uint32_t idesc = make_idesc();
 
   const int nkb = (K + BK - 1) / BK;
-  for (int kb = 0; kb < nkb; ++kb) {
-    const int s = kb & 1;
+  // Register-staged global loads, one k-block ahead: the loads of block kb+1 are issued before the
+  // shared-memory stores / MMAs of block kb, so their latency overlaps the tensor-core work.
+  float4 ra[8];
+  float4 rb4[4];
+  float rb1[16];
+  auto load_block = [&](int kb) {
     const int k0 = kb * BK;
-    if (kb >= 2) mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1));   // MMAs that read stage s are done
-    // ---- A tile: 128 rows x 8 chunks of 16 B; 8 threads per row -> coalesced 128 B per row
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const int row = (tid >> 3) + 16 * p, c = tid & 7;
       const int gm = m0 + row, gk = k0 + c * 4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gm < M && gk < K) v = *reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk);
-      *reinterpret_cast<float4*>(sA[s] + sw_off(row, c * 4)) = to_tf32(v);
+      ra[p] = (gm < M && gk < K) ? __ldg(reinterpret_cast<const float4*>(A + (size_t)gm * lda + gk))
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // ---- B tile: 64 n-rows x 32 k
     if (B_IS_NK) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int row = (tid >> 3) + 16 * p, c = tid & 7;
         const int gn = n0 + row, gk = k0 + c * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (gn < N && gk < K) v = *reinterpret_cast<const float4*>(B + (size_t)gn * ldb + gk);
-        *reinterpret_cast<float4*>(sB[s] + sw_off(row, c * 4)) = to_tf32(v);
+        rb4[p] = (gn < N && gk < K) ? __ldg(reinterpret_cast<const float4*>(B + (size_t)gn * ldb + gk))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     } else {
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int n = tid & 63, k = (tid >> 6) + 2 * p;
         const int gn = n0 + n, gk = k0 + k;
-        float v = 0.f;
-        if (gn < N && gk < K) v = B[(size_t)gk * ldb + gn];          // coalesced along n
-        *reinterpret_cast<float*>(sB[s] + sw_off(n, k)) = to_tf32(v);  // transposed into K-major
+        rb1[p] = (gn < N && gk < K) ? __ldg(B + (size_t)gk * ldb + gn) : 0.f;     // coalesced along n
       }
     }
+  };
+  load_block(0);
+  for (int kb = 0; kb < nkb; ++kb) {
+    const int s = kb & 1;
+    if (kb >= 2) mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1));   // MMAs that read stage s are done
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int row = (tid >> 3) + 16 * p, c = tid & 7;
+      *reinterpret_cast<float4*>(sA[s] + sw_off(row, c * 4)) = to_tf32(ra[p]);
+    }
+    if (B_IS_NK) {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int row = (tid >> 3) + 16 * p, c = tid & 7;
+        *reinterpret_cast<float4*>(sB[s] + sw_off(row, c * 4)) = to_tf32(rb4[p]);
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 16; ++p) {
+        const int n = tid & 63, k = (tid >> 6) + 2 * p;
+        *reinterpret_cast<float*>(sB[s] + sw_off(n, k)) = to_tf32(rb1[p]);        // transposed into K-major
+      }
+    }
+    if (kb + 1 < nkb) load_block(kb + 1);                                        // in flight during the MMAs
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
     __syncthreads();
     if (tid == 0) {
@@ -169,30 +192,65 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
     mbar_wait(&mma_done[last & 1], (uint32_t)((last >> 1) & 1));
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // ---- epilogue: warp w reads TMEM lanes [32w, 32w+32), 16 columns at a time
-  const int row = m0 + warp * 32 + lane;
+  // ---- epilogue: TMEM -> registers -> shared memory (the operand stages are free now) -> coalesced
+  // global rows.  Warp w reads TMEM lanes [32w, 32w+32) (one accumulator row per thread) and parks
+  // them in a [128][64+4] fp32 tile (row pitch 272 B: conflict-free 16-byte stores); then every warp
+  // writes whole 256-byte rows.
+  float* tile = reinterpret_cast<float*>(smem);
+  constexpr int PITCH = BN + 4;
+  {
+    const int r_in_tile = warp * 32 + lane;
 #pragma unroll
-  for (int c0 = 0; c0 < BN; c0 += 16) {
-    uint32_t r[16];
-    const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (row < M) {
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t r[16];
+      const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        const int col = n0 + c0 + q;
-        if (col < N) {
-          float v = __uint_as_float(r[q]);
-          if (epi == EPI_BIAS_RELU) v = fmaxf(v + bias[col], 0.f);
-          else if (epi == EPI_BIAS) v = v + bias[col];
-          else if (epi == EPI_RELU_MASK) v = mask[(size_t)row * ldmask + col] > 0.f ? v : 0.f;
-          C[(size_t)row * ldc + col] = v;
-        }
+      for (int q = 0; q < 16; q += 4)
+        *reinterpret_cast<uint4*>(tile + r_in_tile * PITCH + c0 + q) = make_uint4(r[q], r[q + 1], r[q + 2], r[q + 3]);
+    }
+  }
+  __syncthreads();
+  {
+    const int c4 = (tid & 15) * 4;                 // 16 threads cover one 64-float row
+    const int col = n0 + c4;
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool vec_ok = (col + 3 < N) && ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    if ((epi == EPI_BIAS_RELU || epi == EPI_BIAS) && col < N) {
+      bv.x = bias[col];
+      if (col + 1 < N) bv.y = bias[col + 1];
+      if (col + 2 < N) bv.z = bias[col + 2];
+      if (col + 3 < N) bv.w = bias[col + 3];
+    }
+    for (int rr = tid >> 4; rr < BM; rr += 8) {
+      const int row = m0 + rr;
+      if (row >= M || col >= N) continue;
+      float4 v = *reinterpret_cast<const float4*>(tile + rr * PITCH + c4);
+      if (epi == EPI_BIAS_RELU) {
+        v.x = fmaxf(v.x + bv.x, 0.f); v.y = fmaxf(v.y + bv.y, 0.f); v.z = fmaxf(v.z + bv.z, 0.f); v.w = fmaxf(v.w + bv.w, 0.f);
+      } else if (epi == EPI_BIAS) {
+        v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+      } else if (epi == EPI_RELU_MASK) {
+        const float* mk = mask + (size_t)row * ldmask + col;
+        v.x = mk[0] > 0.f ? v.x : 0.f;
+        if (col + 1 < N) v.y = mk[1] > 0.f ? v.y : 0.f;
+        if (col + 2 < N) v.z = mk[2] > 0.f ? v.z : 0.f;
+        if (col + 3 < N) v.w = mk[3] > 0.f ? v.w : 0.f;
+      }
+      float* dst = C + (size_t)row * ldc + col;
+      if (vec_ok) {
+        *reinterpret_cast<float4*>(dst) = v;
+      } else {
+        dst[0] = v.x;
+        if (col + 1 < N) dst[1] = v.y;
+        if (col + 2 < N) dst[2] = v.z;
+        if (col + 3 < N) dst[3] = v.w;
       }
     }
   }
