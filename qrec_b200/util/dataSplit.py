@@ -1,7 +1,12 @@
-"""Train/test partitioning (reference: util/dataSplit.py:9-44).  The Bernoulli split draws one
-random() per record from Python's global MT19937, exactly like the reference, so a seeded run
-leaves the generator in the same state for the samplers that follow."""
-from random import random
+"""Partitioning of the interaction list into training and test parts.
+
+Behavioural contract (reference: util/dataSplit.py:9-44): the hold-out split spends exactly one
+`random()` draw of Python's global MT19937 per record, in record order, so a seeded run leaves
+the generator where the reference would and the samplers that follow see the same stream; the
+k-fold generator assigns record p to fold p mod k.  With binarised data, records whose rating
+is falsy never enter a test part.
+"""
+import random as _random
 
 from .io import FileIO
 
@@ -9,30 +14,21 @@ from .io import FileIO
 class DataSplit(object):
     @staticmethod
     def dataSplit(data, test_ratio=0.3, output=False, path='./', order=1, binarized=False):
-        if not 0 < test_ratio < 1:
-            test_ratio = 0.3
-        train, test = [], []
-        for rec in data:
-            if random() < test_ratio:
-                if not binarized or rec[2]:
-                    test.append(rec)
-            else:
-                train.append(rec)
+        ratio = test_ratio if 0 < test_ratio < 1 else 0.3
+        draw = _random.random
+        to_test = [draw() < ratio for _ in data]            # one draw per record, in order
+        trainingSet = [rec for rec, t in zip(data, to_test) if not t]
+        testSet = [rec for rec, t in zip(data, to_test) if t and (rec[2] or not binarized)]
         if output:
-            FileIO.writeFile(path, 'testSet[' + str(order) + ']', test)
-            FileIO.writeFile(path, 'trainingSet[' + str(order) + ']', train)
-        return train, test
+            FileIO.writeFile(path, 'testSet[%s]' % order, testSet)
+            FileIO.writeFile(path, 'trainingSet[%s]' % order, trainingSet)
+        return trainingSet, testSet
 
     @staticmethod
     def crossValidation(data, k, output=False, path='./', order=1, binarized=False):
-        if k <= 1 or k > 10:
-            k = 3
-        for fold in range(k):
-            train, test = [], []
-            for pos, rec in enumerate(data):
-                if pos % k == fold:
-                    if not binarized or rec[2]:
-                        test.append(rec[:])
-                else:
-                    train.append(rec[:])
-            yield train, test
+        folds = k if 1 < k <= 10 else 3
+        for held_out in range(folds):
+            train_part = [list(rec) for pos, rec in enumerate(data) if pos % folds != held_out]
+            test_part = [list(rec) for pos, rec in enumerate(data)
+                         if pos % folds == held_out and (rec[2] or not binarized)]
+            yield train_part, test_part
