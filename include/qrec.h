@@ -144,6 +144,13 @@ int qrec_bpr_sgd_batch_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
                            const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
                            float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* Same step and semantics as qrec_bpr_sgd_batch_f32 for d = 64, with the scatter-add done by the
+ * bulk-copy (TMA) engine: row deltas are staged in shared memory and reduced into the tables with
+ * cp.reduce.async.bulk...add.f32 (one 256-byte operation per row) instead of per-lane REDG. */
+int qrec_bpr_sgd_batch_tma_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                               const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                               float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
+
 /* K1 for a row-sharded item table: the Q rows of the batch were fetched from their
  * owner ranks into dev_R (row pos_i[k] / pos_j[k] holds Q[i_k] / Q[j_k]).  Applies BPR.py:45-52,
  * updates P in place and writes the item-row deltas to dev_D at the same positions, ready to be

@@ -54,6 +54,8 @@ SIGNATURES = {
                                            vp, vp, C.c_double, C.c_double, C.c_double, vp, vp]),
     'qrec_bpr_sgd_batch_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                          C.c_float, C.c_float, vp, vp]),
+    'qrec_bpr_sgd_batch_tma_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
+                                             C.c_float, C.c_float, vp, vp]),
     'qrec_bpr_sgd_staged_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                                           C.c_float, vp, vp]),
     'qrec_sumsq_f32': (C.c_int, [vp, C.c_int64, vp, vp]),

@@ -244,13 +244,15 @@ def bpr_sgd_ordered(P, Q, u, i, j, wu, wi, wj, lr, reg_u, reg_i, loss):
     return loss
 
 
-def bpr_sgd_batch(P, Q, u, i, j, lr, reg_u, reg_i, loss):
-    """Throughput mode: fused gather-dot-sigmoid-update-scatter-add over device triples."""
+def bpr_sgd_batch(P, Q, u, i, j, lr, reg_u, reg_i, loss, tma=False):
+    """Throughput mode: fused gather-dot-sigmoid-update-scatter-add over device triples.
+    tma=True (d=64 only) scatters through the bulk-copy engine instead of per-lane REDG."""
     torch = _torch()
     n = u.shape[0]
     d = P.shape[1]
     assert Q.shape[1] == d and i.shape[0] == n and j.shape[0] == n
-    check(lib.qrec_bpr_sgd_batch_f32(_dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), d, n,
+    fn = lib.qrec_bpr_sgd_batch_tma_f32 if tma else lib.qrec_bpr_sgd_batch_f32
+    check(fn(_dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), d, n,
                                      _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'),
                                      _dev(j, torch.int32, 'j'), float(lr), float(reg_u),
                                      float(reg_i), _dev(loss, torch.float64, 'loss'), _stream()),

@@ -308,3 +308,46 @@ def test_sharded_item_table_path_single_rank_equals_batch_kernel(torch, E):
     from oracle import bpr_oracle as O
     dP, dQ, _ = O.bpr_sgd_jacobi(P0, Q0, np.stack([u2, i2, j2], 1), 1e-3, 0.0, 0.0)
     np.testing.assert_allclose(Qc.cpu().numpy()[[7, 9]] - Q0[[7, 9]], dQ[[7, 9]], rtol=1e-3, atol=1e-7)
+
+
+@pytest.mark.parametrize('n', [1, 31, 1000, 4097, 70001])
+def test_batch_tma_variant_equals_red_variant(torch, E, n):
+    """The bulk-copy-engine scatter (cp.reduce.async.bulk) must give what the REDG scatter gives:
+    exactly the reference step on a conflict-free batch, sum of deltas on shared rows."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(n)
+    d = 64
+    nu, ni = max(n, 8), max(2 * n, 16)
+    u, i, j = _conflict_free_triples(rng, nu, ni, n)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(P, Q, _dev(torch, u), _dev(torch, i), _dev(torch, j), 0.05, 0.01, 0.02, loss, tma=True)
+    torch.cuda.synchronize()
+    Pc, Qc = P0.copy(), Q0.copy()
+    closs = c_oracle.bpr_sgd_sequential(Pc, Qc, u, i, j, 0.05, 0.01, 0.02)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qc, rtol=1e-6, atol=1e-7)
+    assert abs(float(loss.item()) - closs) <= 1e-5 * abs(closs) + 1e-6
+
+
+def test_batch_tma_variant_shared_rows_and_bad_d(torch, E):
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(6)
+    nu, ni, n, d = 50, 40, 4000, 64
+    u = rng.integers(0, nu, n).astype(np.int32)
+    i = rng.integers(0, ni, n).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, ni - 1, n)) % ni).astype(np.int32)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_batch(P, Q, _dev(torch, u), _dev(torch, i), _dev(torch, j), 1e-4, REG, REG, loss, tma=True)
+    torch.cuda.synchronize()
+    dP, dQ, jl = O.bpr_sgd_jacobi(P0, Q0, np.stack([u, i, j], 1), 1e-4, REG, REG)
+    assert np.abs(P.cpu().numpy().astype(np.float64) - P0 - dP).max() <= 0.03 * np.abs(dP).max()
+    assert np.abs(Q.cpu().numpy().astype(np.float64) - Q0 - dQ).max() <= 0.03 * np.abs(dQ).max()
+    with pytest.raises(E.QRecError):
+        E.bpr_sgd_batch(torch.zeros(4, 32, device='cuda'), torch.zeros(4, 32, device='cuda'), _dev(torch, u[:1]),
+                        _dev(torch, i[:1] % 4), _dev(torch, j[:1] % 4), 0.1, 0, 0, loss, tma=True)

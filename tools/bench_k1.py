@@ -1,0 +1,39 @@
+#!/usr/bin/env python
+"""K1 variants on the benchmark workload (50 M shuffled triples, 1M x 100K, d=64): REDG scatter vs
+bulk-copy-engine (TMA) scatter.  One JSON line each."""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    from qrec_b200 import engine as E, synthetic
+    dev = torch.device('cuda', 0)
+    U, I, DEG, D = 1_000_000, 100_000, 50, 64
+    data = synthetic.make_interactions(U, I, DEG, device=dev)
+    P, Q = synthetic.init_tables(U, I, D, device=dev)
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    perm = torch.randperm(U * DEG, device=dev, generator=g)
+    u, i = data['u'][perm].contiguous(), data['i'][perm].contiguous()
+    j = E.sample_neg_philox(u, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    for name, tma in (('red', False), ('tma', True), ('red', False), ('tma', True)):
+        for _ in range(3):
+            E.bpr_sgd_batch(P, Q, u, i, j, 0.01, 0.001, 0.001, loss, tma=tma)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            E.bpr_sgd_batch(P, Q, u, i, j, 0.01, 0.001, 0.001, loss, tma=tma)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(json.dumps({'k1_variant': name, 'ms_per_50M': ms, 'G_triples_s': 50 / ms, 'algorithmic_TBs': 50e6 * 1548 / ms / 1e9}))
+
+
+if __name__ == '__main__':
+    main()
