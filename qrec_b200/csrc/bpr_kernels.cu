@@ -18,6 +18,7 @@
 //     REDG.E.ADD.F32x4 (red.global.add.v4.f32).  UNROLL triples per lane group are in flight
 //     before the first use so each warp keeps 2*UNROLL*3 row loads outstanding.
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -323,14 +324,18 @@ bpr_sgd_staged_kernel(float* __restrict__ P, int nvec, long long n, const int* _
 // Shared memory: per warp 2 buffers x (UNROLL*TPW triples x 3 rows x 256 B); a buffer is rewritten
 // only after cp.async.bulk.wait_group.read shows that the engine has read it.
 // ------------------------------------------------------------------------------------------
-template <int UNROLL>
+// TMA_MASK selects which rows go through the bulk engine (bit 0: P[u], bit 1: Q[i], bit 2: Q[j]);
+// the others keep the REDG path, so the two scatter paths can run side by side.
+template <int UNROLL, int TMA_MASK>
 __global__ void __launch_bounds__(256)
 bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long n,
                          const int* __restrict__ u, const int* __restrict__ i,
                          const int* __restrict__ j, float lr, float reg_u, float reg_i,
                          double* loss) {
   constexpr int LPR = 16, TPW = 2, D = 64;
-  constexpr int SLOT_FLOATS = UNROLL * TPW * 3 * D;            // per warp, per buffer
+  constexpr int ROWS = ((TMA_MASK >> 0) & 1) + ((TMA_MASK >> 1) & 1) + ((TMA_MASK >> 2) & 1);
+  constexpr int SLOT_P = 0, SLOT_I = (TMA_MASK & 1), SLOT_J = (TMA_MASK & 1) + ((TMA_MASK >> 1) & 1);
+  constexpr int SLOT_FLOATS = UNROLL * TPW * ROWS * D;         // per warp, per buffer
   extern __shared__ __align__(128) float stage[];              // [8 warps][2 buffers][SLOT_FLOATS]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int sub = lane / LPR, l = lane % LPR;
@@ -384,20 +389,24 @@ bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long
           if (l == 0) lsum += -logf(s);
           float4 dp, dqi, dqj;
           bpr_step4(p[r], qi[r], qj[r], g, a_u, a_i, dp, dqi, dqj);
-          float* trip = slot + (size_t)(r * TPW + sub) * 3 * D;
-          *reinterpret_cast<float4*>(trip + 0 * D + l * 4) = dp;
-          *reinterpret_cast<float4*>(trip + 1 * D + l * 4) = dqi;
-          *reinterpret_cast<float4*>(trip + 2 * D + l * 4) = dqj;
+          float* trip = slot + (size_t)(r * TPW + sub) * ROWS * D;
+          if (TMA_MASK & 1) *reinterpret_cast<float4*>(trip + SLOT_P * D + l * 4) = dp;
+          else red_add_v4(P + (size_t)uu[r] * D + l * 4, dp);
+          if (TMA_MASK & 2) *reinterpret_cast<float4*>(trip + SLOT_I * D + l * 4) = dqi;
+          else red_add_v4(Q + (size_t)ii[r] * D + l * 4, dqi);
+          if (TMA_MASK & 4) *reinterpret_cast<float4*>(trip + SLOT_J * D + l * 4) = dqj;
+          else red_add_v4(Q + (size_t)jj[r] * D + l * 4, dqj);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // st.shared -> visible to the bulk engine
       __syncwarp();
-      if (l < 3) {
+      if (l < 3 && ((TMA_MASK >> l) & 1)) {
+        const int srow = (l == 0) ? SLOT_P : (l == 1 ? SLOT_I : SLOT_J);
 #pragma unroll
         for (int r = 0; r < UNROLL; ++r) {
           if (ok[r]) {
             float* dst = (l == 0) ? (P + (size_t)uu[r] * D) : (Q + (size_t)(l == 1 ? ii[r] : jj[r]) * D);
-            const float* src = slot + (size_t)(r * TPW + sub) * 3 * D + l * D;
+            const float* src = slot + (size_t)(r * TPW + sub) * ROWS * D + srow * D;
             asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(dst),
                          "r"((uint32_t)__cvta_generic_to_shared(src)), "n"(D * 4)
                          : "memory");
@@ -553,16 +562,33 @@ int qrec_bpr_sgd_batch_tma_f32(float* P, float* Q, int32_t d, int64_t n, const i
   if (n == 0) return QREC_OK;
   QREC_REQUIRE(u && i && j, "qrec_bpr_sgd_batch_tma_f32: null index pointer");
   constexpr int UN = 4;
-  constexpr int smem = 8 * 2 * UN * 2 * 3 * 64 * 4;      // 98304 B
-  static bool attr_set = false;
-  if (!attr_set) {
-    QREC_CUDA(cudaFuncSetAttribute(bpr_sgd_batch_tma_kernel<UN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_set = true;
+  // which rows use the bulk engine: P only by default (the measured optimum);
+  // QREC_K1_TMA_MASK=7 sends all three rows through it, 6 the two item rows
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("QREC_K1_TMA_MASK");
+    mask = e ? atoi(e) : 1;
+    if (mask != 1 && mask != 6 && mask != 7) mask = 1;
   }
   const long long blocks_needed = ((n + 31) / 32 + 7) / 8;
-  const long long cap = (long long)sm_count() * 2;       // 2 CTAs per SM fit in shared memory
-  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
-  bpr_sgd_batch_tma_kernel<UN><<<grid, 256, smem, (cudaStream_t)stream>>>(P, Q, n, u, i, j, lr, reg_u, reg_i, loss);
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_TMA(MASK, ROWS, CTAS)                                                                \
+  {                                                                                               \
+    constexpr int smem = 8 * 2 * UN * 2 * ROWS * 64 * 4;                                          \
+    static bool attr_set = false;                                                                 \
+    if (!attr_set) {                                                                              \
+      QREC_CUDA(cudaFuncSetAttribute(bpr_sgd_batch_tma_kernel<UN, MASK>,                          \
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, smem));         \
+      attr_set = true;                                                                            \
+    }                                                                                             \
+    const long long cap = (long long)sm_count() * CTAS;                                           \
+    const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);                            \
+    bpr_sgd_batch_tma_kernel<UN, MASK><<<grid, 256, smem, st>>>(P, Q, n, u, i, j, lr, reg_u, reg_i, loss); \
+  }
+  if (mask == 7) QREC_TMA(7, 3, 2)
+  else if (mask == 6) QREC_TMA(6, 2, 2)
+  else QREC_TMA(1, 1, 2)
+#undef QREC_TMA
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }
