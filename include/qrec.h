@@ -151,6 +151,15 @@ int qrec_bpr_sgd_batch_tma_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
                                const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
                                float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* Throughput mode in the reference's own order (model/ranking/BPR.py:31-33: users in id order, each
+ * user's positives in CSR order): a lane group keeps P[u] in registers across the user's triples, so
+ * P[u] is updated sequentially inside a user -- as in the reference -- and read/written once per
+ * user; the item rows are gathered and scatter-added per triple (atomic sum across users).
+ * rowptr: int64[n_users+1]; i, j: int32[rowptr[n_users]] in that order.  d multiple of 4, <= 128. */
+int qrec_bpr_sgd_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users,
+                               const int64_t* dev_rowptr, const int32_t* dev_i, const int32_t* dev_j,
+                               float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
+
 /* K1 for a row-sharded item table: the Q rows of the batch were fetched from their
  * owner ranks into dev_R (row pos_i[k] / pos_j[k] holds Q[i_k] / Q[j_k]).  Applies BPR.py:45-52,
  * updates P in place and writes the item-row deltas to dev_D at the same positions, ready to be

@@ -429,6 +429,110 @@ bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// throughput mode, user-major (P-stationary): the reference's own iteration order
+// (model/ranking/BPR.py:31-33: for user: for item).  A lane group takes one user, keeps P[u] in
+// registers across that user's triples -- so P[u] is updated SEQUENTIALLY inside a user exactly as
+// in the reference, and costs one row load + one row RED per user instead of per triple -- while
+// the two item rows of every triple are gathered (PF triples ahead) and scatter-added with
+// REDG.E.ADD.F32x4 as in the batch kernel.  Per triple: 2 row loads + 2 row REDs instead of 3 + 3.
+// Input: CSR over users (rowptr), i[] / j[] in that order.
+// ------------------------------------------------------------------------------------------
+template <int LPR>
+__device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gmask, v, o);
+  return v;
+}
+
+template <int LPR, int PF>
+__global__ void __launch_bounds__(256)
+bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
+                         const long long* __restrict__ rowptr, const int* __restrict__ i,
+                         const int* __restrict__ j, float lr, float reg_u, float reg_i,
+                         double* loss) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + sub;
+  const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * GPW;
+  const int d = nvec * 4;
+  const bool act = l < nvec;
+  const float a_u = lr * reg_u, a_i = lr * reg_i;
+  float lsum = 0.f;
+  for (long long uu = group; uu < n_users; uu += ngroups) {
+    const long long beg = __ldg(rowptr + uu), end = __ldg(rowptr + uu + 1);
+    if (end <= beg) continue;
+    float* prow = P + (size_t)uu * d + l * 4;
+    float4 p = act ? *reinterpret_cast<const float4*>(prow) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 p0 = p;
+    for (long long base = beg; base < end; base += LPR) {
+      const int m = (end - base) < LPR ? (int)(end - base) : LPR;
+      int mi = 0, mj = 0;
+      if (l < m) {
+        mi = __ldg(i + base + l);
+        mj = __ldg(j + base + l);
+      }
+      // ring of PF triples' item rows in flight
+      float4 qi[PF], qj[PF];
+      int ri[PF], rj[PF];
+#pragma unroll
+      for (int f = 0; f < PF; ++f) {
+        ri[f] = __shfl_sync(gmask, mi, sub * LPR + (f & (LPR - 1)));
+        rj[f] = __shfl_sync(gmask, mj, sub * LPR + (f & (LPR - 1)));
+        if (f < m && act) {
+          qi[f] = *reinterpret_cast<const float4*>(Q + (size_t)ri[f] * d + l * 4);
+          qj[f] = *reinterpret_cast<const float4*>(Q + (size_t)rj[f] * d + l * 4);
+        } else {
+          qi[f] = qj[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      for (int t0 = 0; t0 < m; t0 += PF) {
+#pragma unroll
+        for (int f = 0; f < PF; ++f) {
+          const int t = t0 + f;
+          if (t < m) {                                   // uniform inside the lane group
+            const float4 ci = qi[f], cj = qj[f];
+            const int ii = ri[f], jj = rj[f];
+            // refill this ring slot with triple t + PF
+            const int tn = t + PF;
+            ri[f] = __shfl_sync(gmask, mi, sub * LPR + (tn & (LPR - 1)));
+            rj[f] = __shfl_sync(gmask, mj, sub * LPR + (tn & (LPR - 1)));
+            if (tn < m && act) {
+              qi[f] = *reinterpret_cast<const float4*>(Q + (size_t)ri[f] * d + l * 4);
+              qj[f] = *reinterpret_cast<const float4*>(Q + (size_t)rj[f] * d + l * 4);
+            }
+            float x = dot4(p, ci) - dot4(p, cj);
+            x = group_sum_masked<LPR>(x, gmask);
+            const float s = 1.0f / (1.0f + expf(-x));
+            const float g = lr * (1.0f - s);
+            if (l == 0) lsum += -logf(s);
+            if (act) {
+              float4 dp, dqi, dqj;
+              bpr_step4(p, ci, cj, g, a_u, a_i, dp, dqi, dqj);
+              p.x += dp.x; p.y += dp.y; p.z += dp.z; p.w += dp.w;       // P[u] stays in registers
+              red_add_v4(Q + (size_t)ii * d + l * 4, dqi);
+              red_add_v4(Q + (size_t)jj * d + l * 4, dqj);
+            }
+          }
+        }
+      }
+    }
+    if (act) red_add_v4(prow, make_float4(p.x - p0.x, p.y - p0.y, p.z - p0.z, p.w - p0.w));
+  }
+  __shared__ float wsum[8];
+  lsum = warp_sum(lsum);
+  if (lane == 0) wsum[threadIdx.x >> 5] = lsum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w];
+    if (t != 0.0) atomicAdd(loss, t);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 sumsq_kernel(const T* __restrict__ x, long long n, double* out) {
@@ -589,6 +693,34 @@ int qrec_bpr_sgd_batch_tma_f32(float* P, float* Q, int32_t d, int64_t n, const i
   else if (mask == 6) QREC_TMA(6, 2, 2)
   else QREC_TMA(1, 1, 2)
 #undef QREC_TMA
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, const int64_t* rowptr,
+                               const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i,
+                               double* loss, void* stream) {
+  QREC_REQUIRE(P && Q && loss, "qrec_bpr_sgd_usermajor_f32: null pointer");
+  QREC_REQUIRE(d >= 4 && d <= 128 && (d % 4) == 0, "qrec_bpr_sgd_usermajor_f32: d=%d unsupported (multiple of 4, 4..128)", d);
+  QREC_REQUIRE(n_users >= 0, "qrec_bpr_sgd_usermajor_f32: n_users < 0");
+  if (n_users == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && i && j, "qrec_bpr_sgd_usermajor_f32: null index pointer");
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_UM(LPR)                                                                             \
+  {                                                                                              \
+    const long long per_block = 8 * (32 / LPR);                                                  \
+    long long blocks = ((long long)n_users + per_block - 1) / per_block;                         \
+    if (blocks > cap) blocks = cap;                                                              \
+    bpr_sgd_usermajor_kernel<LPR, 4><<<(int)blocks, 256, 0, st>>>(                               \
+        P, Q, nvec, n_users, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
+  }
+  if (nvec <= 4) QREC_UM(4)
+  else if (nvec <= 8) QREC_UM(8)
+  else if (nvec <= 16) QREC_UM(16)
+  else QREC_UM(32)
+#undef QREC_UM
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

@@ -351,3 +351,87 @@ def test_batch_tma_variant_shared_rows_and_bad_d(torch, E):
     with pytest.raises(E.QRecError):
         E.bpr_sgd_batch(torch.zeros(4, 32, device='cuda'), torch.zeros(4, 32, device='cuda'), _dev(torch, u[:1]),
                         _dev(torch, i[:1] % 4), _dev(torch, j[:1] % 4), 0.1, 0, 0, loss, tma=True)
+
+
+def _user_major_problem(rng, nu, ni, max_deg, distinct_items=True):
+    deg = rng.integers(0, max_deg + 1, nu)
+    deg[rng.integers(0, nu, 3)] = 0                       # some empty users
+    deg[0] = max_deg                                      # one user longer than a lane-group batch
+    rowptr = np.zeros(nu + 1, np.int64); rowptr[1:] = np.cumsum(deg)
+    n = int(rowptr[-1])
+    if distinct_items:
+        assert 2 * n <= ni
+        items = rng.permutation(ni)[:2 * n].astype(np.int32)
+        i, j = items[:n].copy(), items[n:].copy()
+    else:
+        i = rng.integers(0, ni, n).astype(np.int32)
+        j = ((i + 1 + rng.integers(0, ni - 1, n)) % ni).astype(np.int32)
+    u = np.repeat(np.arange(nu), deg).astype(np.int32)
+    return rowptr, u, i, j
+
+
+@pytest.mark.parametrize('d', [64, 32, 48, 128, 16])
+def test_usermajor_kernel_is_sequential_in_P(torch, E, d):
+    """User-major kernel: P[u] lives in registers across a user's triples, so with globally distinct
+    items the result must equal the SEQUENTIAL reference loop (BPR.py:31-39), users repeating."""
+    from oracle import c_oracle
+    rng = np.random.default_rng(d)
+    nu, max_deg = 300, 70
+    rowptr, u, i, j = _user_major_problem(rng, nu, 60000, max_deg)
+    ni = 60000
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_usermajor(P, Q, _dev(torch, rowptr), _dev(torch, i), _dev(torch, j), 0.05, 0.01, 0.02, loss)
+    torch.cuda.synchronize()
+    Pc, Qc = P0.copy(), Q0.copy()
+    closs = c_oracle.bpr_sgd_sequential(Pc, Qc, u, i, j, 0.05, 0.01, 0.02)
+    np.testing.assert_allclose(P.cpu().numpy(), Pc, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(Q.cpu().numpy(), Qc, rtol=2e-5, atol=2e-6)
+    assert abs(float(loss.item()) - closs) <= 1e-5 * abs(closs)
+
+
+def test_usermajor_kernel_shared_items_and_reference_epoch(torch, E, golden_bpr, bpr_ids):
+    """(a) items shared between users: Q receives the atomic sum of deltas (second-order close to the
+    Jacobi restatement at small lr); (b) the reference's own first-epoch stream (user-major by
+    construction) in one launch tracks the reference's epoch loss far better than a shuffled launch."""
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(77)
+    nu, ni, d = 200, 150, 64
+    rowptr, u, i, j = _user_major_problem(rng, nu, ni, 30, distinct_items=False)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32)
+    Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_usermajor(P, Q, _dev(torch, rowptr), _dev(torch, i), _dev(torch, j), 1e-4, REG, REG, loss)
+    torch.cuda.synchronize()
+    dP, dQ, jl = O.bpr_sgd_jacobi(P0, Q0, np.stack([u, i, j], 1), 1e-4, REG, REG)
+    assert np.abs(P.cpu().numpy().astype(np.float64) - P0 - dP).max() <= 0.03 * np.abs(dP).max()
+    assert np.abs(Q.cpu().numpy().astype(np.float64) - Q0 - dQ).max() <= 0.03 * np.abs(dQ).max()
+    assert abs(loss.item() - jl) <= 1e-3 * jl
+    # (b)
+    _, _, nu, ni = bpr_ids
+    P0, Q0 = _init_tables(nu, ni)
+    t = golden_bpr['triples_epoch'][0]
+    assert np.all(np.diff(t[:, 0]) >= 0)                               # the reference stream is user-major
+    rp = np.zeros(nu + 1, np.int64); np.add.at(rp, t[:, 0] + 1, 1); rp = np.cumsum(rp)
+    P, Q = _dev(torch, P0.astype(np.float32)), _dev(torch, Q0.astype(np.float32))
+    acc = torch.zeros(3, dtype=torch.float64, device='cuda')
+    E.bpr_sgd_usermajor(P, Q, _dev(torch, rp), _dev(torch, t[:, 1]), _dev(torch, t[:, 2]), LR, REG, REG, acc[0:1])
+    E.sumsq(P, acc[1:2]); E.sumsq(Q, acc[2:3])
+    a = acc.cpu().numpy()
+    total = a[0] + REG * (a[1] + a[2])
+    assert abs(total - golden_bpr['loss'][0]) <= 0.06 * golden_bpr['loss'][0]
+
+
+def test_usermajor_empty_and_bad_args(torch, E):
+    P, Q = torch.ones(4, 64, device='cuda'), torch.ones(5, 64, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    z = torch.zeros(0, dtype=torch.int32, device='cuda')
+    E.bpr_sgd_usermajor(P, Q, torch.zeros(5, dtype=torch.int64, device='cuda'), z, z, 0.1, 0.1, 0.1, loss)
+    torch.cuda.synchronize()
+    assert bool((P == 1).all()) and loss.item() == 0.0
+    with pytest.raises(E.QRecError):
+        E.bpr_sgd_usermajor(torch.ones(4, 200, device='cuda'), torch.ones(5, 200, device='cuda'),
+                            torch.zeros(5, dtype=torch.int64, device='cuda'), z, z, 0.1, 0.1, 0.1, loss)

@@ -21,7 +21,33 @@ def main():
     u, i = data['u'][perm].contiguous(), data['i'][perm].contiguous()
     j = E.sample_neg_philox(u, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
-    for name, tma in (('red', False), ('tma', True), ('red', False), ('tma', True)):
+    # user-major (reference order): CSR positives, negatives sampled in the same order
+    ju = E.sample_neg_philox(data['u'], data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
+    rowptr = data['sorted_rowptr']
+    for name, fn in (('usermajor(P in registers)', lambda: E.bpr_sgd_usermajor(P, Q, rowptr, data['i'], ju, 0.01, 0.001, 0.001, loss)),
+                     ('batch kernel on user-major order', lambda: E.bpr_sgd_batch(P, Q, data['u'], data['i'], ju, 0.01, 0.001, 0.001, loss))):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(json.dumps({'k1_variant': name, 'ms_per_50M': ms, 'G_triples_s': 50 / ms, 'algorithmic_TBs': 50e6 * 1548 / ms / 1e9}))
+    for fn_name, fn in (('sampler shuffled order', lambda: E.sample_neg_philox(u, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0, out=j)),
+                        ('sampler user-major order', lambda: E.sample_neg_philox(data['u'], data['sorted_rowptr'], data['sorted_cols'], I, 1, 0, out=ju))):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        print(json.dumps({'kernel': fn_name, 'ms_per_50M': a.elapsed_time(b) / 10}))
+    for name, tma in (('red', False), ('tma', True)):
         for _ in range(3):
             E.bpr_sgd_batch(P, Q, u, i, j, 0.01, 0.001, 0.001, loss, tma=tma)
         torch.cuda.synchronize()
