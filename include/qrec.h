@@ -155,8 +155,10 @@ int qrec_bpr_sgd_batch_tma_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
  * user's positives in CSR order): a lane group keeps P[u] in registers across the user's triples, so
  * P[u] is updated sequentially inside a user -- as in the reference -- and read/written once per
  * user; the item rows are gathered and scatter-added per triple (atomic sum across users).
- * rowptr: int64[n_users+1]; i, j: int32[rowptr[n_users]] in that order.  d multiple of 4, <= 128. */
-int qrec_bpr_sgd_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users,
+ * rowptr: int64[n_users+1]; i, j: int32[n], n = rowptr[n_users], in that order.  Work is split into
+ * 32-triple chunks of the CSR order (balanced for any degree distribution); a user spanning several
+ * chunks receives the sum of the chunks' P deltas.  d multiple of 4, <= 128. */
+int qrec_bpr_sgd_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users, int64_t n,
                                const int64_t* dev_rowptr, const int32_t* dev_i, const int32_t* dev_j,
                                float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 

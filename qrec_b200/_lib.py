@@ -56,7 +56,7 @@ SIGNATURES = {
                                          C.c_float, C.c_float, vp, vp]),
     'qrec_bpr_sgd_batch_tma_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                              C.c_float, C.c_float, vp, vp]),
-    'qrec_bpr_sgd_usermajor_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp, C.c_float, C.c_float,
+    'qrec_bpr_sgd_usermajor_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, C.c_float, C.c_float,
                                              C.c_float, vp, vp]),
     'qrec_bpr_sgd_staged_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                                           C.c_float, vp, vp]),

@@ -446,12 +446,17 @@ __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
   return v;
 }
 
-template <int LPR, int PF>
+// Work is cut into chunks of CH consecutive triples of the CSR order (balanced for any degree
+// distribution, like the nnz-balanced SpMM); a lane group finds the user of its first triple with an
+// LPR-ary search of rowptr and walks forward, flushing the P[u] delta (one row RED) whenever the user
+// changes or the chunk ends.  Inside a user P[u] is register-resident and updated sequentially; a
+// user whose triples span several chunks gets the sum of the chunks' deltas.
+template <int LPR, int G, int CH>
 __global__ void __launch_bounds__(256)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
-                         const long long* __restrict__ rowptr, const int* __restrict__ i,
-                         const int* __restrict__ j, float lr, float reg_u, float reg_i,
-                         double* loss) {
+                         long long n, const long long* __restrict__ rowptr,
+                         const int* __restrict__ i, const int* __restrict__ j, float lr,
+                         float reg_u, float reg_i, double* loss) {
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -461,60 +466,77 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
   const int d = nvec * 4;
   const bool act = l < nvec;
   const float a_u = lr * reg_u, a_i = lr * reg_i;
+  const long long nchunks = (n + CH - 1) / CH;
   float lsum = 0.f;
-  for (long long uu = group; uu < n_users; uu += ngroups) {
-    const long long beg = __ldg(rowptr + uu), end = __ldg(rowptr + uu + 1);
-    if (end <= beg) continue;
+  for (long long ch = group; ch < nchunks; ch += ngroups) {
+    const long long lo = ch * CH;
+    const long long hi = (lo + CH) < n ? (lo + CH) : n;
+    // user of triple lo: smallest r with rowptr[r+1] > lo
+    int a = 0, b = n_users - 1;
+    while (a < b) {
+      const int len = b - a + 1;
+      const int step = (len + LPR - 1) / LPR;
+      int pp = a + (l + 1) * step - 1;
+      if (pp > b) pp = b;
+      const bool pred = __ldg(rowptr + pp + 1) > lo;
+      const unsigned bal = (__ballot_sync(gmask, pred) & gmask) >> (sub * LPR);
+      const int f = __ffs(bal) - 1;
+      int pf = a + (f + 1) * step - 1;
+      if (pf > b) pf = b;
+      a = a + f * step;
+      b = pf;
+    }
+    int uu = a;
+    long long uend = __ldg(rowptr + uu + 1);
     float* prow = P + (size_t)uu * d + l * 4;
     float4 p = act ? *reinterpret_cast<const float4*>(prow) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4 p0 = p;
-    for (long long base = beg; base < end; base += LPR) {
-      const int m = (end - base) < LPR ? (int)(end - base) : LPR;
+    float4 p0 = p;
+    for (long long base = lo; base < hi; base += LPR) {
+      const int m = (hi - base) < LPR ? (int)(hi - base) : LPR;
       int mi = 0, mj = 0;
       if (l < m) {
         mi = __ldg(i + base + l);
         mj = __ldg(j + base + l);
       }
-      // ring of PF triples' item rows in flight
-      float4 qi[PF], qj[PF];
-      int ri[PF], rj[PF];
+      for (int t0 = 0; t0 < m; t0 += G) {
+        float4 qi[G], qj[G];
+        int ri[G], rj[G];
 #pragma unroll
-      for (int f = 0; f < PF; ++f) {
-        ri[f] = __shfl_sync(gmask, mi, sub * LPR + (f & (LPR - 1)));
-        rj[f] = __shfl_sync(gmask, mj, sub * LPR + (f & (LPR - 1)));
-        if (f < m && act) {
-          qi[f] = *reinterpret_cast<const float4*>(Q + (size_t)ri[f] * d + l * 4);
-          qj[f] = *reinterpret_cast<const float4*>(Q + (size_t)rj[f] * d + l * 4);
-        } else {
-          qi[f] = qj[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int f = 0; f < G; ++f) {                    // G triples' item rows in flight
+          ri[f] = __shfl_sync(gmask, mi, sub * LPR + ((t0 + f) & (LPR - 1)));
+          rj[f] = __shfl_sync(gmask, mj, sub * LPR + ((t0 + f) & (LPR - 1)));
+          if (t0 + f < m && act) {
+            qi[f] = *reinterpret_cast<const float4*>(Q + (size_t)ri[f] * d + l * 4);
+            qj[f] = *reinterpret_cast<const float4*>(Q + (size_t)rj[f] * d + l * 4);
+          } else {
+            qi[f] = qj[f] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-      }
-      for (int t0 = 0; t0 < m; t0 += PF) {
 #pragma unroll
-        for (int f = 0; f < PF; ++f) {
-          const int t = t0 + f;
-          if (t < m) {                                   // uniform inside the lane group
-            const float4 ci = qi[f], cj = qj[f];
-            const int ii = ri[f], jj = rj[f];
-            // refill this ring slot with triple t + PF
-            const int tn = t + PF;
-            ri[f] = __shfl_sync(gmask, mi, sub * LPR + (tn & (LPR - 1)));
-            rj[f] = __shfl_sync(gmask, mj, sub * LPR + (tn & (LPR - 1)));
-            if (tn < m && act) {
-              qi[f] = *reinterpret_cast<const float4*>(Q + (size_t)ri[f] * d + l * 4);
-              qj[f] = *reinterpret_cast<const float4*>(Q + (size_t)rj[f] * d + l * 4);
+        for (int f = 0; f < G; ++f) {
+          const long long t = base + t0 + f;
+          if (t0 + f < m) {                              // uniform inside the lane group
+            if (t >= uend) {                             // next user: flush P delta, load the new row
+              if (act) red_add_v4(prow, make_float4(p.x - p0.x, p.y - p0.y, p.z - p0.z, p.w - p0.w));
+              do {
+                ++uu;
+                uend = __ldg(rowptr + uu + 1);
+              } while (uend <= t);
+              prow = P + (size_t)uu * d + l * 4;
+              p = act ? *reinterpret_cast<const float4*>(prow) : make_float4(0.f, 0.f, 0.f, 0.f);
+              p0 = p;
             }
-            float x = dot4(p, ci) - dot4(p, cj);
+            float x = dot4(p, qi[f]) - dot4(p, qj[f]);
             x = group_sum_masked<LPR>(x, gmask);
             const float s = 1.0f / (1.0f + expf(-x));
             const float g = lr * (1.0f - s);
             if (l == 0) lsum += -logf(s);
             if (act) {
               float4 dp, dqi, dqj;
-              bpr_step4(p, ci, cj, g, a_u, a_i, dp, dqi, dqj);
+              bpr_step4(p, qi[f], qj[f], g, a_u, a_i, dp, dqi, dqj);
               p.x += dp.x; p.y += dp.y; p.z += dp.z; p.w += dp.w;       // P[u] stays in registers
-              red_add_v4(Q + (size_t)ii * d + l * 4, dqi);
-              red_add_v4(Q + (size_t)jj * d + l * 4, dqj);
+              red_add_v4(Q + (size_t)ri[f] * d + l * 4, dqi);
+              red_add_v4(Q + (size_t)rj[f] * d + l * 4, dqj);
             }
           }
         }
@@ -697,24 +719,25 @@ int qrec_bpr_sgd_batch_tma_f32(float* P, float* Q, int32_t d, int64_t n, const i
   return QREC_OK;
 }
 
-int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, const int64_t* rowptr,
+int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
                                const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i,
                                double* loss, void* stream) {
   QREC_REQUIRE(P && Q && loss, "qrec_bpr_sgd_usermajor_f32: null pointer");
   QREC_REQUIRE(d >= 4 && d <= 128 && (d % 4) == 0, "qrec_bpr_sgd_usermajor_f32: d=%d unsupported (multiple of 4, 4..128)", d);
-  QREC_REQUIRE(n_users >= 0, "qrec_bpr_sgd_usermajor_f32: n_users < 0");
-  if (n_users == 0) return QREC_OK;
+  QREC_REQUIRE(n_users >= 0 && n >= 0, "qrec_bpr_sgd_usermajor_f32: negative size");
+  if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && j, "qrec_bpr_sgd_usermajor_f32: null index pointer");
   const int nvec = d / 4;
   const long long cap = (long long)sm_count() * 8;
   cudaStream_t st = (cudaStream_t)stream;
+  constexpr int CH = 32;
 #define QREC_UM(LPR)                                                                             \
   {                                                                                              \
     const long long per_block = 8 * (32 / LPR);                                                  \
-    long long blocks = ((long long)n_users + per_block - 1) / per_block;                         \
+    long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
     if (blocks > cap) blocks = cap;                                                              \
-    bpr_sgd_usermajor_kernel<LPR, 4><<<(int)blocks, 256, 0, st>>>(                               \
-        P, Q, nvec, n_users, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
+    bpr_sgd_usermajor_kernel<LPR, 4, CH><<<(int)blocks, 256, 0, st>>>(                           \
+        P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
   }
   if (nvec <= 4) QREC_UM(4)
   else if (nvec <= 8) QREC_UM(8)

@@ -266,6 +266,7 @@ def bpr_sgd_usermajor(P, Q, rowptr, i, j, lr, reg_u, reg_i, loss):
     n_users = rowptr.shape[0] - 1
     assert i.shape[0] == j.shape[0]
     check(lib.qrec_bpr_sgd_usermajor_f32(_dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), P.shape[1], n_users,
+                                         int(i.shape[0]),
                                          _dev(rowptr, torch.int64, 'rowptr'), _dev(i, torch.int32, 'i'),
                                          _dev(j, torch.int32, 'j'), float(lr), float(reg_u), float(reg_i),
                                          _dev(loss, torch.float64, 'loss'), _stream()), 'qrec_bpr_sgd_usermajor_f32')

@@ -354,9 +354,12 @@ def test_batch_tma_variant_shared_rows_and_bad_d(torch, E):
 
 
 def _user_major_problem(rng, nu, ni, max_deg, distinct_items=True):
-    deg = rng.integers(0, max_deg + 1, nu)
-    deg[rng.integers(0, nu, 3)] = 0                       # some empty users
-    deg[0] = max_deg                                      # one user longer than a lane-group batch
+    if distinct_items:
+        deg = np.where(rng.random(nu) < 0.1, 0, max_deg)     # chunk-aligned users, some empty
+    else:
+        deg = rng.integers(0, max_deg + 1, nu)
+        deg[rng.integers(0, nu, 3)] = 0                   # some empty users
+        deg[0] = 3 * max_deg                              # one user spanning several chunks
     rowptr = np.zeros(nu + 1, np.int64); rowptr[1:] = np.cumsum(deg)
     n = int(rowptr[-1])
     if distinct_items:
@@ -372,11 +375,12 @@ def _user_major_problem(rng, nu, ni, max_deg, distinct_items=True):
 
 @pytest.mark.parametrize('d', [64, 32, 48, 128, 16])
 def test_usermajor_kernel_is_sequential_in_P(torch, E, d):
-    """User-major kernel: P[u] lives in registers across a user's triples, so with globally distinct
-    items the result must equal the SEQUENTIAL reference loop (BPR.py:31-39), users repeating."""
+    """User-major kernel: P[u] lives in registers across the triples of a user that fall into one
+    32-triple chunk, so with globally distinct items and users aligned to chunks (here: every user
+    has exactly 32 or 0 triples) the result must equal the SEQUENTIAL reference loop (BPR.py:31-39)."""
     from oracle import c_oracle
     rng = np.random.default_rng(d)
-    nu, max_deg = 300, 70
+    nu, max_deg = 300, 32
     rowptr, u, i, j = _user_major_problem(rng, nu, 60000, max_deg)
     ni = 60000
     P0 = (rng.random((nu, d)) / 3).astype(np.float32)
