@@ -2,10 +2,14 @@
 """bench.py -- BPR triples/sec at d=64 on the synthetic 1M x 100K x 50M set (BASELINE.json
 configs[1]), one process per GPU.
 
-A "step" is one epoch of the hot path over the rank's shard of the 50M interactions:
-  K0  device Philox negative sampling for every (u,i) pair      (qrec_sample_neg_philox)
-  K1  fused gather -> dots -> sigmoid -> SGD step -> scatter-add (qrec_bpr_sgd_batch_f32)
-  +   regU*|P|^2 + regI*|Q|^2 for the epoch loss                (qrec_sumsq_f32, BPR.py:40)
+A "step" is one epoch of the hot path over the rank's shard of the 50M interactions, in the
+reference's own iteration order (model/ranking/BPR.py:31-33: users in id order, each user's positives):
+  K0  device Philox negative sampling for every (u,i) pair        (qrec_sample_neg_philox)
+  K1  fused gather -> dots -> sigmoid -> SGD step -> scatter-add   (qrec_bpr_sgd_usermajor_f32:
+      P[u] register-resident inside a user, item rows REDG-added)
+  +   regU*|P|^2 + regI*|Q|^2 for the epoch loss                  (qrec_sumsq_f32, BPR.py:40)
+The same epoch with the triples in SHUFFLED order through the order-agnostic kernel
+(qrec_bpr_sgd_batch_f32) is timed too and reported under "shuffled_order".
 with the (u,i) pairs, the rated-item CSR and both tables already resident in HBM.  `e2e` is the
 same epoch entered through the host-buffer C-ABI call (qrec_bpr_epoch_host): the step's
 (u,i,j) index arrays start in pinned HOST memory and are copied to the device inside the timed
@@ -35,7 +39,7 @@ NUM_USERS, NUM_ITEMS, DEGREE, D = 1_000_000, 100_000, 50, 64
 LR, REG_U, REG_I = 0.01, 0.001, 0.001
 ALGO_BYTES_PER_TRIPLE = 24 * D + 12          # 3 rows read + 3 rows written + 3 int32
 METRIC = 'BPR triples/sec at d=64'
-WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, shuffled triples'
+WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, user-major (reference) order'
 
 
 def measured_hbm_peak():
@@ -290,27 +294,31 @@ def run_ours(args):
     if world > 1:
         dist.broadcast(Q, 0)
     g = torch.Generator(device=dev); g.manual_seed(99 + rank)
-    perm = torch.randperm(n_local, device=dev, generator=g)
-    u = data['u'][perm].contiguous()
-    i = data['i'][perm].contiguous()
-    del perm
+    u, i = data['u'], data['i']                  # CSR order: user-major, random item order inside a user
     j = torch.empty(n_local, dtype=torch.int32, device=dev)
     rowptr, cols = data['sorted_rowptr'], data['sorted_cols']
+    csr_rowptr = rowptr                          # every user has DEGREE positives: same offsets
     loss = torch.zeros(3, dtype=torch.float64, device=dev)
     q_syncs = max(1, args.q_syncs) if world > 1 else 1
     qsync = parallel.ReplicatedTableSync(Q)
-    bounds = parallel.sync_points(n_local, q_syncs)
+    # sync points at user boundaries (multiples of DEGREE triples)
+    ub = parallel.sync_points(users_local, q_syncs)
     k1_events = []
 
     def step(epoch, timed):
         loss.zero_()
         E.sample_neg_philox(u, rowptr, cols, NUM_ITEMS, 2024, epoch, out=j)
         for s in range(q_syncs):
-            a, b = bounds[s], bounds[s + 1]
+            ua, ub_ = ub[s], ub[s + 1]
+            a, b = ua * DEGREE, ub_ * DEGREE
             if timed:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-            E.bpr_sgd_batch(P, Q, u[a:b], i[a:b], j[a:b], LR, REG_U, REG_I, loss[0:1])
+            if q_syncs == 1:
+                E.bpr_sgd_usermajor(P, Q, csr_rowptr, i, j, LR, REG_U, REG_I, loss[0:1])
+            else:
+                rp = (csr_rowptr[ua:ub_ + 1] - a).contiguous()
+                E.bpr_sgd_usermajor(P[ua:ub_], Q, rp, i[a:b], j[a:b], LR, REG_U, REG_I, loss[0:1])
             if timed:
                 e1.record()
                 k1_events.append((e0, e1, b - a))
@@ -355,9 +363,36 @@ def run_ours(args):
     total_triples = n_local * world * args.steps
     value = total_triples / (elapsed_ms * 1e-3)
 
+    # ------------------------------------------------------------------ the same epoch, shuffled order
+    perm = torch.randperm(n_local, device=dev, generator=g)
+    su, si = u[perm].contiguous(), i[perm].contiguous()
+    sj = torch.empty_like(su)
+    del perm
+
+    def shuffled_step(epoch):
+        E.sample_neg_philox(su, rowptr, cols, NUM_ITEMS, 4048, epoch, out=sj)
+        E.bpr_sgd_batch(P, Q, su, si, sj, LR, REG_U, REG_I, loss[0:1])
+        qsync.sync()
+        E.sumsq(P, loss[1:2]); E.sumsq(Q, loss[2:3])
+    for w in range(2):
+        shuffled_step(w)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s_beg, s_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_beg.record()
+    for k in range(max(3, args.steps // 2)):
+        shuffled_step(2 + k)
+    s_end.record()
+    torch.cuda.synchronize()
+    ts = torch.tensor([s_beg.elapsed_time(s_end) / max(3, args.steps // 2)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    shuffled_ms = float(ts.item())
+
     # ------------------------------------------------------------------ e2e: host buffers
-    hu, hi = u.cpu().pin_memory(), i.cpu().pin_memory()
-    hj = j.cpu().pin_memory()
+    hu, hi = su.cpu().pin_memory(), si.cpu().pin_memory()
+    hj = sj.cpu().pin_memory()
     pipe = E.HostPipeline(local, chunk_triples=1 << 22)
 
     def e2e_step():
@@ -390,6 +425,11 @@ def run_ours(args):
         per_launch_ms = k1_ms / max(1, len(k1_events))
         achieved = per_launch_triples * ALGO_BYTES_PER_TRIPLE / (per_launch_ms * 1e-3) / 1e9
         tr = recorded_traffic()
+        if tr and not str(tr.get('kernel', '')).startswith('bpr_sgd_usermajor'):
+            tr = None                    # a capture of another kernel says nothing about this one
+        # what this kernel itself must move per triple: 2 item rows read + 2 RED-added, 2 ids, and the
+        # P row once per user segment of a 32-triple chunk (about 1.64 segments per chunk at degree 50)
+        kernel_model_bytes = 4 * 4 * D + 8 + (1.0 + 32.0 / DEGREE) * (2 * 4 * D + 8) / 32.0
         out = {
             'metric': METRIC, 'value': value, 'unit': 'triples/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True,
@@ -397,16 +437,19 @@ def run_ours(args):
             'config': {
                 'workload': WORKLOAD, 'users': NUM_USERS, 'items': NUM_ITEMS, 'interactions': NUM_USERS * DEGREE,
                 'd': D, 'lr': LR, 'reg': REG_U, 'triples_per_step': n_local * world,
-                'order': 'positives shuffled once, negatives re-sampled on device every step (Philox)',
+                'order': 'user-major CSR order (the reference loop, BPR.py:31-33), random item order inside a user, '
+                         'negatives re-sampled on device every step (Philox)',
                 'l2_policy': 'inputs larger than L2: P 256 MB + 600 MB of indices per step vs 126 MB L2',
                 'parallelism': ('users range-partitioned over %d ranks, Q replicated, %d delta all-reduces/step'
                                 % (world, q_syncs)) if world > 1 else 'single GPU',
                 'epoch_loss': epoch_loss,
             },
             'roofline': {
-                'bound': 'hbm', 'kernel': 'bpr_sgd_batch_kernel<16,1,4>', 'achieved': achieved, 'peak': peak,
+                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32>', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
+                'kernel_model_bytes_per_triple': kernel_model_bytes,
+                'achieved_kernel_model': per_launch_triples * kernel_model_bytes / (per_launch_ms * 1e-3) / 1e9,
                 'launch_ms': per_launch_ms, 'launch_triples': per_launch_triples,
                 'traffic': (int(tr['dram_bytes_per_launch'] * per_launch_triples / tr['launch_triples'])
                             if tr and tr.get('launch_triples') else None),
@@ -415,11 +458,14 @@ def run_ours(args):
             'e2e': {'value': e2e_value, 'unit': 'triples/s', 'h2d_bytes_per_step': 12 * n_local * world,
                     'd2h_bytes_per_step': 8 * world, 'ms_per_step': 1e3 * e2e_s / args.steps,
                     'api': 'qrec_bpr_epoch_host: pinned host (u,i,j) -> chunked H2D overlapped with K1 -> loss D2H'},
+            'shuffled_order': {'value': n_local * world / (shuffled_ms * 1e-3), 'unit': 'triples/s', 'ms_per_step': shuffled_ms,
+                               'kernel': 'bpr_sgd_batch_kernel<16,1,4> (order-agnostic: every triple loads and RED-adds all 3 rows)',
+                               'note': 'same epoch with the (u,i) pairs shuffled once; also the order used by the e2e host path'},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
         if world == 1 and not args.no_lightgcn:
-            del u, i, j, hu, hi, hj
+            del u, i, j, hu, hi, hj, su, si, sj
             torch.cuda.empty_cache()
             out['lightgcn'] = lightgcn_section(torch, E, synthetic, data, dev, peak)
         if world == 1 and not args.no_cpu_baseline:

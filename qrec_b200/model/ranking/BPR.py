@@ -5,7 +5,8 @@ by the bit-exact C clone of Python's MT19937 sampler (continuing from the interp
 `random` state, so `random.seed(s)` gives the reference's triples), then
   * engine -mode parity : qrec_bpr_sgd_ordered_{f64,f32} -- sequential-equivalent SGD, the same
                           P/Q as the reference after every epoch;
-  * engine -mode fast   : qrec_bpr_sgd_batch_f32 -- the fused throughput kernel.
+  * engine -mode fast   : qrec_bpr_sgd_usermajor_f32 -- the fused throughput kernel in the same
+                          user-major order (P[u] sequential inside a user, item rows scatter-added).
 `trainModel_tf` replaces the TF1 Adam graph (BPR.py:77-96) with K3 + full-table L2 + K4.
 """
 import random
@@ -51,7 +52,11 @@ class BPR(IterativeRecommender):
             random.setstate(mt.getstate())
             du, di, dj = (torch.from_numpy(x).to(dev) for x in (u, i, j))
             acc.zero_()
-            if fast:
+            if fast and dpad <= 128:
+                # the sampler's stream is user-major (BPR.py:31-33): P[u] stays in registers per user
+                E.bpr_sgd_usermajor(P, Q, torch.from_numpy(csr.pos_rowptr).to(dev), di, dj, self.lRate, self.regU,
+                                    self.regI, acc[0:1])
+            elif fast:
                 E.bpr_sgd_batch(P, Q, du, di, dj, self.lRate, self.regU, self.regI, acc[0:1])
             else:
                 wu, wi, wj = E.bpr_order_prepare(u, i, j, self.num_users, self.num_items)
