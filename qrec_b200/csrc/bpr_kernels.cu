@@ -140,6 +140,12 @@ bpr_sgd_ordered_kernel(T* __restrict__ P, T* __restrict__ Q, int d, long long n,
 // ------------------------------------------------------------------------------------------
 // throughput mode
 // ------------------------------------------------------------------------------------------
+// Throughput kernels: sigmoid and -ln(s) on the SFU (ex2.approx / lg2.approx / rcp.approx).  The
+// relative error (~2^-21) is far below the fp32 rounding of the row update it scales; parity mode
+// keeps expf/logf.
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_neg_log(float s) { return -__logf(s); }
+
 template <int LPR>
 __device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
@@ -224,10 +230,10 @@ bpr_sgd_batch_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, lon
 #pragma unroll
         for (int v = 0; v < VPL; ++v) x += dot4(p[r][v], qi[r][v]) - dot4(p[r][v], qj[r][v]);
         x = group_sum<LPR>(x);
-        const float s = 1.0f / (1.0f + expf(-x));
+        const float s = fast_sigmoid(x);
         const float g = lr * (1.0f - s);
         if (ok[r]) {
-          if (l == 0) lsum += -logf(s);
+          if (l == 0) lsum += fast_neg_log(s);
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             if ((l + v * LPR) < nvec) {
@@ -292,10 +298,10 @@ bpr_sgd_staged_kernel(float* __restrict__ P, int nvec, long long n, const int* _
     }
     float x = dot4(p, qi) - dot4(p, qj);
     x = group_sum<LPR>(x);
-    const float s = 1.0f / (1.0f + expf(-x));
+    const float s = fast_sigmoid(x);
     const float g = lr * (1.0f - s);
     if (ok) {
-      if (l == 0) lsum += -logf(s);
+      if (l == 0) lsum += fast_neg_log(s);
       float4 dp, dqi, dqj;
       bpr_step4(p, qi, qj, g, a_u, a_i, dp, dqi, dqj);
       red_add_v4(pr, dp);
@@ -383,10 +389,10 @@ bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long
       for (int r = 0; r < UNROLL; ++r) {
         float x = dot4(p[r], qi[r]) - dot4(p[r], qj[r]);
         x = group_sum<LPR>(x);
-        const float s = 1.0f / (1.0f + expf(-x));
+        const float s = fast_sigmoid(x);
         const float g = lr * (1.0f - s);
         if (ok[r]) {
-          if (l == 0) lsum += -logf(s);
+          if (l == 0) lsum += fast_neg_log(s);
           float4 dp, dqi, dqj;
           bpr_step4(p[r], qi[r], qj[r], g, a_u, a_i, dp, dqi, dqj);
           float* trip = slot + (size_t)(r * TPW + sub) * ROWS * D;
@@ -452,7 +458,7 @@ __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
 // changes or the chunk ends.  Inside a user P[u] is register-resident and updated sequentially; a
 // user whose triples span several chunks gets the sum of the chunks' deltas.
 template <int LPR, int G, int CH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
                          const int* __restrict__ i, const int* __restrict__ j, float lr,
@@ -528,9 +534,9 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
             }
             float x = dot4(p, qi[f]) - dot4(p, qj[f]);
             x = group_sum_masked<LPR>(x, gmask);
-            const float s = 1.0f / (1.0f + expf(-x));
+            const float s = fast_sigmoid(x);
             const float g = lr * (1.0f - s);
-            if (l == 0) lsum += -logf(s);
+            if (l == 0) lsum += fast_neg_log(s);
             if (act) {
               float4 dp, dqi, dqj;
               bpr_step4(p, qi[f], qj[f], g, a_u, a_i, dp, dqi, dqj);
