@@ -445,7 +445,7 @@ def run_ours(args):
                 'epoch_loss': epoch_loss,
             },
             'roofline': {
-                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32>', 'achieved': achieved, 'peak': peak,
+                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32,true>', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
                 'kernel_model_bytes_per_triple': kernel_model_bytes,

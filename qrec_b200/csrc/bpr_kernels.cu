@@ -445,6 +445,22 @@ bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long
 // REDG.E.ADD.F32x4 as in the batch kernel.  Per triple: 2 row loads + 2 row REDs instead of 3 + 3.
 // Input: CSR over users (rowptr), i[] / j[] in that order.
 // ------------------------------------------------------------------------------------------
+// The same step with the decay folded into the coefficients (7 instead of 11 flops per component):
+//   pn = p + g (qi - qj);  p' = (1 - a_u) pn;  dqi = g (1 - a_i) pn - a_i qi;  dqj = -g (1 - a_i) pn - a_i qj
+// (identical algebra to BPR.py:46-52; differs from bpr_step4 by one rounding of the (1-a) product).
+__device__ __forceinline__ void bpr_step4_inplace(float4& p, float4 qi, float4 qj, float g, float one_m_au,
+                                                  float c1, float a_i, float4& dqi, float4& dqj) {
+#define QREC_STEP(c)                                   \
+  {                                                    \
+    const float pn = fmaf(g, qi.c - qj.c, p.c);        \
+    dqi.c = fmaf(c1, pn, -a_i * qi.c);                 \
+    dqj.c = fmaf(-c1, pn, -a_i * qj.c);                \
+    p.c = one_m_au * pn;                               \
+  }
+  QREC_STEP(x) QREC_STEP(y) QREC_STEP(z) QREC_STEP(w)
+#undef QREC_STEP
+}
+
 template <int LPR>
 __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
 #pragma unroll
@@ -457,7 +473,7 @@ __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
 // LPR-ary search of rowptr and walks forward, flushing the P[u] delta (one row RED) whenever the user
 // changes or the chunk ends.  Inside a user P[u] is register-resident and updated sequentially; a
 // user whose triples span several chunks gets the sum of the chunks' deltas.
-template <int LPR, int G, int CH>
+template <int LPR, int G, int CH, bool FULL>     // FULL: d == 4*LPR exactly (every lane owns a slice)
 __global__ void __launch_bounds__(256, 3)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
@@ -469,9 +485,10 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
   const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
   const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + sub;
   const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * GPW;
-  const int d = nvec * 4;
-  const bool act = l < nvec;
+  const int d = FULL ? LPR * 4 : nvec * 4;
+  const bool act = FULL ? true : (l < nvec);
   const float a_u = lr * reg_u, a_i = lr * reg_i;
+  const float one_m_au = 1.0f - a_u, one_m_ai = 1.0f - a_i;
   const long long nchunks = (n + CH - 1) / CH;
   float lsum = 0.f;
   for (long long ch = group; ch < nchunks; ch += ngroups) {
@@ -538,9 +555,8 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
             const float g = lr * (1.0f - s);
             if (l == 0) lsum += fast_neg_log(s);
             if (act) {
-              float4 dp, dqi, dqj;
-              bpr_step4(p, qi[f], qj[f], g, a_u, a_i, dp, dqi, dqj);
-              p.x += dp.x; p.y += dp.y; p.z += dp.z; p.w += dp.w;       // P[u] stays in registers
+              float4 dqi, dqj;
+              bpr_step4_inplace(p, qi[f], qj[f], g, one_m_au, g * one_m_ai, a_i, dqi, dqj);   // P[u] stays in registers
               red_add_v4(Q + (size_t)ri[f] * d + l * 4, dqi);
               red_add_v4(Q + (size_t)rj[f] * d + l * 4, dqj);
             }
@@ -742,8 +758,12 @@ int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, i
     const long long per_block = 8 * (32 / LPR);                                                  \
     long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
     if (blocks > cap) blocks = cap;                                                              \
-    bpr_sgd_usermajor_kernel<LPR, 4, CH><<<(int)blocks, 256, 0, st>>>(                           \
-        P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
+    if (nvec == LPR)                                                                             \
+      bpr_sgd_usermajor_kernel<LPR, 4, CH, true><<<(int)blocks, 256, 0, st>>>(                   \
+          P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
+    else                                                                                         \
+      bpr_sgd_usermajor_kernel<LPR, 4, CH, false><<<(int)blocks, 256, 0, st>>>(                  \
+          P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
   }
   if (nvec <= 4) QREC_UM(4)
   else if (nvec <= 8) QREC_UM(8)
