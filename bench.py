@@ -4,9 +4,9 @@ configs[1]), one process per GPU.
 
 A "step" is one epoch of the hot path over the rank's shard of the 50M interactions, in the
 reference's own iteration order (model/ranking/BPR.py:31-33: users in id order, each user's positives):
-  K0  device Philox negative sampling for every (u,i) pair        (qrec_sample_neg_philox)
-  K1  fused gather -> dots -> sigmoid -> SGD step -> scatter-add   (qrec_bpr_sgd_usermajor_f32:
-      P[u] register-resident inside a user, item rows REDG-added)
+  K0+K1  qrec_bpr_epoch_usermajor_f32: Philox negative sampling (rejection against the user's rated
+         row) fused into gather -> dots -> sigmoid -> SGD step -> scatter-add; P[u] register-resident
+         inside a user, item rows REDG-added, j never written to HBM
   +   regU*|P|^2 + regI*|Q|^2 for the epoch loss                  (qrec_sumsq_f32, BPR.py:40)
 The same epoch with the triples in SHUFFLED order through the order-agnostic kernel
 (qrec_bpr_sgd_batch_f32) is timed too and reported under "shuffled_order".
@@ -307,7 +307,6 @@ def run_ours(args):
 
     def step(epoch, timed):
         loss.zero_()
-        E.sample_neg_philox(u, rowptr, cols, NUM_ITEMS, 2024, epoch, out=j)
         for s in range(q_syncs):
             ua, ub_ = ub[s], ub[s + 1]
             a, b = ua * DEGREE, ub_ * DEGREE
@@ -315,10 +314,11 @@ def run_ours(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if q_syncs == 1:
-                E.bpr_sgd_usermajor(P, Q, csr_rowptr, i, j, LR, REG_U, REG_I, loss[0:1])
+                E.bpr_epoch_usermajor(P, Q, csr_rowptr, i, rowptr, cols, NUM_ITEMS, 2024, epoch, LR, REG_U, REG_I, loss[0:1])
             else:
                 rp = (csr_rowptr[ua:ub_ + 1] - a).contiguous()
-                E.bpr_sgd_usermajor(P[ua:ub_], Q, rp, i[a:b], j[a:b], LR, REG_U, REG_I, loss[0:1])
+                E.bpr_epoch_usermajor(P[ua:ub_], Q, rp, i[a:b], rowptr[ua:ub_ + 1].contiguous(), cols, NUM_ITEMS,
+                                      2024 + s, epoch, LR, REG_U, REG_I, loss[0:1])
             if timed:
                 e1.record()
                 k1_events.append((e0, e1, b - a))
@@ -445,7 +445,7 @@ def run_ours(args):
                 'epoch_loss': epoch_loss,
             },
             'roofline': {
-                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32,true>', 'achieved': achieved, 'peak': peak,
+                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32,true,true> (fused Philox sampling)', 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
                 'kernel_model_bytes_per_triple': kernel_model_bytes,

@@ -162,6 +162,17 @@ int qrec_bpr_sgd_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_
                                const int64_t* dev_rowptr, const int32_t* dev_i, const int32_t* dev_j,
                                float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* One whole epoch of the numpy path (model/ranking/BPR.py:29-39) in a single launch: the user-major
+ * kernel above with the negative sampling fused in.  Lane l of a lane group draws the negative of its
+ * triple k with Philox counter (k, attempt, epoch) -- exactly what qrec_sample_neg_philox produces
+ * for (u[k], k) -- rejecting items in the user's sorted rated row; j never touches HBM unless
+ * dev_j_out is given.  rated_rowptr/rated_cols: CSR of the rejection sets (may equal rowptr's). */
+int qrec_bpr_epoch_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users, int64_t n,
+                                 const int64_t* dev_rowptr, const int32_t* dev_i,
+                                 const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
+                                 int32_t num_items, uint64_t seed, uint32_t epoch, int32_t* dev_j_out,
+                                 float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
+
 /* K1 for a row-sharded item table: the Q rows of the batch were fetched from their
  * owner ranks into dev_R (row pos_i[k] / pos_j[k] holds Q[i_k] / Q[j_k]).  Applies BPR.py:45-52,
  * updates P in place and writes the item-row deltas to dev_D at the same positions, ready to be

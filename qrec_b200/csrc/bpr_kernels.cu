@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.h"
+#include "philox.cuh"
 
 namespace {
 
@@ -473,12 +474,23 @@ __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
 // LPR-ary search of rowptr and walks forward, flushing the P[u] delta (one row RED) whenever the user
 // changes or the chunk ends.  Inside a user P[u] is register-resident and updated sequentially; a
 // user whose triples span several chunks gets the sum of the chunks' deltas.
-template <int LPR, int G, int CH, bool FULL>     // FULL: d == 4*LPR exactly (every lane owns a slice)
+// SAMPLE: the negatives are drawn inside the kernel (lane l draws the negative of triple base+l with
+// the same Philox counter as the stand-alone sampler, so both give identical j) instead of being
+// read from j[]; they are optionally written to j_out.
+struct FusedSampler {
+  const long long* rated_rowptr;   // rejection sets: CSR over users, sorted columns
+  const int* rated_cols;
+  int num_items;
+  uint32_t seed_lo, seed_hi, epoch;
+  int* j_out;                      // may be null
+};
+
+template <int LPR, int G, int CH, bool FULL, bool SAMPLE>   // FULL: d == 4*LPR (every lane owns a slice)
 __global__ void __launch_bounds__(256, 3)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
                          const int* __restrict__ i, const int* __restrict__ j, float lr,
-                         float reg_u, float reg_i, double* loss) {
+                         float reg_u, float reg_i, double* loss, FusedSampler fs) {
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -519,7 +531,20 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
       int mi = 0, mj = 0;
       if (l < m) {
         mi = __ldg(i + base + l);
-        mj = __ldg(j + base + l);
+        if (SAMPLE) {
+          // user of triple base+l: walk forward from the group's current user
+          int us = uu;
+          long long ue = uend;
+          while (ue <= base + l) {
+            ++us;
+            ue = __ldg(rowptr + us + 1);
+          }
+          mj = qrec::sample_negative(base + l, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items, fs.rated_cols,
+                                     __ldg(fs.rated_rowptr + us), __ldg(fs.rated_rowptr + us + 1));
+          if (fs.j_out != nullptr) fs.j_out[base + l] = mj;
+        } else {
+          mj = __ldg(j + base + l);
+        }
       }
       for (int t0 = 0; t0 < m; t0 += G) {
         float4 qi[G], qj[G];
@@ -741,6 +766,33 @@ int qrec_bpr_sgd_batch_tma_f32(float* P, float* Q, int32_t d, int64_t n, const i
   return QREC_OK;
 }
 
+static int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
+                            const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i, double* loss,
+                            bool sample, FusedSampler fs, cudaStream_t st) {
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+  constexpr int CH = 32;
+#define QREC_UM2(LPR, FULLV, SAMPLEV)                                                            \
+  bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV><<<(int)blocks, 256, 0, st>>>(             \
+      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs)
+#define QREC_UM(LPR)                                                                             \
+  {                                                                                              \
+    const long long per_block = 8 * (32 / LPR);                                                  \
+    long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
+    if (blocks > cap) blocks = cap;                                                              \
+    if (nvec == LPR) { if (sample) QREC_UM2(LPR, true, true); else QREC_UM2(LPR, true, false); } \
+    else { if (sample) QREC_UM2(LPR, false, true); else QREC_UM2(LPR, false, false); }           \
+  }
+  if (nvec <= 4) QREC_UM(4)
+  else if (nvec <= 8) QREC_UM(8)
+  else if (nvec <= 16) QREC_UM(16)
+  else QREC_UM(32)
+#undef QREC_UM
+#undef QREC_UM2
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
 int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
                                const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i,
                                double* loss, void* stream) {
@@ -749,29 +801,22 @@ int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, i
   QREC_REQUIRE(n_users >= 0 && n >= 0, "qrec_bpr_sgd_usermajor_f32: negative size");
   if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && j, "qrec_bpr_sgd_usermajor_f32: null index pointer");
-  const int nvec = d / 4;
-  const long long cap = (long long)sm_count() * 8;
-  cudaStream_t st = (cudaStream_t)stream;
-  constexpr int CH = 32;
-#define QREC_UM(LPR)                                                                             \
-  {                                                                                              \
-    const long long per_block = 8 * (32 / LPR);                                                  \
-    long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
-    if (blocks > cap) blocks = cap;                                                              \
-    if (nvec == LPR)                                                                             \
-      bpr_sgd_usermajor_kernel<LPR, 4, CH, true><<<(int)blocks, 256, 0, st>>>(                   \
-          P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
-    else                                                                                         \
-      bpr_sgd_usermajor_kernel<LPR, 4, CH, false><<<(int)blocks, 256, 0, st>>>(                  \
-          P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss); \
-  }
-  if (nvec <= 4) QREC_UM(4)
-  else if (nvec <= 8) QREC_UM(8)
-  else if (nvec <= 16) QREC_UM(16)
-  else QREC_UM(32)
-#undef QREC_UM
-  QREC_LAUNCH_CHECK();
-  return QREC_OK;
+  FusedSampler fs = {nullptr, nullptr, 0, 0u, 0u, 0u, nullptr};
+  return launch_usermajor(P, Q, d, n_users, n, rowptr, i, j, lr, reg_u, reg_i, loss, false, fs, (cudaStream_t)stream);
+}
+
+int qrec_bpr_epoch_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
+                                 const int32_t* i, const int64_t* rated_rowptr, const int32_t* rated_cols,
+                                 int32_t num_items, uint64_t seed, uint32_t epoch, int32_t* j_out, float lr,
+                                 float reg_u, float reg_i, double* loss, void* stream) {
+  QREC_REQUIRE(P && Q && loss, "qrec_bpr_epoch_usermajor_f32: null pointer");
+  QREC_REQUIRE(d >= 4 && d <= 128 && (d % 4) == 0, "qrec_bpr_epoch_usermajor_f32: d=%d unsupported (multiple of 4, 4..128)", d);
+  QREC_REQUIRE(n_users >= 0 && n >= 0 && num_items >= 1, "qrec_bpr_epoch_usermajor_f32: bad size");
+  if (n_users == 0 || n == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && i && rated_rowptr && rated_cols, "qrec_bpr_epoch_usermajor_f32: null index pointer");
+  FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
+                     (uint32_t)(seed >> 32), epoch, j_out};
+  return launch_usermajor(P, Q, d, n_users, n, rowptr, i, nullptr, lr, reg_u, reg_i, loss, true, fs, (cudaStream_t)stream);
 }
 
 int qrec_bpr_sgd_staged_f32(float* P, int32_t d, int64_t n, const int32_t* u, const int32_t* pos_i,

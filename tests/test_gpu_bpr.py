@@ -439,3 +439,31 @@ def test_usermajor_empty_and_bad_args(torch, E):
     with pytest.raises(E.QRecError):
         E.bpr_sgd_usermajor(torch.ones(4, 200, device='cuda'), torch.ones(5, 200, device='cuda'),
                             torch.zeros(5, dtype=torch.int64, device='cuda'), z, z, 0.1, 0.1, 0.1, loss)
+
+
+def test_fused_epoch_equals_sampler_plus_kernel(torch, E, bpr_ids):
+    """qrec_bpr_epoch_usermajor_f32 (sampling fused into the user-major kernel) draws exactly the
+    negatives qrec_sample_neg_philox draws (same Philox counters) and then does the same updates."""
+    u, i, nu, ni = bpr_ids
+    csr = E.RatedCSR(nu, ni, u, i)
+    # CSR order of the positives = the reference's iteration order
+    cu = np.repeat(np.arange(nu), np.diff(csr.pos_rowptr)).astype(np.int32)
+    ci = csr.pos_cols
+    P0, Q0 = _init_tables(nu, ni)
+    Pa, Qa = _dev(torch, P0.astype(np.float32)), _dev(torch, Q0.astype(np.float32))
+    Pb, Qb = Pa.clone(), Qa.clone()
+    rp, rrp, rc = _dev(torch, csr.pos_rowptr), _dev(torch, csr.sorted_rowptr), _dev(torch, csr.sorted_cols)
+    la = torch.zeros(1, dtype=torch.float64, device='cuda'); lb = torch.zeros(1, dtype=torch.float64, device='cuda')
+    j_ref = E.sample_neg_philox(_dev(torch, cu), rrp, rc, ni, 0xfeedface, 5)
+    E.bpr_sgd_usermajor(Pa, Qa, rp, _dev(torch, ci), j_ref, 1e-3, REG, REG, la)
+    j_out = torch.full_like(j_ref, -1)
+    E.bpr_epoch_usermajor(Pb, Qb, rp, _dev(torch, ci), rrp, rc, ni, 0xfeedface, 5, 1e-3, REG, REG, lb, j_out=j_out)
+    torch.cuda.synchronize()
+    assert torch.equal(j_out, j_ref)
+    torch.testing.assert_close(Pb, Pa, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(Qb, Qa, rtol=1e-4, atol=1e-6)            # REDs land in a different order
+    assert abs(la.item() - lb.item()) <= 1e-6 * abs(la.item())
+    # without j_out, and a different epoch gives different negatives
+    E.bpr_epoch_usermajor(Pb, Qb, rp, _dev(torch, ci), rrp, rc, ni, 0xfeedface, 6, 1e-3, REG, REG, lb)
+    j6 = E.sample_neg_philox(_dev(torch, cu), rrp, rc, ni, 0xfeedface, 6)
+    assert not torch.equal(j6, j_ref)
