@@ -217,6 +217,15 @@ int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* dev_r
                                const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
                                float* dev_acc, float acc_scale, void* stream);
 
+/* Y = A X when X is non-zero only in the n_src rows listed in dev_src_rows (the first backward
+ * product of a minibatch step: the loss gradient touches at most 3B rows).  A must be symmetric
+ * (column r = row r), as the normalised joint adjacency is.  Y is zero-filled here, then
+ * Y[c] += a_rc X[r] over the edges of the listed rows; optional acc += acc_scale * Y. */
+int qrec_spmm_csr_scatter_rows_f32(int32_t n_rows, int32_t n_src, const int32_t* dev_src_rows,
+                                   const int64_t* dev_rowptr, const int32_t* dev_cols,
+                                   const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
+                                   float* dev_acc, float acc_scale, void* stream);
+
 /* =====================================================================================
  * K3 -- gather rows of the propagated tables, bpr_loss + batch L2 and its gradient,
  * scatter-added into dense gradient buffers.  util/loss.py:3-6, LightGCN.py:22-24,28-30.

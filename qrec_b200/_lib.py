@@ -70,6 +70,7 @@ SIGNATURES = {
                                       C.c_float, C.c_float, c_f64p]),
     'qrec_spmm_csr_f32': (C.c_int, [C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
     'qrec_spmm_csr_rowsplit_f32': (C.c_int, [C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
+    'qrec_spmm_csr_scatter_rows_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
     'qrec_bpr_grad_scatter_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                             C.c_float, vp, vp, vp, vp]),
     'qrec_adam_dense_tf1_f32': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,

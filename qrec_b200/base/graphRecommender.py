@@ -30,6 +30,11 @@ class DeviceCSR(object):
         self.cols = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
         self.vals = torch.from_numpy(mat.data.astype(np.float32)).to(device)
 
+    def matmul_sparse_rows(self, X, src_rows, out, acc=None, acc_scale=0.0):
+        """out = A @ X when only the rows `src_rows` of X are non-zero (A symmetric)."""
+        from .. import engine
+        return engine.spmm_csr_scatter_rows(self.rowptr, self.cols, self.vals, src_rows, X, out, acc=acc, acc_scale=acc_scale)
+
     def matmul(self, X, out, acc=None, acc_scale=0.0):
         from .. import engine
         return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale,

@@ -241,6 +241,59 @@ spmm_csr_balanced_kernel(int n_rows, long long nnz, const long long* __restrict_
   }
 }
 
+// Sparse-input product for the FIRST backward SpMM of a minibatch step: the gradient w.r.t. the
+// propagated table is non-zero only in the batch's rows (<= 3B of N), so Y = A X reduces to scattering
+// X[r] along the edges of those rows (A is symmetric: column r = row r):  Y[c] += a_rc * X[r].
+// One lane group per 64-edge slice of a source row; Y (and acc) receive REDG.ADD.F32x4.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+spmm_scatter_rows_kernel(int n_src, const int* __restrict__ src_rows, const long long* __restrict__ rowptr,
+                         const int* __restrict__ cols, const float* __restrict__ vals,
+                         const float* __restrict__ X, float* __restrict__ Y, int nvec,
+                         float* __restrict__ acc, float acc_scale) {
+  constexpr int GPW = 32 / LPR, SLICE = 64;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const unsigned gmask = (LPR == 32) ? 0xffffffffu : (((1u << LPR) - 1u) << (sub * LPR));
+  const int d = nvec * 4;
+  const long long group = (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * GPW + sub;
+  const long long ngroups = (((long long)gridDim.x * blockDim.x) >> 5) * GPW;
+  // work items: (source row, slice) enumerated row-major with a fixed number of slices per row
+  // (rows shorter than slice*SLICE simply skip the slice)
+  for (long long w = group;; w += ngroups) {
+    const long long si = w / 64;                 // up to 64 slices (4096 edges) per pass over a row
+    if (si >= n_src) break;
+    const int slice = (int)(w % 64);
+    const int r = __ldg(src_rows + si);
+    const long long start = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    for (long long lo = start + (long long)slice * SLICE; lo < end; lo += 64LL * SLICE) {
+      const long long hi = (lo + SLICE) < end ? (lo + SLICE) : end;
+      const float4 x = (l < nvec) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)r * d) + l)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (long long base = lo; base < hi; base += LPR) {
+        int c = 0;
+        float a = 0.f;
+        if (base + l < hi) {
+          c = __ldg(cols + base + l);
+          a = __ldg(vals + base + l);
+        }
+        const int m = (hi - base) < LPR ? (int)(hi - base) : LPR;
+        for (int t = 0; t < m; ++t) {
+          const int cc = __shfl_sync(gmask, c, sub * LPR + t);
+          const float aa = __shfl_sync(gmask, a, sub * LPR + t);
+          if (l < nvec) {
+            const float4 v = make_float4(aa * x.x, aa * x.y, aa * x.z, aa * x.w);
+            red_add_v4(Y + (size_t)cc * d + l * 4, v);
+            if (acc != nullptr)
+              red_add_v4(acc + (size_t)cc * d + l * 4,
+                         make_float4(acc_scale * v.x, acc_scale * v.y, acc_scale * v.z, acc_scale * v.w));
+          }
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ K3
 template <int LPR, int VPL, int UNROLL>
 __global__ void __launch_bounds__(256)
@@ -448,6 +501,38 @@ int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* rowpt
   else if (nvec <= 32) QREC_SPMM(32, 1)
   else QREC_SPMM(32, 2)
 #undef QREC_SPMM
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_spmm_csr_scatter_rows_f32(int32_t n_rows, int32_t n_src, const int32_t* src_rows,
+                                   const int64_t* rowptr, const int32_t* cols, const float* vals,
+                                   const float* X, float* Y, int32_t d, float* acc, float acc_scale,
+                                   void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && n_src >= 0, "qrec_spmm_csr_scatter_rows_f32: negative size");
+  QREC_REQUIRE(d >= 4 && d <= 128 && d % 4 == 0, "qrec_spmm_csr_scatter_rows_f32: d=%d unsupported (multiple of 4, 4..128)", d);
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && X && Y, "qrec_spmm_csr_scatter_rows_f32: null pointer");
+  QREC_REQUIRE(X != Y, "qrec_spmm_csr_scatter_rows_f32: X and Y must not alias");
+  cudaStream_t st = (cudaStream_t)stream;
+  QREC_CUDA(cudaMemsetAsync(Y, 0, sizeof(float) * (size_t)n_rows * d, st));
+  if (n_src == 0) return QREC_OK;
+  QREC_REQUIRE(src_rows && cols && vals, "qrec_spmm_csr_scatter_rows_f32: null index pointer");
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+#define QREC_SCAT(LPR)                                                                           \
+  {                                                                                              \
+    const long long per_block = 8 * (32 / LPR);                                                  \
+    long long blocks = ((long long)n_src * 64 + per_block - 1) / per_block;                      \
+    if (blocks > cap) blocks = cap;                                                              \
+    spmm_scatter_rows_kernel<LPR><<<(int)blocks, 256, 0, st>>>(                                  \
+        n_src, src_rows, reinterpret_cast<const long long*>(rowptr), cols, vals, X, Y, nvec, acc, acc_scale); \
+  }
+  if (nvec <= 4) QREC_SCAT(4)
+  else if (nvec <= 8) QREC_SCAT(8)
+  else if (nvec <= 16) QREC_SCAT(16)
+  else QREC_SCAT(32)
+#undef QREC_SCAT
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

@@ -361,6 +361,18 @@ def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
     return Y
 
 
+def spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scale=0.0):
+    """Y = A @ X for a symmetric CSR A and an X whose non-zero rows are exactly `src_rows`."""
+    torch = _torch()
+    check(lib.qrec_spmm_csr_scatter_rows_f32(rowptr.shape[0] - 1, src_rows.shape[0], _dev(src_rows, torch.int32, 'src_rows'),
+                                             _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
+                                             _dev(vals, torch.float32, 'vals'), _dev(X, torch.float32, 'X'),
+                                             _dev(Y, torch.float32, 'Y'), X.shape[1],
+                                             _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                             float(acc_scale), _stream()), 'qrec_spmm_csr_scatter_rows_f32')
+    return Y
+
+
 def bpr_grad_scatter(U, V, u, i, j, eps, reg, gU, gV, loss):
     torch = _torch()
     check(lib.qrec_bpr_grad_scatter_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'),

@@ -65,7 +65,13 @@ class LightGCN(GraphRecommender):
         cur = self._grad
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
-            self.norm_adj.matmul(cur, nxt, acc=self._total, acc_scale=s)
+            if k == 0 and hasattr(self.norm_adj, 'matmul_sparse_rows') and u.shape[0] <= 8192:
+                # the loss gradient is non-zero only in the batch's rows: scatter along their edges
+                import torch
+                nz = torch.unique(torch.cat([u, i + self.num_users, j + self.num_users])).int()
+                self.norm_adj.matmul_sparse_rows(cur, nz, nxt, acc=self._total, acc_scale=s)
+            else:
+                self.norm_adj.matmul(cur, nxt, acc=self._total, acc_scale=s)
             cur = nxt
         self._step += 1
         E.adam_dense_tf1(self.ego, self._adam_m, self._adam_v, self._total, self.lRate, self._step)

@@ -165,3 +165,27 @@ def test_adam_tf1(torch, E):
         np.testing.assert_allclose(dv.cpu().numpy(), var, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(dm.cpu().numpy(), m, rtol=1e-5, atol=1e-7)   # fma vs mul+add near 0
         np.testing.assert_allclose(dvv.cpu().numpy(), v, rtol=1e-5, atol=1e-9)
+
+
+def test_spmm_scatter_rows_equals_dense_product(torch, E, golden_graph):
+    """First-backward shortcut: X non-zero only in a few rows -> scatter along those rows' edges."""
+    adj = _golden_adj(golden_graph)
+    n, d = adj.shape[0], 64
+    rng = np.random.default_rng(4)
+    nz = np.unique(rng.integers(0, n, 700)).astype(np.int32)
+    nz = np.concatenate([nz, np.array([int(np.argmax(np.diff(adj.indptr)))], np.int32)])     # + the longest row
+    nz = np.unique(nz)
+    X = np.zeros((n, d), np.float32)
+    X[nz] = rng.standard_normal((len(nz), d)).astype(np.float32)
+    acc0 = rng.standard_normal((n, d)).astype(np.float32)
+    acc = _dev(torch, acc0)
+    Y = torch.full((n, d), 5.0, device='cuda')
+    E.spmm_csr_scatter_rows(_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data),
+                            _dev(torch, nz), _dev(torch, X), Y, acc=acc, acc_scale=0.25)
+    ref = adj.astype(np.float64) @ X.astype(np.float64)
+    np.testing.assert_allclose(Y.cpu().numpy(), ref, rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(acc.cpu().numpy(), acc0 + 0.25 * ref, rtol=1e-4, atol=1e-6)
+    # no source rows: Y is just zero-filled
+    E.spmm_csr_scatter_rows(_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data),
+                            torch.zeros(0, dtype=torch.int32, device='cuda'), _dev(torch, X), Y)
+    assert bool((Y == 0).all())
