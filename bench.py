@@ -187,6 +187,9 @@ def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, wa
     class Adj(object):
         def matmul(self, X, out, acc=None, acc_scale=0.0):
             return E.spmm_csr(rowptr, cols, vals, X, out, acc=acc, acc_scale=acc_scale, rowsplit=True)
+
+        def matmul_sparse_rows(self, X, src_rows, out, acc=None, acc_scale=0.0):
+            return E.spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, out, acc=acc, acc_scale=acc_scale)
     m = Shell()
     m.num_users, m.num_items, m.emb_size, m.n_layers = U, I, D, layers
     m.lRate, m.regU, m.device, m.norm_adj = 0.001, 0.001, dev, Adj()

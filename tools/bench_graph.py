@@ -78,6 +78,9 @@ def main():
     class Adj(object):
         def matmul(self, Xin, out, acc=None, acc_scale=0.0):
             return E.spmm_csr(rowptr, cols, vals, Xin, out, acc=acc, acc_scale=acc_scale, rowsplit=not args.zipf)
+
+        def matmul_sparse_rows(self, Xin, src_rows, out, acc=None, acc_scale=0.0):
+            return E.spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, Xin, out, acc=acc, acc_scale=acc_scale)
     m.norm_adj = Adj()
     m.ego = X.clone()
     m.user_embeddings, m.item_embeddings = m.ego[:U], m.ego[U:]
