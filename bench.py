@@ -11,9 +11,9 @@ reference's own iteration order (model/ranking/BPR.py:31-33: users in id order, 
 The same epoch with the triples in SHUFFLED order through the order-agnostic kernel
 (qrec_bpr_sgd_batch_f32) is timed too and reported under "shuffled_order".
 with the (u,i) pairs, the rated-item CSR and both tables already resident in HBM.  `e2e` is the
-same epoch entered through the host-buffer C-ABI call (qrec_bpr_epoch_host): the step's
-(u,i,j) index arrays start in pinned HOST memory and are copied to the device inside the timed
-region, the loss comes back to the host.
+same epoch entered through the host-buffer C-ABI call (qrec_bpr_epoch_usermajor_host): the step's
+positives (CSR: rowptr + item ids) start in pinned HOST memory and are copied to the device chunk by
+chunk inside the timed region, overlapped with the kernel; the loss comes back to the host.
 
 Multi-GPU (strong scaling of the fixed 50M set): users are range-partitioned, so P rows and each
 user's triples live on one rank; Q (25.6 MB) is replicated and its per-rank deltas are summed
@@ -394,12 +394,15 @@ def run_ours(args):
     shuffled_ms = float(ts.item())
 
     # ------------------------------------------------------------------ e2e: host buffers
-    hu, hi = su.cpu().pin_memory(), si.cpu().pin_memory()
-    hj = sj.cpu().pin_memory()
+    hu, hj = None, None
+    hi = i.cpu().pin_memory()                                  # this epoch's positives, CSR order
+    hrp = csr_rowptr.cpu().pin_memory()
     pipe = E.HostPipeline(local, chunk_triples=1 << 22)
+    e2e_epoch = [1000]
 
     def e2e_step():
-        l = pipe.bpr_epoch(P, Q, hu, hi, hj, LR, REG_U, REG_I)
+        e2e_epoch[0] += 1
+        l = pipe.bpr_epoch_usermajor(P, Q, hrp, hi, rowptr, cols, NUM_ITEMS, 2024, e2e_epoch[0], LR, REG_U, REG_I)
         qsync.sync()
         torch.cuda.synchronize()
         return l
@@ -458,12 +461,14 @@ def run_ours(args):
                             if tr and tr.get('launch_triples') else None),
                 'traffic_note': (tr or {}).get('note', 'no ncu --set full capture recorded yet'),
             },
-            'e2e': {'value': e2e_value, 'unit': 'triples/s', 'h2d_bytes_per_step': 12 * n_local * world,
+            'e2e': {'value': e2e_value, 'unit': 'triples/s',
+                    'h2d_bytes_per_step': (4 * n_local + 8 * (users_local + 1)) * world,
                     'd2h_bytes_per_step': 8 * world, 'ms_per_step': 1e3 * e2e_s / args.steps,
-                    'api': 'qrec_bpr_epoch_host: pinned host (u,i,j) -> chunked H2D overlapped with K1 -> loss D2H'},
+                    'api': 'qrec_bpr_epoch_usermajor_host: pinned host CSR positives (rowptr, i) -> chunked H2D overlapped '
+                           'with the fused sampling+SGD kernel -> loss D2H; negatives are drawn on the device'},
             'shuffled_order': {'value': n_local * world / (shuffled_ms * 1e-3), 'unit': 'triples/s', 'ms_per_step': shuffled_ms,
                                'kernel': 'bpr_sgd_batch_kernel<16,1,4> (order-agnostic: every triple loads and RED-adds all 3 rows)',
-                               'note': 'same epoch with the (u,i) pairs shuffled once; also the order used by the e2e host path'},
+                               'note': 'same epoch with the (u,i) pairs shuffled once (stand-alone Philox sampler + order-agnostic kernel)'},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }

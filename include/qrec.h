@@ -200,6 +200,17 @@ int qrec_bpr_epoch_host(qrec_ctx* ctx, float* dev_P, float* dev_Q, int32_t d, in
                         const int32_t* host_u, const int32_t* host_i, const int32_t* host_j,
                         float lr, float reg_u, float reg_i, double* host_loss);
 
+/* The same pipeline for a user-major epoch (the reference's loop order): the positives live in HOST
+ * memory as CSR (host_rowptr int64[n_users+1], host_i int32[n]); chunks of whole users are copied while
+ * the fused sampling+SGD kernel (qrec_bpr_epoch_usermajor_f32) runs the previous chunk.  Negatives are
+ * drawn on the device against the resident rejection CSR.  No user may have more positives than the
+ * ctx chunk size.  Synchronous on return. */
+int qrec_bpr_epoch_usermajor_host(qrec_ctx* ctx, float* dev_P, float* dev_Q, int32_t d, int32_t n_users,
+                                  const int64_t* host_rowptr, const int32_t* host_i,
+                                  const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
+                                  int32_t num_items, uint64_t seed, uint32_t epoch, float lr,
+                                  float reg_u, float reg_i, double* host_loss);
+
 /* =====================================================================================
  * K2 -- Y = A * X for the normalised joint adjacency, CSR, fp32 values, int32 columns.
  * Replaces tf.sparse_tensor_dense_matmul(norm_adj, E): model/ranking/LightGCN.py:17,

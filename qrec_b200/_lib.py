@@ -68,6 +68,8 @@ SIGNATURES = {
     'qrec_ctx_destroy': (C.c_int, [vp]),
     'qrec_bpr_epoch_host': (C.c_int, [vp, vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                       C.c_float, C.c_float, c_f64p]),
+    'qrec_bpr_epoch_usermajor_host': (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_uint64,
+                                                C.c_uint32, C.c_float, C.c_float, C.c_float, c_f64p]),
     'qrec_spmm_csr_f32': (C.c_int, [C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
     'qrec_spmm_csr_rowsplit_f32': (C.c_int, [C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
     'qrec_spmm_csr_scatter_rows_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),

@@ -490,7 +490,9 @@ __global__ void __launch_bounds__(256, 3)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
                          const int* __restrict__ i, const int* __restrict__ j, float lr,
-                         float reg_u, float reg_i, double* loss, FusedSampler fs) {
+                         float reg_u, float reg_i, double* loss, FusedSampler fs, long long trip_off) {
+  // rowptr holds GLOBAL triple offsets; i/j are indexed relative to trip_off (a chunk of users of a
+  // larger epoch: the host pipeline stages one chunk at a time).  Philox counters use global indices.
   constexpr int GPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -513,7 +515,7 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
       const int step = (len + LPR - 1) / LPR;
       int pp = a + (l + 1) * step - 1;
       if (pp > b) pp = b;
-      const bool pred = __ldg(rowptr + pp + 1) > lo;
+      const bool pred = (__ldg(rowptr + pp + 1) - trip_off) > lo;
       const unsigned bal = (__ballot_sync(gmask, pred) & gmask) >> (sub * LPR);
       const int f = __ffs(bal) - 1;
       int pf = a + (f + 1) * step - 1;
@@ -522,7 +524,7 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
       b = pf;
     }
     int uu = a;
-    long long uend = __ldg(rowptr + uu + 1);
+    long long uend = __ldg(rowptr + uu + 1) - trip_off;
     float* prow = P + (size_t)uu * d + l * 4;
     float4 p = act ? *reinterpret_cast<const float4*>(prow) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 p0 = p;
@@ -537,9 +539,9 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
           long long ue = uend;
           while (ue <= base + l) {
             ++us;
-            ue = __ldg(rowptr + us + 1);
+            ue = __ldg(rowptr + us + 1) - trip_off;
           }
-          mj = qrec::sample_negative(base + l, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items, fs.rated_cols,
+          mj = qrec::sample_negative(base + l + trip_off, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items, fs.rated_cols,
                                      __ldg(fs.rated_rowptr + us), __ldg(fs.rated_rowptr + us + 1));
           if (fs.j_out != nullptr) fs.j_out[base + l] = mj;
         } else {
@@ -568,7 +570,7 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
               if (act) red_add_v4(prow, make_float4(p.x - p0.x, p.y - p0.y, p.z - p0.z, p.w - p0.w));
               do {
                 ++uu;
-                uend = __ldg(rowptr + uu + 1);
+                uend = __ldg(rowptr + uu + 1) - trip_off;
               } while (uend <= t);
               prow = P + (size_t)uu * d + l * 4;
               p = act ? *reinterpret_cast<const float4*>(prow) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -766,15 +768,21 @@ int qrec_bpr_sgd_batch_tma_f32(float* P, float* Q, int32_t d, int64_t n, const i
   return QREC_OK;
 }
 
-static int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
-                            const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i, double* loss,
-                            bool sample, FusedSampler fs, cudaStream_t st) {
+}  // extern "C" (reopened below)
+
+namespace qrec {
+int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
+                     const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i, double* loss,
+                     bool sample, const int64_t* rated_rowptr, const int32_t* rated_cols, int32_t num_items,
+                     uint64_t seed, uint32_t epoch, int32_t* j_out, long long trip_off, cudaStream_t st) {
+  FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
+                     (uint32_t)(seed >> 32), epoch, j_out};
   const int nvec = d / 4;
   const long long cap = (long long)sm_count() * 8;
   constexpr int CH = 32;
 #define QREC_UM2(LPR, FULLV, SAMPLEV)                                                            \
   bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV><<<(int)blocks, 256, 0, st>>>(             \
-      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs)
+      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off)
 #define QREC_UM(LPR)                                                                             \
   {                                                                                              \
     const long long per_block = 8 * (32 / LPR);                                                  \
@@ -792,6 +800,9 @@ static int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int6
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }
+}  // namespace qrec
+
+extern "C" {
 
 int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
                                const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i,
@@ -801,8 +812,8 @@ int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, i
   QREC_REQUIRE(n_users >= 0 && n >= 0, "qrec_bpr_sgd_usermajor_f32: negative size");
   if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && j, "qrec_bpr_sgd_usermajor_f32: null index pointer");
-  FusedSampler fs = {nullptr, nullptr, 0, 0u, 0u, 0u, nullptr};
-  return launch_usermajor(P, Q, d, n_users, n, rowptr, i, j, lr, reg_u, reg_i, loss, false, fs, (cudaStream_t)stream);
+  return qrec::launch_usermajor(P, Q, d, n_users, n, rowptr, i, j, lr, reg_u, reg_i, loss, false, nullptr, nullptr, 0,
+                                0, 0, nullptr, 0, (cudaStream_t)stream);
 }
 
 int qrec_bpr_epoch_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
@@ -814,9 +825,8 @@ int qrec_bpr_epoch_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users,
   QREC_REQUIRE(n_users >= 0 && n >= 0 && num_items >= 1, "qrec_bpr_epoch_usermajor_f32: bad size");
   if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && rated_rowptr && rated_cols, "qrec_bpr_epoch_usermajor_f32: null index pointer");
-  FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
-                     (uint32_t)(seed >> 32), epoch, j_out};
-  return launch_usermajor(P, Q, d, n_users, n, rowptr, i, nullptr, lr, reg_u, reg_i, loss, true, fs, (cudaStream_t)stream);
+  return qrec::launch_usermajor(P, Q, d, n_users, n, rowptr, i, nullptr, lr, reg_u, reg_i, loss, true, rated_rowptr,
+                                rated_cols, num_items, seed, epoch, j_out, 0, (cudaStream_t)stream);
 }
 
 int qrec_bpr_sgd_staged_f32(float* P, int32_t d, int64_t n, const int32_t* u, const int32_t* pos_i,

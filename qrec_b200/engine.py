@@ -346,6 +346,34 @@ class HostPipeline(object):
         return loss.value
 
 
+def _host_ptr(a, dtype_np, dtype_t, name):
+    torch = _torch()
+    if isinstance(a, np.ndarray):
+        assert a.dtype == dtype_np and a.flags.c_contiguous, name
+        return a.ctypes.data, a.shape[0]
+    assert (not a.is_cuda) and a.dtype == dtype_t and a.is_contiguous(), name
+    return a.data_ptr(), a.shape[0]
+
+
+def _bpr_epoch_usermajor_host(self, P, Q, rowptr, i, rated_rowptr, rated_cols, num_items, seed, epoch, lr, reg_u, reg_i):
+    """HostPipeline method: user-major epoch with the positives (CSR: rowptr int64, i int32) in HOST
+    memory (pinned gives overlap) and fused device-side negative sampling; returns sum(-ln s)."""
+    torch = _torch()
+    prp, nr = _host_ptr(rowptr, np.int64, torch.int64, 'rowptr')
+    pi, _ = _host_ptr(i, np.int32, torch.int32, 'i')
+    torch.cuda.current_stream().synchronize()
+    loss = C.c_double(0.0)
+    check(lib.qrec_bpr_epoch_usermajor_host(self._ctx, _dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), P.shape[1],
+                                            nr - 1, prp, pi, _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
+                                            _dev(rated_cols, torch.int32, 'rated_cols'), int(num_items), int(seed),
+                                            int(epoch), float(lr), float(reg_u), float(reg_i), C.byref(loss)),
+          'qrec_bpr_epoch_usermajor_host')
+    return loss.value
+
+
+HostPipeline.bpr_epoch_usermajor = _bpr_epoch_usermajor_host
+
+
 def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
     """Y = A @ X (CSR fp32); optional fused acc += acc_scale * Y.  `rowsplit` selects the plain
     row-partitioned kernel instead of the nnz-balanced default."""

@@ -473,3 +473,36 @@ def test_fused_epoch_equals_sampler_plus_kernel(torch, E, bpr_ids):
     E.bpr_epoch_usermajor(Pb, Qb, rp, _dev(torch, ci), rrp, rc, ni, 0xfeedface, 6, lr, REG, REG, lb)
     j6 = E.sample_neg_philox(_dev(torch, cu), rrp, rc, ni, 0xfeedface, 6)
     assert not torch.equal(j6, j_ref)
+
+
+def test_usermajor_host_pipeline_matches_single_launch(torch, E):
+    """qrec_bpr_epoch_usermajor_host: positives in HOST memory, chunks of whole users staged while the
+    fused kernel runs; Philox counters are global, so the negatives (and, up to the order in which item
+    deltas land, the tables) equal the single-launch fused epoch whatever the chunking."""
+    rng = np.random.default_rng(31)
+    nu, ni, d = 4000, 50000, 64
+    deg = rng.integers(0, 40, nu); deg[5] = 0; deg[17] = 300
+    rowptr = np.zeros(nu + 1, np.int64); rowptr[1:] = np.cumsum(deg)
+    n = int(rowptr[-1])
+    u = np.repeat(np.arange(nu), deg)
+    i = rng.integers(0, ni, n).astype(np.int32)
+    csr = E.RatedCSR(nu, ni, u, i)
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32); Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    Pa, Qa, Pb, Qb = _dev(torch, P0), _dev(torch, Q0), _dev(torch, P0), _dev(torch, Q0)
+    rrp, rc = _dev(torch, csr.sorted_rowptr), _dev(torch, csr.sorted_cols)
+    la = torch.zeros(1, dtype=torch.float64, device='cuda')
+    lr = 1e-3
+    E.bpr_epoch_usermajor(Pa, Qa, _dev(torch, rowptr), _dev(torch, i), rrp, rc, ni, 77, 2, lr, REG, REG, la)
+    pipe = E.HostPipeline(0, chunk_triples=5000)                    # ~16 chunks, one holds the 300-triple user
+    hl = pipe.bpr_epoch_usermajor(Pb, Qb, torch.from_numpy(rowptr).pin_memory(), torch.from_numpy(i).pin_memory(),
+                                  rrp, rc, ni, 77, 2, lr, REG, REG)
+    torch.cuda.synchronize()
+    P0t, Q0t = _dev(torch, P0), _dev(torch, Q0)
+    assert float(((Pa - P0t) - (Pb - P0t)).abs().max()) <= 0.02 * float((Pa - P0t).abs().max())
+    assert float(((Qa - Q0t) - (Qb - Q0t)).abs().max()) <= 0.02 * float((Qa - Q0t).abs().max())
+    assert abs(hl - la.item()) <= 1e-4 * abs(hl)
+    # a user with more positives than the staging chunk is reported, not silently split
+    small = E.HostPipeline(0, chunk_triples=100)
+    with pytest.raises(E.QRecError):
+        small.bpr_epoch_usermajor(Pb, Qb, rowptr, i, rrp, rc, ni, 77, 2, lr, REG, REG)
+    small.close(); pipe.close()
