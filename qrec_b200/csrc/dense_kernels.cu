@@ -224,6 +224,63 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
   }
 }
 
+
+// Tall-skinny product for the NGCF layer transforms: C[M,N] = alpha * A[M,K] * op(B) + beta * C with
+// N, K <= 64 (a d x d weight) and M = #nodes.  One thread owns one output row: op(B) sits in shared
+// memory (read as broadcast LDS.128), the row's N accumulators in registers; the row of A is streamed
+// with 16-byte loads.  FFMA : LDS = 4 : 1, no cross-thread reduction, no __syncthreads in the loop.
+template <bool TB>
+__global__ void __launch_bounds__(128)
+sgemm_skinny_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int lda,
+                    const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc) {
+  __shared__ __align__(16) float W[64 * 64];            // W[k][n], row pitch 64
+  for (int e = threadIdx.x; e < 64 * 64; e += blockDim.x) {
+    const int k = e >> 6, n = e & 63;
+    float v = 0.f;
+    if (k < K && n < N) v = TB ? B[(size_t)n * ldb + k] : B[(size_t)k * ldb + n];
+    W[e] = v;
+  }
+  __syncthreads();
+  const int n4 = (N + 3) >> 2;
+  for (long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x; row < M;
+       row += (long long)gridDim.x * blockDim.x) {
+    float acc[64];
+#pragma unroll
+    for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+    const float* a = A + (size_t)row * lda;
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      const float4 av = *reinterpret_cast<const float4*>(a + k0);
+      const float ak[4] = {av.x, av.y, av.z, av.w};
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4* wrow = reinterpret_cast<const float4*>(W + (k0 + kk) * 64);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+          if (q < n4) {
+            const float4 w = wrow[q];
+            acc[4 * q + 0] = fmaf(ak[kk], w.x, acc[4 * q + 0]);
+            acc[4 * q + 1] = fmaf(ak[kk], w.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(ak[kk], w.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(ak[kk], w.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+    float* c = C + (size_t)row * ldc;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      if (q < n4) {
+        float4 o = make_float4(alpha * acc[4 * q], alpha * acc[4 * q + 1], alpha * acc[4 * q + 2], alpha * acc[4 * q + 3]);
+        if (beta != 0.f) {
+          const float4 old = *reinterpret_cast<const float4*>(c + 4 * q);
+          o.x += beta * old.x; o.y += beta * old.y; o.z += beta * old.z; o.w += beta * old.w;
+        }
+        *reinterpret_cast<float4*>(c + 4 * q) = o;
+      }
+    }
+  }
+}
+
 // ---- NGCF elementwise pieces (NGCF.py:29-40) ------------------------------------------------------
 // forward: H = leaky_relu(Z, 0.2); H *= mask/keep (mask from Philox, keep prob); Nrm = |H| row norm;
 // out = H / max(|H|, 1e-6).  Stores H (post-dropout) for the backward pass.  warp per row.
@@ -467,6 +524,15 @@ int qrec_sgemm_f32(int32_t trans_a, int32_t trans_b, int32_t M, int32_t N, int32
   QREC_REQUIRE(A && B && C, "qrec_sgemm_f32: null pointer");
   const long long tiles = (long long)((M + 63) / 64) * ((N + 63) / 64);
   cudaStream_t st = (cudaStream_t)stream;
+  // tall-skinny fast path: [M, <=64] x [<=64, <=64] with 16-byte aligned rows (the NGCF layer transforms)
+  if (!trans_a && M >= 4096 && N <= 64 && K <= 64 && (N % 4) == 0 && (K % 4) == 0 && (lda % 4) == 0 && (ldc % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0) {
+    const int grid = grid_for(M, 128);
+    if (trans_b) sgemm_skinny_kernel<true><<<grid, 128, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    else sgemm_skinny_kernel<false><<<grid, 128, 0, st>>>(M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    QREC_LAUNCH_CHECK();
+    return QREC_OK;
+  }
   int ksplit = 1;
   const long long target = (long long)sm_count() * 4;
   if (tiles < target / 2 && K >= 4096) {

@@ -28,7 +28,8 @@ def _dev(torch, a):
 
 
 @pytest.mark.parametrize('M,N,K,ta,tb', [(100, 64, 64, 0, 0), (64, 64, 5000, 1, 0), (333, 70, 17, 0, 1),
-                                          (65, 129, 33, 1, 1), (2048, 2048, 64, 0, 1), (64, 64, 70001, 1, 0)])
+                                          (65, 129, 33, 1, 1), (2048, 2048, 64, 0, 1), (64, 64, 70001, 1, 0),
+                                          (50000, 64, 64, 0, 0), (50001, 64, 64, 0, 1), (9000, 52, 52, 0, 0), (4097, 8, 64, 0, 1)])
 def test_sgemm(torch, E, M, N, K, ta, tb):
     g = torch.Generator(device='cuda'); g.manual_seed(M + N + K)
     A = torch.randn((K, M) if ta else (M, K), device='cuda', generator=g)
