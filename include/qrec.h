@@ -116,23 +116,29 @@ int qrec_bpr_order_prepare(int64_t n, const int32_t* u, const int32_t* i, const 
                            int32_t num_users, int32_t num_items, int32_t* wait_u,
                            int32_t* wait_i, int32_t* wait_j);
 
+/* Depth of the dependency DAG of the sequential loop (number of levels; n / depth = how many triples
+ * are independent on average).  Host, O(n).  Returns -1 on an out-of-range id. */
+int64_t qrec_bpr_order_depth(int64_t n, const int32_t* u, const int32_t* i, const int32_t* j,
+                             int32_t num_users, int32_t num_items);
+
 /* Parity mode: results identical to running BPR.optimization over the triples in array
  * order (Gauss-Seidel SGD, BPR.py:31-39), executed as a dataflow over the per-row
  * dependency chains.  dev_ver_p / dev_ver_q: int32[num_users] / int32[num_items] row
  * version counters, dev_ticket: uint64[1]; all three must be ZERO on entry.
- * dev_loss: double[1], the kernel ADDS sum_k -ln(s_k) (BPR.py:53).  Any d >= 1. */
+ * dev_loss: double[1], the kernel ADDS sum_k -ln(s_k) (BPR.py:53).  Any d >= 1 (<= 256).
+ * n_warps: number of polling warps (0 = fill the GPU); about 4x the DAG width n / depth is best. */
 int qrec_bpr_sgd_ordered_f32(float* dev_P, float* dev_Q, int32_t d, int64_t n,
                              const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
                              const int32_t* dev_wait_u, const int32_t* dev_wait_i,
                              const int32_t* dev_wait_j, int32_t* dev_ver_p, int32_t* dev_ver_q,
                              unsigned long long* dev_ticket, float lr, float reg_u, float reg_i,
-                             double* dev_loss, void* stream);
+                             double* dev_loss, int32_t n_warps, void* stream);
 int qrec_bpr_sgd_ordered_f64(double* dev_P, double* dev_Q, int32_t d, int64_t n,
                              const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
                              const int32_t* dev_wait_u, const int32_t* dev_wait_i,
                              const int32_t* dev_wait_j, int32_t* dev_ver_p, int32_t* dev_ver_q,
                              unsigned long long* dev_ticket, double lr, double reg_u,
-                             double reg_i, double* dev_loss, void* stream);
+                             double reg_i, double* dev_loss, int32_t n_warps, void* stream);
 
 /* Throughput mode: one fused gather -> 2 dots -> sigmoid -> BPR step -> scatter-add kernel.
  * Every triple reads its three rows, applies BPR.py:45-52 to its private copy and adds the

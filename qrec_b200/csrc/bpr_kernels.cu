@@ -648,7 +648,7 @@ template <typename T>
 int launch_ordered(T* P, T* Q, int d, long long n, const int* u, const int* i, const int* j,
                    const int* wu, const int* wi, const int* wj, int* ver_p, int* ver_q,
                    unsigned long long* ticket, T lr, T reg_u, T reg_i, double* loss,
-                   cudaStream_t st) {
+                   int n_warps, cudaStream_t st) {
   QREC_REQUIRE(P && Q && loss && ticket && ver_p && ver_q, "bpr_sgd_ordered: null pointer");
   QREC_REQUIRE(d >= 1 && d <= 256, "bpr_sgd_ordered: d=%d unsupported (1..256)", d);
   QREC_REQUIRE(n >= 0, "bpr_sgd_ordered: n < 0");
@@ -658,7 +658,15 @@ int launch_ordered(T* P, T* Q, int d, long long n, const int* u, const int* i, c
   // 2 CTAs of 8 warps per SM: enough warps to cover the dependency DAG's width at the
   // synthetic scale (~25 independent triples per level in user-major order) without
   // drowning the LSU in pollers.
-  const int grid = sm_count() * 2;
+  // n_warps > 0: the caller knows the width of the dependency DAG (qrec_bpr_order_depth) and asks
+  // for about that many pollers -- thousands of idle warps hammering the version counters slow the
+  // few that can make progress (1.4 independent triples per level on FilmTrust, ~25 at SYN scale)
+  int grid = sm_count() * 2;
+  if (n_warps > 0) {
+    grid = (n_warps + 7) / 8;
+    if (grid < 1) grid = 1;
+    if (grid > sm_count() * 2) grid = sm_count() * 2;
+  }
 #define QREC_ORD(E)                                                                              \
   bpr_sgd_ordered_kernel<T, E><<<grid, 256, 0, st>>>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p,     \
                                                      ver_q, ticket, lr, reg_u, reg_i, loss)
@@ -708,18 +716,18 @@ int qrec_bpr_sgd_ordered_f32(float* P, float* Q, int32_t d, int64_t n, const int
                              const int32_t* i, const int32_t* j, const int32_t* wu,
                              const int32_t* wi, const int32_t* wj, int32_t* ver_p,
                              int32_t* ver_q, unsigned long long* ticket, float lr, float reg_u,
-                             float reg_i, double* loss, void* stream) {
+                             float reg_i, double* loss, int32_t n_warps, void* stream) {
   return launch_ordered<float>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p, ver_q, ticket, lr, reg_u,
-                               reg_i, loss, (cudaStream_t)stream);
+                               reg_i, loss, n_warps, (cudaStream_t)stream);
 }
 
 int qrec_bpr_sgd_ordered_f64(double* P, double* Q, int32_t d, int64_t n, const int32_t* u,
                              const int32_t* i, const int32_t* j, const int32_t* wu,
                              const int32_t* wi, const int32_t* wj, int32_t* ver_p,
                              int32_t* ver_q, unsigned long long* ticket, double lr,
-                             double reg_u, double reg_i, double* loss, void* stream) {
+                             double reg_u, double reg_i, double* loss, int32_t n_warps, void* stream) {
   return launch_ordered<double>(P, Q, d, n, u, i, j, wu, wi, wj, ver_p, ver_q, ticket, lr, reg_u,
-                                reg_i, loss, (cudaStream_t)stream);
+                                reg_i, loss, n_warps, (cudaStream_t)stream);
 }
 
 int qrec_bpr_sgd_batch_f32(float* P, float* Q, int32_t d, int64_t n, const int32_t* u,

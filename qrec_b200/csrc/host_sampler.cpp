@@ -210,6 +210,25 @@ int qrec_sample_pointwise(qrec_mt19937* st, int64_t n, int32_t num_items, const 
   return QREC_OK;
 }
 
+int64_t qrec_bpr_order_depth(int64_t n, const int32_t* u, const int32_t* i, const int32_t* j,
+                             int32_t num_users, int32_t num_items) {
+  if (n <= 0 || !u || !i || !j || num_users <= 0 || num_items <= 0) return 0;
+  // level(k) = 1 + max level of the previous toucher of P[u_k], Q[i_k], Q[j_k]
+  std::vector<int64_t> lu((size_t)num_users, 0), lq((size_t)num_items, 0);
+  int64_t depth = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const int32_t uu = u[k], ii = i[k], jj = j[k];
+    if (uu < 0 || uu >= num_users || ii < 0 || ii >= num_items || jj < 0 || jj >= num_items) return -1;
+    int64_t lv = lu[uu];
+    if (lq[ii] > lv) lv = lq[ii];
+    if (lq[jj] > lv) lv = lq[jj];
+    ++lv;
+    lu[uu] = lq[ii] = lq[jj] = lv;
+    if (lv > depth) depth = lv;
+  }
+  return depth;
+}
+
 int qrec_bpr_order_prepare(int64_t n, const int32_t* u, const int32_t* i, const int32_t* j,
                            int32_t num_users, int32_t num_items, int32_t* wait_u,
                            int32_t* wait_i, int32_t* wait_j) {

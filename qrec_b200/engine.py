@@ -176,6 +176,17 @@ class MT19937(object):
         return ou, oi, oy
 
 
+def bpr_order_depth(u, i, j, num_users, num_items):
+    """Number of levels of the sequential loop's dependency DAG (host, O(n))."""
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    j = np.ascontiguousarray(j, dtype=np.int32)
+    depth = int(lib.qrec_bpr_order_depth(u.shape[0], _i32p(u), _i32p(i), _i32p(j), int(num_users), int(num_items)))
+    if depth < 0:
+        raise QRecError('qrec_bpr_order_depth: id out of range')
+    return depth
+
+
 def bpr_order_prepare(u, i, j, num_users, num_items):
     """Row-version numbers for the dependency-ordered kernel (host, O(n))."""
     u = np.ascontiguousarray(u, dtype=np.int32)
@@ -224,8 +235,9 @@ def sample_neg_philox(u, sorted_rowptr, sorted_cols, num_items, seed, epoch, out
     return out
 
 
-def bpr_sgd_ordered(P, Q, u, i, j, wu, wi, wj, lr, reg_u, reg_i, loss):
-    """Parity mode: sequential-equivalent BPR.optimization over the triples in array order."""
+def bpr_sgd_ordered(P, Q, u, i, j, wu, wi, wj, lr, reg_u, reg_i, loss, n_warps=0):
+    """Parity mode: sequential-equivalent BPR.optimization over the triples in array order.
+    n_warps: pollers to launch (0 = fill the GPU); ~4x the DAG width (n / bpr_order_depth) is best."""
     torch = _torch()
     f64 = P.dtype == torch.float64
     dt = torch.float64 if f64 else torch.float32
@@ -240,7 +252,7 @@ def bpr_sgd_ordered(P, Q, u, i, j, wu, wi, wj, lr, reg_u, reg_i, loss):
              _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'), _dev(wu, torch.int32, 'wu'),
              _dev(wi, torch.int32, 'wi'), _dev(wj, torch.int32, 'wj'), ver_p.data_ptr(),
              ver_q.data_ptr(), ticket.data_ptr(), float(lr), float(reg_u), float(reg_i),
-             _dev(loss, torch.float64, 'loss'), _stream()), 'qrec_bpr_sgd_ordered')
+             _dev(loss, torch.float64, 'loss'), int(n_warps), _stream()), 'qrec_bpr_sgd_ordered')
     return loss
 
 
