@@ -63,7 +63,7 @@ class BPR(IterativeRecommender):
                 width = len(u) / max(1, E.bpr_order_depth(u, i, j, self.num_users, self.num_items))
                 E.bpr_sgd_ordered(P, Q, du, di, dj, torch.from_numpy(wu).to(dev), torch.from_numpy(wi).to(dev),
                                   torch.from_numpy(wj).to(dev), self.lRate, self.regU, self.regI, acc[0:1],
-                                  n_warps=int(min(2368, max(32, 4 * width))))
+                                  n_warps=int(min(2368, max(64, 16 * width))))
             E.sumsq(P, acc[1:2])
             E.sumsq(Q, acc[2:3])
             a = acc.cpu().numpy()
