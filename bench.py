@@ -489,7 +489,7 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--q-syncs', type=int, default=4, help='item-table all-reduces per step when N>1')
+    ap.add_argument('--q-syncs', type=int, default=2, help='item-table all-reduces per step when N>1')
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
     ap.add_argument('--ref-sample', type=int, default=4_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
