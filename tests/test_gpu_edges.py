@@ -51,7 +51,7 @@ def test_bad_arguments_are_reported(torch, E):
         lambda: E.bpr_sgd_batch(torch.zeros(4, 260, device='cuda'), torch.zeros(4, 260, device='cuda'), i1, i1, i1, 0.1, 0, 0, loss),
         lambda: E.bpr_sgd_batch(good, good, i1.long(), i1, i1, 0.1, 0, 0, loss),               # wrong index dtype
         lambda: E.bpr_sgd_batch(good.double(), good, i1, i1, i1, 0.1, 0, 0, loss),            # wrong table dtype
-        lambda: E.bpr_sgd_batch(good.t(), good, i1, i1, i1, 0.1, 0, 0, loss),                 # non-contiguous
+        lambda: E.bpr_sgd_batch(torch.zeros(64, 8, device='cuda').t(), torch.zeros(4, 64, device='cuda'), i1, i1, i1, 0.1, 0, 0, loss),  # non-contiguous
         lambda: E.spmm_csr(torch.zeros(5, dtype=torch.int64, device='cuda'), i1, torch.zeros(1, device='cuda'), good, good),  # X aliases Y
         lambda: E.adam_dense_tf1(good, good, good, good, 0.1, 0),                              # t must be >= 1
         lambda: E.tc_gemm(torch.zeros(8, 6, device='cuda'), torch.zeros(6, 4, device='cuda'), torch.zeros(8, 4, device='cuda')),  # K % 4
