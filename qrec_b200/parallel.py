@@ -262,3 +262,101 @@ class ShardedItemTableBPR(object):
         self._scatter(self.Q, local_rows, back)
         self.bytes_sent += 4 * 2 * n + 2 * 4 * d * (2 * n - sc[self.rank])
         return self.loss
+
+
+# =============================================================================================
+# LightGCN, user-partitioned / item-replicated (the decomposition that scales: SURVEY.md 8e, config 3)
+# =============================================================================================
+def shard_bipartite_by_user(rowptr, cols, vals, num_users, num_items, rank, world):
+    """Blocks of the normalised joint adjacency that rank `rank` needs when it owns the users
+    [lo, hi) and every rank holds ALL item rows:
+        A_ui [hi-lo, I]  rows = local users, cols = item ids          (user rows of the joint CSR)
+        A_iu [I, hi-lo]  rows = items, cols = LOCAL user ids          (its transpose, same values)
+    Inputs: the joint (U+I)x(U+I) CSR as device tensors.  Setup code (torch ops)."""
+    dev = rowptr.device
+    lo, hi = user_range(rank, world, num_users)
+    a, b = int(rowptr[lo].item()), int(rowptr[hi].item())
+    ui_rowptr = (rowptr[lo:hi + 1] - a).contiguous()
+    ui_cols = (cols[a:b] - num_users).int().contiguous()
+    ui_vals = vals[a:b].contiguous()
+    nloc = hi - lo
+    lens = ui_rowptr[1:] - ui_rowptr[:-1]
+    users_local = torch.repeat_interleave(torch.arange(nloc, device=dev), lens)
+    key = ui_cols.long() * nloc + users_local                 # sort edges by (item, local user)
+    order = torch.argsort(key)
+    iu_cols = users_local[order].int().contiguous()
+    iu_vals = ui_vals[order].contiguous()
+    counts = torch.bincount(ui_cols.long(), minlength=num_items)
+    iu_rowptr = torch.zeros(num_items + 1, dtype=torch.int64, device=dev)
+    iu_rowptr[1:] = torch.cumsum(counts, 0)
+    return (ui_rowptr, ui_cols, ui_vals), (iu_rowptr, iu_cols, iu_vals), (lo, hi)
+
+
+class UserShardedLightGCN(object):
+    """LightGCN minibatch step (model/ranking/LightGCN.py:13-39 semantics) with the USER rows of the ego
+    table partitioned over the ranks and the (25.6 MB at the benchmark scale) ITEM rows replicated.
+
+    One propagation layer on rank r:
+        users:  Y_u = A_ui E_i                      local K2 SpMM, no communication
+        items:  Y_i = sum_r A_iu^(r) E_u^(r)        local K2 SpMM of the rank's own edges, then an NCCL
+                                                    all-reduce of the [I, d] partial sums
+    so the traffic per layer is one all-reduce of the item table instead of an all-gather of the whole
+    (U+I) table.  K3 runs on the triples whose user the rank owns (item gradients are partial sums,
+    all-reduced once); the backward pass is the same operator; Adam is local for users and identical
+    (replicated) for items."""
+
+    def __init__(self, A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, group=None,
+                 spmm=None, grad=None, adam=None, scale=None, axpy=None):
+        from . import engine as E
+        self.A_ui, self.A_iu = A_ui, A_iu
+        self.Eu, self.Ei = E_u_local, E_i
+        self.n_layers, self.lr, self.reg, self.lo = n_layers, lr, reg, user_lo
+        self.group = group
+        dev, d = E_i.device, E_i.shape[1]
+        nu, ni = E_u_local.shape[0], E_i.shape[0]
+        z = lambda n: torch.zeros(n, d, device=dev)           # noqa: E731
+        self.bu, self.bi = [z(nu), z(nu)], [z(ni), z(ni)]
+        self.mean_u, self.mean_i = z(nu), z(ni)
+        self.tot_u, self.tot_i = z(nu), z(ni)
+        self.gu, self.gi = z(nu), z(ni)
+        self.mu, self.vu, self.mi, self.vi = z(nu), z(nu), z(ni), z(ni)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self.step = 0
+        self._spmm = spmm or (lambda A, X, Y, acc, s: E.spmm_csr(A[0], A[1], A[2], X, Y, acc=acc, acc_scale=s, rowsplit=True))
+        self._grad = grad or (lambda U_, V_, u, i, j, gU, gV, loss: E.bpr_grad_scatter(U_, V_, u, i, j, 10e-8, self.reg, gU, gV, loss))
+        self._adam = adam or (lambda var, m, v, g, t: E.adam_dense_tf1(var, m, v, g, self.lr, t))
+        self._scale = scale or (lambda dst, src, s: E.axpby(dst, src, src, s, 0.0))
+        self._axpy = axpy or (lambda dst, src, s: E.axpby(dst, dst, src, 1.0, s))
+
+    def _allreduce(self, t):
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def _propagate(self, src_u, src_i, acc_u, acc_i):
+        s = 1.0 / (self.n_layers + 1)
+        self._scale(acc_u, src_u, s)
+        self._scale(acc_i, src_i, s)
+        cu, ci = src_u, src_i
+        for k in range(self.n_layers):
+            nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            self._spmm(self.A_ui, ci, nu_, acc_u, s)          # users: local
+            self._spmm(self.A_iu, cu, ni_, None, 0.0)         # items: this rank's partial sums
+            self._allreduce(ni_)
+            self._axpy(acc_i, ni_, s)
+            cu, ci = nu_, ni_
+
+    def train_step(self, u, i, j):
+        """u, i, j: the WHOLE minibatch (global ids, int32 device tensors) on every rank."""
+        self._propagate(self.Eu, self.Ei, self.mean_u, self.mean_i)
+        mine = (u >= self.lo) & (u < self.lo + self.Eu.shape[0])
+        lu, li, lj = (u[mine] - self.lo).contiguous(), i[mine].contiguous(), j[mine].contiguous()
+        self.gu.zero_(); self.gi.zero_(); self.loss.zero_()
+        if lu.numel():
+            self._grad(self.mean_u, self.mean_i, lu, li, lj, self.gu, self.gi, self.loss)
+        self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
+        self._allreduce(self.loss)
+        self._propagate(self.gu, self.gi, self.tot_u, self.tot_i)
+        self.step += 1
+        self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
+        self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
+        return self.loss

@@ -228,3 +228,61 @@ def test_sharded_item_table_bpr_world2():
     out = mgr.dict()
     mp.spawn(_sharded_bpr_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+# ---------------------------------------------------------------------------------------------
+# LightGCN, user-partitioned / item-replicated: one all-reduce of the item block per layer
+# ---------------------------------------------------------------------------------------------
+def _user_sharded_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import bpr_oracle as O
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        U, I, d, L, lr, reg = 9, 6, 4, 2, 0.01, 0.001          # U not a multiple of the world size
+        A = _toy_graph(U, I, seed=3)
+        rp, co, va = (torch.from_numpy(x) for x in (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data))
+        A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, U, I, rank, world)
+        # the two blocks are transposes of each other and together cover the rank's edges
+        D_ui = torch.sparse_csr_tensor(A_ui[0], A_ui[1].long(), A_ui[2], size=(hi - lo, I)).to_dense()
+        D_iu = torch.sparse_csr_tensor(A_iu[0], A_iu[1].long(), A_iu[2], size=(I, hi - lo)).to_dense()
+        assert torch.equal(D_ui.t(), D_iu)
+        assert np.allclose(D_ui.numpy(), A.toarray()[lo:hi, U:])
+        rng = np.random.default_rng(1)
+        ego = (rng.standard_normal((U + I, d)) * 0.1).astype(np.float32)
+
+        def spmm(Ablk, X, Y, acc, s):
+            M = torch.sparse_csr_tensor(Ablk[0], Ablk[1].long(), Ablk[2], size=(Ablk[0].numel() - 1, X.shape[0]))
+            Y.copy_(M @ X)
+            if acc is not None:
+                acc.add_(Y, alpha=s)
+
+        def grad(Ue, Ve, u, i, j, gU, gV, loss):
+            l, a, b = O.bpr_loss_grad(Ue.numpy(), Ve.numpy(), u.numpy(), i.numpy(), j.numpy(), 10e-8, reg)
+            gU.add_(torch.from_numpy(a).float()); gV.add_(torch.from_numpy(b).float())
+            loss += l
+        m = parallel.UserShardedLightGCN(
+            A_ui, A_iu, torch.from_numpy(ego[lo:hi].copy()), torch.from_numpy(ego[U:].copy()), L, lr, reg, lo,
+            spmm=spmm, grad=grad, adam=lambda var, mm, v, g, t: O.adam_tf1(var.numpy(), mm.numpy(), v.numpy(), g.numpy(), lr, t),
+            scale=lambda dst, src, s: dst.copy_(src * s), axpy=lambda dst, src, s: dst.add_(src, alpha=s))
+        Ur, Vr = ego[:U].copy(), ego[U:].copy()
+        mU, vU, mV, vV = (np.zeros_like(x) for x in (Ur, Ur, Vr, Vr))
+        for step in range(3):
+            u = rng.integers(0, U, 7).astype(np.int32); i = rng.integers(0, I, 7).astype(np.int32)
+            j = rng.integers(0, I, 7).astype(np.int32)
+            ref_loss = O.lightgcn_step(A, Ur, Vr, mU, vU, mV, vV, u, i, j, L, lr, reg, step + 1)
+            loss = m.train_step(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
+            assert np.allclose(m.Eu.numpy(), Ur[lo:hi], rtol=1e-3, atol=1e-6), (rank, step)
+            assert np.allclose(m.Ei.numpy(), Vr, rtol=1e-3, atol=1e-6), (rank, step)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_user_sharded_lightgcn_matches_single_process_world2():
+    port = 35500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_user_sharded_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}

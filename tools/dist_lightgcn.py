@@ -18,6 +18,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--layers', type=int, default=3)
     ap.add_argument('--batch', type=int, default=2048)
+    ap.add_argument('--scheme', default='user', choices=['user', 'rows'],
+                    help='user: users partitioned + items replicated (all-reduce of the item block per layer); '
+                         'rows: all rows partitioned (all-gather of the whole table per layer)')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -32,12 +35,19 @@ def main():
     def build(U, I):
         data = synthetic.make_interactions(U, I, DEG, device=dev)           # same seed on every rank
         rp, co, va = synthetic.build_norm_adj(data, U, I, dev)
-        part = parallel.NodePartition(U, I, world)
-        lrp, lco, lva = parallel.shard_adjacency(rp, co, va, part, rank)
         g = torch.Generator(device=dev); g.manual_seed(3)
         ego = torch.randn(U + I, D, device=dev, generator=g) * 0.005
-        mine = part.local_nodes(rank).to(dev)
-        m = parallel.ShardedLightGCN(part, rank, lrp, lco, lva, ego[mine].contiguous(), args.layers, 0.001, 0.001)
+        if args.scheme == 'rows':
+            part = parallel.NodePartition(U, I, world)
+            lrp, lco, lva = parallel.shard_adjacency(rp, co, va, part, rank)
+            mine = part.local_nodes(rank).to(dev)
+            m = parallel.ShardedLightGCN(part, rank, lrp, lco, lva, ego[mine].contiguous(), args.layers, 0.001, 0.001)
+        else:
+            A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, U, I, rank, world)
+            part = None
+            mine = torch.cat([torch.arange(lo, hi, device=dev), torch.arange(U, U + I, device=dev)])
+            m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[lo:hi].clone(), ego[U:].clone(), args.layers, 0.001, 0.001, lo)
+            m.local_nnz = int(A_ui[1].numel()) * 2
         return data, (rp, co, va), ego, part, mine, m
 
     # ---------------- parity on a small graph (every rank also runs the 1-GPU step)
@@ -68,9 +78,10 @@ def main():
         l_ref = ref.train_step(bu, bi, bj).item()
         l = m.train_step(bu, bi, bj).item()
         assert abs(l - l_ref) <= 1e-5 * abs(l_ref), (l, l_ref)
-        torch.testing.assert_close(m.ego, ref.ego[mine], rtol=2e-3, atol=2e-6)
+        got = m.ego if args.scheme == 'rows' else torch.cat([m.Eu, m.Ei])
+        torch.testing.assert_close(got, ref.ego[mine], rtol=2e-3, atol=2e-6)
     if rank == 0:
-        print(json.dumps({'parity': 'sharded == single-GPU LightGCN step', 'world': world, 'graph': [U, I, U * DEG]}))
+        print(json.dumps({'parity': 'sharded (%s) == single-GPU LightGCN step' % args.scheme, 'world': world, 'graph': [U, I, U * DEG]}))
     del data, rp, co, va, ego, m, ref
     torch.cuda.empty_cache()
 
@@ -99,7 +110,8 @@ def main():
     if rank == 0:
         ms = float(t.item())
         print(json.dumps({'lightgcn_sharded_step_ms': ms, 'world': world, 'layers': args.layers, 'batch': args.batch,
-                          'epoch_s_at_batch': ms * (-(-U * DEG // args.batch)) / 1e3, 'local_nnz': int(m.cols.numel())}))
+                          'epoch_s_at_batch': ms * (-(-U * DEG // args.batch)) / 1e3, 'scheme': args.scheme,
+                          'local_nnz': int(m.cols.numel()) if args.scheme == 'rows' else m.local_nnz}))
     if world > 1:
         dist.destroy_process_group()
 
