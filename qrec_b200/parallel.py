@@ -327,20 +327,30 @@ class UserShardedLightGCN(object):
         self._adam = adam or (lambda var, m, v, g, t: E.adam_dense_tf1(var, m, v, g, self.lr, t))
         self._scale = scale or (lambda dst, src, s: E.axpby(dst, src, src, s, 0.0))
         self._axpy = axpy or (lambda dst, src, s: E.axpby(dst, dst, src, 1.0, s))
+        # sparse-source product (first backward layer): Y[dst] += a * X[src] over the edges of the listed
+        # source rows; only available with the CUDA kernels (the gloo test injects dense stand-ins)
+        self._scatter = None if spmm is not None else (
+            lambda A, rows, X, Y, acc, s: E.spmm_csr_scatter_rows(A[0], A[1], A[2], rows, X, Y, acc=acc, acc_scale=s))
 
     def _allreduce(self, t):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
-    def _propagate(self, src_u, src_i, acc_u, acc_i):
+    def _propagate(self, src_u, src_i, acc_u, acc_i, nz_u=None, nz_i=None):
+        """nz_u / nz_i: the only non-zero rows of src_u / src_i (the loss gradient touches the batch rows
+        only), so the first layer scatters along those rows' edges instead of a full SpMM."""
         s = 1.0 / (self.n_layers + 1)
         self._scale(acc_u, src_u, s)
         self._scale(acc_i, src_i, s)
         cu, ci = src_u, src_i
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
-            self._spmm(self.A_ui, ci, nu_, acc_u, s)          # users: local
-            self._spmm(self.A_iu, cu, ni_, None, 0.0)         # items: this rank's partial sums
+            if k == 0 and nz_u is not None and self._scatter is not None:
+                self._scatter(self.A_iu, nz_i, ci, nu_, acc_u, s)     # A_ui G_i through the items' edge lists
+                self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)    # A_iu G_u through the users' edge lists
+            else:
+                self._spmm(self.A_ui, ci, nu_, acc_u, s)      # users: local
+                self._spmm(self.A_iu, cu, ni_, None, 0.0)     # items: this rank's partial sums
             self._allreduce(ni_)
             self._axpy(acc_i, ni_, s)
             cu, ci = nu_, ni_
@@ -355,7 +365,11 @@ class UserShardedLightGCN(object):
             self._grad(self.mean_u, self.mean_i, lu, li, lj, self.gu, self.gi, self.loss)
         self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
         self._allreduce(self.loss)
-        self._propagate(self.gu, self.gi, self.tot_u, self.tot_i)
+        if u.shape[0] <= 8192 and self._scatter is not None:
+            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=torch.unique(lu).int(),
+                            nz_i=torch.unique(torch.cat([i, j])).int())
+        else:
+            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i)
         self.step += 1
         self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
         self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
