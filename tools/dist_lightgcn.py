@@ -79,7 +79,12 @@ def main():
         l = m.train_step(bu, bi, bj).item()
         assert abs(l - l_ref) <= 1e-5 * abs(l_ref), (l, l_ref)
         got = m.ego if args.scheme == 'rows' else torch.cat([m.Eu, m.Ei])
-        torch.testing.assert_close(got, ref.ego[mine], rtol=2e-3, atol=2e-6)
+        # gradients first (Adam's first steps turn a tiny gradient difference into a visible table
+        # difference wherever |g| ~ eps, so the tables get a looser absolute tolerance)
+        gtot = m.total if args.scheme == 'rows' else torch.cat([m.tot_u, m.tot_i])
+        gref = ref._total[mine]
+        assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max()), 'gradient mismatch'
+        torch.testing.assert_close(got, ref.ego[mine], rtol=2e-3, atol=2e-4)
     if rank == 0:
         print(json.dumps({'parity': 'sharded (%s) == single-GPU LightGCN step' % args.scheme, 'world': world, 'graph': [U, I, U * DEG]}))
     del data, rp, co, va, ego, m, ref
