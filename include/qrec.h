@@ -235,10 +235,11 @@ int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* dev_r
                                const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
                                float* dev_acc, float acc_scale, void* stream);
 
-/* Y = A X when X is non-zero only in the n_src rows listed in dev_src_rows (the first backward
- * product of a minibatch step: the loss gradient touches at most 3B rows).  A must be symmetric
- * (column r = row r), as the normalised joint adjacency is.  Y is zero-filled here, then
- * Y[c] += a_rc X[r] over the edges of the listed rows; optional acc += acc_scale * Y. */
+/* Sparse-source product (the first backward layer of a minibatch step: the loss gradient touches at
+ * most 3B rows).  (rowptr, cols, vals) is a CSR whose ROWS are source nodes and whose column ids index
+ * rows of Y; Y (n_rows rows) is zero-filled here, then Y[c] += a_rc X[r] over the edges of the n_src
+ * listed source rows r; optional acc[c] += acc_scale * a_rc X[r].  With the symmetric joint adjacency
+ * this is Y = A X for an X that is non-zero only in the listed rows. */
 int qrec_spmm_csr_scatter_rows_f32(int32_t n_rows, int32_t n_src, const int32_t* dev_src_rows,
                                    const int64_t* dev_rowptr, const int32_t* dev_cols,
                                    const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,

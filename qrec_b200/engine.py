@@ -402,9 +402,12 @@ def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
 
 
 def spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scale=0.0):
-    """Y = A @ X for a symmetric CSR A and an X whose non-zero rows are exactly `src_rows`."""
+    """Y[dst] += a * X[src] over the edge lists (CSR rows) of the source rows `src_rows`, after
+    zero-filling Y: Y = B^T X for the CSR matrix B = (rowptr, cols, vals) restricted to those rows.
+    For the symmetric joint adjacency this is Y = A X with an X whose non-zero rows are `src_rows`."""
     torch = _torch()
-    check(lib.qrec_spmm_csr_scatter_rows_f32(rowptr.shape[0] - 1, src_rows.shape[0], _dev(src_rows, torch.int32, 'src_rows'),
+    assert X.shape[0] == rowptr.shape[0] - 1, 'X has one row per CSR row (source node)'
+    check(lib.qrec_spmm_csr_scatter_rows_f32(Y.shape[0], src_rows.shape[0], _dev(src_rows, torch.int32, 'src_rows'),
                                              _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
                                              _dev(vals, torch.float32, 'vals'), _dev(X, torch.float32, 'X'),
                                              _dev(Y, torch.float32, 'Y'), X.shape[1],
