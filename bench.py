@@ -174,33 +174,21 @@ def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, wa
     (model/ranking/LightGCN.py:35-39) -- on the 1M x 100K x 50M-edge graph.  Step time does not
     depend on the batch size B (SpMM bound), so the epoch time is step x ceil(50M / B); both the
     reference-style B=2048 and a large batch are reported, extrapolated from `steps` timed steps."""
-    from qrec_b200.model.ranking.LightGCN import LightGCN
     U, I, N = NUM_USERS, NUM_ITEMS, NUM_USERS + NUM_ITEMS
     rowptr, cols, vals = synthetic.build_norm_adj(data, U, I, dev)
     nnz = int(cols.numel())
 
-    class Shell(LightGCN):
-        def __init__(self):
-            pass
-
-    class Adj(object):
-        def matmul(self, X, out, acc=None, acc_scale=0.0):
-            return E.spmm_csr(rowptr, cols, vals, X, out, acc=acc, acc_scale=acc_scale, rowsplit=True)
-
-        def matmul_sparse_rows(self, X, src_rows, out, acc=None, acc_scale=0.0):
-            return E.spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, out, acc=acc, acc_scale=acc_scale)
-    m = Shell()
-    m.num_users, m.num_items, m.emb_size, m.n_layers = U, I, D, layers
-    m.lRate, m.regU, m.device, m.norm_adj = 0.001, 0.001, dev, Adj()
+    # the step runs on the bipartite blocks A_ui [U,I] / A_iu [I,U] of the normalised adjacency (the
+    # same operator as the joint (U+I)^2 matrix; it is also the multi-GPU decomposition, world = 1 here)
+    from qrec_b200 import parallel
+    A_ui, A_iu, _ = parallel.shard_bipartite_by_user(rowptr, cols, vals, U, I, 0, 1)
     g = torch.Generator(device=dev); g.manual_seed(5)
-    m.ego = torch.randn(N, D, device=dev, generator=g) * 0.005
-    m.user_embeddings, m.item_embeddings = m.ego[:U], m.ego[U:]
-    m._buf = [torch.empty(N, D, device=dev) for _ in range(2)]
-    m._mean, m._grad, m._total = (torch.zeros(N, D, device=dev) for _ in range(3))
-    m._adam_m, m._adam_v = torch.zeros(N, D, device=dev), torch.zeros(N, D, device=dev)
-    m._loss, m._step = torch.zeros(1, dtype=torch.float64, device=dev), 0
+    ego = torch.randn(N, D, device=dev, generator=g) * 0.005
+    m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[:U].clone(), ego[U:].clone(), layers, 0.001, 0.001, 0)
+    m._loss = m.loss
     spmm_algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)                 # SURVEY 8(d) no-reuse gather model
-    res = {'layers': layers, 'rows': N, 'nnz': nnz, 'semantics': 'full propagation + backward + dense Adam per minibatch'}
+    res = {'layers': layers, 'rows': N, 'nnz': nnz, 'semantics': 'full propagation + backward + dense Adam per minibatch',
+           'impl': 'parallel.UserShardedLightGCN at world=1: bipartite blocks A_ui/A_iu, sparse first backward layer'}
     perm = torch.randperm(U * DEGREE, device=dev, generator=g)
     for B in (2048, 65536):
         idx = perm[:B]
@@ -221,7 +209,7 @@ def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, wa
         res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
                                'epoch_extrapolated_from_steps': steps, 'algorithmic_GB_per_step': step_bytes / 1e9,
                                'frac_of_hbm_peak': step_bytes / ms / 1e6 / peak, 'loss': float(m._loss.item())}
-    X, Y = m.ego, m._buf[0]
+    X, Y = ego, torch.empty_like(ego)
     for _ in range(warmup):
         E.spmm_csr(rowptr, cols, vals, X, Y, rowsplit=True)
     torch.cuda.synchronize()
