@@ -59,7 +59,16 @@ class GraphRecommender(DeepRecommender):
         return scale.dot(adj).dot(scale)
 
     def create_joint_sparse_adj_tensor(self):
-        return DeviceCSR(self.create_joint_sparse_adjaceny(), self._device())
+        """The same matrix as create_joint_sparse_adjaceny(), assembled on the device from the
+        id-mapped training pairs (sort + run-length; duplicates summed like scipy's constructor)."""
+        import torch
+        from ..graph_build import norm_adjacency_csr
+        dev = self._device()
+        u, i, _ = self.data.training_ids()
+        rowptr, cols, vals = norm_adjacency_csr(torch.from_numpy(u), torch.from_numpy(i), self.num_users,
+                                                self.num_items, device=dev)
+        n = self.num_users + self.num_items
+        return DeviceCSR.from_tensors((n, n), rowptr, cols, vals)
 
     def create_sparse_rating_matrix(self):
         """(U x I) COO float32, entry = 1/|items rated by the user| (graphRecommender.py:41-51)."""

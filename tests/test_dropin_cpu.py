@@ -115,3 +115,25 @@ def test_shuffle_training_data_equals_random_shuffle(golden_bpr):
     random.seed(5)
     m.shuffle_training_data()
     assert m.data.trainingData == expect and random.getstate() == st
+
+
+def test_device_adjacency_builder_equals_reference_matrix(golden_graph, graph_ids):
+    """graph_build.norm_adjacency_csr (sort + run-length, here on CPU tensors) reproduces the scipy
+    matrix of base/graphRecommender.py:10-29 recorded from the reference -- structure exactly, values
+    to fp32 rounding -- including summed duplicate interactions and an isolated node."""
+    import torch
+    from qrec_b200.graph_build import norm_adjacency_csr
+    g = golden_graph
+    u, i, nu, ni = graph_ids
+    rowptr, cols, vals = norm_adjacency_csr(torch.from_numpy(u), torch.from_numpy(i), nu, ni)
+    assert np.array_equal(rowptr.numpy(), g['adj_indptr'])
+    assert np.array_equal(cols.numpy(), g['adj_indices'])
+    np.testing.assert_allclose(vals.numpy(), g['adj_data'], rtol=5e-7, atol=0)       # <= 2 ulp of fp32
+    # duplicates are summed before normalisation; node without edges keeps an empty row
+    from oracle import bpr_oracle as O
+    uu = np.array([0, 0, 1, 1, 1, 3]); ii = np.array([2, 2, 0, 2, 0, 1])
+    ref = O.norm_adjacency(5, 3, uu, ii)
+    rp, co, va = norm_adjacency_csr(torch.from_numpy(uu), torch.from_numpy(ii), 5, 3)
+    assert np.array_equal(rp.numpy(), ref.indptr) and np.array_equal(co.numpy(), ref.indices)
+    np.testing.assert_allclose(va.numpy(), ref.data, rtol=5e-7)
+    assert rp[3] == rp[2] and rp[5] == rp[4] + 0                       # users 2 and 4 are isolated
