@@ -20,15 +20,25 @@ class DeviceCSR(object):
         import torch
         mat = mat.tocsr()
         mat.sort_indices()
-        self.shape = mat.shape
-        self.nnz = mat.nnz
+        self._finish(mat.shape, torch.from_numpy(mat.indptr.astype(np.int64)).to(device),
+                     torch.from_numpy(mat.indices.astype(np.int32)).to(device),
+                     torch.from_numpy(mat.data.astype(np.float32)).to(device))
+
+    @classmethod
+    def from_tensors(cls, shape, rowptr, cols, vals):
+        """Wraps CSR arrays that already live on the device (graph_build.norm_adjacency_csr)."""
+        self = cls.__new__(cls)
+        self._finish(tuple(shape), rowptr, cols, vals)
+        return self
+
+    def _finish(self, shape, rowptr, cols, vals):
+        self.shape = shape
+        self.rowptr, self.cols, self.vals = rowptr, cols, vals
+        self.nnz = int(cols.shape[0])
         # short, even rows: one lane group per row is fastest (no atomics); a long-tailed degree
         # distribution needs the nnz-balanced kernel or the hot rows serialise the launch
-        lengths = np.diff(mat.indptr)
-        self.rowsplit = bool(lengths.size == 0 or lengths.max() <= 4096)
-        self.rowptr = torch.from_numpy(mat.indptr.astype(np.int64)).to(device)
-        self.cols = torch.from_numpy(mat.indices.astype(np.int32)).to(device)
-        self.vals = torch.from_numpy(mat.data.astype(np.float32)).to(device)
+        lengths = rowptr[1:] - rowptr[:-1]
+        self.rowsplit = bool(lengths.numel() == 0 or int(lengths.max().item()) <= 4096)
 
     def matmul_sparse_rows(self, X, src_rows, out, acc=None, acc_scale=0.0):
         """out = A @ X when only the rows `src_rows` of X are non-zero (A symmetric)."""

@@ -137,3 +137,19 @@ def test_device_adjacency_builder_equals_reference_matrix(golden_graph, graph_id
     assert np.array_equal(rp.numpy(), ref.indptr) and np.array_equal(co.numpy(), ref.indices)
     np.testing.assert_allclose(va.numpy(), ref.data, rtol=5e-7)
     assert rp[3] == rp[2] and rp[5] == rp[4] + 0                       # users 2 and 4 are isolated
+
+
+def test_device_csr_constructors_agree():
+    """DeviceCSR from a scipy matrix and from device-built arrays expose the same fields (CPU tensors
+    here; the kernels are exercised by the GPU suites)."""
+    import scipy.sparse as sp
+    import torch
+    from qrec_b200.base.graphRecommender import DeviceCSR
+    A = sp.random(30, 30, density=0.2, format='csr', dtype=np.float32, random_state=0)
+    a = DeviceCSR(A, 'cpu')
+    b = DeviceCSR.from_tensors(A.shape, a.rowptr, a.cols, a.vals)
+    assert (a.nnz, a.shape, a.rowsplit) == (b.nnz, b.shape, b.rowsplit) and a.nnz == A.nnz
+    for name in ('matmul', 'matmul_sparse_rows'):
+        assert hasattr(b, name)
+    long_row = sp.csr_matrix((np.ones(5000, np.float32), (np.zeros(5000, int), np.arange(5000))), shape=(2, 5000))
+    assert DeviceCSR(long_row, 'cpu').rowsplit is False
