@@ -153,3 +153,23 @@ def test_device_csr_constructors_agree():
         assert hasattr(b, name)
     long_row = sp.csr_matrix((np.ones(5000, np.float32), (np.zeros(5000, int), np.arange(5000))), shape=(2, 5000))
     assert DeviceCSR(long_row, 'cpu').rowsplit is False
+
+
+def test_graph_recommender_adj_tensor_method_on_cpu_tensors(golden_graph, tmp_path, monkeypatch):
+    """GraphRecommender.create_joint_sparse_adj_tensor end to end with the device stubbed to 'cpu':
+    the DeviceCSR it returns holds the reference's matrix."""
+    import torch
+    from qrec_b200.base.graphRecommender import GraphRecommender
+    g = golden_graph
+    monkeypatch.chdir(tmp_path)
+    train = [[u, i, 1.0] for u, i in zip(g['train_users'].tolist(), g['train_items'].tolist())]
+    m = GraphRecommender(_conf(str(g['conf'])), train, [])
+    monkeypatch.setattr(GraphRecommender, '_device', lambda self: torch.device('cpu'))
+    adj = m.create_joint_sparse_adj_tensor()
+    assert adj.shape == tuple(g['adj_shape']) and adj.nnz == len(g['adj_indices']) and adj.rowsplit
+    assert np.array_equal(adj.rowptr.numpy(), g['adj_indptr']) and np.array_equal(adj.cols.numpy(), g['adj_indices'])
+    np.testing.assert_allclose(adj.vals.numpy(), g['adj_data'], rtol=5e-7)
+    # and the scipy-returning method is still the reference's matrix
+    sp_adj = m.create_joint_sparse_adjaceny().tocsr(); sp_adj.sort_indices()
+    assert np.array_equal(sp_adj.indices, g['adj_indices'])
+    np.testing.assert_allclose(sp_adj.data, g['adj_data'], rtol=1e-6)
