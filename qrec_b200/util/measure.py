@@ -24,10 +24,17 @@ class Measure(object):
 
     @staticmethod
     def NDCG(origin, res, N):
+        # plain left-to-right accumulation, like the reference: Python >= 3.12's sum() compensates
+        # (Neumaier) and would change the last digit of the printed metric
         total = 0
         for user in res:
-            dcg = sum(1.0 / math.log(rank + 2) for rank, item in enumerate(res[user]) if item[0] in origin[user])
-            idcg = sum(1.0 / math.log(rank + 2) for rank in range(min(N, len(origin[user]))))
+            dcg = 0
+            for rank, item in enumerate(res[user]):
+                if item[0] in origin[user]:
+                    dcg += 1.0 / math.log(rank + 2)
+            idcg = 0
+            for rank in range(min(N, len(origin[user]))):
+                idcg += 1.0 / math.log(rank + 2)
             total += dcg / idcg
         return total / len(res)
 
@@ -51,11 +58,17 @@ class Measure(object):
 
     @staticmethod
     def MAE(res):
-        return sum(abs(e[2] - e[3]) for e in res) / len(res) if res else 0
+        error = 0
+        for e in res:
+            error += abs(e[2] - e[3])
+        return error / len(res) if res else error
 
     @staticmethod
     def RMSE(res):
-        return math.sqrt(sum((e[2] - e[3]) ** 2 for e in res) / len(res)) if res else 0
+        error = 0
+        for e in res:
+            error += (e[2] - e[3]) ** 2
+        return math.sqrt(error / len(res)) if res else error
 
     @staticmethod
     def ratingMeasure(res):
