@@ -21,12 +21,12 @@ def ref():
     sys.modules.setdefault('tensorflow', types.ModuleType('tensorflow'))
     saved = {k: sys.modules.get(k) for k in ('util', 'util.config', 'util.measure', 'util.qmath', 'util.dataSplit',
                                              'util.io', 'util.log', 'data', 'data.rating', 'base', 'base.recommender',
-                                             'base.iterativeRecommender')}
+                                             'base.iterativeRecommender', 'base.deepRecommender')}
     sys.path.insert(0, REF)
     try:
         mods = {}
         for name in ('util.config', 'util.measure', 'util.qmath', 'util.io', 'util.dataSplit', 'data.rating',
-                     'util.log', 'base.recommender', 'base.iterativeRecommender'):
+                     'util.log', 'base.recommender', 'base.iterativeRecommender', 'base.deepRecommender'):
             mods[name] = importlib.import_module(name)
         yield mods
     finally:
@@ -188,3 +188,37 @@ def test_eval_ranking_and_lr_schedule_equal_reference(ref, tmp_path, monkeypatch
     assert outs[0][1] == outs[1][1]                 # every recommendation line, scores included
     assert outs[0][2] == outs[1][2]                 # metric strings
     assert outs[0][3] == outs[1][3] and outs[0][4] == outs[1][4]   # MT19937 state and shuffled list
+
+
+@pytest.mark.parametrize('seed', [0, 7, 2024])
+def test_minibatch_samplers_equal_reference_on_random_data(ref, tmp_path, monkeypatch, seed):
+    """DeepRecommender.next_batch_pairwise / next_batch_pointwise (C MT19937 clone underneath) against
+    the reference generators (Python `random`) on random interaction lists with duplicates and
+    non-binary ratings: every batch, the shuffled list and the generator state afterwards."""
+    import contextlib
+    import io
+    from qrec_b200.base.deepRecommender import DeepRecommender as Mine
+    from qrec_b200.util.config import ModelConf
+    Theirs = ref['base.deepRecommender'].DeepRecommender
+    monkeypatch.chdir(tmp_path)
+    rng = random.Random(seed)
+    conf_text = ('ratings=x\nratings.setup=-columns 0 1 2\nmodel.name=LightGCN\nevaluation.setup=-ap 0.2\n'
+                 'item.ranking=on -topN 10\nnum.factors=8\nnum.max.epoch=1\nbatch_size=128\n'
+                 'learnRate=-init 0.01 -max 1\nreg.lambda=-u 0.001 -i 0.001 -b 0.2 -s 0.2\noutput.setup=off -dir ./results/\n')
+    train = [['u%d' % rng.randint(0, 50), 'i%d' % rng.randint(0, 80), float(rng.randint(1, 5))] for _ in range(1000)]
+    rc = ref['util.config'].ModelConf.__new__(ref['util.config'].ModelConf)
+    rc.config = dict(ModelConf.from_string(conf_text).config)
+    a = Mine(ModelConf.from_string(conf_text), [r[:] for r in train], [])
+    b = Theirs(rc, [r[:] for r in train], [])
+    results = []
+    for m in (a, b):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m.readConfiguration()
+        random.seed(seed)
+        pair = [tuple(np.asarray(x).tolist() for x in batch) for batch in m.next_batch_pairwise()]
+        point = [tuple(np.asarray(x).tolist() for x in batch) for batch in m.next_batch_pointwise()]
+        results.append((pair, point, [r[:] for r in m.data.trainingData], random.getstate()))
+    assert len(results[0][0]) == 8 and len(results[0][0][-1][0]) == 1000 - 7 * 128
+    assert results[0][0] == results[1][0]          # pairwise batches (u, i, j)
+    assert results[0][1] == results[1][1]          # pointwise batches (u, i, y), 5 rows per interaction
+    assert results[0][2] == results[1][2] and results[0][3] == results[1][3]
