@@ -132,3 +132,36 @@ def test_order_prepare():
         E.bpr_order_prepare(np.array([0], np.int32), np.array([1], np.int32), np.array([1], np.int32), 1, 2)
     with pytest.raises(E.QRecError):
         E.bpr_order_prepare(np.array([5], np.int32), np.array([1], np.int32), np.array([0], np.int32), 1, 2)
+
+
+def test_bpr_epoch_with_non_binarised_ratings_uses_positive_set_only():
+    """BPR.trainModel builds PositiveSet from ratings >= 1 (model/ranking/BPR.py:21-25), iterates it and
+    rejects negatives against IT (not against every rated item).  Restated inline with Python's
+    `random`; the C sampler must give the same triples and leave the same generator state."""
+    from collections import defaultdict
+    from qrec_b200.data.rating import Rating
+    from qrec_b200.util.config import ModelConf
+    rng = random.Random(3)
+    train = [['u%d' % rng.randint(0, 30), 'i%d' % rng.randint(0, 40), float(rng.choice([0.5, 1, 2, 3]))] for _ in range(500)]
+    d = Rating(ModelConf.from_string('ratings=x\nevaluation.setup=-ap 0.2\n'), [r[:] for r in train], [])
+    positive = defaultdict(dict)
+    for user in d.user:
+        for item in d.trainSet_u[user]:
+            if d.trainSet_u[user][item] >= 1:
+                positive[user][item] = 1
+    item_list = list(d.item.keys())
+    random.seed(5)
+    ref = []
+    for user in positive:
+        for item in positive[user]:
+            neg = random.choice(item_list)
+            while neg in positive[user]:
+                neg = random.choice(item_list)
+            ref.append((d.user[user], d.item[item], d.item[neg]))
+    state = random.getstate()
+    random.seed(5)
+    m = E.MT19937()
+    m.setstate(random.getstate())
+    u, i, j = m.sample_bpr_epoch(d.rated_csr())
+    assert np.array_equal(np.stack([u, i, j], 1), np.array(ref)) and m.getstate() == state
+    assert any(v < 1 for row in d.trainSet_u.values() for v in row.values())      # the filter mattered
