@@ -485,8 +485,8 @@ struct FusedSampler {
   int* j_out;                      // may be null
 };
 
-template <int LPR, int G, int CH, bool FULL, bool SAMPLE>   // FULL: d == 4*LPR (every lane owns a slice)
-__global__ void __launch_bounds__(256, 3)
+template <int LPR, int G, int CH, bool FULL, bool SAMPLE, int MINB = 3>   // FULL: d == 4*LPR (every lane owns a slice)
+__global__ void __launch_bounds__(256, MINB)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
                          const int* __restrict__ i, const int* __restrict__ j, float lr,
@@ -788,6 +788,14 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
   const int nvec = d / 4;
   const long long cap = (long long)sm_count() * 8;
   constexpr int CH = 32;
+  // experiment switch (d = 64 only), measured on 50 M triples: 0 = 3 CTAs/SM, 4 triples in flight
+  // (default, 5.80 ms); 1 = 4 CTAs/SM at 64 registers (spills, 7.08 ms); 2 = 2 CTAs/SM, 8 triples in
+  // flight (5.75 ms) -- occupancy and load depth are not the limiter any more
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("QREC_K1_UM_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
 #define QREC_UM2(LPR, FULLV, SAMPLEV)                                                            \
   bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV><<<(int)blocks, 256, 0, st>>>(             \
       P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off)
@@ -796,6 +804,13 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
     const long long per_block = 8 * (32 / LPR);                                                  \
     long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
     if (blocks > cap) blocks = cap;                                                              \
+    if (nvec == LPR && LPR == 16 && variant == 1) {                                              \
+      if (sample) bpr_sgd_usermajor_kernel<16, 4, CH, true, true, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+      else bpr_sgd_usermajor_kernel<16, 4, CH, true, false, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+    } else if (nvec == LPR && LPR == 16 && variant == 2) {                                       \
+      if (sample) bpr_sgd_usermajor_kernel<16, 8, CH, true, true, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+      else bpr_sgd_usermajor_kernel<16, 8, CH, true, false, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+    } else                                                                                       \
     if (nvec == LPR) { if (sample) QREC_UM2(LPR, true, true); else QREC_UM2(LPR, true, false); } \
     else { if (sample) QREC_UM2(LPR, false, true); else QREC_UM2(LPR, false, false); }           \
   }
