@@ -222,3 +222,21 @@ def test_minibatch_samplers_equal_reference_on_random_data(ref, tmp_path, monkey
     assert results[0][0] == results[1][0]          # pairwise batches (u, i, j)
     assert results[0][1] == results[1][1]          # pointwise batches (u, i, y), 5 rows per interaction
     assert results[0][2] == results[1][2] and results[0][3] == results[1][3]
+
+
+def test_interaction_table_equals_reference_loader_and_rating(ref):
+    """f-3: the array-backed table built from the shipped FilmTrust file has the reference's id space."""
+    import contextlib
+    import io
+    from qrec_b200.data.interactions import InteractionTable
+    path = os.path.join(REF, 'dataset', 'FilmTrust', 'ratings.txt')
+    rc = ref['util.config'].ModelConf.__new__(ref['util.config'].ModelConf)
+    rc.config = {'ratings.setup': '-columns 0 1 2', 'evaluation.setup': '-ap 0.2 -b 1'}
+    with contextlib.redirect_stdout(io.StringIO()):
+        recs = ref['util.io'].FileIO.loadDataSet(rc, path, binarized=True, threshold=1.0)
+    data = ref['data.rating'].Rating(rc, recs, [])
+    t = InteractionTable.from_text(path, binarize_threshold=1.0)
+    assert len(t) == len(recs) == 34437
+    assert t.user_names.tolist() == [data.id2user[k] for k in range(len(data.user))]
+    assert t.item_names.tolist() == [data.id2item[k] for k in range(len(data.item))]
+    assert t.u.tolist() == [data.user[r[0]] for r in recs] and t.i.tolist() == [data.item[r[1]] for r in recs]
