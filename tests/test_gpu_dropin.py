@@ -223,3 +223,39 @@ def test_user_sharded_lightgcn_world1_equals_dropin_step(golden_graph, tmp_path)
         gtot = torch.cat([m.tot_u, m.tot_i])
         assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max())
         torch.testing.assert_close(torch.cat([m.Eu, m.Ei]), ref.ego, rtol=2e-3, atol=2e-4)
+
+
+def test_scale_bpr_from_interaction_table(golden_bpr, tmp_path):
+    """f-3 end to end: InteractionTable -> ScaleBPR (fused user-major epochs, device negatives) trains
+    FilmTrust to the quality band of the drop-in class, follows the reference's lr schedule rules, and
+    ranks through the batched device evaluation."""
+    from qrec_b200.data.interactions import InteractionTable
+    from qrec_b200.scale import ScaleBPR
+    from qrec_b200.util.measure import Measure
+    g = golden_bpr
+    train, test = _lists(g)
+    table = InteractionTable.from_records(train)
+    assert table.user_names.tolist() == g['user_names'].tolist() and table.item_names.tolist() == g['item_names'].tolist()
+    np.random.seed(0)
+    m = ScaleBPR(table, emb_size=64, lr=0.01, reg_u=0.001, reg_i=0.001, seed=5).fit(30)
+    P0 = np.random.RandomState(0).rand(len(g['user_names']), 64) / 3
+    losses = [h[1] for h in m.history]
+    assert losses[0] > losses[5] > losses[-1] and abs(losses[0] - g['loss'][0]) < 0.15 * g['loss'][0]
+    for (e0, l0, d0, lr0), (e1, l1, d1, lr1) in zip(m.history, m.history[1:]):
+        expect = lr0 if e0 == 1 else lr0 * (1.05 if d0 > 0 else 0.5)        # rule applied after epoch e0
+        assert abs(lr1 - min(expect, 1.0)) < 1e-12
+    P, Q = m.tables()
+    assert P.shape == P0.shape and np.isfinite(P).all() and np.isfinite(Q).all()
+    # evaluate on the test users that exist in training
+    lut_u = {n: k for k, n in enumerate(table.user_names.tolist())}
+    origin = {}
+    for u, i, r in test:
+        if u in lut_u:
+            origin.setdefault(u, {})[i] = r
+    users = list(origin)
+    ids, vals = m.top_n([lut_u[u] for u in users], 10)
+    names = table.item_names
+    res = {u: [(names[k], float(v)) for k, v in zip(ids[r], vals[r])] for r, u in enumerate(users)}
+    out = Measure.rankingMeasure(origin, res, [10])
+    got = {x.split(':')[0]: float(x.split(':')[1]) for x in out[1:]}
+    assert got['Precision'] > 0.30 and got['NDCG'] > 0.45
