@@ -99,7 +99,8 @@ int qrec_sample_pointwise(qrec_mt19937* st, int64_t n, int32_t num_items, const 
  * K0 (fast) -- device sampler: Philox4x32-10 counter RNG + binary-search rejection.
  * Same role as base/deepRecommender.py:47-49 for throughput runs (the MT19937 stream is
  * serial by construction).  j[k] = (philox(seed; k, attempt, epoch).x * num_items) >> 32,
- * attempt = 0,1,... until j is not rated by u[k].  Deterministic in (seed, epoch, k).
+ * attempt = 0,1,... until j is not rated by u[k].  Deterministic in (seed, epoch, k).  A user whose row
+ * already contains every item gets the first draw (no valid negative exists; the kernel must not spin).
  * ===================================================================================== */
 int qrec_sample_neg_philox(int64_t n, int32_t num_items, const int32_t* dev_u,
                            const int64_t* dev_sorted_rowptr, const int32_t* dev_sorted_cols,

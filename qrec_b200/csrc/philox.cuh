@@ -24,11 +24,15 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ int sample_negative(long long k, uint32_t epoch, uint32_t seed_lo, uint32_t seed_hi,
                                                int num_items, const int* __restrict__ cols, long long lo0,
                                                long long hi0) {
+  // a user whose (deduplicated) row already holds every item has no negative: take the first draw
+  // instead of spinning forever (the host sampler reports this case as an error; a kernel cannot)
+  const bool saturated = (hi0 - lo0) >= (long long)num_items;
   uint32_t attempt = 0;
   while (true) {
     uint32_t w[4];
     philox4x32_10((uint32_t)k, (uint32_t)((unsigned long long)k >> 32), attempt, epoch, seed_lo, seed_hi, w);
     const int j = (int)(((unsigned long long)w[0] * (unsigned long long)(uint32_t)num_items) >> 32);
+    if (saturated) return j;
     long long lo = lo0, hi = hi0;
     bool hit = false;
     while (lo < hi) {

@@ -242,6 +242,12 @@ def test_philox_sampler_bit_exact_and_valid(torch, E, bpr_ids):
     uu = torch.zeros(257, dtype=torch.int32, device='cuda')
     j2 = E.sample_neg_philox(uu, _dev(torch, csr2.sorted_rowptr), _dev(torch, csr2.sorted_cols), ni, 9, 1)
     assert bool((j2 == ni - 1).all())
+    # a user that rated EVERY item has no negative: the kernel returns the first draw instead of hanging
+    csr3 = E.RatedCSR(1, 37, np.zeros(37, np.int64), np.arange(37))
+    j3 = E.sample_neg_philox(torch.zeros(100, dtype=torch.int32, device='cuda'), _dev(torch, csr3.sorted_rowptr),
+                             _dev(torch, csr3.sorted_cols), 37, 3, 0)
+    torch.cuda.synchronize()
+    assert int(j3.min()) >= 0 and int(j3.max()) < 37
 
 
 def test_sumsq(torch, E):
