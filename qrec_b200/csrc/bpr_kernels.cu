@@ -86,12 +86,16 @@ bpr_sgd_ordered_kernel(T* __restrict__ P, T* __restrict__ Q, int d, long long n,
     // lanes 0..2 each watch one row version
     const int* vp = lane == 0 ? ver_p + uu : (lane == 1 ? ver_q + ii : ver_q + jj);
     const int need = lane == 0 ? wu[k] : (lane == 1 ? wi[k] : wj[k]);
-    unsigned backoff = 8;
+    unsigned backoff = 8, polls = 0;
     while (true) {
       const int have = lane < 3 ? ld_acquire_gpu(vp) : need;
       if (__all_sync(0xffffffffu, have == need)) break;
       __nanosleep(backoff);
       if (backoff < 64) backoff <<= 1;
+      // a ticket waits for at most (#resident warps) predecessors, i.e. milliseconds; ~10 s of polling
+      // means the wait_* arrays do not describe this triple stream -- abort the launch instead of
+      // hanging the GPU (the host sees a launch failure)
+      if (++polls > (1u << 27)) __trap();
     }
     T* pr = P + (size_t)uu * d;
     T* qir = Q + (size_t)ii * d;
