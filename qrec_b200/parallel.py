@@ -336,6 +336,13 @@ class UserShardedLightGCN(object):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
 
+    def _allreduce_async(self, t):
+        """Starts the all-reduce and returns its handle (None at world size 1): the caller launches the
+        user-side SpMM of the same layer before waiting, so the NVLink transfer hides behind it."""
+        if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return None
+
     def _propagate(self, src_u, src_i, acc_u, acc_i, nz_u=None, nz_i=None):
         """nz_u / nz_i: the only non-zero rows of src_u / src_i (the loss gradient touches the batch rows
         only), so the first layer scatters along those rows' edges instead of a full SpMM."""
@@ -345,13 +352,19 @@ class UserShardedLightGCN(object):
         cu, ci = src_u, src_i
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
-            if k == 0 and nz_u is not None and self._scatter is not None:
-                self._scatter(self.A_iu, nz_i, ci, nu_, acc_u, s)     # A_ui G_i through the items' edge lists
+            sparse = k == 0 and nz_u is not None and self._scatter is not None
+            # item side first (this rank's partial sums), its all-reduce in flight during the user side
+            if sparse:
                 self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)    # A_iu G_u through the users' edge lists
             else:
-                self._spmm(self.A_ui, ci, nu_, acc_u, s)      # users: local
-                self._spmm(self.A_iu, cu, ni_, None, 0.0)     # items: this rank's partial sums
-            self._allreduce(ni_)
+                self._spmm(self.A_iu, cu, ni_, None, 0.0)
+            work = self._allreduce_async(ni_)
+            if sparse:
+                self._scatter(self.A_iu, nz_i, ci, nu_, acc_u, s)     # A_ui G_i through the items' edge lists
+            else:
+                self._spmm(self.A_ui, ci, nu_, acc_u, s)      # users: local, no communication
+            if work is not None:
+                work.wait()
             self._axpy(acc_i, ni_, s)
             cu, ci = nu_, ni_
 
