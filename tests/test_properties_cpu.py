@@ -1,0 +1,96 @@
+"""Property tests (hypothesis) of the host-side building blocks: the structures the kernels index into
+must agree with the reference's dict-of-dicts semantics for ANY interaction list."""
+import random
+
+import numpy as np
+import torch
+from hypothesis import given, settings, strategies as st
+
+from qrec_b200 import engine as E
+from qrec_b200 import parallel
+from qrec_b200.data.interactions import InteractionTable
+
+records = st.lists(st.tuples(st.integers(0, 12), st.integers(0, 15), st.sampled_from([0.5, 1.0, 2.0, 4.0])),
+                   min_size=0, max_size=120)
+
+
+@settings(max_examples=150, deadline=None)
+@given(records)
+def test_rated_csr_is_the_dict_of_dicts(recs):
+    nu, ni = 13, 16
+    u = np.array([r[0] for r in recs], dtype=np.int64)
+    i = np.array([r[1] for r in recs], dtype=np.int64)
+    r = np.array([r[2] for r in recs], dtype=np.float64)
+    csr = E.RatedCSR(nu, ni, u, i, r)
+    rows = [dict() for _ in range(nu)]
+    for a, b, c in recs:
+        rows[a][b] = c                          # insertion position of the first write, value of the last
+    for a in range(nu):
+        s0, s1 = csr.sorted_rowptr[a], csr.sorted_rowptr[a + 1]
+        assert csr.sorted_cols[s0:s1].tolist() == sorted(rows[a])
+        p0, p1 = csr.pos_rowptr[a], csr.pos_rowptr[a + 1]
+        assert csr.pos_cols[p0:p1].tolist() == [k for k, v in rows[a].items() if v >= 1]
+        assert csr.possorted_cols[p0:p1].tolist() == sorted(k for k, v in rows[a].items() if v >= 1)
+
+
+@settings(max_examples=100, deadline=None)
+@given(st.lists(st.sampled_from(['a', 'b', 'c', 'dd', 'e1', 'zz', '7', '10']), min_size=0, max_size=60))
+def test_first_appearance_ids(names):
+    ids, vocab = (InteractionTable._first_appearance_ids(np.array(names)) if names
+                  else (np.zeros(0, np.int32), np.zeros(0, str)))
+    d = {}
+    for n in names:
+        if n not in d:
+            d[n] = len(d)
+    assert ids.tolist() == [d[n] for n in names] and vocab.tolist() == list(d)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(0, 2**40), st.integers(0, 400))
+def test_mt_clone_shuffle_and_randbelow_track_cpython(seed, n):
+    r = random.Random(seed)
+    m = E.MT19937(seed)
+    x = list(range(n))
+    r.shuffle(x)
+    a = np.arange(n, dtype=np.int32)
+    m.shuffle(a)
+    assert a.tolist() == x
+    for bound in (1, 2, 3, 1000, 2**31 - 1):
+        assert m.randbelow(bound) == r._randbelow(bound)
+    assert m.random() == r.random() and m.getstate() == r.getstate()
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 8), st.integers(1, 40), st.integers(1, 30))
+def test_node_partition_is_a_bijection(world, bu, bi):
+    U, I = world * bu, world * bi
+    part = parallel.NodePartition(U, I, world)
+    g = part.to_gathered(torch.arange(U + I))
+    assert sorted(g.tolist()) == list(range(U + I))
+    seen = torch.cat([part.local_nodes(r) for r in range(world)])
+    assert sorted(seen.tolist()) == list(range(U + I))
+    for r in range(world):                       # a rank's nodes occupy exactly its block of the gathered order
+        pos = part.to_gathered(part.local_nodes(r))
+        assert pos.tolist() == list(range(r * part.block, (r + 1) * part.block))
+
+
+@settings(max_examples=80, deadline=None)
+@given(records, st.integers(1, 4))
+def test_bipartite_shards_tile_the_adjacency(recs, world):
+    """shard_bipartite_by_user: the ranks' A_ui blocks stack to the user rows of the joint matrix and each
+    A_iu block is the transpose of its A_ui block."""
+    from oracle import bpr_oracle as O
+    nu, ni = 13, 16
+    if not recs:
+        return
+    u = np.array([r[0] for r in recs]); i = np.array([r[1] for r in recs])
+    A = O.norm_adjacency(nu, ni, u, i)
+    rp, co, va = (torch.from_numpy(x) for x in (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data))
+    dense = A.toarray()
+    for rank in range(world):
+        A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, nu, ni, rank, world)
+        if hi == lo:
+            continue
+        D_ui = torch.sparse_csr_tensor(A_ui[0], A_ui[1].long(), A_ui[2], size=(hi - lo, ni)).to_dense().numpy()
+        D_iu = torch.sparse_csr_tensor(A_iu[0], A_iu[1].long(), A_iu[2], size=(ni, hi - lo)).to_dense().numpy()
+        assert np.array_equal(D_ui, dense[lo:hi, nu:]) and np.array_equal(D_iu, D_ui.T)
