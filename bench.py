@@ -459,12 +459,20 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        # the secondary sections must never cost the headline line: report their failure instead
         if world == 1 and not args.no_lightgcn:
             del u, i, j, hu, hi, hj, su, si, sj
             torch.cuda.empty_cache()
-            out['lightgcn'] = lightgcn_section(torch, E, synthetic, data, dev, peak)
+            try:
+                out['lightgcn'] = lightgcn_section(torch, E, synthetic, data, dev, peak)
+            except Exception as exc:                     # noqa: BLE001
+                out['lightgcn'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
         if world == 1 and not args.no_cpu_baseline:
-            out['cpu_baseline'] = cpu_baseline(args.cpu_sample)
+            try:
+                out['cpu_baseline'] = cpu_baseline(args.cpu_sample)
+            except Exception as exc:                     # noqa: BLE001
+                out['cpu_baseline'] = {'value': None, 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
+                                       'sample': 'failed: %s: %s' % (type(exc).__name__, exc)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
