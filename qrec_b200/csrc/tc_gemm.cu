@@ -274,6 +274,7 @@ extern "C" int qrec_tc_gemm_tf32(int32_t b_is_nk, int32_t M, int32_t N, int32_t 
                "qrec_tc_gemm_tf32: A must be 16-byte aligned with K and lda multiples of 4");
   QREC_REQUIRE(!b_is_nk || (ldb % 4 == 0 && (reinterpret_cast<uintptr_t>(B) & 15) == 0),
                "qrec_tc_gemm_tf32: [N,K] B must be 16-byte aligned with ldb a multiple of 4");
+  QREC_REQUIRE((M + BM - 1) / BM <= 65535, "qrec_tc_gemm_tf32: M=%d exceeds the 65535 x 128 rows of one launch; split the batch", M);
   QREC_REQUIRE(epilogue >= 0 && epilogue <= 3, "qrec_tc_gemm_tf32: unknown epilogue %d", epilogue);
   QREC_REQUIRE((epilogue != EPI_BIAS_RELU && epilogue != EPI_BIAS) || bias, "qrec_tc_gemm_tf32: bias epilogue without bias");
   QREC_REQUIRE(epilogue != EPI_RELU_MASK || mask, "qrec_tc_gemm_tf32: mask epilogue without mask");
