@@ -74,3 +74,33 @@ class ScaleBPR(object):
         """Top-N item ids and scores per user (rated items scored 0, as base/recommender.py:147-149)."""
         from .evaluate import batched_top_n
         return batched_top_n(self.P, self.Q, user_ids, self.csr, N, block=block)
+
+    def evaluate(self, test_table_or_triples, tops=(10,), block=2048):
+        """Ranking metrics (the reference's definitions, util/measure.py:24-138) for the test interactions of
+        users known from training.  `test_table_or_triples`: (user_names, item_names, ratings) arrays or a
+        list of [user, item, rating] records.  Returns the reference-format list of metric strings."""
+        from .util.fastmeasure import ranking_measures
+        if isinstance(test_table_or_triples, tuple):
+            tu, ti = (np.asarray(x) for x in test_table_or_triples[:2])
+        else:
+            tu = np.array([rec[0] for rec in test_table_or_triples])
+            ti = np.array([rec[1] for rec in test_table_or_triples])
+        lut_u = {n: k for k, n in enumerate(self.table.user_names.tolist())}
+        lut_i = {n: k for k, n in enumerate(self.table.item_names.tolist())}
+        # the reference keeps test users unknown to training (they get globalMean scores); this path ranks
+        # the known ones -- items unseen in training can never be recommended and only count in |test_u|
+        next_unknown = len(lut_i)
+        pairs = {}
+        for a, b in zip(tu.tolist(), ti.tolist()):
+            if a in lut_u:
+                if b not in lut_i:
+                    lut_i[b] = next_unknown
+                    next_unknown += 1
+                pairs.setdefault(lut_u[a], {})[lut_i[b]] = 1
+        users = list(pairs)
+        rowptr = np.zeros(len(users) + 1, np.int64)
+        rowptr[1:] = np.cumsum([len(pairs[u]) for u in users])
+        cols = np.array([c for u in users for c in pairs[u]], dtype=np.int64)
+        N = max(tops)
+        ids, _ = self.top_n(users, N, block=block)
+        return ranking_measures(ids, rowptr, cols, list(tops))

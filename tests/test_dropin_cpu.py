@@ -173,3 +173,30 @@ def test_graph_recommender_adj_tensor_method_on_cpu_tensors(golden_graph, tmp_pa
     sp_adj = m.create_joint_sparse_adjaceny().tocsr(); sp_adj.sort_indices()
     assert np.array_equal(sp_adj.indices, g['adj_indices'])
     np.testing.assert_allclose(sp_adj.data, g['adj_data'], rtol=1e-6)
+
+
+def test_vectorised_measures_equal_measure_class():
+    """util/fastmeasure.ranking_measures == Measure.rankingMeasure (hence the reference's) on random
+    rankings: same strings up to the last printed digit of the float sums."""
+    import random as pyrandom
+    from qrec_b200.util.fastmeasure import ranking_measures
+    rng = pyrandom.Random(0)
+    n_items = 80
+    for trial in range(30):
+        n_users = rng.randint(1, 25)
+        tests = [rng.sample(range(n_items), rng.randint(1, 18)) for _ in range(n_users)]
+        top = np.array([rng.sample(range(n_items), 20) for _ in range(n_users)])
+        rowptr = np.zeros(n_users + 1, np.int64); rowptr[1:] = np.cumsum([len(t) for t in tests])
+        cols = np.concatenate([np.array(t) for t in tests]).astype(np.int32)
+        origin = {'u%d' % k: {'i%d' % it: 1.0 for it in tests[k]} for k in range(n_users)}
+        res = {'u%d' % k: [('i%d' % it, 0.0) for it in top[k]] for k in range(n_users)}
+        tops = sorted(rng.sample([1, 5, 10, 20], rng.randint(1, 3)))
+        fast = ranking_measures(top, rowptr, cols, tops)
+        slow = Measure.rankingMeasure(origin, res, tops)
+        assert len(fast) == len(slow)
+        for a, b in zip(fast, slow):
+            if ':' not in a:
+                assert a == b
+            else:
+                (ka, va), (kb, vb) = a.strip().split(':'), b.strip().split(':')
+                assert ka == kb and abs(float(va) - float(vb)) <= 1e-12 * max(1.0, abs(float(vb)))
