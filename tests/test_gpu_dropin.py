@@ -259,3 +259,7 @@ def test_scale_bpr_from_interaction_table(golden_bpr, tmp_path):
     out = Measure.rankingMeasure(origin, res, [10])
     got = {x.split(':')[0]: float(x.split(':')[1]) for x in out[1:]}
     assert got['Precision'] > 0.30 and got['NDCG'] > 0.45
+    # the vectorised evaluation path gives the same numbers as the dict-based Measure
+    fast = m.evaluate(test, tops=(10,))
+    for a, b in zip(fast[1:], out[1:]):
+        assert a.split(':')[0] == b.split(':')[0] and abs(float(a.split(':')[1]) - float(b.split(':')[1])) < 1e-9
