@@ -28,6 +28,10 @@ def _load():
     lib.oracle_bpr_sgd_sequential_f32.restype = C.c_double
     lib.oracle_bpr_sgd_sequential_f32.argtypes = [f32p, f32p, C.c_int, C.c_int64, i32p, i32p, i32p,
                                                   C.c_float, C.c_float, C.c_float]
+    for name, fp, ft in (('oracle_mf_sgd_sequential_f64', f64p, C.c_double), ('oracle_mf_sgd_sequential_f32', f32p, C.c_float)):
+        fn = getattr(lib, name)
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_int, fp, fp, C.c_int, C.c_int64, i32p, i32p, fp, ft, ft, ft, fp, fp, ft, ft]
     lib.oracle_spmm_csr_f32.restype = None
     lib.oracle_spmm_csr_f32.argtypes = [C.c_int32, i64p, i32p, f32p, f32p, f32p, C.c_int]
     return lib
@@ -69,3 +73,18 @@ def spmm_csr(rowptr, cols, vals, X):
     lib().oracle_spmm_csr_f32(len(rowptr) - 1, _p(rowptr, C.c_int64), _p(cols, C.c_int32),
                               _p(vals, C.c_float), _p(X, C.c_float), _p(Y, C.c_float), X.shape[1])
     return Y
+
+
+def mf_sgd_sequential(kind, P, Q, u, i, r, lr, reg_u=0.0, reg_i=0.0, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0):
+    """In place on P, Q (and Bu, Bi for kind 2 = SVD); kind 0 BasicMF, 1 PMF; returns sum(error^2)."""
+    u = np.ascontiguousarray(u, np.int32); i = np.ascontiguousarray(i, np.int32)
+    assert P.flags.c_contiguous and Q.flags.c_contiguous and P.dtype == Q.dtype
+    ct, fn = ((C.c_double, lib().oracle_mf_sgd_sequential_f64) if P.dtype == np.float64
+              else (C.c_float, lib().oracle_mf_sgd_sequential_f32))
+    r = np.ascontiguousarray(r, P.dtype)
+    if kind == 2:
+        assert Bu.dtype == P.dtype and Bi.dtype == P.dtype and Bu.flags.c_contiguous and Bi.flags.c_contiguous
+    bu = _p(Bu, ct) if kind == 2 else None
+    bi = _p(Bi, ct) if kind == 2 else None
+    return fn(kind, _p(P, ct), _p(Q, ct), P.shape[1], len(u), _p(u, C.c_int32), _p(i, C.c_int32), _p(r, ct),
+              lr, reg_u, reg_i, bu, bi, reg_b, global_mean)

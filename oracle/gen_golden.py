@@ -14,12 +14,15 @@ What is exercised (reference file:line):
   * DeepRecommender.next_batch_pairwise / next_batch_pointwise  base/deepRecommender.py:29-77
   * GraphRecommender.create_joint_sparse_adjaceny / create_sparse_rating_matrix
                               base/graphRecommender.py:10-29,41-51
+  * BasicMF / PMF / SVD .trainModel   model/rating/BasicMF.py:9-25, PMF.py:9-28, SVD.py:9-36
+    (pointwise sequential SGD; §8 f-4), with the per-epoch shuffle of isConverged and the
+    MAE / RMSE of evalRatings (base/recommender.py:95-125, util/measure.py)
 
 `tensorflow` and `mkl` are absent from this image; both are stubbed with empty
 modules because the reference imports them at module level (model/ranking/BPR.py:7,
 QRec.py:6).  The numpy path never calls into either.
 
-Usage:  python oracle/gen_golden.py            (writes tests/golden/*.npz)
+Usage:  python oracle/gen_golden.py [bpr] [mf]   (default: all sections; writes tests/golden/*.npz)
 """
 import os
 import sys
@@ -62,6 +65,20 @@ reg.lambda=-u 0.001 -i 0.001 -b 0.2 -s 0.2
 output.setup=on -dir ./results/
 """
 
+CONF_MF = """ratings=./dataset/FilmTrust/trainset.txt
+ratings.setup=-columns 0 1 2
+model.name=%(name)s
+evaluation.setup=-testSet ./dataset/FilmTrust/testset.txt
+item.ranking=off -topN 10
+num.factors=%(d)d
+num.max.epoch=3
+batch_size=1024
+learnRate=-init %(lr)s -max 1
+reg.lambda=-u 0.01 -i 0.02 -b 0.03 -s 0.1
+output.setup=on -dir ./results/
+"""
+MF_RUNS = (('BasicMF', 20, '0.03', 11), ('PMF', 10, '0.02', 12), ('SVD', 20, '0.005', 13))   # name, d, lr, seed
+
 
 def _stub_modules():
     sys.modules.setdefault('tensorflow', types.ModuleType('tensorflow'))
@@ -78,7 +95,7 @@ def _state_to_array(state):
     return np.array(internal, dtype=np.uint32)
 
 
-def main():
+def _enter_workdir():
     assert os.path.isdir(REF), 'reference checkout not mounted'
     _stub_modules()
     sys.path.insert(0, REF)
@@ -87,6 +104,9 @@ def main():
     os.symlink(os.path.join(REF, 'dataset'), 'dataset')
     os.makedirs('log', exist_ok=True)
     os.makedirs('results', exist_ok=True)
+
+
+def gen_bpr():
     with open('BPR_ft.conf', 'w') as f:
         f.write(CONF_BPR)
     with open('LGCN_ft.conf', 'w') as f:
@@ -230,6 +250,95 @@ def main():
     )
     print('samplers: pairwise batches', len(pair_batches), 'last', pair_batches[-1].shape,
           'pointwise b0', point_batches[0].shape, 'adj nnz', adj.nnz, 'rmat nnz', rmat.nnz)
+
+
+def gen_mf():
+    """One fixture per rating-prediction MF model: the order the entries were visited in each epoch
+    (a permutation of the initial training list), the tables after every epoch, the epoch losses,
+    the learning-rate schedule, the MT19937 state after every epoch's shuffle and the final
+    MAE / RMSE lines."""
+    import importlib
+    from util.config import ModelConf
+    from QRec import QRec
+    for name, d, lr, seed in MF_RUNS:
+        cname = '%s_ft.conf' % name
+        with open(cname, 'w') as f:
+            f.write(CONF_MF % dict(name=name, d=d, lr=lr))
+        random.seed(seed)
+        np.random.seed(seed)
+        conf = ModelConf(cname)
+        with contextlib.redirect_stdout(io.StringIO()):
+            q = QRec(conf)
+        cls = getattr(importlib.import_module('model.rating.' + name), name)
+        model = cls(conf, q.trainingData, q.testData)
+        first = list(model.data.trainingData)
+        where = {id(e): k for k, e in enumerate(first)}
+        rec = dict(order=[], P=[], Q=[], Bu=[], Bi=[], loss=[], lrate=[], states=[], rmse=[])
+        orig_conv = cls.isConverged
+
+        def spy_conv(self, epoch):
+            rec['order'].append(np.array([where[id(e)] for e in self.data.trainingData], dtype=np.int32))
+            rec['P'].append(self.P.copy())
+            rec['Q'].append(self.Q.copy())
+            if hasattr(self, 'Bu'):
+                rec['Bu'].append(self.Bu.copy())
+                rec['Bi'].append(self.Bi.copy())
+            rec['loss'].append(float(self.loss))
+            lr_before = self.lRate
+            r = orig_conv(self, epoch)
+            rec['rmse'].append([m.strip() for m in self.measure])
+            rec['lrate'].append((lr_before, self.lRate))
+            rec['states'].append(_state_to_array(random.getstate()))
+            return r
+
+        cls.isConverged = spy_conv
+        try:
+            with contextlib.redirect_stdout(io.StringIO()):
+                model.readConfiguration()
+                model.initializing_log()
+                state_before = _state_to_array(random.getstate())
+                model.initModel()
+                init = dict(P0=model.P.copy(), Q0=model.Q.copy())
+                if hasattr(model, 'Bu'):
+                    init.update(Bu0=model.Bu.copy(), Bi0=model.Bi.copy())
+                model.trainModel()
+                model.evalRatings()
+        finally:
+            cls.isConverged = orig_conv
+        measure = [m.strip() for m in model.measure]
+        print(name, 'FilmTrust: train', model.data.trainingSize(), 'losses', rec['loss'], 'measure', measure)
+        extra = {}
+        if rec['Bu']:
+            extra = dict(Bu_last=rec['Bu'][-1], Bi_last=rec['Bi'][-1])
+        np.savez_compressed(
+            os.path.join(OUT, 'mf_%s_filmtrust.npz' % name.lower()),
+            user_names=np.array([model.data.id2user[k] for k in range(len(model.data.user))]),
+            item_names=np.array([model.data.id2item[k] for k in range(len(model.data.item))]),
+            train_users=np.array([e[0] for e in first]), train_items=np.array([e[1] for e in first]),
+            train_rating=np.array([e[2] for e in first], dtype=np.float64),
+            test_users=np.array([e[0] for e in model.data.testData]),
+            test_items=np.array([e[1] for e in model.data.testData]),
+            test_rating=np.array([e[2] for e in model.data.testData], dtype=np.float64),
+            test_pred=np.array([e[3] for e in model.data.testData], dtype=np.float64),
+            global_mean=np.array(model.data.globalMean),
+            mt_state_before=state_before, mt_state_after_epoch=np.stack(rec['states']),
+            order_epoch=np.stack(rec['order']),               # [E, n] indices into the initial list
+            # tables after the first epoch (fp32 copy, loose checks) and after the last (float64, exact)
+            P_epoch1=rec['P'][0].astype(np.float32), Q_epoch1=rec['Q'][0].astype(np.float32),
+            P_last=rec['P'][-1], Q_last=rec['Q'][-1],
+            loss=np.array(rec['loss']), lrate=np.array(rec['lrate']),
+            epoch_measure=np.array(rec['rmse']), measure=np.array(measure),
+            seed=np.array(seed), conf=np.array(CONF_MF % dict(name=name, d=d, lr=lr)),
+            **init, **extra)
+
+
+def main():
+    what = set(sys.argv[1:]) or {'bpr', 'mf'}
+    _enter_workdir()
+    if 'bpr' in what:
+        gen_bpr()
+    if 'mf' in what:
+        gen_mf()
 
 
 if __name__ == '__main__':
