@@ -369,6 +369,53 @@ int qrec_mask_rated_f32(float* dev_scores, int32_t n_rows, int64_t ld, const int
                         const int64_t* dev_rowptr, const int32_t* dev_cols, float value,
                         void* stream);
 
+/* =====================================================================================
+ * K9 (next row f-4) -- the rating-prediction MF family: one entry (u, i, r) per step.
+ *   kind 0  BasicMF  model/rating/BasicMF.py:13-23   P[u] += (lr*e)*Q[i];  Q[i] += (lr*e)*P[u]
+ *   kind 1  PMF      model/rating/PMF.py:13-22       P[u] += lr*(e*Q[i]-regU*P[u]);  Q[i] += lr*(e*P[u]-regI*Q[i])
+ *   kind 2  SVD      model/rating/SVD.py:17-32,84-90 kind 1 with e taken against P.Q + mean + Bi[i] + Bu[u]
+ *                                                    and Bu[u] += lr*(e-regB*Bu[u]), Bi[i] likewise
+ * e = r - prediction; the item row is updated from the NEW user row (`p` is a view in the reference).
+ * dev_loss: double[1], accumulates sum e^2.  Bias pointers may be null unless kind == 2.
+ * STATUS: written in round 1 after the GPU budget was spent -- compiled for sm_100a and covered by
+ * the oracle, not yet run on hardware (tests gated by QREC_TEST_UNVALIDATED=1).
+ * ===================================================================================== */
+/* wait_u[k] / wait_i[k] = number of earlier entries touching P[u[k]] / Q[i[k]] (host, O(n)). */
+int qrec_mf_order_prepare(int64_t n, const int32_t* u, const int32_t* i, int32_t num_users,
+                          int32_t num_items, int32_t* wait_u, int32_t* wait_i);
+/* Length of the longest dependency chain of the stream (n / depth = average parallel width). */
+int64_t qrec_mf_order_depth(int64_t n, const int32_t* u, const int32_t* i, int32_t num_users,
+                            int32_t num_items);
+/* Parity mode: sequential-equivalent epoch (dataflow over row versions, see qrec_bpr_sgd_ordered_*).
+ * ver_p[num_users], ver_q[num_items], ticket[1] must be zero on entry. */
+int qrec_mf_sgd_ordered_f64(int32_t kind, double* dev_P, double* dev_Q, int32_t d, int64_t n,
+                            const int32_t* dev_u, const int32_t* dev_i, const double* dev_r,
+                            const int32_t* dev_wait_u, const int32_t* dev_wait_i, int32_t* dev_ver_p,
+                            int32_t* dev_ver_q, unsigned long long* dev_ticket, double lr, double reg_u,
+                            double reg_i, double* dev_Bu, double* dev_Bi, double reg_b, double global_mean,
+                            double* dev_loss, int32_t n_warps, void* stream);
+int qrec_mf_sgd_ordered_f32(int32_t kind, float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                            const int32_t* dev_u, const int32_t* dev_i, const float* dev_r,
+                            const int32_t* dev_wait_u, const int32_t* dev_wait_i, int32_t* dev_ver_p,
+                            int32_t* dev_ver_q, unsigned long long* dev_ticket, float lr, float reg_u,
+                            float reg_i, float* dev_Bu, float* dev_Bi, float reg_b, float global_mean,
+                            double* dev_loss, int32_t n_warps, void* stream);
+/* Throughput mode: every entry reads its two rows, applies the step to its private copy and adds the
+ * row deltas back with red.global.add.v4.f32 (rows shared inside a launch get the sum of the deltas).
+ * d: multiple of 4, 4..128 (pad with zero columns; they stay zero). */
+int qrec_mf_sgd_batch_f32(int32_t kind, float* dev_P, float* dev_Q, int32_t d, int64_t n,
+                          const int32_t* dev_u, const int32_t* dev_i, const float* dev_r, float lr,
+                          float reg_u, float reg_i, float* dev_Bu, float* dev_Bi, float reg_b,
+                          float global_mean, double* dev_loss, void* stream);
+/* out[k] = P[u[k]].Q[i[k]]  (+ global_mean + Bi[i[k]] + Bu[u[k]] when the bias vectors are given):
+ * predictForRating for known (user, item) pairs (iterativeRecommender.py:66-73, SVD.py:84-90). */
+int qrec_mf_predict_pairs_f32(const float* dev_P, const float* dev_Q, int32_t d, int64_t n,
+                              const int32_t* dev_u, const int32_t* dev_i, const float* dev_Bu,
+                              const float* dev_Bi, float global_mean, float* dev_out, void* stream);
+int qrec_mf_predict_pairs_f64(const double* dev_P, const double* dev_Q, int32_t d, int64_t n,
+                              const int32_t* dev_u, const int32_t* dev_i, const double* dev_Bu,
+                              const double* dev_Bi, double global_mean, double* dev_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,5 +1,6 @@
 """`QRec`: loads the data named by a ModelConf, partitions it and runs the model
-(reference: QRec.py:8-118).  Model classes are resolved by name from qrec_b200.model.ranking."""
+(reference: QRec.py:8-118).  Model classes are resolved by name, model.rating first and then
+model.ranking like the reference (QRec.py:51-56)."""
 import importlib
 import sys
 from time import strftime, localtime, time
@@ -11,10 +12,13 @@ from .util.io import FileIO
 
 def _model_class(name):
     try:
-        mod = importlib.import_module('qrec_b200.model.ranking.' + name)
-    except ImportError as e:
-        print('model %s is not available on the B200 engine (%s)' % (name, e))
-        sys.exit(-1)
+        mod = importlib.import_module('qrec_b200.model.rating.' + name)
+    except ImportError:
+        try:
+            mod = importlib.import_module('qrec_b200.model.ranking.' + name)
+        except ImportError as e:
+            print('model %s is not available on the B200 engine (%s)' % (name, e))
+            sys.exit(-1)
     return getattr(mod, name)
 
 

@@ -247,4 +247,35 @@ int qrec_bpr_order_prepare(int64_t n, const int32_t* u, const int32_t* i, const 
   return QREC_OK;
 }
 
+// pointwise streams (u,i): two rows per entry (model/rating/PMF.py:13-22 and siblings)
+int64_t qrec_mf_order_depth(int64_t n, const int32_t* u, const int32_t* i, int32_t num_users,
+                            int32_t num_items) {
+  if (n <= 0 || !u || !i || num_users <= 0 || num_items <= 0) return 0;
+  std::vector<int64_t> lu((size_t)num_users, 0), lq((size_t)num_items, 0);
+  int64_t depth = 0;
+  for (int64_t k = 0; k < n; ++k) {
+    const int32_t uu = u[k], ii = i[k];
+    if (uu < 0 || uu >= num_users || ii < 0 || ii >= num_items) return -1;
+    const int64_t lv = (lu[uu] > lq[ii] ? lu[uu] : lq[ii]) + 1;
+    lu[uu] = lq[ii] = lv;
+    if (lv > depth) depth = lv;
+  }
+  return depth;
+}
+
+int qrec_mf_order_prepare(int64_t n, const int32_t* u, const int32_t* i, int32_t num_users,
+                          int32_t num_items, int32_t* wait_u, int32_t* wait_i) {
+  QREC_REQUIRE(n == 0 || (u && i && wait_u && wait_i), "qrec_mf_order_prepare: null pointer");
+  QREC_REQUIRE(num_users >= 0 && num_items >= 0, "qrec_mf_order_prepare: bad sizes");
+  std::vector<int32_t> cu((size_t)num_users, 0), cq((size_t)num_items, 0);
+  for (int64_t k = 0; k < n; ++k) {
+    const int32_t uu = u[k], ii = i[k];
+    QREC_REQUIRE(uu >= 0 && uu < num_users && ii >= 0 && ii < num_items,
+                 "qrec_mf_order_prepare: id out of range at entry %lld", (long long)k);
+    wait_u[k] = cu[uu]++;
+    wait_i[k] = cq[ii]++;
+  }
+  return QREC_OK;
+}
+
 }  // extern "C"

@@ -199,6 +199,27 @@ def bpr_order_prepare(u, i, j, num_users, num_items):
     return wu, wi, wj
 
 
+def mf_order_prepare(u, i, num_users, num_items):
+    """Row-version numbers of a pointwise (u, i) stream for mf_sgd_ordered (host, O(n))."""
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    n = u.shape[0]
+    wu, wi = np.empty(n, np.int32), np.empty(n, np.int32)
+    check(lib.qrec_mf_order_prepare(n, _i32p(u), _i32p(i), int(num_users), int(num_items), _i32p(wu), _i32p(wi)),
+          'qrec_mf_order_prepare')
+    return wu, wi
+
+
+def mf_order_depth(u, i, num_users, num_items):
+    """Longest dependency chain of a pointwise stream (host, O(n))."""
+    u = np.ascontiguousarray(u, dtype=np.int32)
+    i = np.ascontiguousarray(i, dtype=np.int32)
+    depth = int(lib.qrec_mf_order_depth(u.shape[0], _i32p(u), _i32p(i), int(num_users), int(num_items)))
+    if depth < 0:
+        raise QRecError('qrec_mf_order_depth: id out of range')
+    return depth
+
+
 # =============================================================================================
 # device entry points
 # =============================================================================================
@@ -581,3 +602,61 @@ def mask_rated(scores, users, rowptr, cols, value=0.0):
                                   _dev(users, torch.int32, 'users'), _dev(rowptr, torch.int64, 'rowptr'),
                                   _dev(cols, torch.int32, 'cols'), float(value), _stream()), 'qrec_mask_rated_f32')
     return scores
+
+
+# ---------------------------------------------------------------------------------------------
+# K9: rating-prediction MF family (kind 0 BasicMF, 1 PMF, 2 SVD)
+# ---------------------------------------------------------------------------------------------
+MF_KINDS = {'BasicMF': 0, 'PMF': 1, 'SVD': 2}
+
+
+def _opt(t, dtype, name):
+    return _dev(t, dtype, name) if t is not None else None
+
+
+def mf_sgd_ordered(kind, P, Q, u, i, r, wu, wi, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0,
+                   global_mean=0.0, n_warps=0):
+    """Parity mode: sequential-equivalent pass over the entries (u, i, r) in array order."""
+    torch = _torch()
+    f64 = P.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    d = P.shape[1]
+    assert Q.shape[1] == d and u.shape[0] == i.shape[0] == r.shape[0]
+    ver_p = torch.zeros(P.shape[0], dtype=torch.int32, device=P.device)
+    ver_q = torch.zeros(Q.shape[0], dtype=torch.int32, device=P.device)
+    ticket = torch.zeros(1, dtype=torch.int64, device=P.device)
+    fn = lib.qrec_mf_sgd_ordered_f64 if f64 else lib.qrec_mf_sgd_ordered_f32
+    check(fn(int(kind), _dev(P, dt, 'P'), _dev(Q, dt, 'Q'), d, u.shape[0], _dev(u, torch.int32, 'u'),
+             _dev(i, torch.int32, 'i'), _dev(r, dt, 'r'), _dev(wu, torch.int32, 'wu'), _dev(wi, torch.int32, 'wi'),
+             ver_p.data_ptr(), ver_q.data_ptr(), ticket.data_ptr(), float(lr), float(reg_u), float(reg_i),
+             _opt(Bu, dt, 'Bu'), _opt(Bi, dt, 'Bi'), float(reg_b), float(global_mean),
+             _dev(loss, torch.float64, 'loss'), int(n_warps), _stream()), 'qrec_mf_sgd_ordered')
+    return loss
+
+
+def mf_sgd_batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0):
+    """Throughput mode: fused gather-dot-step-scatter-add over device entries (fp32, d % 4 == 0)."""
+    torch = _torch()
+    d = P.shape[1]
+    assert Q.shape[1] == d and u.shape[0] == i.shape[0] == r.shape[0]
+    f32 = torch.float32
+    check(lib.qrec_mf_sgd_batch_f32(int(kind), _dev(P, f32, 'P'), _dev(Q, f32, 'Q'), d, u.shape[0],
+                                    _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'), _dev(r, f32, 'r'),
+                                    float(lr), float(reg_u), float(reg_i), _opt(Bu, f32, 'Bu'), _opt(Bi, f32, 'Bi'),
+                                    float(reg_b), float(global_mean), _dev(loss, torch.float64, 'loss'), _stream()),
+          'qrec_mf_sgd_batch_f32')
+    return loss
+
+
+def mf_predict_pairs(P, Q, u, i, Bu=None, Bi=None, global_mean=0.0, out=None):
+    """out[k] = P[u[k]].Q[i[k]] (+ global_mean + Bi + Bu): predictForRating for known pairs."""
+    torch = _torch()
+    f64 = P.dtype == torch.float64
+    dt = torch.float64 if f64 else torch.float32
+    if out is None:
+        out = torch.empty(u.shape[0], dtype=dt, device=P.device)
+    fn = lib.qrec_mf_predict_pairs_f64 if f64 else lib.qrec_mf_predict_pairs_f32
+    check(fn(_dev(P, dt, 'P'), _dev(Q, dt, 'Q'), P.shape[1], u.shape[0], _dev(u, torch.int32, 'u'),
+             _dev(i, torch.int32, 'i'), _opt(Bu, dt, 'Bu'), _opt(Bi, dt, 'Bi'), float(global_mean),
+             _dev(out, dt, 'out'), _stream()), 'qrec_mf_predict_pairs')
+    return out
