@@ -92,8 +92,8 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
   __shared__ uint64_t mma_done[2];
   __shared__ uint32_t tmem_base_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA[2] = {smem, smem + STAGE_A + STAGE_B};
-  uint8_t* sB[2] = {smem + STAGE_A, smem + 2 * STAGE_A + STAGE_B};
+  // stage s: A tile at smem + s*(STAGE_A+STAGE_B), B tile right behind it (computed, not looked up:
+  // a pointer array indexed by the stage lands in local memory)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
 
@@ -147,23 +147,25 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
   load_block(0);
   for (int kb = 0; kb < nkb; ++kb) {
     const int s = kb & 1;
+    uint8_t* const sA_s = smem + s * (STAGE_A + STAGE_B);
+    uint8_t* const sB_s = sA_s + STAGE_A;
     if (kb >= 2) mbar_wait(&mma_done[s], (uint32_t)(((kb >> 1) - 1) & 1));   // MMAs that read stage s are done
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
       const int row = (tid >> 3) + 16 * p, c = tid & 7;
-      *reinterpret_cast<float4*>(sA[s] + sw_off(row, c * 4)) = to_tf32(ra[p]);
+      *reinterpret_cast<float4*>(sA_s + sw_off(row, c * 4)) = to_tf32(ra[p]);
     }
     if (B_IS_NK) {
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
         const int row = (tid >> 3) + 16 * p, c = tid & 7;
-        *reinterpret_cast<float4*>(sB[s] + sw_off(row, c * 4)) = to_tf32(rb4[p]);
+        *reinterpret_cast<float4*>(sB_s + sw_off(row, c * 4)) = to_tf32(rb4[p]);
       }
     } else {
 #pragma unroll
       for (int p = 0; p < 16; ++p) {
         const int n = tid & 63, k = (tid >> 6) + 2 * p;
-        *reinterpret_cast<float*>(sB[s] + sw_off(n, k)) = to_tf32(rb1[p]);        // transposed into K-major
+        *reinterpret_cast<float*>(sB_s + sw_off(n, k)) = to_tf32(rb1[p]);        // transposed into K-major
       }
     }
     if (kb + 1 < nkb) load_block(kb + 1);                                        // in flight during the MMAs
@@ -171,7 +173,7 @@ tc_gemm_tf32_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
     __syncthreads();
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint64_t da = make_desc(smem_u32(sA[s])), db = make_desc(smem_u32(sB[s]));
+      const uint64_t da = make_desc(smem_u32(sA_s)), db = make_desc(smem_u32(sB_s));
 #pragma unroll
       for (int k4 = 0; k4 < BK / 8; ++k4) {
         const uint32_t acc = (kb > 0 || k4 > 0) ? 1u : 0u;
