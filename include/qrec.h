@@ -402,11 +402,15 @@ int qrec_mf_sgd_ordered_f32(int32_t kind, float* dev_P, float* dev_Q, int32_t d,
                             double* dev_loss, int32_t n_warps, void* stream);
 /* Throughput mode: every entry reads its two rows, applies the step to its private copy and adds the
  * row deltas back with red.global.add.v4.f32 (rows shared inside a launch get the sum of the deltas).
- * d: multiple of 4, 4..128 (pad with zero columns; they stay zero). */
+ * d: multiple of 4, 4..128 (pad with zero columns; they stay zero).
+ * max_inflight: 0 = fill the GPU; > 0 = size the grid so that about this many entries sit between
+ * their row reads and their reductions at any time.  A row hit c times inside that window moves as
+ * with c*lr (every hit reads the same stale row) and the squared-error gradient is unbounded, so
+ * small or skewed data needs a window of roughly (0.25/lr) / (share of the most frequent row). */
 int qrec_mf_sgd_batch_f32(int32_t kind, float* dev_P, float* dev_Q, int32_t d, int64_t n,
                           const int32_t* dev_u, const int32_t* dev_i, const float* dev_r, float lr,
                           float reg_u, float reg_i, float* dev_Bu, float* dev_Bi, float reg_b,
-                          float global_mean, double* dev_loss, void* stream);
+                          float global_mean, double* dev_loss, int64_t max_inflight, void* stream);
 /* out[k] = P[u[k]].Q[i[k]]  (+ global_mean + Bi[i[k]] + Bu[u[k]] when the bias vectors are given):
  * predictForRating for known (user, item) pairs (iterativeRecommender.py:66-73, SVD.py:84-90). */
 int qrec_mf_predict_pairs_f32(const float* dev_P, const float* dev_Q, int32_t d, int64_t n,

@@ -348,8 +348,10 @@ int qrec_mf_sgd_ordered_f32(int32_t kind, float* P, float* Q, int32_t d, int64_t
 
 int qrec_mf_sgd_batch_f32(int32_t kind, float* P, float* Q, int32_t d, int64_t n, const int32_t* u,
                           const int32_t* i, const float* r, float lr, float reg_u, float reg_i, float* Bu,
-                          float* Bi, float reg_b, float global_mean, double* loss, void* stream) {
+                          float* Bi, float reg_b, float global_mean, double* loss, int64_t max_inflight,
+                          void* stream) {
   QREC_REQUIRE(kind >= 0 && kind <= 2, "mf_sgd_batch: kind=%d (0 BasicMF, 1 PMF, 2 SVD)", kind);
+  QREC_REQUIRE(max_inflight >= 0, "mf_sgd_batch: max_inflight < 0");
   QREC_REQUIRE(P && Q && loss, "mf_sgd_batch: null pointer");
   QREC_REQUIRE(kind != 2 || (Bu && Bi), "mf_sgd_batch: kind 2 needs the bias vectors");
   QREC_REQUIRE(d >= 4 && d <= 128 && d % 4 == 0, "mf_sgd_batch: d=%d unsupported (multiple of 4, 4..128)", d);
@@ -361,6 +363,15 @@ int qrec_mf_sgd_batch_f32(int32_t kind, float* P, float* Q, int32_t d, int64_t n
   long long blocks = (n + 255) / 256;                    // 32 entries per warp and pass
   const long long cap = (long long)sm_count() * 8;
   if (blocks > cap) blocks = cap;
+  if (max_inflight > 0) {
+    // a lane group has UNROLL = 4 entries between their row reads and their reductions: bound the
+    // number of such entries across the grid (the staleness window of the Hogwild update)
+    const int lpr = nvec <= 4 ? 4 : (nvec <= 8 ? 8 : (nvec <= 16 ? 16 : 32));
+    const long long per_block = 8LL * (32 / lpr) * 4;
+    long long want = (max_inflight + per_block - 1) / per_block;
+    if (want < 1) want = 1;
+    if (blocks > want) blocks = want;
+  }
 #define QREC_MFB(LPR, K)                                                                                  \
   mf_sgd_batch_kernel<LPR, K, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n, u, i, r, lr, reg_u, reg_i,   \
                                                               Bu, Bi, reg_b, global_mean, loss)

@@ -634,8 +634,10 @@ def mf_sgd_ordered(kind, P, Q, u, i, r, wu, wi, lr, reg_u, reg_i, loss, Bu=None,
     return loss
 
 
-def mf_sgd_batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0):
-    """Throughput mode: fused gather-dot-step-scatter-add over device entries (fp32, d % 4 == 0)."""
+def mf_sgd_batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0,
+                 max_inflight=0):
+    """Throughput mode: fused gather-dot-step-scatter-add over device entries (fp32, d % 4 == 0).
+    max_inflight > 0 bounds the entries concurrently between read and reduction (grid sizing)."""
     torch = _torch()
     d = P.shape[1]
     assert Q.shape[1] == d and u.shape[0] == i.shape[0] == r.shape[0]
@@ -643,7 +645,8 @@ def mf_sgd_batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, 
     check(lib.qrec_mf_sgd_batch_f32(int(kind), _dev(P, f32, 'P'), _dev(Q, f32, 'Q'), d, u.shape[0],
                                     _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'), _dev(r, f32, 'r'),
                                     float(lr), float(reg_u), float(reg_i), _opt(Bu, f32, 'Bu'), _opt(Bi, f32, 'Bi'),
-                                    float(reg_b), float(global_mean), _dev(loss, torch.float64, 'loss'), _stream()),
+                                    float(reg_b), float(global_mean), _dev(loss, torch.float64, 'loss'),
+                                    int(max_inflight), _stream()),
           'qrec_mf_sgd_batch_f32')
     return loss
 

@@ -5,12 +5,13 @@ reshuffles the list after every epoch (model/rating/PMF.py:13-22, base/iterative
 Here an epoch is one launch over the id-mapped (u, i, r) arrays of the list's current order:
   * engine -mode parity : qrec_mf_sgd_ordered_{f64,f32} -- sequential-equivalent, same tables as the
                           reference after every epoch;
-  * engine -mode fast   : qrec_mf_sgd_batch_f32 over a shuffled list in minibatch launches (Hogwild
-                          inside a launch, launches in sequence), test pairs scored on the device.
-                          A row hit c times inside one launch moves as if the learning rate were c*lr
-                          (every hit reads the same stale row), and the squared-error gradient is
-                          unbounded, so the launch size is capped at (0.25/lr) / (share of the most
-                          frequent row): 33 750 user-sorted FilmTrust entries in one launch diverge.
+  * engine -mode fast   : one qrec_mf_sgd_batch_f32 launch per epoch over a shuffled list (Hogwild),
+                          test pairs scored on the device.  A row hit c times while those hits are
+                          in flight moves as if the learning rate were c*lr (every hit reads the same
+                          stale row), and the squared-error gradient is unbounded, so the kernel's
+                          in-flight window is bounded to (0.25/lr) / (share of the most frequent row)
+                          entries: 33 750 user-sorted FilmTrust entries applied as one stale step
+                          diverge.
 STATUS: the kernels behind this module were written after round 1's GPU budget was spent; they
 compile for sm_100a and the oracle is pinned, but no hardware run has validated them yet.
 """
@@ -22,7 +23,7 @@ from ...util.measure import Measure
 
 class PointwiseMF(IterativeRecommender):
     KIND = 1                       # 0 BasicMF, 1 PMF, 2 SVD (include/qrec.h, K9)
-    FAST_MAX_LAUNCH = 1 << 20      # entries per launch in fast mode, upper bound
+    FAST_MAX_INFLIGHT = 1 << 20    # in-flight window of the fast kernel, upper bound (0 would fill the GPU)
 
     # ------------------------------------------------------------------ reference surface
     def initModel(self):
@@ -78,14 +79,13 @@ class PointwiseMF(IterativeRecommender):
         epoch = 0
         while epoch < self.maxEpoch:
             u, i, r = self.data.training_ids()                      # current (shuffled) list order
-            step = self._fast_launch_size(top_share)
+            window = self._fast_window(top_share)
             du, di = torch.from_numpy(u).to(dev), torch.from_numpy(i).to(dev)
             dr = torch.from_numpy(r).to(device=dev, dtype=dtype)
             acc.zero_()
             if fast:
-                for b in range(0, len(u), step):
-                    E.mf_sgd_batch(self.KIND, P, Q, du[b:b + step], di[b:b + step], dr[b:b + step], self.lRate,
-                                   self.regU, self.regI, acc[0:1], Bu, Bi, self.regB, gm)
+                E.mf_sgd_batch(self.KIND, P, Q, du, di, dr, self.lRate, self.regU, self.regI, acc[0:1], Bu, Bi,
+                               self.regB, gm, max_inflight=window)
             else:
                 wu, wi = E.mf_order_prepare(u, i, self.num_users, self.num_items)
                 width = len(u) / max(1, E.mf_order_depth(u, i, self.num_users, self.num_items))
@@ -108,10 +108,10 @@ class PointwiseMF(IterativeRecommender):
 
     buildModel = trainModel
 
-    def _fast_launch_size(self, top_share):
-        """Entries per fast-mode launch: the most frequent row is hit about 0.25/lr times per launch."""
+    def _fast_window(self, top_share):
+        """In-flight entries of the fast kernel: the most frequent row is hit about 0.25/lr times in it."""
         hits = max(1.0, 0.25 / max(self.lRate, 1e-12))
-        return int(min(self.FAST_MAX_LAUNCH, max(32, hits / max(top_share, 1e-12))))
+        return int(min(self.FAST_MAX_INFLIGHT, max(32, hits / max(top_share, 1e-12))))
 
     def _epoch_end(self, epoch):
         """PMF / BasicMF stop when converged (PMF.py:26-27); SVD ignores the flag (SVD.py:36)."""

@@ -177,6 +177,26 @@ def test_edges(torch, E):
     assert float(loss.item()) == 1.0
 
 
+@pytest.mark.parametrize('window', [1, 64, 100000])
+def test_batch_kernel_window_only_changes_the_grid(torch, E, window):
+    """max_inflight sizes the grid, not the result: on a launch without repeated rows every window
+    gives the Jacobi (= sequential) update."""
+    from oracle import mf_oracle as M
+    rng = np.random.default_rng(window)
+    nu, ni, n, d = 3000, 2500, 2000, 32
+    P0 = (rng.random((nu, d)) / 3).astype(np.float32); Q0 = (rng.random((ni, d)) / 3).astype(np.float32)
+    u = rng.permutation(nu)[:n].astype(np.int32); i = rng.permutation(ni)[:n].astype(np.int32)
+    r = (rng.integers(1, 9, n) / 2.0).astype(np.float32)
+    dP, dQ, _, _, ref = M.mf_sgd_jacobi(1, P0, Q0, u, i, r, 0.01, 0.01, 0.02)
+    P, Q = _dev(torch, P0), _dev(torch, Q0)
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.mf_sgd_batch(1, P, Q, _dev(torch, u), _dev(torch, i), _dev(torch, r), 0.01, 0.01, 0.02, loss, max_inflight=window)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(P.cpu().numpy(), P0 + dP, rtol=2e-5, atol=2e-6)
+    np.testing.assert_allclose(Q.cpu().numpy(), Q0 + dQ, rtol=2e-5, atol=2e-6)
+    assert abs(float(loss.item()) - ref) <= 1e-5 * ref
+
+
 @pytest.mark.parametrize('name', NAMES)
 def test_dropin_parity_mode_reproduces_reference_run(torch, name, tmp_path, monkeypatch):
     """The drop-in class, default engine mode (parity, float64), from the same seeds as the golden run:

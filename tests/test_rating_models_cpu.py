@@ -33,14 +33,20 @@ def _install_oracle_engine(monkeypatch, calls):
         loss += M.mf_sgd_sequential(kind, np_of(P), np_of(Q), u.numpy(), i.numpy(), r.numpy(), lr, reg_u, reg_i,
                                     np_of(Bu), np_of(Bi), reg_b, global_mean)
 
-    def batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0):
-        calls.append(('batch', len(u)))
-        dP, dQ, dBu, dBi, l = M.mf_sgd_jacobi(kind, np_of(P), np_of(Q), u.numpy(), i.numpy(), r.numpy(), lr, reg_u,
-                                              reg_i, np_of(Bu), np_of(Bi), reg_b, global_mean)
-        P += torch.from_numpy(dP).to(P.dtype); Q += torch.from_numpy(dQ).to(Q.dtype)
-        if kind == 2:
-            Bu += torch.from_numpy(dBu).to(Bu.dtype); Bi += torch.from_numpy(dBi).to(Bi.dtype)
-        loss += l
+    def batch(kind, P, Q, u, i, r, lr, reg_u, reg_i, loss, Bu=None, Bi=None, reg_b=0.0, global_mean=0.0,
+              max_inflight=0):
+        # worst case of the Hogwild kernel: every window of `max_inflight` entries is one stale (Jacobi) step
+        calls.append(('batch', len(u), max_inflight))
+        w = max_inflight if max_inflight > 0 else len(u)
+        for b in range(0, len(u), w):
+            sl = slice(b, b + w)
+            dP, dQ, dBu, dBi, l = M.mf_sgd_jacobi(kind, np_of(P), np_of(Q), u.numpy()[sl], i.numpy()[sl],
+                                                  r.numpy()[sl], lr, reg_u, reg_i, np_of(Bu), np_of(Bi), reg_b,
+                                                  global_mean)
+            P += torch.from_numpy(dP).to(P.dtype); Q += torch.from_numpy(dQ).to(Q.dtype)
+            if kind == 2:
+                Bu += torch.from_numpy(dBu).to(Bu.dtype); Bi += torch.from_numpy(dBi).to(Bi.dtype)
+            loss += l
 
     def sumsq(x, out):
         out += float((x.double() * x.double()).sum())
@@ -111,17 +117,17 @@ def test_qrec_front_end_resolves_rating_models(monkeypatch, tmp_path):
 
 @pytest.mark.parametrize('name', ['PMF', 'SVD'])
 def test_fast_mode_trains_and_scores_on_device_tables(name, monkeypatch, tmp_path):
-    """-mode fast: fp32 tables padded to a multiple of 4 columns, launches capped so that the most
-    frequent row is hit ~0.25/lr times per launch (the stand-in applies a launch as one Jacobi step,
-    the worst case of the Hogwild kernel), test pairs scored from the resident tables; the run lands
-    near the reference's error."""
+    """-mode fast: fp32 tables padded to a multiple of 4 columns, one launch per epoch whose in-flight
+    window is sized so that the most frequent row is hit ~0.25/lr times in it (the stand-in applies
+    each window as one Jacobi step, the worst case of the Hogwild kernel), test pairs scored from the
+    resident tables; the run lands near the reference's error."""
     calls = []
     _install_oracle_engine(monkeypatch, calls)
     g, model = _build(name, monkeypatch, tmp_path, extra='engine=-mode fast\n')
     measure = model.execute()
     n = len(g['train_users'])
-    sizes = [c[1] for c in calls if c[0] == 'batch']
-    assert sum(sizes) == 3 * n and 32 <= max(sizes) <= 4096
+    launches = [c for c in calls if c[0] == 'batch']
+    assert [c[1] for c in launches] == [n] * 3 and all(32 <= c[2] <= 4096 for c in launches)
     assert [c[0] for c in calls].count('predict') == 3      # one device scoring per epoch
     assert model.P.shape == g['P_last'].shape and model.P.dtype == np.float64
     rmse = float(measure[1].strip().split(':')[1])

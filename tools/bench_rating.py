@@ -1,7 +1,6 @@
 #!/usr/bin/env python
 """K9 (rating-prediction MF step) on the benchmark-scale synthetic set: 1M x 100K x 50M ratings, d=64,
-shuffled order.  Times qrec_mf_sgd_batch_f32 per kind (one launch over the whole list and in 1 M-entry
-launches) and qrec_mf_predict_pairs_f32, plus the C port on a 2 M-entry sample.  One JSON line each.
+shuffled order.  Times qrec_mf_sgd_batch_f32 per kind (full grid and two bounded in-flight windows) and qrec_mf_predict_pairs_f32, plus the C port on a 2 M-entry sample.  One JSON line each.
 Algorithmic bytes per entry: 2 rows x (read + reduce) x 4d + 12 B of (u, i, r) = 1036 B at d = 64."""
 import json
 import os
@@ -43,13 +42,12 @@ def main():
     bytes_per_entry = 2 * 2 * 4 * D + 12
     for kind, name in ((0, 'BasicMF'), (1, 'PMF'), (2, 'SVD')):
         P, Q = synthetic.init_tables(U, I, D, device=dev)
-        for launch in (n, 1 << 20):
+        for window in (0, 1 << 16, 1 << 13):
             def epoch():
-                for b in range(0, n, launch):
-                    E.mf_sgd_batch(kind, P, Q, u[b:b + launch], i[b:b + launch], r[b:b + launch], 1e-4, 0.01, 0.01,
-                                   loss, Bu if kind == 2 else None, Bi if kind == 2 else None, 0.01, 2.5)
+                E.mf_sgd_batch(kind, P, Q, u, i, r, 1e-4, 0.01, 0.01, loss, Bu if kind == 2 else None,
+                               Bi if kind == 2 else None, 0.01, 2.5, max_inflight=window)
             ms = timed(torch, epoch, reps=5, warm=2)
-            print(json.dumps({'k9': name, 'entries_per_launch': launch, 'ms_per_50M': ms, 'G_entries_s': n / ms / 1e6,
+            print(json.dumps({'k9': name, 'max_inflight': window, 'ms_per_50M': ms, 'G_entries_s': n / ms / 1e6,
                               'algorithmic_TBs': n * bytes_per_entry / ms / 1e9,
                               'finite': bool(torch.isfinite(P).all().item())}))
     P, Q = synthetic.init_tables(U, I, D, device=dev)
