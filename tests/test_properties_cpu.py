@@ -94,3 +94,42 @@ def test_bipartite_shards_tile_the_adjacency(recs, world):
         D_ui = torch.sparse_csr_tensor(A_ui[0], A_ui[1].long(), A_ui[2], size=(hi - lo, ni)).to_dense().numpy()
         D_iu = torch.sparse_csr_tensor(A_iu[0], A_iu[1].long(), A_iu[2], size=(ni, hi - lo)).to_dense().numpy()
         assert np.array_equal(D_ui, dense[lo:hi, nu:]) and np.array_equal(D_iu, D_ui.T)
+
+
+@settings(max_examples=120, deadline=None)
+@given(records)
+def test_row_version_schedule_replays_the_sequential_order(recs):
+    """qrec_mf_order_prepare / qrec_bpr_order_prepare: executing entries whenever their rows have reached
+    the recorded versions (any admissible interleaving, here: always the LAST ready entry) touches every
+    row in exactly the sequential order, and the depth is the longest dependency chain."""
+    nu, ni = 13, 16
+    u = np.array([r[0] for r in recs], dtype=np.int32)
+    i = np.array([r[1] for r in recs], dtype=np.int32)
+    wu, wi = E.mf_order_prepare(u, i, nu, ni)
+    ver_p, ver_q = np.zeros(nu, int), np.zeros(ni, int)
+    pending = list(range(len(recs)))
+    seen_p, seen_q = [[] for _ in range(nu)], [[] for _ in range(ni)]
+    while pending:
+        ready = [k for k in pending if ver_p[u[k]] == wu[k] and ver_q[i[k]] == wi[k]]
+        assert ready and pending[0] in ready            # the oldest entry is always runnable: no deadlock
+        k = ready[-1]
+        pending.remove(k)
+        seen_p[u[k]].append(k); seen_q[i[k]].append(k)
+        ver_p[u[k]] += 1; ver_q[i[k]] += 1
+    for a in range(nu):
+        assert seen_p[a] == [k for k in range(len(recs)) if u[k] == a]
+    for b in range(ni):
+        assert seen_q[b] == [k for k in range(len(recs)) if i[k] == b]
+    level_p, level_q, depth = np.zeros(nu, int), np.zeros(ni, int), 0
+    for k in range(len(recs)):
+        lv = max(level_p[u[k]], level_q[i[k]]) + 1
+        level_p[u[k]] = level_q[i[k]] = lv
+        depth = max(depth, lv)
+    assert E.mf_order_depth(u, i, nu, ni) == depth
+    # the pairwise version with j = (i + 1) mod ni shares the item counters between both item rows
+    j = ((i + 1) % ni).astype(np.int32)
+    bu, bi, bj = E.bpr_order_prepare(u, i, j, nu, ni)
+    cq = np.zeros(ni, int)
+    for k in range(len(recs)):
+        assert bu[k] == wu[k] and bi[k] == cq[i[k]] and bj[k] == cq[j[k]]          # i != j here
+        cq[i[k]] += 1; cq[j[k]] += 1
