@@ -459,6 +459,23 @@ def run_ours(args):
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
+        # What actually bounds the fused kernel is the LSU's REDG issue rate, not HBM: every
+        # triple retires 2 item rows x 16 lanes of red.global.add.v4.f32 (+ the amortised P row), and
+        # /opt/skills/guides/B300_MICROARCH.md measures 0.854 (single address) .. 1.29 (spread) cycles per
+        # REDG lane per SM.  Reported beside the HBM roofline; never allowed to cost the headline line.
+        try:
+            mhz = float((clocks or {}).get('sm_mhz') or 0.0)
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            lanes = 2 * (D // 4) + (1.0 + 32.0 / DEGREE) * (D // 4) / 32.0
+            if mhz > 0:
+                lo, hi = (sms * mhz * 1e6 / (lanes * c) for c in (1.29, 0.854))
+                rate = per_launch_triples / (per_launch_ms * 1e-3)
+                out['roofline']['redg_issue_floor'] = {
+                    'redg_lanes_per_triple': lanes, 'cycles_per_lane': [1.29, 0.854], 'sms': sms, 'sm_mhz': mhz,
+                    'triples_per_s': [lo, hi], 'kernel_triples_per_s': rate, 'frac_of_spread_floor': rate / lo,
+                    'source': 'B300_MICROARCH.md atomics table (REDG spread / single address), measured on B300'}
+        except Exception as exc:                         # noqa: BLE001
+            out['roofline']['redg_issue_floor'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
         # the secondary sections must never cost the headline line: report their failure instead
         if world == 1 and not args.no_lightgcn:
             del u, i, j, hu, hi, hj, su, si, sj
