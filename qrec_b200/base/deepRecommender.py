@@ -10,8 +10,6 @@
 """
 import random
 
-import numpy as np
-
 from .iterativeRecommender import IterativeRecommender
 
 
