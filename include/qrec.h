@@ -181,6 +181,21 @@ int qrec_bpr_epoch_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t 
                                  int32_t num_items, uint64_t seed, uint32_t epoch, int32_t* dev_j_out,
                                  float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* The fused epoch with a pre-test in the sampler: rated_sig holds 16 words per user, bit (c & 511) set
+ * for every rated column c (qrec_rated_signature_build; static per data set).  A clear bit proves a
+ * draw is not rated, so about 1 - deg/512 of the draws skip the binary search -- the dependent-load
+ * chain that holds 20 % of the kernel's stall samples (profiles/README.md).  No false negatives:
+ * the negatives, hence P and Q, are identical to qrec_bpr_epoch_usermajor_f32.  d in {16,32,64,128}.
+ * STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware. */
+int qrec_rated_signature_build(int32_t n_users, const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
+                               uint32_t* dev_sig, void* stream);
+int qrec_bpr_epoch_usermajor_sig_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users, int64_t n,
+                                     const int64_t* dev_rowptr, const int32_t* dev_i,
+                                     const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
+                                     const uint32_t* dev_rated_sig, int32_t num_items, uint64_t seed,
+                                     uint32_t epoch, int32_t* dev_j_out, float lr, float reg_u, float reg_i,
+                                     double* dev_loss, void* stream);
+
 /* K1 for a row-sharded item table: the Q rows of the batch were fetched from their
  * owner ranks into dev_R (row pos_i[k] / pos_j[k] holds Q[i_k] / Q[j_k]).  Applies BPR.py:45-52,
  * updates P in place and writes the item-row deltas to dev_D at the same positions, ready to be

@@ -489,12 +489,14 @@ struct FusedSampler {
   int* j_out;                      // may be null
 };
 
-template <int LPR, int G, int CH, bool FULL, bool SAMPLE, int MINB = 3>   // FULL: d == 4*LPR (every lane owns a slice)
+// SIG: the sampler pre-tests every draw against the user's 512-bit rated signature (philox.cuh).
+template <int LPR, int G, int CH, bool FULL, bool SAMPLE, int MINB = 3, bool SIG = false>   // FULL: d == 4*LPR (every lane owns a slice)
 __global__ void __launch_bounds__(256, MINB)
 bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, int n_users,
                          long long n, const long long* __restrict__ rowptr,
                          const int* __restrict__ i, const int* __restrict__ j, float lr,
-                         float reg_u, float reg_i, double* loss, FusedSampler fs, long long trip_off) {
+                         float reg_u, float reg_i, double* loss, FusedSampler fs, long long trip_off,
+                         const uint32_t* __restrict__ rated_sig) {
   // rowptr holds GLOBAL triple offsets; i/j are indexed relative to trip_off (a chunk of users of a
   // larger epoch: the host pipeline stages one chunk at a time).  Philox counters use global indices.
   constexpr int GPW = 32 / LPR;
@@ -545,8 +547,13 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
             ++us;
             ue = __ldg(rowptr + us + 1) - trip_off;
           }
-          mj = qrec::sample_negative(base + l + trip_off, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items, fs.rated_cols,
-                                     __ldg(fs.rated_rowptr + us), __ldg(fs.rated_rowptr + us + 1));
+          if (SIG)
+            mj = qrec::sample_negative_sig(base + l + trip_off, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items,
+                                           fs.rated_cols, __ldg(fs.rated_rowptr + us), __ldg(fs.rated_rowptr + us + 1),
+                                           rated_sig + (size_t)us * qrec::RATED_SIG_WORDS);
+          else
+            mj = qrec::sample_negative(base + l + trip_off, fs.epoch, fs.seed_lo, fs.seed_hi, fs.num_items, fs.rated_cols,
+                                       __ldg(fs.rated_rowptr + us), __ldg(fs.rated_rowptr + us + 1));
           if (fs.j_out != nullptr) fs.j_out[base + l] = mj;
         } else {
           mj = __ldg(j + base + l);
@@ -605,6 +612,22 @@ bpr_sgd_usermajor_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec,
     double t = 0.0;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += (double)wsum[w];
     if (t != 0.0) atomicAdd(loss, t);
+  }
+}
+
+// one warp per user: bit (c & 511) of the user's 16-word signature for every rated column c
+__global__ void __launch_bounds__(256)
+rated_signature_kernel(int n_users, const long long* __restrict__ rowptr, const int* __restrict__ cols,
+                       uint32_t* __restrict__ sig) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long uu = warp; uu < n_users; uu += nwarps) {
+    const long long lo = __ldg(rowptr + uu), hi = __ldg(rowptr + uu + 1);
+    for (long long e = lo + lane; e < hi; e += 32) {
+      const int c = __ldg(cols + e);
+      atomicOr(sig + (size_t)uu * qrec::RATED_SIG_WORDS + ((c >> 5) & (qrec::RATED_SIG_WORDS - 1)), 1u << (c & 31));
+    }
   }
 }
 
@@ -786,7 +809,8 @@ namespace qrec {
 int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
                      const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i, double* loss,
                      bool sample, const int64_t* rated_rowptr, const int32_t* rated_cols, int32_t num_items,
-                     uint64_t seed, uint32_t epoch, int32_t* j_out, long long trip_off, cudaStream_t st) {
+                     uint64_t seed, uint32_t epoch, int32_t* j_out, long long trip_off, cudaStream_t st,
+                     const uint32_t* rated_sig) {
   FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
                      (uint32_t)(seed >> 32), epoch, j_out};
   const int nvec = d / 4;
@@ -802,18 +826,20 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
   }
 #define QREC_UM2(LPR, FULLV, SAMPLEV)                                                            \
   bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV><<<(int)blocks, 256, 0, st>>>(             \
-      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off)
+      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr)
 #define QREC_UM(LPR)                                                                             \
   {                                                                                              \
     const long long per_block = 8 * (32 / LPR);                                                  \
     long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
     if (blocks > cap) blocks = cap;                                                              \
-    if (nvec == LPR && LPR == 16 && variant == 1) {                                              \
-      if (sample) bpr_sgd_usermajor_kernel<16, 4, CH, true, true, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
-      else bpr_sgd_usermajor_kernel<16, 4, CH, true, false, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+    if (nvec == LPR && sample && rated_sig != nullptr) {                                         \
+      bpr_sgd_usermajor_kernel<LPR, 4, CH, true, true, 3, true><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, rated_sig); \
+    } else if (nvec == LPR && LPR == 16 && variant == 1) {                                       \
+      if (sample) bpr_sgd_usermajor_kernel<16, 4, CH, true, true, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
+      else bpr_sgd_usermajor_kernel<16, 4, CH, true, false, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
     } else if (nvec == LPR && LPR == 16 && variant == 2) {                                       \
-      if (sample) bpr_sgd_usermajor_kernel<16, 8, CH, true, true, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
-      else bpr_sgd_usermajor_kernel<16, 8, CH, true, false, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off); \
+      if (sample) bpr_sgd_usermajor_kernel<16, 8, CH, true, true, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
+      else bpr_sgd_usermajor_kernel<16, 8, CH, true, false, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
     } else                                                                                       \
     if (nvec == LPR) { if (sample) QREC_UM2(LPR, true, true); else QREC_UM2(LPR, true, false); } \
     else { if (sample) QREC_UM2(LPR, false, true); else QREC_UM2(LPR, false, false); }           \
@@ -840,7 +866,7 @@ int qrec_bpr_sgd_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, i
   if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && j, "qrec_bpr_sgd_usermajor_f32: null index pointer");
   return qrec::launch_usermajor(P, Q, d, n_users, n, rowptr, i, j, lr, reg_u, reg_i, loss, false, nullptr, nullptr, 0,
-                                0, 0, nullptr, 0, (cudaStream_t)stream);
+                                0, 0, nullptr, 0, (cudaStream_t)stream, nullptr);
 }
 
 int qrec_bpr_epoch_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
@@ -853,7 +879,37 @@ int qrec_bpr_epoch_usermajor_f32(float* P, float* Q, int32_t d, int32_t n_users,
   if (n_users == 0 || n == 0) return QREC_OK;
   QREC_REQUIRE(rowptr && i && rated_rowptr && rated_cols, "qrec_bpr_epoch_usermajor_f32: null index pointer");
   return qrec::launch_usermajor(P, Q, d, n_users, n, rowptr, i, nullptr, lr, reg_u, reg_i, loss, true, rated_rowptr,
-                                rated_cols, num_items, seed, epoch, j_out, 0, (cudaStream_t)stream);
+                                rated_cols, num_items, seed, epoch, j_out, 0, (cudaStream_t)stream, nullptr);
+}
+
+int qrec_rated_signature_build(int32_t n_users, const int64_t* rated_rowptr, const int32_t* rated_cols,
+                               uint32_t* sig, void* stream) {
+  QREC_REQUIRE(n_users >= 0, "qrec_rated_signature_build: n_users < 0");
+  if (n_users == 0) return QREC_OK;
+  QREC_REQUIRE(rated_rowptr && rated_cols && sig, "qrec_rated_signature_build: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  QREC_CUDA(cudaMemsetAsync(sig, 0, (size_t)n_users * qrec::RATED_SIG_WORDS * sizeof(uint32_t), st));
+  long long blocks = ((long long)n_users + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  rated_signature_kernel<<<(int)blocks, 256, 0, st>>>(n_users, reinterpret_cast<const long long*>(rated_rowptr),
+                                                     rated_cols, sig);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_epoch_usermajor_sig_f32(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
+                                     const int32_t* i, const int64_t* rated_rowptr, const int32_t* rated_cols,
+                                     const uint32_t* rated_sig, int32_t num_items, uint64_t seed, uint32_t epoch,
+                                     int32_t* j_out, float lr, float reg_u, float reg_i, double* loss, void* stream) {
+  QREC_REQUIRE(P && Q && loss, "qrec_bpr_epoch_usermajor_sig_f32: null pointer");
+  QREC_REQUIRE(d == 16 || d == 32 || d == 64 || d == 128,
+               "qrec_bpr_epoch_usermajor_sig_f32: d=%d unsupported (16, 32, 64 or 128); use qrec_bpr_epoch_usermajor_f32", d);
+  QREC_REQUIRE(n_users >= 0 && n >= 0 && num_items >= 1, "qrec_bpr_epoch_usermajor_sig_f32: bad size");
+  if (n_users == 0 || n == 0) return QREC_OK;
+  QREC_REQUIRE(rowptr && i && rated_rowptr && rated_cols && rated_sig, "qrec_bpr_epoch_usermajor_sig_f32: null index pointer");
+  return qrec::launch_usermajor(P, Q, d, n_users, n, rowptr, i, nullptr, lr, reg_u, reg_i, loss, true, rated_rowptr,
+                                rated_cols, num_items, seed, epoch, j_out, 0, (cudaStream_t)stream, rated_sig);
 }
 
 int qrec_bpr_sgd_staged_f32(float* P, int32_t d, int64_t n, const int32_t* u, const int32_t* pos_i,

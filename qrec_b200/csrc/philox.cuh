@@ -47,4 +47,35 @@ __device__ __forceinline__ int sample_negative(long long k, uint32_t epoch, uint
   }
 }
 
+// The same draw with a pre-test: `sig` points at the user's 512-bit signature (16 words, bit c & 511
+// set for every rated column c, built by rated_signature_kernel).  A clear bit proves j is not rated,
+// so ~1 - deg/512 of the draws skip the dependent-load bisection; a set bit falls through to it.  The
+// signature has no false negatives, hence the result is identical to sample_negative().
+constexpr int RATED_SIG_WORDS = 16;
+__device__ __forceinline__ int sample_negative_sig(long long k, uint32_t epoch, uint32_t seed_lo, uint32_t seed_hi,
+                                                   int num_items, const int* __restrict__ cols, long long lo0,
+                                                   long long hi0, const uint32_t* __restrict__ sig) {
+  const bool saturated = (hi0 - lo0) >= (long long)num_items;
+  uint32_t attempt = 0;
+  while (true) {
+    uint32_t w[4];
+    philox4x32_10((uint32_t)k, (uint32_t)((unsigned long long)k >> 32), attempt, epoch, seed_lo, seed_hi, w);
+    const int j = (int)(((unsigned long long)w[0] * (unsigned long long)(uint32_t)num_items) >> 32);
+    if (saturated) return j;
+    const uint32_t word = __ldg(sig + ((j >> 5) & (RATED_SIG_WORDS - 1)));
+    if (((word >> (j & 31)) & 1u) == 0u) return j;
+    long long lo = lo0, hi = hi0;
+    bool hit = false;
+    while (lo < hi) {
+      const long long mid = (lo + hi) >> 1;
+      const int c = __ldg(cols + mid);
+      if (c < j) lo = mid + 1;
+      else if (c > j) hi = mid;
+      else { hit = true; break; }
+    }
+    if (!hit) return j;
+    ++attempt;
+  }
+}
+
 }  // namespace qrec

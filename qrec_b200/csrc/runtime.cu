@@ -18,7 +18,8 @@ int launch_bpr_batch(float* P, float* Q, int d, long long n, const int* u, const
 int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, const int64_t* rowptr,
                      const int32_t* i, const int32_t* j, float lr, float reg_u, float reg_i, double* loss,
                      bool sample, const int64_t* rated_rowptr, const int32_t* rated_cols, int32_t num_items,
-                     uint64_t seed, uint32_t epoch, int32_t* j_out, long long trip_off, cudaStream_t st);
+                     uint64_t seed, uint32_t epoch, int32_t* j_out, long long trip_off, cudaStream_t st,
+                     const uint32_t* rated_sig = nullptr);
 }
 
 struct qrec_ctx {

@@ -320,6 +320,35 @@ def bpr_epoch_usermajor(P, Q, rowptr, i, rated_rowptr, rated_cols, num_items, se
     return loss
 
 
+def rated_signature(rated_rowptr, rated_cols):
+    """512-bit rated-set signature per user ([n_users, 16] int32 storage of uint32 words) for the
+    pre-testing sampler of bpr_epoch_usermajor_sig; static per data set."""
+    torch = _torch()
+    n_users = rated_rowptr.shape[0] - 1
+    sig = torch.empty(n_users, 16, dtype=torch.int32, device=rated_rowptr.device)
+    check(lib.qrec_rated_signature_build(n_users, _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
+                                         _dev(rated_cols, torch.int32, 'rated_cols'), sig.data_ptr(), _stream()),
+          'qrec_rated_signature_build')
+    return sig
+
+
+def bpr_epoch_usermajor_sig(P, Q, rowptr, i, rated_rowptr, rated_cols, rated_sig, num_items, seed, epoch, lr, reg_u,
+                            reg_i, loss, j_out=None):
+    """bpr_epoch_usermajor with the signature pre-test in the sampler (same negatives, same update)."""
+    torch = _torch()
+    if rated_sig.shape != (rated_rowptr.shape[0] - 1, 16):
+        raise QRecError('rated_sig must be [n_users, 16] (rated_signature)')
+    check(lib.qrec_bpr_epoch_usermajor_sig_f32(_dev(P, torch.float32, 'P'), _dev(Q, torch.float32, 'Q'), P.shape[1],
+                                               rowptr.shape[0] - 1, int(i.shape[0]), _dev(rowptr, torch.int64, 'rowptr'),
+                                               _dev(i, torch.int32, 'i'), _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
+                                               _dev(rated_cols, torch.int32, 'rated_cols'),
+                                               _dev(rated_sig, torch.int32, 'rated_sig'), int(num_items), int(seed),
+                                               int(epoch), _dev(j_out, torch.int32, 'j_out') if j_out is not None else None,
+                                               float(lr), float(reg_u), float(reg_i), _dev(loss, torch.float64, 'loss'),
+                                               _stream()), 'qrec_bpr_epoch_usermajor_sig_f32')
+    return loss
+
+
 def bpr_sgd_staged(P, u, pos_i, pos_j, R, D, lr, reg_u, reg_i, loss):
     """K1 against item rows staged in R (row-sharded Q); item deltas come back in D."""
     torch = _torch()

@@ -37,6 +37,27 @@ def main():
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 10
         print(json.dumps({'k1_variant': name, 'ms_per_50M': ms, 'G_triples_s': 50 / ms, 'algorithmic_TBs': 50e6 * 1548 / ms / 1e9}))
+    # fused sampling, without / with the signature pre-test (the latter only once validated on hardware)
+    seeds = iter(range(1000))
+    fused = [('fused sampling', lambda: E.bpr_epoch_usermajor(P, Q, rowptr, data['i'], data['sorted_rowptr'], data['sorted_cols'],
+                                                            I, 1, next(seeds), 0.01, 0.001, 0.001, loss))]
+    if os.environ.get('QREC_TEST_UNVALIDATED') == '1':
+        sig = E.rated_signature(data['sorted_rowptr'], data['sorted_cols'])
+        fused.append(('fused sampling + signature pre-test',
+                      lambda: E.bpr_epoch_usermajor_sig(P, Q, rowptr, data['i'], data['sorted_rowptr'], data['sorted_cols'], sig,
+                                                        I, 1, next(seeds), 0.01, 0.001, 0.001, loss)))
+    for name, fn in fused:
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 10
+        print(json.dumps({'k1_variant': name, 'ms_per_50M': ms, 'G_triples_s': 50 / ms}))
     for fn_name, fn in (('sampler shuffled order', lambda: E.sample_neg_philox(u, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0, out=j)),
                         ('sampler user-major order', lambda: E.sample_neg_philox(data['u'], data['sorted_rowptr'], data['sorted_cols'], I, 1, 0, out=ju))):
         fn(); torch.cuda.synchronize()
