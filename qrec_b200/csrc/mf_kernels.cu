@@ -23,6 +23,7 @@
 //   * mf_predict_pairs_kernel -- predictForRating for a list of (u,i) pairs (the per-epoch
 //     rating_performance of iterativeRecommender.py:104-113 without moving the tables).
 #include "common.h"
+#include "mf_step.cuh"
 
 namespace {
 
@@ -39,12 +40,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
@@ -100,33 +95,26 @@ mf_sgd_ordered_kernel(T* __restrict__ P, T* __restrict__ Q, int d, long long n,
       }
     }
     dot = warp_sum(dot);
-    T pred = dot, bu = 0, bi = 0;
+    T bu = 0, bi = 0;
     if (KIND == 2) {
       bu = __ldcg(Bu + uu);
       bi = __ldcg(Bi + ii);
-      pred = add_rn(add_rn(add_rn(dot, global_mean), bi), bu);   // SVD.py:88
     }
-    const T err = sub_rn(rating, pred);
-    const T g = mul_rn(lr, err);                                 // BasicMF.py:22: lRate*error*q
+    const T err = qrec::mf_sub(rating, qrec::mf_prediction<T, KIND>(dot, global_mean, bi, bu));   // SVD.py:88
+    const T g = qrec::mf_mul(lr, err);                           // BasicMF.py:22: lRate*error*q
 #pragma unroll
     for (int e = 0; e < E; ++e) {
       const int c = e * 32 + lane;
       if (c < d) {
         T pn, qn;
-        if (KIND == 0) {
-          pn = add_rn(p[e], mul_rn(g, q[e]));
-          qn = add_rn(q[e], mul_rn(g, pn));
-        } else {
-          pn = add_rn(p[e], mul_rn(lr, sub_rn(mul_rn(err, q[e]), mul_rn(reg_u, p[e]))));
-          qn = add_rn(q[e], mul_rn(lr, sub_rn(mul_rn(err, pn), mul_rn(reg_i, q[e]))));
-        }
+        qrec::mf_update_parity<T, KIND>(p[e], q[e], err, g, lr, reg_u, reg_i, pn, qn);
         __stcg(pr + c, pn);
         __stcg(qr + c, qn);
       }
     }
     if (KIND == 2) {
-      if (lane == 0) __stcg(Bu + uu, add_rn(bu, mul_rn(lr, sub_rn(err, mul_rn(reg_b, bu)))));
-      if (lane == 1) __stcg(Bi + ii, add_rn(bi, mul_rn(lr, sub_rn(err, mul_rn(reg_b, bi)))));
+      if (lane == 0) __stcg(Bu + uu, qrec::mf_bias_parity<T>(bu, err, lr, reg_b));
+      if (lane == 1) __stcg(Bi + ii, qrec::mf_bias_parity<T>(bi, err, lr, reg_b));
     }
     __threadfence();
     __syncwarp();
@@ -206,18 +194,10 @@ mf_sgd_batch_kernel(float* __restrict__ P, float* __restrict__ Q, int nvec, long
         if (ok[f]) {
           if (act) {
             float4 dp, dq;
-#define QREC_MF(c)                                                   \
-  {                                                                  \
-    if (KIND == 0) {                                                 \
-      dp.c = (lr * e) * q[f].c;                                      \
-      dq.c = (lr * e) * (p[f].c + dp.c);                             \
-    } else {                                                         \
-      dp.c = lr * (e * q[f].c - reg_u * p[f].c);                     \
-      dq.c = lr * (e * (p[f].c + dp.c) - reg_i * q[f].c);            \
-    }                                                                \
-  }
-            QREC_MF(x) QREC_MF(y) QREC_MF(z) QREC_MF(w)
-#undef QREC_MF
+            qrec::mf_delta_fast<KIND>(p[f].x, q[f].x, e, lr, reg_u, reg_i, dp.x, dq.x);
+            qrec::mf_delta_fast<KIND>(p[f].y, q[f].y, e, lr, reg_u, reg_i, dp.y, dq.y);
+            qrec::mf_delta_fast<KIND>(p[f].z, q[f].z, e, lr, reg_u, reg_i, dp.z, dq.z);
+            qrec::mf_delta_fast<KIND>(p[f].w, q[f].w, e, lr, reg_u, reg_i, dp.w, dq.w);
             red_add_v4(pr[f], dp);
             red_add_v4(qr[f], dq);
           }
