@@ -352,6 +352,16 @@ int qrec_tc_gemm_tf32(int32_t b_is_nk, int32_t M, int32_t N, int32_t K, const fl
                       int32_t lda, const float* dev_B, int32_t ldb, float* dev_C, int32_t ldc,
                       int32_t epilogue, const float* dev_bias, const float* dev_mask,
                       int32_t ldmask, void* stream);
+/* The same product through a persistent, warp-specialised pipeline: one CTA per SM keeps a 64-column
+ * block of B resident in shared memory, A arrives by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B tensor
+ * map) through a 4-stage mbarrier ring, one thread issues tcgen05.mma into two alternating TMEM
+ * accumulators, four epilogue warps drain them.  Same arguments and epilogues; K <= 320, N <= 64 x #SMs.
+ * A is consumed as raw fp32 bits (TF32 truncation, error <= 2^-10 per operand; v1 rounds to nearest).
+ * STATUS: written after round 1's GPU budget was spent; compiled, not yet run on hardware. */
+int qrec_tc_gemm_tf32_v2(int32_t b_is_nk, int32_t M, int32_t N, int32_t K, const float* dev_A,
+                         int32_t lda, const float* dev_B, int32_t ldb, float* dev_C, int32_t ldc,
+                         int32_t epilogue, const float* dev_bias, const float* dev_mask,
+                         int32_t ldmask, void* stream);
 
 /* =====================================================================================
  * K5 -- NeuMF (model/ranking/NeuMF.py:12-123): row gather / scatter-add around the tensor-core

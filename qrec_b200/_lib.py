@@ -113,6 +113,8 @@ SIGNATURES = {
     'qrec_mask_rated_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float, vp]),
     'qrec_tc_gemm_tf32': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp,
                                     C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]),
+    'qrec_tc_gemm_tf32_v2': (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, vp, C.c_int32, vp,
+                                    C.c_int32, C.c_int32, vp, vp, C.c_int32, vp]),
 }
 
 

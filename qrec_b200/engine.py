@@ -596,6 +596,21 @@ def tc_gemm(A, B, C, b_is_nk=False, epilogue=EPI_NONE, bias=None, mask=None):
     return C
 
 
+def tc_gemm_v2(A, B, C, b_is_nk=False, epilogue=EPI_NONE, bias=None, mask=None):
+    """tc_gemm through the persistent TMA-fed pipeline (K <= 320; A taken as raw fp32 bits = TF32
+    truncation).  Not yet validated on hardware."""
+    torch = _torch()
+    M, K = A.shape
+    N = B.shape[0] if b_is_nk else B.shape[1]
+    assert (B.shape[1] if b_is_nk else B.shape[0]) == K and tuple(C.shape) == (M, N)
+    check(lib.qrec_tc_gemm_tf32_v2(int(b_is_nk), M, N, K, _dev(A, torch.float32, 'A'), A.stride(0),
+                                   _dev(B, torch.float32, 'B'), B.stride(0), _dev(C, torch.float32, 'C'), C.stride(0),
+                                   int(epilogue), _dev(bias, torch.float32, 'bias') if bias is not None else None,
+                                   _dev(mask, torch.float32, 'mask') if mask is not None else None,
+                                   mask.stride(0) if mask is not None else 0, _stream()), 'qrec_tc_gemm_tf32_v2')
+    return C
+
+
 def gather_rows(T, idx, out):
     """out[b, :d] = T[idx[b]]; `out` may be a column block of a wider matrix."""
     torch = _torch()
