@@ -133,3 +133,25 @@ def test_fast_mode_trains_and_scores_on_device_tables(name, monkeypatch, tmp_pat
     rmse = float(measure[1].strip().split(':')[1])
     ref = float(str(g['measure'][1]).split(':')[1])
     assert abs(rmse - ref) < 0.05
+
+
+def test_module_entry_point_runs_a_conf_file(monkeypatch, tmp_path, capsys):
+    """`python -m qrec_b200 model.conf --seed S` == seeding + QRec(ModelConf(path)).execute(): the PMF
+    golden run again, this time from files on disk through the loader."""
+    calls = []
+    _install_oracle_engine(monkeypatch, calls)
+    g = np.load(os.path.join(GOLD, 'mf_pmf_filmtrust.npz'))
+    monkeypatch.chdir(tmp_path)
+    os.makedirs('dataset/FilmTrust')
+    with open('dataset/FilmTrust/trainset.txt', 'w') as f:
+        for u, i, r in zip(g['train_users'].tolist(), g['train_items'].tolist(), g['train_rating'].tolist()):
+            f.write('%s %s %s\n' % (u, i, r))
+    with open('dataset/FilmTrust/testset.txt', 'w') as f:
+        for u, i, r in zip(g['test_users'].tolist(), g['test_items'].tolist(), g['test_rating'].tolist()):
+            f.write('%s %s %s\n' % (u, i, r))
+    with open('pmf.conf', 'w') as f:
+        f.write(str(g['conf']))
+    from qrec_b200.__main__ import main
+    measure = main(['pmf.conf', '--seed', str(int(g['seed']))])
+    assert [m.strip() for m in measure] == g['measure'].tolist()
+    assert 'Running time:' in capsys.readouterr().out
