@@ -184,11 +184,15 @@ def lightgcn_section(torch, E, synthetic, data, dev, peak, layers=3, steps=5, wa
     A_ui, A_iu, _ = parallel.shard_bipartite_by_user(rowptr, cols, vals, U, I, 0, 1)
     g = torch.Generator(device=dev); g.manual_seed(5)
     ego = torch.randn(N, D, device=dev, generator=g) * 0.005
-    m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[:U].clone(), ego[U:].clone(), layers, 0.001, 0.001, 0)
+    # experiment switch (default 1 = the measured path): column-blocked item-side SpMM, DESIGN.md section 10
+    item_blocks = int(os.environ.get('QREC_LGCN_ITEM_BLOCKS', '1'))
+    m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[:U].clone(), ego[U:].clone(), layers, 0.001, 0.001, 0,
+                                     item_side_blocks=item_blocks)
     m._loss = m.loss
     spmm_algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)                 # SURVEY 8(d) no-reuse gather model
     res = {'layers': layers, 'rows': N, 'nnz': nnz, 'semantics': 'full propagation + backward + dense Adam per minibatch',
-           'impl': 'parallel.UserShardedLightGCN at world=1: bipartite blocks A_ui/A_iu, sparse first backward layer'}
+           'impl': 'parallel.UserShardedLightGCN at world=1: bipartite blocks A_ui/A_iu, sparse first backward layer',
+           'item_side_blocks': item_blocks}
     perm = torch.randperm(U * DEGREE, device=dev, generator=g)
     for B in (2048, 65536):
         idx = perm[:B]

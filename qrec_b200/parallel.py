@@ -292,6 +292,39 @@ def shard_bipartite_by_user(rowptr, cols, vals, num_users, num_items, rank, worl
     return (ui_rowptr, ui_cols, ui_vals), (iu_rowptr, iu_cols, iu_vals), (lo, hi)
 
 
+def split_csr_columns(csr, n_cols, n_blocks):
+    """Cuts a CSR (rowptr int64, cols int32 sorted inside every row, vals) into `n_blocks` CSRs over the
+    same rows, block b holding the non-zeros whose column lies in [b*w, (b+1)*w), w = ceil(n_cols /
+    n_blocks); column ids stay global.  sum_b A_b X == A X.  Setup code (torch ops, any device)."""
+    rowptr, cols, vals = csr
+    if n_blocks <= 1:
+        return [csr]
+    width = -(-int(n_cols) // int(n_blocks))
+    block_of = torch.div(cols.long(), width, rounding_mode='floor')
+    n_rows = rowptr.shape[0] - 1
+    row_of = torch.repeat_interleave(torch.arange(n_rows, device=rowptr.device), rowptr[1:] - rowptr[:-1])
+    out = []
+    for b in range(n_blocks):
+        keep = block_of == b
+        counts = torch.bincount(row_of[keep], minlength=n_rows)
+        rp = torch.zeros(n_rows + 1, dtype=torch.int64, device=rowptr.device)
+        rp[1:] = torch.cumsum(counts, 0)
+        out.append((rp, cols[keep].contiguous(), vals[keep].contiguous()))      # masks keep the CSR order
+    return out
+
+
+def blocked_spmm(spmm, blocks, X, Y, scratch, acc, s):
+    """Y = (sum_b A_b) X with the product `spmm(A, X, Y, acc, s)` (Y = A X; acc += s Y): block 0 writes Y,
+    every further block writes `scratch` and accumulates it into Y; the caller's acc is applied last.
+    Each pass gathers only the rows of X inside one column block, so a block that fits the L2 is read
+    from DRAM once per pass instead of once per non-zero."""
+    spmm(blocks[0], X, Y, None, 0.0)
+    for A_b in blocks[1:]:
+        spmm(A_b, X, scratch, Y, 1.0)
+    if acc is not None:
+        acc.add_(Y, alpha=s)
+
+
 class UserShardedLightGCN(object):
     """LightGCN minibatch step (model/ranking/LightGCN.py:13-39 semantics) with the USER rows of the ego
     table partitioned over the ranks and the (25.6 MB at the benchmark scale) ITEM rows replicated.
@@ -306,9 +339,13 @@ class UserShardedLightGCN(object):
     (replicated) for items."""
 
     def __init__(self, A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, group=None,
-                 spmm=None, grad=None, adam=None, scale=None, axpy=None):
+                 spmm=None, grad=None, adam=None, scale=None, axpy=None, item_side_blocks=1):
+        """item_side_blocks > 1 (experimental, default off): the item-side product A_iu E_u runs as that
+        many passes over column blocks of local users (split_csr_columns / blocked_spmm), so each pass
+        gathers user rows from a slice of E_u that fits the L2."""
         from . import engine as E
         self.A_ui, self.A_iu = A_ui, A_iu
+        self.A_iu_blocks = split_csr_columns(A_iu, E_u_local.shape[0], item_side_blocks) if item_side_blocks > 1 else None
         self.Eu, self.Ei = E_u_local, E_i
         self.n_layers, self.lr, self.reg, self.lo = n_layers, lr, reg, user_lo
         self.group = group
@@ -322,6 +359,7 @@ class UserShardedLightGCN(object):
         self.mu, self.vu, self.mi, self.vi = z(nu), z(nu), z(ni), z(ni)
         self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
         self.step = 0
+        self._scratch_i = z(ni) if self.A_iu_blocks is not None else None
         self._spmm = spmm or (lambda A, X, Y, acc, s: E.spmm_csr(A[0], A[1], A[2], X, Y, acc=acc, acc_scale=s, rowsplit=True))
         self._grad = grad or (lambda U_, V_, u, i, j, gU, gV, loss: E.bpr_grad_scatter(U_, V_, u, i, j, 10e-8, self.reg, gU, gV, loss))
         self._adam = adam or (lambda var, m, v, g, t: E.adam_dense_tf1(var, m, v, g, self.lr, t))
@@ -356,6 +394,8 @@ class UserShardedLightGCN(object):
             # item side first (this rank's partial sums), its all-reduce in flight during the user side
             if sparse:
                 self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)    # A_iu G_u through the users' edge lists
+            elif self.A_iu_blocks is not None:
+                blocked_spmm(self._spmm, self.A_iu_blocks, cu, ni_, self._scratch_i, None, 0.0)
             else:
                 self._spmm(self.A_iu, cu, ni_, None, 0.0)
             work = self._allreduce_async(ni_)

@@ -233,7 +233,7 @@ def test_sharded_item_table_bpr_world2():
 # ---------------------------------------------------------------------------------------------
 # LightGCN, user-partitioned / item-replicated: one all-reduce of the item block per layer
 # ---------------------------------------------------------------------------------------------
-def _user_sharded_worker(rank, world, port, out):
+def _user_sharded_worker(rank, world, port, out, blocks=1):
     import numpy as np
     from oracle import bpr_oracle as O
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -264,7 +264,8 @@ def _user_sharded_worker(rank, world, port, out):
         m = parallel.UserShardedLightGCN(
             A_ui, A_iu, torch.from_numpy(ego[lo:hi].copy()), torch.from_numpy(ego[U:].copy()), L, lr, reg, lo,
             spmm=spmm, grad=grad, adam=lambda var, mm, v, g, t: O.adam_tf1(var.numpy(), mm.numpy(), v.numpy(), g.numpy(), lr, t),
-            scale=lambda dst, src, s: dst.copy_(src * s), axpy=lambda dst, src, s: dst.add_(src, alpha=s))
+            scale=lambda dst, src, s: dst.copy_(src * s), axpy=lambda dst, src, s: dst.add_(src, alpha=s),
+            item_side_blocks=blocks)
         Ur, Vr = ego[:U].copy(), ego[U:].copy()
         mU, vU, mV, vV = (np.zeros_like(x) for x in (Ur, Ur, Vr, Vr))
         for step in range(3):
@@ -285,4 +286,14 @@ def test_user_sharded_lightgcn_matches_single_process_world2():
     mgr = mp.Manager()
     out = mgr.dict()
     mp.spawn(_user_sharded_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+def test_user_sharded_lightgcn_with_column_blocked_item_side_world2():
+    """item_side_blocks=2: the item-side product runs as two passes over column blocks of the local
+    users (split_csr_columns + blocked_spmm); same training trajectory as the single-process oracle."""
+    port = 37500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_user_sharded_worker, args=(2, port, out, 2), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}

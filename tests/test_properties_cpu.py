@@ -133,3 +133,40 @@ def test_row_version_schedule_replays_the_sequential_order(recs):
     for k in range(len(recs)):
         assert bu[k] == wu[k] and bi[k] == cq[i[k]] and bj[k] == cq[j[k]]          # i != j here
         cq[i[k]] += 1; cq[j[k]] += 1
+
+
+@settings(max_examples=80, deadline=None)
+@given(records, st.integers(1, 5))
+def test_column_blocks_sum_to_the_matrix(recs, n_blocks):
+    """parallel.split_csr_columns: the blocks partition the non-zeros by column range, keep every row's
+    order, and blocked_spmm over them equals the unsplit product."""
+    import scipy.sparse as sp
+    nu, ni = 13, 16
+    M = sp.csr_matrix((np.array([r[2] for r in recs], np.float32),
+                       (np.array([r[0] for r in recs], int), np.array([r[1] for r in recs], int))), shape=(nu, ni))
+    M.sum_duplicates(); M.sort_indices()
+    csr = (torch.from_numpy(M.indptr.astype(np.int64)), torch.from_numpy(M.indices.astype(np.int32)),
+           torch.from_numpy(M.data.astype(np.float32)))
+    blocks = parallel.split_csr_columns(csr, ni, n_blocks)
+    assert len(blocks) == max(1, n_blocks)
+    width = -(-ni // n_blocks)
+    total = np.zeros((nu, ni), np.float32)
+    for b, (rp, co, va) in enumerate(blocks):
+        assert rp.dtype == torch.int64 and co.dtype == torch.int32 and int(rp[-1]) == co.numel() == va.numel()
+        if n_blocks > 1:
+            assert bool(((co >= b * width) & (co < (b + 1) * width)).all())
+        D = sp.csr_matrix((va.numpy(), co.numpy(), rp.numpy()), shape=(nu, ni))
+        assert D.has_sorted_indices or D.nnz == 0
+        total += D.toarray()
+    assert np.array_equal(total, M.toarray())
+
+    def spmm(A, X, Y, acc, s):
+        D = torch.from_numpy(sp.csr_matrix((A[2].numpy(), A[1].numpy(), A[0].numpy()), shape=(nu, ni)).toarray())
+        Y.copy_(D @ X)
+        if acc is not None:
+            acc.add_(Y, alpha=s)
+    X = torch.arange(ni * 3, dtype=torch.float32).reshape(ni, 3) / 7
+    Y, scratch, acc = torch.full((nu, 3), 9.0), torch.full((nu, 3), 5.0), torch.ones(nu, 3)
+    parallel.blocked_spmm(spmm, blocks, X, Y, scratch, acc, 0.5)
+    ref = torch.from_numpy(M.toarray()) @ X
+    assert torch.allclose(Y, ref, atol=1e-5) and torch.allclose(acc, 1 + 0.5 * ref, atol=1e-5)

@@ -18,6 +18,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--layers', type=int, default=3)
     ap.add_argument('--batch', type=int, default=2048)
+    ap.add_argument('--item-blocks', type=int, default=1, help='column blocks of the item-side SpMM (experimental)')
     ap.add_argument('--scheme', default='user', choices=['user', 'rows'],
                     help='user: users partitioned + items replicated (all-reduce of the item block per layer); '
                          'rows: all rows partitioned (all-gather of the whole table per layer)')
@@ -46,7 +47,8 @@ def main():
             A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, U, I, rank, world)
             part = None
             mine = torch.cat([torch.arange(lo, hi, device=dev), torch.arange(U, U + I, device=dev)])
-            m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[lo:hi].clone(), ego[U:].clone(), args.layers, 0.001, 0.001, lo)
+            m = parallel.UserShardedLightGCN(A_ui, A_iu, ego[lo:hi].clone(), ego[U:].clone(), args.layers, 0.001, 0.001, lo,
+                                             item_side_blocks=args.item_blocks)
             m.local_nnz = int(A_ui[1].numel()) * 2
         return data, (rp, co, va), ego, part, mine, m
 
