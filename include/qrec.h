@@ -251,6 +251,15 @@ int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* dev_r
                                const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
                                float* dev_acc, float acc_scale, void* stream);
 
+/* Experiment entry point (d = 64): the row-split product with the number of outstanding gathers and
+ * the occupancy as a parameter -- variant 0 = the production configuration, 1/2 = 5/6 CTAs per SM,
+ * 3 = 16 gathers per batch, 4/5 = software-pipelined double buffers (csrc/spmm_variants.cu).  The
+ * floating-point order is the production kernel's, so every variant returns its bits.
+ * STATUS: compiled, not yet run on hardware. */
+int qrec_spmm_csr_rowsplit_var_f32(int32_t variant, int32_t n_rows, const int64_t* dev_rowptr,
+                                   const int32_t* dev_cols, const float* dev_vals, const float* dev_X,
+                                   float* dev_Y, int32_t d, float* dev_acc, float acc_scale, void* stream);
+
 /* Sparse-source product (the first backward layer of a minibatch step: the loss gradient touches at
  * most 3B rows).  (rowptr, cols, vals) is a CSR whose ROWS are source nodes and whose column ids index
  * rows of Y; Y (n_rows rows) is zero-filled here, then Y[c] += a_rc X[r] over the edges of the n_src

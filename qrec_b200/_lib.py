@@ -56,6 +56,7 @@ SIGNATURES = {
     'qrec_rated_signature_build': (C.c_int, [C.c_int32, vp, vp, vp, vp]),
     'qrec_bpr_epoch_usermajor_sig_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_int32,
                                                    C.c_uint64, C.c_uint32, vp, C.c_float, C.c_float, C.c_float, vp, vp]),
+    'qrec_spmm_csr_rowsplit_var_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, C.c_int32, vp, C.c_float, vp]),
     'qrec_mf_order_prepare': (C.c_int, [C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, c_i32p, c_i32p]),
     'qrec_mf_order_depth': (C.c_int64, [C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32]),
     'qrec_mf_sgd_ordered_f32': (C.c_int, [C.c_int32, vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp,

@@ -451,6 +451,18 @@ def spmm_csr(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
     return Y
 
 
+def spmm_csr_rowsplit_variant(variant, rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0):
+    """Experimental row-split SpMM configurations (d = 64; csrc/spmm_variants.cu); same bits as
+    spmm_csr(..., rowsplit=True)."""
+    torch = _torch()
+    check(lib.qrec_spmm_csr_rowsplit_var_f32(int(variant), rowptr.shape[0] - 1, _dev(rowptr, torch.int64, 'rowptr'),
+                                             _dev(cols, torch.int32, 'cols'), _dev(vals, torch.float32, 'vals'),
+                                             _dev(X, torch.float32, 'X'), _dev(Y, torch.float32, 'Y'), X.shape[1],
+                                             _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                             float(acc_scale), _stream()), 'qrec_spmm_csr_rowsplit_var_f32')
+    return Y
+
+
 def spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scale=0.0):
     """Y[dst] += a * X[src] over the edge lists (CSR rows) of the source rows `src_rows`, after
     zero-filling Y: Y = B^T X for the CSR matrix B = (rowptr, cols, vals) restricted to those rows.

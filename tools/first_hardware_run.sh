@@ -9,15 +9,16 @@ export QREC_TEST_UNVALIDATED=1
 out=gpurun_out/first_run
 mkdir -p "$out"
 python -c "import __graft_entry__ as g; g.build()" > "$out/build.log" 2>&1 || { echo "build failed"; tail -20 "$out/build.log"; exit 1; }
-for t in test_gpu_k1_sig test_gpu_rating test_gpu_lightgcn_blocked test_gpu_tcgemm_v2; do
+for t in test_gpu_k1_sig test_gpu_rating test_gpu_lightgcn_blocked test_gpu_spmm_variants test_gpu_tcgemm_v2; do
   timeout 600 python -m pytest "tests/$t.py" -m gpu -x -q > "$out/$t.log" 2>&1
   echo "$t: exit $? -- $(tail -1 "$out/$t.log")"
 done
 timeout 600 python tools/bench_k1.py      > "$out/bench_k1.jsonl"      2> "$out/bench_k1.err";      echo "bench_k1: exit $?"
 timeout 600 python tools/bench_rating.py  > "$out/bench_rating.jsonl"  2> "$out/bench_rating.err";  echo "bench_rating: exit $?"
+timeout 600 python tools/bench_graph.py --spmm-only > "$out/bench_spmm.jsonl" 2> "$out/bench_spmm.err"; echo "bench_spmm: exit $?"
 timeout 600 python tools/bench_tcgemm.py  > "$out/bench_tcgemm.jsonl"  2> "$out/bench_tcgemm.err";  echo "bench_tcgemm: exit $?"
 for b in 1 2 3 4; do
   QREC_LGCN_ITEM_BLOCKS=$b timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_lgcn_blocks$b.json" 2> "$out/bench_lgcn_blocks$b.err"
   echo "lightgcn item blocks $b: $(python -c "import json,sys; d=json.load(open('$out/bench_lgcn_blocks$b.json')); print(d.get('lightgcn'))" 2>/dev/null | cut -c1-300)"
 done
-grep -h "k1_variant\|k9\|tc_gemm" "$out"/*.jsonl | cut -c1-220
+grep -h "k1_variant\|k9\|tc_gemm\|spmm" "$out"/*.jsonl | cut -c1-220
