@@ -17,7 +17,7 @@ timeout 600 python tools/bench_k1.py      > "$out/bench_k1.jsonl"      2> "$out/
 timeout 600 python tools/bench_rating.py  > "$out/bench_rating.jsonl"  2> "$out/bench_rating.err";  echo "bench_rating: exit $?"
 timeout 600 python tools/bench_graph.py --spmm-only > "$out/bench_spmm.jsonl" 2> "$out/bench_spmm.err"; echo "bench_spmm: exit $?"
 timeout 600 python tools/bench_tcgemm.py  > "$out/bench_tcgemm.jsonl"  2> "$out/bench_tcgemm.err";  echo "bench_tcgemm: exit $?"
-for b in 1 2 3 4; do
+for b in 1 3; do
   QREC_LGCN_ITEM_BLOCKS=$b timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_lgcn_blocks$b.json" 2> "$out/bench_lgcn_blocks$b.err"
   echo "lightgcn item blocks $b: $(python -c "import json,sys; d=json.load(open('$out/bench_lgcn_blocks$b.json')); print(d.get('lightgcn'))" 2>/dev/null | cut -c1-300)"
 done
