@@ -110,6 +110,19 @@ int qrec_sample_neg_philox(int64_t n, int32_t num_items, const int32_t* dev_u,
  * K1 -- BPR.optimization(u,i,j), model/ranking/BPR.py:45-53 (statement order as there).
  * ===================================================================================== */
 
+/* Per-user item sets of an id-mapped interaction list (host; next row f-3): the reference keeps them as
+ * a dict of dicts (data/rating.py:48-55), so a repeated (user, item) line keeps the position of its
+ * first occurrence and the value of its last.  Outputs (caller-allocated, column arrays of length n):
+ *   sorted_rowptr / sorted_cols   every rated item per user, ascending ids (the rejection sets)
+ *   pos_rowptr / pos_cols         items with rating >= positive_threshold in insertion order
+ *                                 (the iteration order of model/ranking/BPR.py:22-25,31-33)
+ *   possorted_cols                the same positives in ascending ids (rows as in pos_rowptr)
+ * rating may be null (every rating 1).  Stable counting sort by user + a small sort per user, threaded. */
+int qrec_build_rated_csr(int64_t n, const int64_t* u, const int64_t* i, const double* rating,
+                         int32_t num_users, int32_t num_items, double positive_threshold,
+                         int64_t* sorted_rowptr, int32_t* sorted_cols, int64_t* pos_rowptr,
+                         int32_t* pos_cols, int32_t* possorted_cols);
+
 /* Host prepass for the dependency-ordered kernel: for triple k, wait_x[k] = number of
  * earlier triples (k' < k) that touch the same table row (P[u_k]; Q[i_k]; Q[j_k], where a
  * Q row counts touches both as i and as j). */

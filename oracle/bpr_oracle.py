@@ -86,6 +86,40 @@ def shuffle_pairs(rng, a, b):
     return arr[:, 0].copy(), arr[:, 1].copy()
 
 
+
+# ---------------------------------------------------------------------------------------------
+# per-user item sets (data/rating.py:48-55 dict-of-dicts semantics; model/ranking/BPR.py:22-25)
+# ---------------------------------------------------------------------------------------------
+def rated_csr_numpy(num_users, num_items, u_ids, i_ids, ratings=None, positive_threshold=1.0):
+    """The numpy construction the engine used before qrec_build_rated_csr (three full-length sorts);
+    kept as the checker of the native builder.  A repeated (user, item) keeps the position of its first
+    occurrence and the value of its last.  Returns a dict of the five arrays."""
+    u_ids = np.ascontiguousarray(u_ids, dtype=np.int64)
+    i_ids = np.ascontiguousarray(i_ids, dtype=np.int64)
+    n = u_ids.shape[0]
+    if ratings is None:
+        ratings = np.ones(n, dtype=np.float64)
+    ratings = np.asarray(ratings, dtype=np.float64)
+    key = u_ids * int(num_items) + i_ids
+    order = np.argsort(key, kind='stable')
+    ks = key[order]
+    first = np.ones(n, dtype=bool)
+    first[1:] = ks[1:] != ks[:-1]
+    last = np.ones(n, dtype=bool)
+    last[:-1] = ks[1:] != ks[:-1]
+    first_pos = order[first]
+    last_rating = ratings[order[last]]
+    uniq_u, uniq_i = u_ids[first_pos], i_ids[first_pos]
+    sorted_rowptr = np.zeros(num_users + 1, dtype=np.int64)
+    sorted_rowptr[1:] = np.cumsum(np.bincount(uniq_u, minlength=num_users))
+    keep = last_rating >= positive_threshold
+    pu, pi, ppos = uniq_u[keep], uniq_i[keep], first_pos[keep]
+    o2 = np.lexsort((ppos, pu))
+    pos_rowptr = np.zeros(num_users + 1, dtype=np.int64)
+    pos_rowptr[1:] = np.cumsum(np.bincount(pu, minlength=num_users))
+    return dict(sorted_rowptr=sorted_rowptr, sorted_cols=uniq_i.astype(np.int32), pos_rowptr=pos_rowptr,
+                pos_cols=pi[o2].astype(np.int32), possorted_cols=pi.astype(np.int32))
+
 # ---------------------------------------------------------------------------------------------
 # K1: BPR.optimization (model/ranking/BPR.py:45-53) and the epoch bookkeeping around it
 # ---------------------------------------------------------------------------------------------

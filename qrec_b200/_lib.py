@@ -46,6 +46,8 @@ SIGNATURES = {
                                         c_i32p, c_i32p, c_i32p]),
     'qrec_sample_neg_philox': (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, C.c_uint64, C.c_uint32,
                                          vp, vp]),
+    'qrec_build_rated_csr': (C.c_int, [C.c_int64, c_i64p, c_i64p, c_f64p, C.c_int32, C.c_int32, C.c_double, c_i64p, c_i32p,
+                                       c_i64p, c_i32p, c_i32p]),
     'qrec_bpr_order_prepare': (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32,
                                          c_i32p, c_i32p, c_i32p]),
     'qrec_bpr_order_depth': (C.c_int64, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32]),

@@ -46,42 +46,32 @@ class RatedCSR(object):
         u_ids = np.ascontiguousarray(u_ids, dtype=np.int64)
         i_ids = np.ascontiguousarray(i_ids, dtype=np.int64)
         n = u_ids.shape[0]
-        if ratings is None:
-            ratings = np.ones(n, dtype=np.float64)
-        ratings = np.asarray(ratings, dtype=np.float64)
+        if i_ids.shape[0] != n:
+            raise QRecError('RatedCSR: u_ids and i_ids differ in length')
+        r = None
+        if ratings is not None:
+            r = np.ascontiguousarray(ratings, dtype=np.float64)
+            if r.shape[0] != n:
+                raise QRecError('RatedCSR: ratings and ids differ in length')
         self.num_users, self.num_items = int(num_users), int(num_items)
-        key = u_ids * self.num_items + i_ids
-        # dict semantics: position of the FIRST occurrence, value of the LAST one
-        order = np.argsort(key, kind='stable')
-        ks = key[order]
-        first = np.ones(n, dtype=bool)
-        first[1:] = ks[1:] != ks[:-1]
-        last = np.ones(n, dtype=bool)
-        last[:-1] = ks[1:] != ks[:-1]
-        first_pos = order[first]                 # original index of first occurrence per pair
-        last_rating = ratings[order[last]]       # rating of last occurrence per pair
-        uniq_u = u_ids[first_pos]
-        uniq_i = i_ids[first_pos]
-        # sorted rows: pairs are already ordered by (u, i)
+        # qrec_build_rated_csr (csrc/host_csr.cpp): counting sort by user + a small sort per user, threaded
         self.sorted_rowptr = np.zeros(self.num_users + 1, dtype=np.int64)
-        np.add.at(self.sorted_rowptr, uniq_u + 1, 1)
-        np.cumsum(self.sorted_rowptr, out=self.sorted_rowptr)
-        self.sorted_cols = np.ascontiguousarray(uniq_i, dtype=np.int32)
-        # positive rows in insertion order
-        keep = last_rating >= positive_threshold
-        pu, pi, ppos = uniq_u[keep], uniq_i[keep], first_pos[keep]
-        o2 = np.lexsort((ppos, pu))
         self.pos_rowptr = np.zeros(self.num_users + 1, dtype=np.int64)
-        np.add.at(self.pos_rowptr, pu + 1, 1)
-        np.cumsum(self.pos_rowptr, out=self.pos_rowptr)
-        self.pos_cols = np.ascontiguousarray(pi[o2], dtype=np.int32)
+        sorted_cols, pos_cols, possorted_cols = (np.empty(n, dtype=np.int32) for _ in range(3))
+        check(lib.qrec_build_rated_csr(n, _i64p(u_ids), _i64p(i_ids), r.ctypes.data_as(C.POINTER(C.c_double)) if r is not None else None,
+                                       self.num_users, self.num_items, float(positive_threshold), _i64p(self.sorted_rowptr),
+                                       _i32p(sorted_cols), _i64p(self.pos_rowptr), _i32p(pos_cols), _i32p(possorted_cols)),
+              'qrec_build_rated_csr')
+        n_rated, n_pos = int(self.sorted_rowptr[-1]), int(self.pos_rowptr[-1])
+        self.sorted_cols = np.ascontiguousarray(sorted_cols[:n_rated])
+        self.pos_cols = np.ascontiguousarray(pos_cols[:n_pos])
         # the positives again, ascending ids: BPR.trainModel rejects against PositiveSet only
         # (model/ranking/BPR.py:36); identical to sorted_* when every rating is >= threshold
-        if bool(keep.all()):
+        if n_pos == n_rated:
             self.possorted_rowptr, self.possorted_cols = self.sorted_rowptr, self.sorted_cols
         else:
             self.possorted_rowptr = self.pos_rowptr
-            self.possorted_cols = np.ascontiguousarray(pi, dtype=np.int32)   # (u,i)-sorted already
+            self.possorted_cols = np.ascontiguousarray(possorted_cols[:n_pos])
 
     @property
     def num_positives(self):

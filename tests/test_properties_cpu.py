@@ -170,3 +170,41 @@ def test_column_blocks_sum_to_the_matrix(recs, n_blocks):
     parallel.blocked_spmm(spmm, blocks, X, Y, scratch, acc, 0.5)
     ref = torch.from_numpy(M.toarray()) @ X
     assert torch.allclose(Y, ref, atol=1e-5) and torch.allclose(acc, 1 + 0.5 * ref, atol=1e-5)
+
+
+@settings(max_examples=150, deadline=None)
+@given(records, st.sampled_from([0.5, 1.0, 2.5]))
+def test_native_rated_csr_equals_numpy_construction(recs, threshold):
+    """qrec_build_rated_csr (counting sort + per-user sorts, threaded) against the numpy construction it
+    replaced (oracle.rated_csr_numpy): all five arrays, for repeated pairs, empty users and mixed ratings."""
+    from oracle import bpr_oracle as O
+    nu, ni = 13, 16
+    u = np.array([r[0] for r in recs], dtype=np.int64)
+    i = np.array([r[1] for r in recs], dtype=np.int64)
+    r = np.array([r[2] for r in recs], dtype=np.float64)
+    got = E.RatedCSR(nu, ni, u, i, r, positive_threshold=threshold)
+    want = O.rated_csr_numpy(nu, ni, u, i, r, positive_threshold=threshold)
+    assert np.array_equal(got.sorted_rowptr, want['sorted_rowptr']) and np.array_equal(got.sorted_cols, want['sorted_cols'])
+    assert np.array_equal(got.pos_rowptr, want['pos_rowptr']) and np.array_equal(got.pos_cols, want['pos_cols'])
+    assert np.array_equal(got.possorted_rowptr, got.pos_rowptr if len(got.pos_cols) != len(got.sorted_cols) else got.sorted_rowptr)
+    assert np.array_equal(got.possorted_cols, want['possorted_cols'])
+
+
+def test_native_rated_csr_large_threaded_and_errors():
+    from oracle import bpr_oracle as O
+    rng = np.random.default_rng(3)
+    nu, ni, n = 40000, 5000, 1_500_000                    # several threads, repeated pairs, skewed users
+    u = np.minimum(rng.zipf(1.3, n) - 1, nu - 1).astype(np.int64)
+    i = rng.integers(0, ni, n)
+    r = rng.integers(0, 5, n) / 1.0
+    got = E.RatedCSR(nu, ni, u, i, r)
+    want = O.rated_csr_numpy(nu, ni, u, i, r)
+    for k in ('sorted_rowptr', 'sorted_cols', 'pos_rowptr', 'pos_cols', 'possorted_cols'):
+        assert np.array_equal(getattr(got, k), want[k]), k
+    import pytest
+    with pytest.raises(E.QRecError):
+        E.RatedCSR(3, 4, np.array([0, 3]), np.array([1, 1]))          # user id out of range
+    with pytest.raises(E.QRecError):
+        E.RatedCSR(3, 4, np.array([0, 1]), np.array([1, -1]))         # negative item id
+    with pytest.raises(E.QRecError):
+        E.RatedCSR(3, 4, np.array([0, 1]), np.array([1]))
