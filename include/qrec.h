@@ -110,6 +110,22 @@ int qrec_sample_neg_philox(int64_t n, int32_t num_items, const int32_t* dev_u,
  * K1 -- BPR.optimization(u,i,j), model/ranking/BPR.py:45-53 (statement order as there).
  * ===================================================================================== */
 
+/* Native reader of rating files (host; next row f-3): FileIO.loadDataSet (util/io.py:31-76) with the
+ * default delimiter set -- strip, split at every single ' ', ',' or tab, optional header, column
+ * selection, optional binarisation -- plus the first-appearance id mapping of Rating.__generateSet
+ * (data/rating.py:33-54).  col_r < 0: no rating column (every rating 1.0).  Returns NULL with a message
+ * in qrec_last_error() for anything it is not sure about (short line, unusual number syntax) so that
+ * the caller can fall back to the reference-style Python path. */
+typedef struct qrec_text_table qrec_text_table;
+qrec_text_table* qrec_text_load(const char* path, int32_t col_u, int32_t col_i, int32_t col_r, int32_t header,
+                                int32_t binarize, double threshold);
+int64_t qrec_text_rows(const qrec_text_table* t);
+int32_t qrec_text_vocab_size(const qrec_text_table* t, int32_t which /* 0 users, 1 items */);
+int qrec_text_copy(const qrec_text_table* t, int32_t* u, int32_t* i, double* r);
+/* names in id order joined by '\n'; returns the byte count (copies into buf when buf != NULL) */
+int64_t qrec_text_names(const qrec_text_table* t, int32_t which, char* buf, int64_t capacity);
+void qrec_text_free(qrec_text_table* t);
+
 /* Per-user item sets of an id-mapped interaction list (host; next row f-3): the reference keeps them as
  * a dict of dicts (data/rating.py:48-55), so a repeated (user, item) line keeps the position of its
  * first occurrence and the value of its last.  Outputs (caller-allocated, column arrays of length n):

@@ -46,6 +46,12 @@ SIGNATURES = {
                                         c_i32p, c_i32p, c_i32p]),
     'qrec_sample_neg_philox': (C.c_int, [C.c_int64, C.c_int32, vp, vp, vp, C.c_uint64, C.c_uint32,
                                          vp, vp]),
+    'qrec_text_load': (vp, [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double]),
+    'qrec_text_rows': (C.c_int64, [vp]),
+    'qrec_text_vocab_size': (C.c_int32, [vp, C.c_int32]),
+    'qrec_text_copy': (C.c_int, [vp, c_i32p, c_i32p, c_f64p]),
+    'qrec_text_names': (C.c_int64, [vp, C.c_int32, C.c_char_p, C.c_int64]),
+    'qrec_text_free': (None, [vp]),
     'qrec_build_rated_csr': (C.c_int, [C.c_int64, c_i64p, c_i64p, c_f64p, C.c_int32, C.c_int32, C.c_double, c_i64p, c_i32p,
                                        c_i64p, c_i32p, c_i32p]),
     'qrec_bpr_order_prepare': (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int32, C.c_int32,

@@ -11,6 +11,8 @@ import re
 
 import numpy as np
 
+DEFAULT_DELIM = ' |,|\\t'          # util/io.py:36: the reference's default `-delim`
+
 
 class InteractionTable(object):
     def __init__(self, user_names, item_names, u, i, r):
@@ -43,10 +45,48 @@ class InteractionTable(object):
         return cls(un, inn, u, i, r)
 
     @classmethod
-    def from_text(cls, path, columns=(0, 1, 2), delim=' |,|\\t', header=False, binarize_threshold=None):
+    def _from_text_native(cls, path, columns, header, binarize_threshold):
+        """qrec_text_load (csrc/host_loader.cpp): one pass over the file in C++, hash-map id assignment.
+        Returns None when the native reader declines the file (short line, unusual number syntax): the
+        Python loop below then decides, with the reference's own behaviour."""
+        import ctypes as C
+        from .._lib import lib
+        col_r = columns[2] if len(columns) >= 3 else -1
+        if binarize_threshold is not None and col_r < 0:
+            return None
+        h = lib.qrec_text_load(os.fsencode(path), int(columns[0]), int(columns[1]), int(col_r), int(bool(header)),
+                               int(binarize_threshold is not None), float(binarize_threshold or 0.0))
+        if not h:
+            if not os.path.exists(path):
+                raise FileNotFoundError(path)
+            return None
+        try:
+            n = lib.qrec_text_rows(h)
+            u, i, r = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.float64)
+            lib.qrec_text_copy(h, u.ctypes.data_as(C.POINTER(C.c_int32)), i.ctypes.data_as(C.POINTER(C.c_int32)),
+                               r.ctypes.data_as(C.POINTER(C.c_double)))
+            names = []
+            for which in (0, 1):
+                size = lib.qrec_text_names(h, which, None, 0)
+                buf = C.create_string_buffer(max(1, size))
+                lib.qrec_text_names(h, which, buf, size)
+                count = lib.qrec_text_vocab_size(h, which)
+                names.append(np.array(buf.raw[:size].decode().split('\n')) if count else np.zeros(0, str))
+        except UnicodeDecodeError:
+            return None
+        finally:
+            lib.qrec_text_free(h)
+        return cls(names[0], names[1], u, i, r)
+
+    @classmethod
+    def from_text(cls, path, columns=(0, 1, 2), delim=DEFAULT_DELIM, header=False, binarize_threshold=None):
         """Same parsing rules as FileIO.loadDataSet (util/io.py:31-76): regex-split lines, `columns`
         picks user / item / rating, rows with rating < threshold are dropped and the rest set to 1 when
         binarising, a missing rating column means 1."""
+        if delim == DEFAULT_DELIM:
+            table = cls._from_text_native(path, columns, header, binarize_threshold)
+            if table is not None:
+                return table
         splitter = re.compile(delim)
         users, items, ratings = [], [], []
         with open(path) as fh:

@@ -87,3 +87,77 @@ def test_empty_table(tmp_path):
     t = InteractionTable.from_text(str(p))
     assert len(t) == 0 and t.num_users == 0 and t.rated_csr().num_positives == 0
     assert InteractionTable.from_records([]).to_records() == []
+
+
+# --------------------------------------------------------------------------------------------- native reader
+def _python_path(path, **kw):
+    """InteractionTable.from_text with the native reader switched off (an equivalent delimiter regex)."""
+    return InteractionTable.from_text(path, delim='[ ,\t]', **kw)
+
+
+def _same(a, b):
+    return (a.user_names.tolist() == b.user_names.tolist() and a.item_names.tolist() == b.item_names.tolist()
+            and np.array_equal(a.u, b.u) and np.array_equal(a.i, b.i) and np.array_equal(a.r, b.r))
+
+
+@pytest.mark.parametrize('kw', [dict(), dict(header=True), dict(binarize_threshold=2.0), dict(columns=(1, 0, 2)),
+                                dict(columns=(0, 1)), dict(columns=(0, 2, 3), binarize_threshold=1.0)])
+def test_native_reader_equals_python_loop(tmp_path, kw, monkeypatch):
+    rng = random.Random(len(repr(kw)))
+    lines = []
+    for n in range(3000):
+        u, i = 'user%d' % rng.randint(0, 200), 'itém%d' % rng.randint(0, 300)        # non-ASCII names
+        r = rng.choice(['0.5', '1', '2.0', '3.5', '4', '1e0', '+2', '.5'])
+        sep = rng.choice([' ', ',', '\t'])
+        lead, trail = rng.choice(['', ' ', '\t']), rng.choice(['', ' ', '\r', ' \t'])
+        lines.append(lead + sep.join([u, i, r, '7']) + trail + '\n')
+    lines[-1] = lines[-1].rstrip('\n')                                                   # no final newline
+    p = tmp_path / 'r.txt'
+    p.write_text(''.join(lines), encoding='utf-8')
+    calls = []
+    orig = InteractionTable._from_text_native.__func__
+    monkeypatch.setattr(InteractionTable, '_from_text_native',
+                        classmethod(lambda cls, *a: (calls.append(1), orig(cls, *a))[1]))
+    a = InteractionTable.from_text(str(p), **kw)
+    assert calls == [1]
+    b = _python_path(str(p), **kw)
+    assert len(calls) == 1 and _same(a, b) and len(a) > 0
+
+
+def test_native_reader_keeps_empty_fields_like_re_split(tmp_path):
+    """re.split(' |,|\\t') does not merge separators: 'a  b 3' is ['a', '', 'b', '3']."""
+    p = tmp_path / 'r.txt'
+    p.write_text('a  b 3\nc ,d 4\n')
+    t = InteractionTable.from_text(str(p), columns=(0, 2, 3))
+    assert t.user_names.tolist() == ['a', 'c'] and t.item_names.tolist() == ['b', 'd'] and t.r.tolist() == [3.0, 4.0]
+    t = InteractionTable.from_text(str(p), columns=(0, 1, 3))
+    assert t.item_names.tolist() == [''] and _same(t, _python_path(str(p), columns=(0, 1, 3)))
+
+
+def test_native_reader_declines_and_python_path_decides(tmp_path):
+    p = tmp_path / 'r.txt'
+    p.write_text('a b 1_0\nc d 2\n')                      # float('1_0') == 10.0 in Python, not a strtod number
+    t = InteractionTable.from_text(str(p))
+    assert t.r.tolist() == [10.0, 2.0]
+    p.write_text('a b 1\nshort\n')                         # the reference fails with IndexError on a short line
+    with pytest.raises(IndexError):
+        InteractionTable.from_text(str(p))
+    with pytest.raises(FileNotFoundError):
+        InteractionTable.from_text(str(tmp_path / 'absent.txt'))
+    p.write_text('a b nan\n')
+    assert np.isnan(InteractionTable.from_text(str(p)).r[0])
+
+
+def test_native_reader_parses_decimals_like_float(tmp_path):
+    """The short-decimal fast path (digits / 10^k, both exact) and the strtod path must give float()'s
+    bits for every token."""
+    rng = random.Random(11)
+    toks = ['0', '5', '4.', '.25', '0.1', '0.30000000000000004', '123456789012345', '1234567.89012345', '9.999999999999999',
+            '1e-3', '-2.5', '+7', '00012.5000', '179769313486231', '0.000000000000001']
+    for _ in range(3000):
+        a, b = rng.randrange(0, 10 ** rng.randrange(1, 9)), rng.randrange(0, 10 ** rng.randrange(1, 8))
+        toks.append('%d.%0*d' % (a, rng.randrange(1, 8), b))
+    p = tmp_path / 'r.txt'
+    p.write_text(''.join('u%d i%d %s\n' % (k, k % 7, t) for k, t in enumerate(toks)))
+    t = InteractionTable.from_text(str(p))
+    assert t.r.tolist() == [float(x) for x in toks]
