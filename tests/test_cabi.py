@@ -57,3 +57,18 @@ def test_sm100a_only_and_blackwell_sass():
     sass = subprocess.run([cuobjdump, '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'REDG.E.ADD.F32x4' in sass          # red.global.add.v4.f32 scatter-add
     assert 'LDG.E.128' in sass                 # 128-bit row gathers
+
+
+def test_integration_doc_snippets_are_valid_python_and_name_real_symbols():
+    """The binding a maintainer would copy from INTEGRATION.md must at least parse, and every C entry
+    point it calls must exist in the header."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    blocks = re.findall(r'```python\n(.*?)```', text, re.S)
+    assert blocks
+    header = open(os.path.join(root, 'include', 'qrec.h')).read()
+    for code in blocks:
+        compile(code, 'INTEGRATION.md', 'exec')
+        for name in re.findall(r'lib\.(qrec_[a-z0-9_]+)', code):
+            assert re.search(r'\b%s\s*\(' % name, header), name
