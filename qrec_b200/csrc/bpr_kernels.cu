@@ -22,8 +22,11 @@
 
 #include "common.h"
 #include "philox.cuh"
+#include "bpr_step.cuh"
 
 namespace {
+
+using namespace qrec::bpr;
 
 // ------------------------------------------------------------------------------------------
 // helpers
@@ -41,20 +44,6 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
-
-// Round-to-nearest mul/add/sub that ptxas never contracts into an FMA: numpy evaluates
-// `P[u] += g*(Q[i]-Q[j])` as separate multiply and add, and parity mode follows it.
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-
-__device__ __forceinline__ float sigmoid_full(float x) { return 1.0f / (1.0f + expf(-x)); }
-__device__ __forceinline__ double sigmoid_full(double x) { return 1.0 / (1.0 + exp(-x)); }
-__device__ __forceinline__ double neg_log(float s) { return -(double)logf(s); }
-__device__ __forceinline__ double neg_log(double s) { return -log(s); }
 
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
@@ -123,12 +112,8 @@ bpr_sgd_ordered_kernel(T* __restrict__ P, T* __restrict__ Q, int d, long long n,
     for (int e = 0; e < E; ++e) {
       const int c = e * 32 + lane;
       if (c < d) {
-        T pn = add_rn(p[e], mul_rn(g, sub_rn(qi[e], qj[e])));
-        T qin = add_rn(qi[e], mul_rn(g, pn));
-        T qjn = sub_rn(qj[e], mul_rn(g, pn));
-        pn = sub_rn(pn, mul_rn(a_u, pn));
-        qin = sub_rn(qin, mul_rn(a_i, qin));
-        qjn = sub_rn(qjn, mul_rn(a_i, qjn));
+        T pn, qin, qjn;
+        bpr_update_parity(p[e], qi[e], qj[e], g, a_u, a_i, pn, qin, qjn);
         __stcg(pr + c, pn);
         __stcg(qir + c, qin);
         __stcg(qjr + c, qjn);
@@ -160,22 +145,6 @@ __device__ __forceinline__ float group_sum(float v) {
 
 __device__ __forceinline__ float dot4(float4 a, float4 b) {
   return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-}
-
-// One BPR step on a 4-wide slice; returns the three deltas.
-__device__ __forceinline__ void bpr_step4(float4 p, float4 qi, float4 qj, float g, float a_u,
-                                          float a_i, float4& dp, float4& dqi, float4& dqj) {
-#define QREC_STEP(c)                                  \
-  {                                                   \
-    float pn = p.c + g * (qi.c - qj.c);               \
-    float qin = qi.c + g * pn;                        \
-    float qjn = qj.c - g * pn;                        \
-    dp.c = (pn - a_u * pn) - p.c;                     \
-    dqi.c = (qin - a_i * qin) - qi.c;                 \
-    dqj.c = (qjn - a_i * qjn) - qj.c;                 \
-  }
-  QREC_STEP(x) QREC_STEP(y) QREC_STEP(z) QREC_STEP(w)
-#undef QREC_STEP
 }
 
 template <int LPR, int VPL, int UNROLL>
@@ -450,22 +419,6 @@ bpr_sgd_batch_tma_kernel(float* __restrict__ P, float* __restrict__ Q, long long
 // REDG.E.ADD.F32x4 as in the batch kernel.  Per triple: 2 row loads + 2 row REDs instead of 3 + 3.
 // Input: CSR over users (rowptr), i[] / j[] in that order.
 // ------------------------------------------------------------------------------------------
-// The same step with the decay folded into the coefficients (7 instead of 11 flops per component):
-//   pn = p + g (qi - qj);  p' = (1 - a_u) pn;  dqi = g (1 - a_i) pn - a_i qi;  dqj = -g (1 - a_i) pn - a_i qj
-// (identical algebra to BPR.py:46-52; differs from bpr_step4 by one rounding of the (1-a) product).
-__device__ __forceinline__ void bpr_step4_inplace(float4& p, float4 qi, float4 qj, float g, float one_m_au,
-                                                  float c1, float a_i, float4& dqi, float4& dqj) {
-#define QREC_STEP(c)                                   \
-  {                                                    \
-    const float pn = fmaf(g, qi.c - qj.c, p.c);        \
-    dqi.c = fmaf(c1, pn, -a_i * qi.c);                 \
-    dqj.c = fmaf(-c1, pn, -a_i * qj.c);                \
-    p.c = one_m_au * pn;                               \
-  }
-  QREC_STEP(x) QREC_STEP(y) QREC_STEP(z) QREC_STEP(w)
-#undef QREC_STEP
-}
-
 template <int LPR>
 __device__ __forceinline__ float group_sum_masked(float v, unsigned gmask) {
 #pragma unroll
