@@ -44,6 +44,14 @@ class IterativeRecommender(Recommender):
             print('engine option is invalid! use -mode parity|fast -precision f64|f32')
             sys.exit(-1)
 
+    def _device(self):
+        """The CUDA device named by `engine=-device N` (made current); the one place the numpy-style
+        models touch torch.cuda, so that host-logic tests can swap it."""
+        import torch
+        dev = torch.device('cuda', self.engine_device)
+        torch.cuda.set_device(dev)
+        return dev
+
     def printAlgorConfig(self):
         super(IterativeRecommender, self).printAlgorConfig()
         print('Embedding Dimension:', self.emb_size)

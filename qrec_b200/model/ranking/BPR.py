@@ -28,8 +28,7 @@ class BPR(IterativeRecommender):
         from ... import engine as E
         print('Preparing item sets...')
         csr = self.data.rated_csr()
-        dev = torch.device('cuda', self.engine_device)
-        torch.cuda.set_device(dev)
+        dev = self._device()
         fast = self.engine_mode == 'fast'
         dtype = torch.float32 if (fast or self.engine_precision == 'f32') else torch.float64
         d = self.emb_size
@@ -96,8 +95,7 @@ class BPR(IterativeRecommender):
         truncated_normal(0.005) (iterativeRecommender.py:44-45)."""
         import torch
         from ... import engine as E
-        dev = torch.device('cuda', self.engine_device)
-        torch.cuda.set_device(dev)
+        dev = self._device()
         if not hasattr(self, 'batch_size'):
             self.batch_size = int(self.config['batch_size'])
         d = self.emb_size

@@ -35,12 +35,6 @@ class PointwiseMF(IterativeRecommender):
         return self.regU * sums[0] + self.regI * sums[1]
 
     # ------------------------------------------------------------------ engine
-    def _device(self):
-        import torch
-        dev = torch.device('cuda', self.engine_device)
-        torch.cuda.set_device(dev)
-        return dev
-
     def _upload(self, a, dev, dtype, dpad=None):
         import torch
         if a.ndim == 1:
