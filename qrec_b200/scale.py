@@ -12,8 +12,7 @@ class ScaleBPR(object):
         import torch
         self.table = table
         self.emb_size, self.lRate, self.maxLRate, self.regU, self.regI = emb_size, lr, max_lr, reg_u, reg_i
-        self.device = torch.device('cuda', device)
-        torch.cuda.set_device(self.device)
+        self.device = self._make_device(device)
         self.seed = seed
         csr = table.rated_csr()
         self.num_users, self.num_items = table.num_users, table.num_items
@@ -34,6 +33,14 @@ class ScaleBPR(object):
         self._acc = torch.zeros(3, dtype=torch.float64, device=dev)
         self.loss, self.lastLoss, self.epoch = 0.0, 0.0, 0
         self.history = []
+
+    @staticmethod
+    def _make_device(index):
+        """The CUDA device (made current); the one place this class touches torch.cuda."""
+        import torch
+        dev = torch.device('cuda', index)
+        torch.cuda.set_device(dev)
+        return dev
 
     def run_epoch(self):
         """One epoch; returns True when the reference's convergence test fires."""
