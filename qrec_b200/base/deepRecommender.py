@@ -24,12 +24,6 @@ class DeepRecommender(IterativeRecommender):
     def printAlgorConfig(self):
         super(DeepRecommender, self).printAlgorConfig()
 
-    def _device(self):
-        import torch
-        dev = torch.device('cuda', self.engine_device)
-        torch.cuda.set_device(dev)
-        return dev
-
     @staticmethod
     def truncated_normal(shape, stddev, device, generator=None):
         import torch
