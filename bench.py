@@ -111,28 +111,34 @@ class ClockSampler(object):
 # reference arm / cpu baseline: the oracle port of the reference's numpy loop on host cores
 # ---------------------------------------------------------------------------------------------
 def host_workload(n_triples, seed=7):
+    """A user-major sample of the bench workload for the host-side legs: the first n_triples/DEGREE
+    users (sample users, DEGREE triples each, in the reference's iteration order BPR.py:31-33), items and
+    negatives uniform over the 100K items (the rejection of rated negatives changes 0.05 % of them)."""
     rng = np.random.default_rng(seed)
-    P = rng.random((NUM_USERS, D)) / 3            # float64, like base/iterativeRecommender.py:37-38
+    users = n_triples // DEGREE
+    P = rng.random((users, D)) / 3                # float64, like base/iterativeRecommender.py:37-38
     Q = rng.random((NUM_ITEMS, D)) / 3
-    u = rng.integers(0, NUM_USERS, n_triples).astype(np.int32)
-    i = rng.integers(0, NUM_ITEMS, n_triples).astype(np.int32)
-    j = ((i + 1 + rng.integers(0, NUM_ITEMS - 1, n_triples)) % NUM_ITEMS).astype(np.int32)
+    u = np.repeat(np.arange(users, dtype=np.int32), DEGREE)
+    i = rng.integers(0, NUM_ITEMS, users * DEGREE).astype(np.int32)
+    j = ((i + 1 + rng.integers(0, NUM_ITEMS - 1, users * DEGREE)) % NUM_ITEMS).astype(np.int32)
     return P, Q, u, i, j
 
 
 def cpu_baseline(sample_triples):
-    """Times oracle/bpr_ref.c (float64 restatement of model/ranking/BPR.py:45-53) on one host core."""
+    """Times oracle/bpr_ref.c (float64 restatement of model/ranking/BPR.py:45-53) on one host core on a
+    user-major sample (used when the full-epoch parity check, which times the whole epoch, is off)."""
     from oracle import c_oracle
     P, Q, u, i, j = host_workload(sample_triples)
+    n = len(u)
     c_oracle.bpr_sgd_sequential(P, Q, u[:100000], i[:100000], j[:100000], LR, REG_U, REG_I)  # warm
     t0 = time.perf_counter()
     c_oracle.bpr_sgd_sequential(P, Q, u, i, j, LR, REG_U, REG_I)
     dt = time.perf_counter() - t0
-    return {'value': sample_triples / dt, 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
-            'sample': '%d shuffled triples of the same 1M x 100K d=64 workload, float64 C port of the '
+    return {'value': n / dt, 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
+            'sample': '%d user-major triples (%d users x %d) of the same 1M x 100K d=64 workload, float64 C port of the '
                       'reference numpy loop (oracle/bpr_ref.c); the loop is a serial dependency chain, '
-                      'so 1 thread (host has %d cores)' % (sample_triples, os.cpu_count() or 0),
-            'seconds': dt}
+                      'so 1 thread (host has %d cores)' % (n, n // DEGREE, DEGREE, os.cpu_count() or 0),
+            'seconds': dt, 'host_cores': os.cpu_count()}
 
 
 def run_reference(args):
@@ -151,7 +157,7 @@ def run_reference(args):
         c_oracle.bpr_sgd_sequential(P, Q, u[s], i[s], j[s], LR, REG_U, REG_I)
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    desc = ('%d shuffled triples per step of the same workload; float64 C port (oracle/bpr_ref.c) of '
+    desc = ('%d user-major triples per step (fresh users each step) of the same workload; float64 C port (oracle/bpr_ref.c) of '
             'model/ranking/BPR.py:45-53; the Python reference itself cannot travel to the GPU box '
             '(measured here: ~95 K triples/s); serial dependency chain => 1 thread of %d' % (sample, os.cpu_count() or 0))
     print(json.dumps({
@@ -163,6 +169,69 @@ def run_reference(args):
         'e2e': {'value': value, 'unit': 'triples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }))
+
+
+# ---------------------------------------------------------------------------------------------
+# parity of the BENCHMARKED path at the benchmarked size: the fused user-major epoch (all ranks)
+# against the reference's sequential loop on the same (u, i, j) stream
+# ---------------------------------------------------------------------------------------------
+def table_errors(X, Xref, X0):
+    """max-norm relative error of the table (the metric of the fp32 parity tests) and the error
+    relative to what the epoch moved: ||X - Xref||_F / ||Xref - X0||_F."""
+    X = np.asarray(X, np.float64)
+    diff = X - Xref
+    mv = Xref - X0
+    return {'max_abs_err': float(np.abs(diff).max()), 'max_norm_rel': float(np.abs(diff).max() / np.abs(Xref).max()),
+            'rms_err_over_rms_update': float(np.sqrt((diff * diff).mean()) / max(1e-300, np.sqrt((mv * mv).mean())))}
+
+
+def oracle_epoch(P0, Q0, u, i, j, dtype, user_block_perm=None):
+    """model/ranking/BPR.py:29-53 through the C port on one host thread; returns P, Q, sum(-ln s), seconds.
+    user_block_perm: visit blocks of 1024 users in a permuted order (still user-major inside a block) -- the
+    reference's own sensitivity to the iteration order, as a yardstick for the parallel kernel's error."""
+    from oracle import c_oracle
+    P, Q = P0.astype(dtype), Q0.astype(dtype)
+    t0 = time.perf_counter()
+    if user_block_perm is None:
+        l = c_oracle.bpr_sgd_sequential(P, Q, u, i, j, LR, REG_U, REG_I)
+    else:
+        l = 0.0
+        blk = 1024 * DEGREE
+        for b in user_block_perm:
+            sl = slice(b * blk, min(len(u), (b + 1) * blk))
+            l += c_oracle.bpr_sgd_sequential(P, Q, u[sl], i[sl], j[sl], LR, REG_U, REG_I)
+    return P, Q, float(l), time.perf_counter() - t0
+
+
+def parity_against_sequential(P0, Q0, u, i, j, P_gpu, Q_gpu, loss_gpu, full=True):
+    """Compares one GPU epoch from (P0, Q0) on the stream (u, i, j) with the sequential reference loop.
+    full: also run the fp32 sequential port (rounding yardstick) and a block-permuted float64 run
+    (iteration-order yardstick), the three on separate host threads."""
+    from concurrent.futures import ThreadPoolExecutor
+    P0d, Q0d = P0.astype(np.float64), Q0.astype(np.float64)
+    Pr, Qr, lr_, secs = oracle_epoch(P0d, Q0d, u, i, j, np.float64)          # alone: this one is also the CPU timing
+    out = {'oracle': 'oracle/bpr_ref.c float64, sequential, the same (u,i,j) stream in the same user-major order '
+                     '(model/ranking/BPR.py:29-53)',
+           'triples': int(len(u)), 'oracle_seconds': secs, 'oracle_triples_per_s': len(u) / secs,
+           'loss_sum_neg_log_sigmoid': {'gpu': float(loss_gpu), 'oracle_f64': lr_, 'rel_err': abs(loss_gpu - lr_) / lr_},
+           'P': table_errors(P_gpu, Pr, P0d), 'Q': table_errors(Q_gpu, Qr, Q0d)}
+    if full:
+        nblk = -(-(len(u) // DEGREE) // 1024)
+        perm = np.random.default_rng(3).permutation(nblk)
+        with ThreadPoolExecutor(2) as ex:
+            f32 = ex.submit(oracle_epoch, P0d, Q0d, u, i, j, np.float32)
+            prm = ex.submit(oracle_epoch, P0d, Q0d, u, i, j, np.float64, perm)
+            P32, Q32, l32, _ = f32.result()
+            Pp, Qp, lp, _ = prm.result()
+        out['yardstick_f32_sequential_vs_f64'] = {'loss_rel_err': abs(l32 - lr_) / lr_, 'P': table_errors(P32, Pr, P0d),
+                                                  'Q': table_errors(Q32, Qr, Q0d)}
+        out['yardstick_f64_user_blocks_permuted_vs_in_order'] = {
+            'note': 'same sequential float64 loop, blocks of 1024 users visited in a random order',
+            'loss_rel_err': abs(lp - lr_) / lr_, 'P': table_errors(Pp, Pr, P0d), 'Q': table_errors(Qp, Qr, Q0d)}
+        out['gpu_vs_f32_sequential'] = {'loss_rel_err': abs(loss_gpu - l32) / l32,
+                                        'P': table_errors(P_gpu, P32.astype(np.float64), P0d),
+                                        'Q': table_errors(Q_gpu, Q32.astype(np.float64), Q0d)}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -299,24 +368,31 @@ def run_ours(args):
     ub = parallel.sync_points(users_local, q_syncs)
     k1_events = []
 
-    def step(epoch, timed):
-        loss.zero_()
+    def epoch_on(Pt, Qt, sync, epoch, loss_t, j_out=None, events=None):
+        """One epoch of the rank's shard on tables (Pt, Qt): q_syncs fused launches, each followed by the
+        item-table delta all-reduce when N>1.  j_out (int32[n_local]) receives the sampled negatives."""
         for s in range(q_syncs):
             ua, ub_ = ub[s], ub[s + 1]
             a, b = ua * DEGREE, ub_ * DEGREE
-            if timed:
+            if events is not None:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if q_syncs == 1:
-                E.bpr_epoch_usermajor(P, Q, csr_rowptr, i, rowptr, cols, NUM_ITEMS, 2024, epoch, LR, REG_U, REG_I, loss[0:1])
+                E.bpr_epoch_usermajor(Pt, Qt, csr_rowptr, i, rowptr, cols, NUM_ITEMS, 2024, epoch, LR, REG_U, REG_I,
+                                      loss_t[0:1], j_out=j_out)
             else:
                 rp = (csr_rowptr[ua:ub_ + 1] - a).contiguous()
-                E.bpr_epoch_usermajor(P[ua:ub_], Q, rp, i[a:b], rowptr[ua:ub_ + 1].contiguous(), cols, NUM_ITEMS,
-                                      2024 + s, epoch, LR, REG_U, REG_I, loss[0:1])
-            if timed:
+                E.bpr_epoch_usermajor(Pt[ua:ub_], Qt, rp, i[a:b], rowptr[ua:ub_ + 1].contiguous(), cols, NUM_ITEMS,
+                                      2024 + s, epoch, LR, REG_U, REG_I, loss_t[0:1],
+                                      j_out=None if j_out is None else j_out[a:b])
+            if events is not None:
                 e1.record()
-                k1_events.append((e0, e1, b - a))
-            qsync.sync()          # N>1: NCCL all-reduce of this rank's item-row deltas (no-op at N=1)
+                events.append((e0, e1, b - a))
+            sync.sync()           # N>1: NCCL all-reduce of this rank's item-row deltas (no-op at N=1)
+
+    def step(epoch, timed):
+        loss.zero_()
+        epoch_on(P, Q, qsync, epoch, loss, events=k1_events if timed else None)
         E.sumsq(P, loss[1:2])
         E.sumsq(Q, loss[2:3])
 
@@ -416,6 +492,44 @@ def run_ours(args):
     pipe.close()
     e2e_value = total_triples / e2e_s
 
+    # ------------------------------------------------------------------ parity of this very path at this size
+    parity = None
+    if not args.no_parity:
+        P1, Q1 = synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + rank, device=dev)
+        if world > 1:
+            dist.broadcast(Q1, 0)
+        Q0_host = Q1.cpu().numpy() if rank == 0 else None
+        sync1 = parallel.ReplicatedTableSync(Q1)
+        jx = torch.empty(n_local, dtype=torch.int32, device=dev)
+        l1 = torch.zeros(3, dtype=torch.float64, device=dev)
+        epoch_on(P1, Q1, sync1, 0, l1, j_out=jx)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.all_reduce(l1)
+            gi = torch.empty(n_local * world, dtype=torch.int32, device=dev)
+            gj = torch.empty(n_local * world, dtype=torch.int32, device=dev)
+            gP = torch.empty(users_local * world, D, dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(gi, i.contiguous())
+            dist.all_gather_into_tensor(gj, jx)
+            dist.all_gather_into_tensor(gP, P1)
+        else:
+            gi, gj, gP = i, jx, P1
+        if rank == 0:
+            P0_host = np.concatenate([synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + r, device=dev)[0].cpu().numpy()
+                                      for r in range(world)])
+            hu_all = np.repeat(np.arange(users_local * world, dtype=np.int32), DEGREE)
+            parity = parity_against_sequential(P0_host, Q0_host, hu_all, gi.cpu().numpy(), gj.cpu().numpy(),
+                                               gP.cpu().numpy(), Q1.cpu().numpy(), float(l1[0].item()), full=(world == 1))
+            parity['what'] = ('epoch 0 of the benchmarked path (qrec_bpr_epoch_usermajor_f32, fused Philox sampling, %d GPU(s), '
+                              '%d item-table syncs) from the initial tables, negatives exported through j_out, against the '
+                              'sequential reference loop on the same stream' % (world, q_syncs))
+            parity['bound_held_in_tests'] = 'loss rel_err <= 1e-3 (tests/test_gpu_parity_config2.py)'
+            del P0_host, hu_all
+        del P1, Q1, jx, gi, gj, gP, sync1
+        torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
+
     if rank == 0:
         peak, peak_src = measured_hbm_peak()
         per_launch_triples = k1_triples / max(1, len(k1_events))
@@ -488,7 +602,16 @@ def run_ours(args):
                 out['lightgcn'] = lightgcn_section(torch, E, synthetic, data, dev, peak)
             except Exception as exc:                     # noqa: BLE001
                 out['lightgcn'] = {'error': '%s: %s' % (type(exc).__name__, exc)}
-        if world == 1 and not args.no_cpu_baseline:
+        if parity is not None:
+            out['parity_check'] = parity
+        if world == 1 and parity is not None:
+            out['cpu_baseline'] = {
+                'value': parity['oracle_triples_per_s'], 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
+                'seconds': parity['oracle_seconds'], 'host_cores': os.cpu_count(),
+                'sample': 'the WHOLE 50M-triple user-major epoch of this workload (the stream the GPU epoch sampled), float64 '
+                          'C port of the reference numpy loop (oracle/bpr_ref.c) -- a serial dependency chain, so 1 thread '
+                          'of the %d host cores; the same run is the parity oracle' % (os.cpu_count() or 0)}
+        elif world == 1 and not args.no_cpu_baseline:
             try:
                 out['cpu_baseline'] = cpu_baseline(args.cpu_sample)
             except Exception as exc:                     # noqa: BLE001
@@ -510,6 +633,7 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=4_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-lightgcn', action='store_true')
+    ap.add_argument('--no-parity', action='store_true', help='skip the full-epoch parity check against the sequential oracle')
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     if args.impl == 'reference':

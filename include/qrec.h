@@ -238,6 +238,13 @@ int qrec_bpr_sgd_staged_f32(float* dev_P, int32_t d, int64_t n, const int32_t* d
 int qrec_sumsq_f32(const float* dev_x, int64_t n, double* dev_out, void* stream);
 int qrec_sumsq_f64(const double* dev_x, int64_t n, double* dev_out, void* stream);
 
+/* Measurement aid for the K1 roofline (bench.py "row_op_peak"; not on the product path): issues
+ * n_ops 256-byte row operations against random rows of dev_table [rows, 64] fp32 with nothing else in
+ * the loop -- mode 0: LDG.E.128 gathers, 1: REDG.E.ADD.F32x4 scatter-adds (value 1e-9 alternating in
+ * sign), 2: one gather + one scatter-add per op (K1's mix on the item table, BPR.py:45-52). */
+int qrec_ubench_row_ops_f32(float* dev_table, int64_t rows, int64_t n_ops, int32_t mode, uint32_t seed,
+                            float* dev_sink, void* stream);
+
 /* =====================================================================================
  * Pipelined host entry (what trainModel calls when the triples live in HOST memory):
  * chunks the index arrays, overlaps H2D copies (copy stream) with the K1 kernel (compute

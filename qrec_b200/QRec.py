@@ -65,7 +65,10 @@ class QRec(object):
             if line[:3] == 'Top':
                 res.append(line)
                 continue
-            res.append(line.split(':')[0] + ':' + str(sum(float(f[pos].split(':')[1]) for f in folds) / k) + '\n')
+            total = 0                                  # left-to-right `+=` like the reference (builtin sum() is compensated on 3.12)
+            for f in folds:
+                total += float(f[pos].split(':')[1])
+            res.append(line.split(':')[0] + ':' + str(total / k) + '\n')
         stamp = strftime("%Y-%m-%d %H-%M-%S", localtime(time()))
         FileIO.writeFile(OptionConf(self.config['output.setup'])['-dir'],
                          self.config['model.name'] + '@' + stamp + '-' + str(k) + '-fold-cv' + '.txt', res)

@@ -87,6 +87,7 @@ SIGNATURES = {
                                                C.c_uint64, C.c_uint32, vp, C.c_float, C.c_float, C.c_float, vp, vp]),
     'qrec_bpr_sgd_staged_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, vp, vp, C.c_float, C.c_float,
                                           C.c_float, vp, vp]),
+    'qrec_ubench_row_ops_f32': (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, C.c_uint32, vp, vp]),
     'qrec_sumsq_f32': (C.c_int, [vp, C.c_int64, vp, vp]),
     'qrec_sumsq_f64': (C.c_int, [vp, C.c_int64, vp, vp]),
     'qrec_ctx_create': (C.c_int, [C.c_int, C.c_int64, C.POINTER(vp)]),

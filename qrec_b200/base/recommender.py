@@ -192,19 +192,16 @@ class Recommender(object):
             print('Initializing model %s...' % self.foldInfo)
             self.initModel()
             print('Building Model %s...' % self.foldInfo)
-            use_tf = False
-            if self.evalSettings.contains('-tf'):
-                try:
-                    import tensorflow  # noqa: F401
-                    use_tf = True
-                except ImportError:
-                    use_tf = False
-            try:
-                if use_tf:
-                    self.trainModel_tf()
-                else:
-                    self.trainModel()
-            except ImportError:
+            # `-tf` selects the minibatch/Adam variant (base/recommender.py:195-203 of the reference).  The
+            # engine never imports TensorFlow, so the switch does not depend on it being installed; a model
+            # that does not define its own trainModel_tf (the reference's base hook is `pass`, which would
+            # evaluate the random initial tables) falls back to trainModel with a warning.
+            own_tf = type(self).trainModel_tf is not Recommender.trainModel_tf
+            if self.evalSettings.contains('-tf') and own_tf:
+                self.trainModel_tf()
+            else:
+                if self.evalSettings.contains('-tf'):
+                    print('WARNING: %s has no trainModel_tf; `-tf` ignored, running trainModel().' % self.modelName)
                 self.trainModel()
         print('Predicting %s...' % self.foldInfo)
         if self.ranking.isMainOn():

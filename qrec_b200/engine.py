@@ -350,6 +350,17 @@ def bpr_sgd_staged(P, u, pos_i, pos_j, R, D, lr, reg_u, reg_i, loss):
     return loss
 
 
+def ubench_row_ops(table, n_ops, mode, seed=1):
+    """Roofline aid: n_ops random 256-byte row gathers (mode 0) / scatter-adds (1) / one of each (2) on
+    table [rows, 64] fp32 with no arithmetic (csrc/microbench.cu).  Perturbs the table by ~1e-9 per op."""
+    torch = _torch()
+    if table.dim() != 2 or table.shape[1] != 64:
+        raise QRecError('ubench_row_ops: table must be [rows, 64] fp32')
+    sink = torch.zeros(1, dtype=torch.float32, device=table.device)
+    check(lib.qrec_ubench_row_ops_f32(_dev(table, torch.float32, 'table'), table.shape[0], int(n_ops), int(mode),
+                                      int(seed) & 0xffffffff, sink.data_ptr(), _stream()), 'qrec_ubench_row_ops_f32')
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

@@ -68,6 +68,10 @@ class BPR(IterativeRecommender):
             a = acc.cpu().numpy()
             self.loss = float(a[0] + self.regU * a[1] + self.regI * a[2])      # BPR.py:40,53
             epoch += 1
+            if not self.ranking.isMainOn():
+                # isConverged -> rating_performance reads self.P/self.Q (the reference updates them in place)
+                self.P = np.ascontiguousarray(P[:, :d].cpu().numpy())
+                self.Q = np.ascontiguousarray(Q[:, :d].cpu().numpy())
             if self.isConverged(epoch):
                 break
         self.P = np.ascontiguousarray(P[:, :d].cpu().numpy())
@@ -99,8 +103,11 @@ class BPR(IterativeRecommender):
         if not hasattr(self, 'batch_size'):
             self.batch_size = int(self.config['batch_size'])
         d = self.emb_size
-        U = torch.nn.init.trunc_normal_(torch.empty(self.num_users, d, device=dev), std=0.005, a=-0.01, b=0.01)
-        V = torch.nn.init.trunc_normal_(torch.empty(self.num_items, d, device=dev), std=0.005, a=-0.01, b=0.01)
+        dp = (d + 3) // 4 * 4        # kernels take rows that are a multiple of 4 wide (BPR.conf ships d=50 -> 52);
+        U = torch.zeros(self.num_users, dp, device=dev)          # the zero columns stay exactly zero under K3 + Adam
+        V = torch.zeros(self.num_items, dp, device=dev)
+        U[:, :d] = torch.nn.init.trunc_normal_(torch.empty(self.num_users, d, device=dev), std=0.005, a=-0.01, b=0.01)
+        V[:, :d] = torch.nn.init.trunc_normal_(torch.empty(self.num_items, d, device=dev), std=0.005, a=-0.01, b=0.01)
         state = [torch.zeros_like(t) for t in (U, U, V, V)]            # mU, vU, mV, vV
         gU, gV = torch.zeros_like(U), torch.zeros_like(V)
         loss = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -120,7 +127,7 @@ class BPR(IterativeRecommender):
                 if n % 50 == 0:
                     l = loss.cpu().numpy()
                     print('training:', epoch + 1, 'batch', n, 'loss:', l[0] + self.regU * 0.5 * (l[1] + l[2]))
-        self.P, self.Q = U.cpu().numpy(), V.cpu().numpy()
+        self.P, self.Q = np.ascontiguousarray(U[:, :d].cpu().numpy()), np.ascontiguousarray(V[:, :d].cpu().numpy())
 
     def device_tables(self):
         import torch

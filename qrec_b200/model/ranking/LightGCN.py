@@ -65,7 +65,7 @@ class LightGCN(GraphRecommender):
         cur = self._grad
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
-            if k == 0 and hasattr(self.norm_adj, 'matmul_sparse_rows') and u.shape[0] <= 8192:
+            if k == 0 and hasattr(self.norm_adj, 'matmul_sparse_rows') and u.shape[0] <= 8192 and self.emb_pad <= 128:
                 # the loss gradient is non-zero only in the batch's rows: scatter along their edges
                 import torch
                 nz = torch.unique(torch.cat([u, i + self.num_users, j + self.num_users])).int()

@@ -418,7 +418,7 @@ class UserShardedLightGCN(object):
             self._grad(self.mean_u, self.mean_i, lu, li, lj, self.gu, self.gi, self.loss)
         self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
         self._allreduce(self.loss)
-        if u.shape[0] <= 8192 and self._scatter is not None:
+        if u.shape[0] <= 8192 and self._scatter is not None and self.Eu.shape[1] <= 128:
             self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=torch.unique(lu).int(),
                             nz_i=torch.unique(torch.cat([i, j])).int())
         else:

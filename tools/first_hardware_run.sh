@@ -18,7 +18,9 @@ timeout 600 python tools/bench_rating.py  > "$out/bench_rating.jsonl"  2> "$out/
 timeout 600 python tools/bench_graph.py --spmm-only > "$out/bench_spmm.jsonl" 2> "$out/bench_spmm.err"; echo "bench_spmm: exit $?"
 timeout 600 python tools/bench_tcgemm.py  > "$out/bench_tcgemm.jsonl"  2> "$out/bench_tcgemm.err";  echo "bench_tcgemm: exit $?"
 for b in 1 3; do
-  QREC_LGCN_ITEM_BLOCKS=$b timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > "$out/bench_lgcn_blocks$b.json" 2> "$out/bench_lgcn_blocks$b.err"
+  QREC_LGCN_ITEM_BLOCKS=$b timeout 600 python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity > "$out/bench_lgcn_blocks$b.json" 2> "$out/bench_lgcn_blocks$b.err"
   echo "lightgcn item blocks $b: $(python -c "import json,sys; d=json.load(open('$out/bench_lgcn_blocks$b.json')); print(d.get('lightgcn'))" 2>/dev/null | cut -c1-300)"
 done
 grep -h "k1_variant\|k9\|tc_gemm\|spmm" "$out"/*.jsonl | cut -c1-220
+timeout 900 python bench.py --steps 10 --warmup 3 --no-lightgcn > "$out/bench_parity.json" 2> "$out/bench_parity.err"; echo "bench parity: exit $?"
+python -c "import json; d=json.load(open('$out/bench_parity.json')); print(json.dumps(d.get('parity_check'), indent=1)[:3000]); print(d['value'], d['e2e']['value'])"
