@@ -238,6 +238,24 @@ int qrec_bpr_sgd_staged_f32(float* dev_P, int32_t d, int64_t n, const int32_t* d
 int qrec_sumsq_f32(const float* dev_x, int64_t n, double* dev_out, void* stream);
 int qrec_sumsq_f64(const double* dev_x, int64_t n, double* dev_out, void* stream);
 
+/* =====================================================================================
+ * Replicated item table across GPUs (BPR throughput mode: users range-partitioned, Q
+ * replicated; the data-parallel form of the in-place item updates of BPR.py:50-52).  B is the table all
+ * ranks agreed on at the last exchange.  delta: D = Q - B (and S = D when S != NULL), one read of Q per
+ * element while K1 may keep RED-adding into it.  merge: Q += S - D with float atomics, B += S, where S is
+ * the sum of all ranks' D -- so updates that landed in Q after delta read it stay in Q - B and travel with
+ * the next exchange; K1 never waits.  The two *_p2p entry points are the exchange itself over peer
+ * memory (NVLink P2P loads; peer_* are host arrays of `world` device pointers to the ranks' symmetric
+ * buffers): reduce-scatter of D into this rank's slice of S, then all-gather fused with the merge.
+ * The caller separates the phases with a cross-rank barrier.  n multiple of 4, pointers 16-byte aligned.
+ * ===================================================================================== */
+int qrec_table_delta_f32(const float* dev_Q, const float* dev_B, float* dev_D, float* dev_S, int64_t n, void* stream);
+int qrec_table_merge_f32(float* dev_Q, float* dev_B, const float* dev_D, const float* dev_S, int64_t n, void* stream);
+int qrec_table_reduce_scatter_p2p_f32(const float* const* peer_D, int32_t world, int32_t rank, float* dev_S, int64_t n,
+                                      void* stream);
+int qrec_table_gather_merge_p2p_f32(const float* const* peer_S, int32_t world, float* dev_Q, float* dev_B,
+                                    const float* dev_D, int64_t n, void* stream);
+
 /* Measurement aid for the K1 roofline (bench.py "row_op_peak"; not on the product path): issues
  * n_ops 256-byte row operations against random rows of dev_table [rows, 64] fp32 with nothing else in
  * the loop -- mode 0: LDG.E.128 gathers, 1: REDG.E.ADD.F32x4 scatter-adds (value 1e-9 alternating in

@@ -767,7 +767,16 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
   FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
                      (uint32_t)(seed >> 32), epoch, j_out};
   const int nvec = d / 4;
-  const long long cap = (long long)sm_count() * 8;
+  // CTAs per SM the grid is capped at (3 are resident): 8 = each CTA walks ~1/1184 of the launch.  A larger cap
+  // makes CTAs shorter-lived, so a concurrent high-priority stream (the item-table exchange of
+  // parallel.OverlappedTableSync) finds free slots sooner.  QREC_K1_UM_CAP overrides (experiment switch).
+  static int cap_mult = -1;
+  if (cap_mult < 0) {
+    const char* e = getenv("QREC_K1_UM_CAP");
+    cap_mult = e ? atoi(e) : 8;
+    if (cap_mult < 1) cap_mult = 8;
+  }
+  const long long cap = (long long)sm_count() * cap_mult;
   constexpr int CH = 32;
   // experiment switch (d = 64 only), measured on 50 M triples: 0 = 3 CTAs/SM, 4 triples in flight
   // (default, 5.80 ms); 1 = 4 CTAs/SM at 64 registers (spills, 7.08 ms); 2 = 2 CTAs/SM, 8 triples in

@@ -361,6 +361,42 @@ def ubench_row_ops(table, n_ops, mode, seed=1):
                                       int(seed) & 0xffffffff, sink.data_ptr(), _stream()), 'qrec_ubench_row_ops_f32')
 
 
+def table_delta(Q, B, D, S=None):
+    """D = Q - B (and S = D): this rank's not-yet-exchanged item-row updates (csrc/table_sync.cu)."""
+    torch = _torch()
+    check(lib.qrec_table_delta_f32(_dev(Q, torch.float32, 'Q'), _dev(B, torch.float32, 'B'), _dev(D, torch.float32, 'D'),
+                                   _dev(S, torch.float32, 'S') if S is not None else None, Q.numel(), _stream()),
+          'qrec_table_delta_f32')
+
+
+def table_merge(Q, B, D, S):
+    """Q += S - D (float atomics, commutes with a running K1), B += S; S = sum over ranks of D."""
+    torch = _torch()
+    check(lib.qrec_table_merge_f32(_dev(Q, torch.float32, 'Q'), _dev(B, torch.float32, 'B'), _dev(D, torch.float32, 'D'),
+                                   _dev(S, torch.float32, 'S'), Q.numel(), _stream()), 'qrec_table_merge_f32')
+
+
+def _ptr_array(ptrs):
+    import ctypes as C
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def table_reduce_scatter_p2p(peer_D_ptrs, rank, S, n):
+    """This rank's slice of S = sum over ranks of their D (P2P loads over NVLink; symmetric-memory pointers)."""
+    torch = _torch()
+    check(lib.qrec_table_reduce_scatter_p2p_f32(_ptr_array(peer_D_ptrs), len(peer_D_ptrs), int(rank),
+                                                _dev(S, torch.float32, 'S'), int(n), _stream()),
+          'qrec_table_reduce_scatter_p2p_f32')
+
+
+def table_gather_merge_p2p(peer_S_ptrs, Q, B, D):
+    """All-gather of the summed slices from their owners fused with the merge (Q += S - D; B += S)."""
+    torch = _torch()
+    check(lib.qrec_table_gather_merge_p2p_f32(_ptr_array(peer_S_ptrs), len(peer_S_ptrs), _dev(Q, torch.float32, 'Q'),
+                                              _dev(B, torch.float32, 'B'), _dev(D, torch.float32, 'D'), Q.numel(), _stream()),
+          'qrec_table_gather_merge_p2p_f32')
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

@@ -51,6 +51,122 @@ class ReplicatedTableSync(object):
         return self.table
 
 
+class OverlappedTableSync(object):
+    """Asynchronous exchange of a replicated table's deltas, hidden behind the next K1 launch.
+
+    compute stream :  K1(wave k) -> wave_done(): [wait merge_{k-1}] delta_k: D = Q - B -> K1(wave k+1) ...
+    side stream    :                                 exchange_k: S = sum_r D_r -> merge_k: Q += S - D, B += S
+
+    K1 never waits for the exchange: the merge adds the other ranks' contribution with float atomics,
+    which commute with K1's own scatter-adds, and whatever lands in Q after delta read it is part of the
+    next delta (csrc/table_sync.cu).  Other ranks' updates of wave k therefore become visible during wave
+    k+1.  `backend`: 'p2p' = reduce-scatter / all-gather kernels over symmetric (peer) memory on NVLink,
+    separated by symmetric-memory barriers; 'nccl' = ncclAllReduce of S on the side stream; 'auto' tries
+    p2p and falls back to nccl when symmetric memory cannot be set up (gloo groups always use the
+    collective).  finalize() drains the pipeline and leaves table == base on every rank, bit-identical."""
+
+    def __init__(self, table, group=None, backend='auto'):
+        from . import engine as E
+        self.E = E
+        self.table = table
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.syncs = 0
+        self.backend = 'none'
+        if self.world == 1:
+            return
+        n = table.numel()
+        if n % 4:
+            raise ValueError('OverlappedTableSync: table size must be a multiple of 4 floats')
+        self.base = table.clone()
+        self.side = torch.cuda.Stream(device=table.device, priority=-1) if table.is_cuda else None
+        self.ev_delta = torch.cuda.Event() if table.is_cuda else None
+        self.ev_merge = torch.cuda.Event() if table.is_cuda else None
+        self._pending = False
+        self.hD = self.hS = None
+        if backend in ('auto', 'p2p') and table.is_cuda:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                g = group if group is not None else dist.group.WORLD
+                self.D = symm.empty(n, dtype=torch.float32, device=table.device)
+                self.S = symm.empty(n, dtype=torch.float32, device=table.device)
+                self.hD = symm.rendezvous(self.D, g)
+                self.hS = symm.rendezvous(self.S, g)
+                self.pD = [int(p) for p in self.hD.buffer_ptrs]
+                self.pS = [int(p) for p in self.hS.buffer_ptrs]
+                self.backend = 'p2p'
+            except Exception as exc:                                   # noqa: BLE001
+                if backend == 'p2p':
+                    raise
+                self.p2p_error = '%s: %s' % (type(exc).__name__, exc)
+                self.hD = self.hS = None
+        if self.backend != 'p2p':
+            self.D = torch.empty(n, dtype=torch.float32, device=table.device)
+            self.S = torch.empty(n, dtype=torch.float32, device=table.device)
+            self.backend = 'nccl' if table.is_cuda else 'collective'
+
+    # -- the two local kernels; the CPU (gloo) tests replace them with torch arithmetic ------------------
+    def _delta(self):
+        self.E.table_delta(self.table.view(-1), self.base.view(-1), self.D, self.S if self.backend != 'p2p' else None)
+
+    def _merge(self):
+        self.E.table_merge(self.table.view(-1), self.base.view(-1), self.D, self.S)
+
+    def wave_done(self):
+        """Call on the compute stream right after a K1 launch.  Returns immediately."""
+        if self.world == 1:
+            return self.table
+        if self.side is None:                               # CPU tensors (gloo tests): same algebra, in order
+            self._delta()
+            dist.all_reduce(self.S, op=dist.ReduceOp.SUM, group=self.group)
+            self._merge()
+            self.syncs += 1
+            return self.table
+        cur = torch.cuda.current_stream()
+        if self._pending:
+            cur.wait_event(self.ev_merge)                   # D / B are reused: the previous merge must be done
+        self._delta()
+        self.ev_delta.record(cur)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(self.ev_delta)
+            if self.backend == 'p2p':
+                self.hD.barrier(channel=0)                  # every rank's D is complete
+                self.E.table_reduce_scatter_p2p(self.pD, self.rank, self.S, self.D.numel())
+                self.hS.barrier(channel=0)                  # every slice of S is summed
+                self.E.table_gather_merge_p2p(self.pS, self.table.view(-1), self.base.view(-1), self.D)
+            else:
+                dist.all_reduce(self.S, op=dist.ReduceOp.SUM, group=self.group)
+                self._merge()
+            self.ev_merge.record(self.side)
+        self._pending = True
+        self.syncs += 1
+        return self.table
+
+    sync = wave_done                                        # drop-in for ReplicatedTableSync.sync
+
+    def after_merge(self, fn):
+        """Runs fn() stream-ordered after the pending merge, when self.base is the table all ranks agree
+        on at this wave boundary (e.g. the epoch's regI*|Q|^2 term).  fn must only launch kernels."""
+        if self.world == 1 or self.side is None:
+            fn()
+            return
+        with torch.cuda.stream(self.side):
+            fn()
+            self.ev_merge.record(self.side)
+
+    def finalize(self):
+        """Drain: after this, every rank holds the same table (== base), bit for bit."""
+        if self.world == 1:
+            return self.table
+        if self.side is not None and self._pending:
+            torch.cuda.current_stream().wait_event(self.ev_merge)
+            self._pending = False
+        # table - base is now only the rounding residue of the last merge (no K1 ran since its delta)
+        self.table.copy_(self.base)
+        return self.table
+
+
 def sync_points(n, pieces):
     """Boundaries that cut n triples into `pieces` nearly equal launches: [0, ..., n]."""
     pieces = max(1, int(pieces))

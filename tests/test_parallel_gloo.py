@@ -297,3 +297,81 @@ def test_user_sharded_lightgcn_with_column_blocked_item_side_world2():
     out = mgr.dict()
     mp.spawn(_user_sharded_worker, args=(2, port, out, 2), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+class _CpuOverlappedSync(parallel.OverlappedTableSync):
+    """The two local kernels of csrc/table_sync.cu restated with torch arithmetic (CPU stand-ins, as the
+    other gloo tests do for the engine kernels); `late` is applied to the table BETWEEN delta and merge,
+    i.e. it plays the K1 wave that keeps running while the exchange is in flight."""
+    late = None
+
+    def _delta(self):
+        torch.sub(self.table.view(-1), self.base.view(-1), out=self.D)
+        self.S.copy_(self.D)
+
+    def _merge(self):
+        if self.late is not None:
+            self.late()
+            self.late = None
+        self.table.view(-1).add_(self.S - self.D)
+        self.base.view(-1).add_(self.S)
+
+
+def _overlap_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        Q0 = torch.randn(50, 8)
+        Q = Q0.clone()
+        sync = _CpuOverlappedSync(Q)
+        assert sync.backend == 'collective' and sync.world == world
+        expect = Q0.clone()
+
+        def updates(seed):
+            gg = torch.Generator().manual_seed(seed)
+            return torch.randint(0, 50, (30,), generator=gg), torch.randn(30, 8, generator=gg)
+        for rnd in range(3):
+            for r in range(world):                     # wave `rnd`: every rank scatter-adds its own updates
+                rows, upd = updates(100 * rnd + r)
+                expect.index_add_(0, rows, upd)
+                if r == rank:
+                    Q.index_add_(0, rows, upd)
+            # ... and the NEXT wave is already running when the merge lands: its updates must survive the
+            # merge untouched and be exchanged by the following wave_done
+            rows_l, upd_l = updates(7000 + 100 * rnd + rank)
+            sync.late = lambda rows_l=rows_l, upd_l=upd_l: Q.index_add_(0, rows_l, upd_l)
+            sync.wave_done()
+            mine = torch.zeros_like(Q0).index_add_(0, rows_l, upd_l)
+            assert torch.allclose(Q, expect + mine, atol=1e-5), 'rank %d round %d: local late updates lost' % (rank, rnd)
+            assert torch.allclose(sync.base, expect, atol=1e-5), 'base is the globally agreed table'
+            for r in range(world):                     # the late updates of all ranks join the global table next time
+                rows_r, upd_r = updates(7000 + 100 * rnd + r)
+                expect.index_add_(0, rows_r, upd_r)
+        sync.wave_done()
+        sync.finalize()
+        assert torch.allclose(Q, expect, atol=1e-5) and torch.equal(Q, sync.base)
+        gathered = [torch.empty_like(Q) for _ in range(world)]
+        dist.all_gather(gathered, Q)
+        assert all(torch.equal(gathered[0], t) for t in gathered), 'ranks must end bit-identical'
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_table_sync_world2():
+    """parallel.OverlappedTableSync: updates that land in Q while an exchange is in flight are neither lost
+    nor double-counted (Q - base == not-yet-exchanged local updates, for any interleaving)."""
+    world = 2
+    port = 31500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_overlap_worker, args=(world, port, out), nprocs=world, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
+def test_overlapped_sync_single_process_is_identity():
+    Q = torch.ones(4, 4)
+    s = parallel.OverlappedTableSync(Q)
+    Q += 1
+    assert s.wave_done() is Q and s.finalize() is Q and bool((Q == 2).all()) and s.world == 1
