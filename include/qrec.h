@@ -256,6 +256,16 @@ int qrec_table_reduce_scatter_p2p_f32(const float* const* peer_D, int32_t world,
 int qrec_table_gather_merge_p2p_f32(const float* const* peer_S, int32_t world, float* dev_Q, float* dev_B,
                                     const float* dev_D, int64_t n, void* stream);
 
+/* K8: batched ranking evaluation, replaces the per-user loop of Recommender.evalRanking
+ * (base/recommender.py:143-152) + find_k_largest (util/qmath.py:134-146).  For every row r of the block:
+ * scores = V . U[user_ids[r]] (fp32), rated items of that user (sorted CSR) score `rated_value` (the reference
+ * writes 0, it does not remove them), the N best (score descending, ties by ascending item id) go to
+ * out_ids / out_scores [n_rows, N].  The score matrix is never materialised.  1 <= N <= 100. */
+int qrec_score_topn_f32(const float* dev_U, const float* dev_V, int32_t d, int32_t n_items,
+                        const int32_t* dev_user_ids, int32_t n_rows, const int64_t* dev_rated_rowptr,
+                        const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,
+                        float* dev_out_scores, void* stream);
+
 /* Measurement aid for the K1 roofline (bench.py "row_op_peak"; not on the product path): issues
  * n_ops 256-byte row operations against random rows of dev_table [rows, 64] fp32 with nothing else in
  * the loop -- mode 0: LDG.E.128 gathers, 1: REDG.E.ADD.F32x4 scatter-adds (value 1e-9 alternating in

@@ -1,0 +1,196 @@
+// K8: batched ranking evaluation in ONE kernel.
+//
+// The reference ranks one test user at a time (base/recommender.py:143-152): candidates = Q.dot(P[u]), the
+// user's rated items are overwritten with 0 (not removed: `candidates[item] = 0`), then a heap keeps the N
+// best, replacing its minimum only on a strictly larger score (util/qmath.py:134-146), and the result is
+// sorted by score, descending.  Here a block of 64 users is scored against the item table tile by tile
+// (fp32 FMA, k ascending -- the same sums as the GEMV up to the order of the partial sums) and the scores
+// never leave the SM: every score is compared in registers with its row's current N-th best, the rated test
+// (binary search of the user's sorted rated row) runs only for the few that pass, survivors are appended to a
+// per-row candidate buffer in shared memory and a warp-level bitonic sort compacts a row back to N whenever
+// its buffer could overflow.  Nothing of the [users x items] score matrix is written to memory.
+//
+// Ordering: (score descending, item id ascending) -- a total order, so the result does not depend on the
+// scan order.  It agrees with the reference heap on which items survive a tie at the cut (the heap keeps the
+// earlier item: strict `>`), and makes the order among equal scores deterministic (the heap's is an
+// implementation detail of heapq).
+#include "common.h"
+
+namespace {
+
+constexpr int BM = 64;     // users per CTA
+constexpr int BN = 128;    // items per tile
+constexpr int BK = 32;     // k chunk
+constexpr int CAP = 256;   // candidate slots per user (>= N_max + BN)
+constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
+constexpr int AS = BM + 4, BS = BN + 1;
+
+__device__ __forceinline__ uint32_t ord_of(float s) {          // monotone float -> uint
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float score_of(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ unsigned long long key_of(float s, int item) {
+  return ((unsigned long long)ord_of(s) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)item);
+}
+
+__device__ __forceinline__ bool is_rated(const int* __restrict__ cols, long long lo, long long hi, int item) {
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    const int c = __ldg(cols + mid);
+    if (c == item) return true;
+    if (c < item) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+// one warp sorts the CAP keys of one row, descending (bitonic network in shared memory)
+__device__ __forceinline__ void warp_sort_desc(unsigned long long* k, int lane) {
+#pragma unroll 1
+  for (int size = 2; size <= CAP; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < CAP / 2; t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));           // index of the lower partner
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = k[lo], b = k[hi];
+        if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__global__ void __launch_bounds__(256)
+score_topn_kernel(const float* __restrict__ U, const float* __restrict__ V, int d, int n_items,
+                  const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
+                  const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
+                  float* __restrict__ out_scores) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  unsigned long long* cand = reinterpret_cast<unsigned long long*>(smem_raw);            // [BM][CAP]
+  unsigned long long* thr = cand + BM * CAP;                                            // [BM] key of the N-th best so far
+  float* As = reinterpret_cast<float*>(thr + BM);                                       // [BK][AS]
+  float* Bs = As + BK * AS;                                                             // [BK][BS]
+  int* cnt = reinterpret_cast<int*>(Bs + BK * BS);                                      // [BM]
+  int* uid = cnt + BM;                                                                  // [BM]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * BM;
+  const int tx = tid & 15, ty = tid >> 4;                                               // 16 x 16 threads: 8 cols x 4 rows each
+  for (int r = tid; r < BM; r += 256) {
+    cnt[r] = 0;
+    thr[r] = 0ULL;
+    uid[r] = (row0 + r < n_rows) ? user_ids[row0 + r] : -1;
+  }
+  for (int t = tid; t < BM * CAP; t += 256) cand[t] = 0ULL;
+  __syncthreads();
+  const unsigned long long rated_key_hi = (unsigned long long)ord_of(rated_value) << 32;
+
+  for (int c0 = 0; c0 < n_items; c0 += BN) {
+    // ---- compaction: a row that could overflow during this tile goes back to its N best
+    for (int r = warp; r < BM; r += 8) {
+      if (cnt[r] > CAP - BN) {
+        unsigned long long* k = cand + r * CAP;
+        warp_sort_desc(k, lane);
+        for (int t = N + lane; t < CAP; t += 32) k[t] = 0ULL;
+        if (lane == 0) { cnt[r] = N; thr[r] = k[N - 1]; }
+      }
+    }
+    // ---- scores of the tile: acc[i][j] = U[uid[ty*4+i]] . V[c0 + tx + 16 j]
+    float acc[4][8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < d; k0 += BK) {
+      __syncthreads();
+      for (int t = tid; t < BM * BK; t += 256) {                    // A chunk, transposed: As[k][r]
+        const int r = t / BK, k = t % BK;
+        const int u = uid[r];
+        As[k * AS + r] = (u >= 0 && k0 + k < d) ? __ldg(U + (size_t)u * d + k0 + k) : 0.f;
+      }
+      for (int t = tid; t < BN * BK; t += 256) {                    // B chunk, transposed: Bs[k][c]
+        const int c = t / BK, k = t % BK;
+        Bs[k * BS + c] = (c0 + c < n_items && k0 + k < d) ? __ldg(V + (size_t)(c0 + c) * d + k0 + k) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int k = 0; k < BK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(As + k * AS + ty * 4);
+        float b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) b[j] = Bs[k * BS + tx + 16 * j];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[0][j] = fmaf(a.x, b[j], acc[0][j]);
+          acc[1][j] = fmaf(a.y, b[j], acc[1][j]);
+          acc[2][j] = fmaf(a.z, b[j], acc[2][j]);
+          acc[3][j] = fmaf(a.w, b[j], acc[3][j]);
+        }
+      }
+    }
+    // ---- selection in registers
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty * 4 + i;
+      const int u = uid[r];
+      if (u < 0) continue;
+      const unsigned long long th = thr[r];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int c = c0 + tx + 16 * j;
+        if (c >= n_items) continue;
+        const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
+        unsigned long long key = ((unsigned long long)ord_of(acc[i][j]) << 32) | low;
+        // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
+        if (key > th || (rated_key_hi | low) > th) {
+          if (is_rated(rated_cols, __ldg(rated_rowptr + u), __ldg(rated_rowptr + u + 1), c)) key = rated_key_hi | low;
+          if (key > th) {
+            const int slot = atomicAdd(cnt + r, 1);
+            cand[r * CAP + slot] = key;                             // slot < CAP by the compaction rule
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // ---- final order and output
+  for (int r = warp; r < BM; r += 8) {
+    if (uid[r] < 0) continue;
+    unsigned long long* k = cand + r * CAP;
+    warp_sort_desc(k, lane);
+    for (int t = lane; t < N; t += 32) {
+      const unsigned long long key = k[t];
+      out_ids[(size_t)(row0 + r) * N + t] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffULL));
+      out_scores[(size_t)(row0 + r) * N + t] = score_of((uint32_t)(key >> 32));
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int qrec_score_topn_f32(const float* dev_U, const float* dev_V, int32_t d, int32_t n_items,
+                                   const int32_t* dev_user_ids, int32_t n_rows, const int64_t* dev_rated_rowptr,
+                                   const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,
+                                   float* dev_out_scores, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && n_items >= 1 && d >= 1, "qrec_score_topn_f32: bad size");
+  QREC_REQUIRE(N >= 1 && N <= NMAX && N <= n_items, "qrec_score_topn_f32: N=%d must be in 1..min(%d, n_items)", N, NMAX);
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(dev_U && dev_V && dev_user_ids && dev_rated_rowptr && dev_rated_cols && dev_out_ids && dev_out_scores,
+               "qrec_score_topn_f32: null pointer");
+  const size_t smem = (size_t)BM * CAP * 8 + BM * 8 + (size_t)(BK * AS + BK * BS) * 4 + 2 * BM * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    QREC_CUDA(cudaFuncSetAttribute(score_topn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int grid = (n_rows + BM - 1) / BM;
+  score_topn_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(
+      dev_U, dev_V, d, n_items, dev_user_ids, n_rows, reinterpret_cast<const long long*>(dev_rated_rowptr), dev_rated_cols,
+      rated_value, N, dev_out_ids, dev_out_scores);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}

@@ -397,6 +397,25 @@ def table_gather_merge_p2p(peer_S_ptrs, Q, B, D):
           'qrec_table_gather_merge_p2p_f32')
 
 
+def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None):
+    """K8: the N best items of every listed user in one kernel (scores, rated -> rated_value, top-N; nothing
+    materialised).  Returns (ids int32 [n, N], scores fp32 [n, N]), best first, ties by ascending item id."""
+    torch = _torch()
+    n = int(user_ids.shape[0])
+    if U.shape[1] != V.shape[1]:
+        raise QRecError('score_topn: U and V must have the same width')
+    if out_ids is None:
+        out_ids = torch.empty(n, N, dtype=torch.int32, device=U.device)
+    if out_scores is None:
+        out_scores = torch.empty(n, N, dtype=torch.float32, device=U.device)
+    check(lib.qrec_score_topn_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'), U.shape[1], V.shape[0],
+                                  _dev(user_ids, torch.int32, 'user_ids'), n, _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
+                                  _dev(rated_cols, torch.int32, 'rated_cols'), float(rated_value), int(N),
+                                  _dev(out_ids, torch.int32, 'out_ids'), _dev(out_scores, torch.float32, 'out_scores'),
+                                  _stream()), 'qrec_score_topn_f32')
+    return out_ids, out_scores
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

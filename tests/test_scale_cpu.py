@@ -34,6 +34,19 @@ def _stub(monkeypatch, calls):
         for row, u in enumerate(users.numpy().tolist()):
             scores[row, torch.from_numpy(co[rp[u]:rp[u + 1]].astype(np.int64))] = value
 
+    def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None):
+        # K8 stand-in: the reference's per-user flow (recommender.py:143-152), ties by ascending item id
+        rp, co = rated_rowptr.numpy(), rated_cols.numpy()
+        ids = torch.empty(len(user_ids), N, dtype=torch.int32)
+        val = torch.empty(len(user_ids), N, dtype=torch.float32)
+        for row, u in enumerate(user_ids.numpy().tolist()):
+            sc = (V @ U[u]).numpy().copy()
+            sc[co[rp[u]:rp[u + 1]]] = rated_value
+            top = np.argsort(-sc, kind='stable')[:N]
+            ids[row] = torch.from_numpy(top.astype(np.int32)); val[row] = torch.from_numpy(sc[top])
+        return ids, val
+
+    monkeypatch.setattr(E, 'score_topn', score_topn)
     monkeypatch.setattr(ScaleBPR, '_make_device', staticmethod(lambda index: torch.device('cpu')))
     for name, fn in (('bpr_epoch_usermajor', epoch), ('sumsq', sumsq), ('sgemm', sgemm), ('mask_rated', mask_rated)):
         monkeypatch.setattr(E, name, fn)
