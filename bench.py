@@ -291,6 +291,77 @@ def hbm_bound_config(torch, E, synthetic, dev, peak, steps=5):
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE config 4: NeuMF (GMF + MLP) minibatch steps, tensor-core MLP path
+# ---------------------------------------------------------------------------------------------
+def neumf_section(torch, E, data, dev, peak_hbm, steps=10, warmup=3, batch=2048):
+    """One minibatch = `batch` interactions x (1 positive + 4 sampled negatives) = 5*batch samples through the
+    drop-in NeuMF class (model/ranking/NeuMF.py:12-100 of the reference): gathers, 3-layer MLP forward/backward on
+    tcgen05 (TF32), fused head + BCE, scatter-add of the row gradients and TF1's dense Adam over every reached
+    table.  Both the reference's widths (2d -> 5d -> 2d -> d) and BASELINE.json's [256,128,64]; phases 0/1/2 =
+    GMF / MLP / fused NeuMF.  FLOPs: 3 products forward, 2x that backward (dX and dW)."""
+    from qrec_b200.model.ranking.NeuMF import NeuMF
+
+    class FakeData(object):
+        user, item = range(NUM_USERS), range(NUM_ITEMS)
+
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            tc_peak = float(json.load(f)['bf16_tflops_sustained']) / 2      # TF32 dense = half the bf16 rate
+        tc_src = 'MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32)'
+    except Exception:                                                      # noqa: BLE001
+        tc_peak, tc_src = 2250.0 / 2, 'nominal 2.25 PF bf16 / 2'
+    g = torch.Generator(device=dev); g.manual_seed(17)
+    B = 5 * batch
+    batches = []
+    n = NUM_USERS * DEGREE
+    for t in range(steps + warmup):
+        idx = torch.randint(0, n, (batch,), device=dev, generator=g)
+        pu = data['u'][idx].repeat_interleave(5).contiguous()
+        pi = torch.randint(0, NUM_ITEMS, (B,), device=dev, generator=g, dtype=torch.int32)
+        pi[::5] = data['i'][idx]
+        pr = torch.zeros(B, device=dev); pr[::5] = 1.0
+        batches.append((pu, pi, pr))
+    out = {'samples_per_step': B, 'batch_interactions': batch, 'tensor_peak_TFLOPs': tc_peak, 'tensor_peak_source': tc_src,
+           'dtype': 'tf32 MMA (tcgen05, fp32 accumulate in TMEM), fp32 everywhere else'}
+    for name, widths in (('reference_2d_5d_2d_d', None), ('baseline_256_128_64', (256, 128, 64))):
+        m = NeuMF.__new__(NeuMF)
+        m.data = FakeData()
+        m.num_users, m.num_items, m.emb_size, m.batch_size = NUM_USERS, NUM_ITEMS, D, batch
+        m.lRate, m.regU, m.regI, m.engine_device, m.engine_seed, m.device = 0.001, 0.001, 0.001, dev.index or 0, 0, dev
+        if widths:
+            m.mlp_widths = widths
+        _neumf_init(m)
+        w1, w2, w3 = m.mlp_widths
+        fwd = 2 * (2 * D * w1 + w1 * w2 + w2 * w3)
+        sec = {'mlp_widths': [2 * D, w1, w2, w3], 'mlp_flop_per_sample_fwd_bwd': 3 * fwd}
+        for mode, label in ((0, 'gmf'), (1, 'mlp'), (2, 'neumf')):
+            for t in range(warmup):
+                m.train_step(mode, *batches[t])
+            it = iter(range(warmup, warmup + steps))
+            ms = _time_ms(torch, lambda: m.train_step(mode, *batches[next(it)]), steps)
+            tables = (2 if mode != 2 else 4) * (NUM_USERS + NUM_ITEMS) * D
+            sec[label] = {'ms_per_step': ms, 'samples_per_s': B / (ms * 1e-3),
+                          'mlp_TFLOPs': (3 * fwd * B / (ms * 1e-3) / 1e12) if mode else 0.0,
+                          'dense_adam_GB_per_step': tables * 28 / 1e9,
+                          'dense_adam_floor_ms': tables * 28 / 1e9 / peak_hbm * 1e3, 'loss': float(m._loss.item())}
+        out[name] = sec
+        del m
+        torch.cuda.empty_cache()
+    return out
+
+
+def _neumf_init(m):
+    """NeuMF.initModel without the DeepRecommender/IterativeRecommender data plumbing (synthetic ids)."""
+    from qrec_b200.base.deepRecommender import DeepRecommender
+    orig = DeepRecommender.initModel
+    DeepRecommender.initModel = lambda self: None
+    try:
+        type(m).initModel(m)
+    finally:
+        DeepRecommender.initModel = orig
+
+
+# ---------------------------------------------------------------------------------------------
 # second half of the headline metric: LightGCN epoch time on the same synthetic graph
 # ---------------------------------------------------------------------------------------------
 def local_bipartite_blocks(torch, dist, data, users_local, num_items, world):
@@ -661,6 +732,14 @@ def run_ours(args):
                 raise                                # a rank that drops out would hang the others' collectives
             lightgcn = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
+    neumf = None
+    if world == 1 and not args.no_neumf:
+        try:
+            neumf = neumf_section(torch, E, data, dev, measured_hbm_peak()[0])
+        except Exception as exc:                     # noqa: BLE001
+            neumf = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        torch.cuda.empty_cache()
+
     roofs, hbm_cfg = None, None
     if rank == 0 and world == 1 and not args.no_roofs:
         try:
@@ -755,6 +834,8 @@ def run_ours(args):
             out['roofline']['hbm_bound_config'] = hbm_cfg
         if lightgcn is not None:
             out['lightgcn'] = lightgcn
+        if neumf is not None:
+            out['neumf'] = neumf
         if parity is not None:
             out['parity_check'] = parity
         if world == 1 and parity is not None and 'error' not in parity:
@@ -788,6 +869,7 @@ def main():
     ap.add_argument('--ref-sample', type=int, default=4_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-lightgcn', action='store_true')
+    ap.add_argument('--no-neumf', action='store_true')
     ap.add_argument('--no-roofs', action='store_true', help='skip the row-op microbenchmark and the HBM-bound configuration')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-epoch parity check against the sequential oracle')
     args = ap.parse_args()

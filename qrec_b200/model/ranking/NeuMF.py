@@ -32,6 +32,13 @@ class NeuMF(DeepRecommender):
         if self.emb_size % 4:
             raise ValueError('NeuMF on the B200 engine needs num.factors to be a multiple of 4 (got %d)' % self.emb_size)
         dev, d = self.device, self.emb_size
+        # MLP widths after the 2d-wide input: the reference hard-codes 5d -> 2d -> d (NeuMF.py:39-49); BASELINE.json's
+        # config 4 names [256,128,64].  The attribute `mlp_widths` overrides; the last width feeds the fused head
+        # together with the d-wide GMF vector (qrec_neumf_head_f32), so it must equal d as in the reference.
+        w = getattr(self, 'mlp_widths', None) or (5 * d, 2 * d, d)
+        if len(w) != 3 or any(int(x) % 4 for x in w) or int(w[2]) != d:
+            raise ValueError('NeuMF: mlp_widths must be three multiples of 4 ending in d=%d, got %r' % (d, w))
+        self.mlp_widths = w1, w2, w3 = tuple(int(x) for x in w)
         gen = torch.Generator(device=dev)
         gen.manual_seed(self.engine_seed + 3)
 
@@ -42,10 +49,10 @@ class NeuMF(DeepRecommender):
         self.params = {
             'PG': xavier(self.num_users, d), 'QG': xavier(self.num_items, d),
             'PM': xavier(self.num_users, d), 'QM': xavier(self.num_items, d),
-            'h_mf': xavier(d), 'h_mlp': xavier(d),
-            'W1': xavier(2 * d, 5 * d), 'b1': torch.zeros(5 * d, device=dev),
-            'W2': xavier(5 * d, 2 * d), 'b2': torch.zeros(2 * d, device=dev),
-            'W3': xavier(2 * d, d), 'b3': torch.zeros(d, device=dev),
+            'h_mf': xavier(d), 'h_mlp': xavier(w3),
+            'W1': xavier(2 * d, w1), 'b1': torch.zeros(w1, device=dev),
+            'W2': xavier(w1, w2), 'b2': torch.zeros(w2, device=dev),
+            'W3': xavier(w2, w3), 'b3': torch.zeros(w3, device=dev),
         }
         self.grads = {k: torch.zeros_like(v) for k, v in self.params.items()}
         mlp_vars = ['PM', 'QM', 'W1', 'b1', 'W2', 'b2', 'W3', 'b3', 'h_mlp']
@@ -61,12 +68,13 @@ class NeuMF(DeepRecommender):
         if B <= self._ws_rows:
             return
         dev, d = self.device, self.emb_size
+        w1, w2, w3 = self.mlp_widths
         new = lambda *s: torch.empty(*s, device=dev)          # noqa: E731
         self._UG, self._IG, self._GMF, self._dUG, self._dIG = (new(B, d) for _ in range(5))
         self._X0, self._dX0 = new(B, 2 * d), new(B, 2 * d)
-        self._H1, self._dH1 = new(B, 5 * d), new(B, 5 * d)
-        self._H2, self._dH2 = new(B, 2 * d), new(B, 2 * d)
-        self._H3, self._dH3 = new(B, d), new(B, d)
+        self._H1, self._dH1 = new(B, w1), new(B, w1)
+        self._H2, self._dH2 = new(B, w2), new(B, w2)
+        self._H3, self._dH3 = new(B, w3), new(B, w3)
         self._y, self._dz = new(B), new(B)
         self._ones = torch.ones(B, 1, device=dev)
         self._ws_rows = B
