@@ -375,6 +375,11 @@ int qrec_axpby_f32(float* dev_dst, const float* dev_a, const float* dev_b, float
 int qrec_simgcl_perturb_f32(float* dev_E, int64_t n_rows, int32_t d, int32_t d_valid, float eps, uint64_t seed,
                             uint32_t tag, uint32_t step, float* dev_acc, float acc_scale,
                             void* stream);
+/* The same perturbation for a block of rows of a ROW-SHARDED table: the noise of local row r is that of global
+ * row row_offset + r, so a sharded run draws exactly the single-GPU run's noise. */
+int qrec_simgcl_perturb_rows_f32(float* dev_E, int64_t n_rows, int64_t row_offset, int32_t d, int32_t d_valid,
+                                 float eps, uint64_t seed, uint32_t tag, uint32_t step, float* dev_acc,
+                                 float acc_scale, void* stream);
 
 /* Z[r,:] = l2_normalize(T[idx[r],:]) (tf.nn.l2_normalize, epsilon 1e-12 on the squared norm);
  * norms[r] = the divisor.  SimGCL.py:61-69. */

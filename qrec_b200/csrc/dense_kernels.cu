@@ -32,17 +32,18 @@ int sm_count() {
 __global__ void __launch_bounds__(256)
 simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, int d_valid, float eps, uint32_t k0,
                       uint32_t k1, uint32_t tag, uint32_t step, float* __restrict__ acc,
-                      float acc_scale) {
+                      float acc_scale, long long row_off) {   // row_off: global id of row 0 (row-sharded tables)
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp; r < n_rows; r += nwarps) {
     float4* row = reinterpret_cast<float4*>(E) + r * nvec;
+    const unsigned long long gr = (unsigned long long)(r + row_off);   // the noise is a function of the GLOBAL row
     float ss = 0.f;
     // first pass: squared norm of the row's noise (regenerated below; Philox is cheaper than HBM)
     for (int v = lane; v < nvec; v += 32) {
       uint32_t w[4];
-      philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
+      philox4x32_10((uint32_t)gr, (uint32_t)(gr >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
       // columns >= d_valid are zero padding of the table: they carry no noise
       const float a = (v * 4 + 0 < d_valid) ? u01(w[0]) : 0.f, b = (v * 4 + 1 < d_valid) ? u01(w[1]) : 0.f;
       const float c = (v * 4 + 2 < d_valid) ? u01(w[2]) : 0.f, d4 = (v * 4 + 3 < d_valid) ? u01(w[3]) : 0.f;
@@ -53,7 +54,7 @@ simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, int d_v
     const float inv = eps * rsqrtf(fmaxf(ss, 1e-12f));       // tf.nn.l2_normalize epsilon
     for (int v = lane; v < nvec; v += 32) {
       uint32_t w[4];
-      philox4x32_10((uint32_t)r, (uint32_t)((unsigned long long)r >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
+      philox4x32_10((uint32_t)gr, (uint32_t)(gr >> 32) ^ (uint32_t)v, tag, step, k0, k1, w);
       float4 e = row[v];
       e.x += sgn(e.x) * u01(w[0]) * inv;
       e.y += sgn(e.y) * u01(w[1]) * inv;
@@ -475,15 +476,21 @@ inline int grid_for(long long work_items, int per_block) {
 
 extern "C" {
 
-int qrec_simgcl_perturb_f32(float* E, int64_t n_rows, int32_t d, int32_t d_valid, float eps, uint64_t seed,
-                            uint32_t tag, uint32_t step, float* acc, float acc_scale, void* stream) {
-  QREC_REQUIRE(n_rows >= 0 && d >= 4 && d % 4 == 0, "qrec_simgcl_perturb_f32: bad shape (d multiple of 4)");
+int qrec_simgcl_perturb_rows_f32(float* E, int64_t n_rows, int64_t row_offset, int32_t d, int32_t d_valid, float eps,
+                                 uint64_t seed, uint32_t tag, uint32_t step, float* acc, float acc_scale, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && row_offset >= 0 && d >= 4 && d % 4 == 0, "qrec_simgcl_perturb_f32: bad shape (d multiple of 4)");
   if (n_rows == 0) return QREC_OK;
   QREC_REQUIRE(E != nullptr, "qrec_simgcl_perturb_f32: null table");
   simgcl_perturb_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
-      E, n_rows, d / 4, (d_valid > 0 && d_valid < d) ? d_valid : d, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc, acc_scale);
+      E, n_rows, d / 4, (d_valid > 0 && d_valid < d) ? d_valid : d, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc,
+      acc_scale, row_offset);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
+}
+
+int qrec_simgcl_perturb_f32(float* E, int64_t n_rows, int32_t d, int32_t d_valid, float eps, uint64_t seed,
+                            uint32_t tag, uint32_t step, float* acc, float acc_scale, void* stream) {
+  return qrec_simgcl_perturb_rows_f32(E, n_rows, 0, d, d_valid, eps, seed, tag, step, acc, acc_scale, stream);
 }
 
 int qrec_gather_normalize_f32(const float* T, const int32_t* idx, int32_t n, int32_t d, float* Z,

@@ -565,12 +565,14 @@ def axpby(dst, a, b, alpha, beta):
 # ---------------------------------------------------------------------------------------------
 # K6 / dense helpers (SimGCL, NGCF)
 # ---------------------------------------------------------------------------------------------
-def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0):
+def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
+    """E += sign(E) * l2_normalize(U[0,1)^d) * eps (SimGCL.py:33-35); row_offset = global id of Emb's row 0 when
+    Emb is a block of a row-sharded table (the noise is a function of the global row)."""
     torch = _torch()
-    check(lib.qrec_simgcl_perturb_f32(_dev(Emb, torch.float32, 'E'), Emb.shape[0], Emb.shape[1], int(d_valid), float(eps),
-                                      int(seed), int(tag), int(step),
-                                      _dev(acc, torch.float32, 'acc') if acc is not None else None,
-                                      float(acc_scale), _stream()), 'qrec_simgcl_perturb_f32')
+    check(lib.qrec_simgcl_perturb_rows_f32(_dev(Emb, torch.float32, 'E'), Emb.shape[0], int(row_offset), Emb.shape[1],
+                                           int(d_valid), float(eps), int(seed), int(tag), int(step),
+                                           _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                           float(acc_scale), _stream()), 'qrec_simgcl_perturb_rows_f32')
     return Emb
 
 

@@ -543,3 +543,141 @@ class UserShardedLightGCN(object):
         self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
         self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
         return self.loss
+
+
+# =============================================================================================
+# SimGCL over a row-sharded user table (BASELINE config 5: 10M users x 1M items on 8 GPUs)
+# =============================================================================================
+class UserShardedSimGCL(UserShardedLightGCN):
+    """SimGCL minibatch step (model/ranking/SimGCL.py:22-38 encoders, :60-78 InfoNCE, :92-108 step) with the
+    USER rows of the ego table (and their Adam slots) row-sharded over the ranks and the item rows replicated.
+
+    Per step: three encoders (clean + two perturbed views; mean of E_1..E_n, E_0 excluded) -- every layer is the
+    local user-side SpMM plus the rank's item-side partial sums and ONE all-reduce of the [I, d] block, launched
+    asynchronously and hidden behind the user-side product; the uniform-noise perturbation is a function of
+    the GLOBAL row id (qrec_simgcl_perturb_rows_f32), so every rank draws the single-GPU run's noise and the
+    replicated item rows stay bit-identical.  Losses: BPR + batch L2 on the triples whose user the rank owns
+    (item gradients all-reduced once); InfoNCE over the batch's unique users needs every batch user's two
+    views: each rank normalises the rows it owns into a zero [b, d] block and the blocks are summed (one small
+    all-reduce), after which the b x b similarity, its loss and dS are computed identically everywhere and each
+    rank back-propagates only its own rows; the item InfoNCE is replicated work on replicated rows.  The three
+    backward passes collapse into ONE propagation of the summed gradient (the noise is additive and tf.sign
+    has zero gradient), then TF1 dense Adam: local for users, identical for items."""
+
+    def __init__(self, A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, num_users_total, cl_rate, eps,
+                 tau=0.2, noise_seed=0x5151, d_valid=0, group=None):
+        super(UserShardedSimGCL, self).__init__(A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, group=group)
+        from . import engine as E
+        self.E = E
+        self.U_total = int(num_users_total)
+        self.cl_rate, self.eps, self.tau, self.noise_seed, self.d_valid = cl_rate, eps, tau, noise_seed, d_valid
+        dev, d = E_i.device, E_i.shape[1]
+        nu, ni = E_u_local.shape[0], E_i.shape[0]
+        z = lambda n: torch.zeros(n, d, device=dev)           # noqa: E731
+        self.p_u, self.p_i = [z(nu), z(nu)], [z(ni), z(ni)]     # the two perturbed views
+        self.losses_dev = torch.zeros(2, dtype=torch.float64, device=dev)       # [rec, cl (unscaled)]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def _encode(self, out_u, out_i, view):
+        """out <- mean(E_1..E_n) of encoder `view` (0 clean, 1 / 2 perturbed); SimGCL.py:22-38."""
+        E, s = self.E, 1.0 / self.n_layers
+        out_u.zero_(); out_i.zero_()
+        cu, ci = self.Eu, self.Ei
+        for k in range(self.n_layers):
+            nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            self._spmm(self.A_iu, cu, ni_, None, 0.0)                       # item side: this rank's partial sums
+            work = self._allreduce_async(ni_)
+            if view == 0:
+                self._spmm(self.A_ui, ci, nu_, out_u, s)                    # users: local; layer mean fused
+            else:
+                self._spmm(self.A_ui, ci, nu_, None, 0.0)
+                E.simgcl_perturb(nu_, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_u, acc_scale=s,
+                                 d_valid=self.d_valid, row_offset=self.lo)
+            if work is not None:
+                work.wait()
+            if view == 0:
+                self._axpy(out_i, ni_, s)
+            else:                                                           # sign() of the FULL sum: after the all-reduce
+                E.simgcl_perturb(ni_, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_i, acc_scale=s,
+                                 d_valid=self.d_valid, row_offset=self.U_total)
+            cu, ci = nu_, ni_
+
+    def _backward(self, gu, gi, tot_u, tot_i):
+        """tot <- 1/n * sum_{k=1..n} A^k G (the encoders' common backward map; E_0 is not in the mean)."""
+        s = 1.0 / self.n_layers
+        tot_u.zero_(); tot_i.zero_()
+        cu, ci = gu, gi
+        for k in range(self.n_layers):
+            nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            self._spmm(self.A_iu, cu, ni_, None, 0.0)
+            work = self._allreduce_async(ni_)
+            self._spmm(self.A_ui, ci, nu_, tot_u, s)
+            if work is not None:
+                work.wait()
+            self._axpy(tot_i, ni_, s)
+            cu, ci = nu_, ni_
+
+    def _infonce(self, tab1, tab2, idx_rows, own_pos, own_local, grad_rows, replicated):
+        """InfoNCE between two views on the batch's unique rows.  idx_rows: b global-batch positions; own_pos:
+        positions (within the b rows) this rank owns, own_local: their local row ids in tab1 / tab2.
+        replicated: the rows live on every rank (items) -- no exchange, every rank does the same work."""
+        E = self.E
+        b, d = int(idx_rows), tab1.shape[1]
+        dev = tab1.device
+        Z1, Z2 = torch.zeros(b, d, device=dev), torch.zeros(b, d, device=dev)
+        n1, n2 = torch.zeros(b, device=dev), torch.zeros(b, device=dev)
+        m = int(own_local.shape[0])
+        if m:
+            z1, z2 = torch.empty(m, d, device=dev), torch.empty(m, d, device=dev)
+            a1, a2 = torch.empty(m, device=dev), torch.empty(m, device=dev)
+            E.gather_normalize(tab1, own_local, z1, a1)
+            E.gather_normalize(tab2, own_local, z2, a2)
+            Z1[own_pos], Z2[own_pos], n1[own_pos], n2[own_pos] = z1, z2, a1, a2
+        if not replicated and self.world > 1:
+            pack = torch.cat([Z1.view(-1), Z2.view(-1), n1, n2])
+            dist.all_reduce(pack, group=self.group)             # every row has exactly one owner: the sum is a gather
+            Z1, Z2 = pack[:b * d].view(b, d), pack[b * d:2 * b * d].view(b, d)
+            n1, n2 = pack[2 * b * d:2 * b * d + b], pack[2 * b * d + b:]
+        S = torch.empty(b, b, device=dev)
+        E.sgemm(Z1.contiguous(), Z2.contiguous(), S, trans_b=True)
+        E.infonce_rows(S, self.tau, self.losses_dev[1:2])        # S <- dLoss/dS; the loss is counted once per rank
+        dZ1, dZ2 = torch.empty(b, d, device=dev), torch.empty(b, d, device=dev)
+        E.sgemm(S, Z2.contiguous(), dZ1)
+        E.sgemm(S, Z1.contiguous(), dZ2, trans_a=True)
+        if m:
+            E.normalize_bwd_scatter(dZ1[own_pos].contiguous(), Z1[own_pos].contiguous(), n1[own_pos].contiguous(), own_local,
+                                    self.cl_rate, grad_rows)
+            E.normalize_bwd_scatter(dZ2[own_pos].contiguous(), Z2[own_pos].contiguous(), n2[own_pos].contiguous(), own_local,
+                                    self.cl_rate, grad_rows)
+
+    def train_step(self, u, i, j):
+        """u, i, j: the WHOLE minibatch (global ids, int32 device tensors) on every rank.  Returns the device
+        tensor [rec_loss, cl_loss (unscaled)] -- identical on every rank."""
+        E = self.E
+        self.step += 1
+        nloc = self.Eu.shape[0]
+        self._encode(self.mean_u, self.mean_i, 0)
+        self._encode(self.p_u[0], self.p_i[0], 1)
+        self._encode(self.p_u[1], self.p_i[1], 2)
+        mine = (u >= self.lo) & (u < self.lo + nloc)
+        lu, li, lj = (u[mine] - self.lo).contiguous(), i[mine].contiguous(), j[mine].contiguous()
+        self.gu.zero_(); self.gi.zero_(); self.losses_dev.zero_()
+        if lu.numel():
+            E.bpr_grad_scatter(self.mean_u, self.mean_i, lu, li, lj, 10e-8, self.reg, self.gu, self.gi, self.losses_dev[0:1])
+        self._allreduce(self.gi)                               # BPR item gradients: sum of the ranks' partials
+        self._allreduce(self.losses_dev[0:1])
+        uu = torch.unique(u)                                    # tf.unique (order is irrelevant to the sums)
+        ii = torch.unique(i).int()
+        own = ((uu >= self.lo) & (uu < self.lo + nloc)).nonzero().view(-1)
+        self._infonce(self.p_u[0], self.p_u[1], uu.shape[0], own, (uu[own] - self.lo).int().contiguous(), self.gu, False)
+        allpos = torch.arange(ii.shape[0], device=ii.device)
+        self._infonce(self.p_i[0], self.p_i[1], ii.shape[0], allpos, ii.contiguous(), self.gi, True)
+        self._backward(self.gu, self.gi, self.tot_u, self.tot_i)
+        self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
+        self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
+        return self.losses_dev
+
+    def losses(self):
+        l = self.losses_dev.cpu().numpy()
+        rec, cl = float(l[0]), self.cl_rate * float(l[1])
+        return rec + cl, rec, cl

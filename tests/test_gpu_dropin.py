@@ -263,3 +263,40 @@ def test_scale_bpr_from_interaction_table(golden_bpr, tmp_path):
     fast = m.evaluate(test, tops=(10,))
     for a, b in zip(fast[1:], out[1:]):
         assert a.split(':')[0] == b.split(':')[0] and abs(float(a.split(':')[1]) - float(b.split(':')[1])) < 1e-9
+
+
+def test_user_sharded_simgcl_world1_equals_dropin_step(golden_graph, tmp_path):
+    """parallel.UserShardedSimGCL (BASELINE config 5's decomposition: user rows sharded, item rows replicated;
+    world = 1 here, so the collectives are no-ops) against the drop-in SimGCL class -- itself checked against the
+    float64 autograd restatement of model/ranking/SimGCL.py -- on the reference's FilmTrust graph: same Philox
+    noise (function of the global row), same losses, same collapsed backward pass, same Adam step."""
+    import torch
+    from qrec_b200 import parallel
+    from qrec_b200.util.config import ModelConf
+    from qrec_b200.model.ranking.SimGCL import SimGCL
+    g = golden_graph
+    os.chdir(tmp_path)
+    train = [[u, i, 1.0] for u, i in zip(g['train_users'].tolist(), g['train_items'].tolist())]
+    conf = str(g['conf']).replace('model.name=LightGCN', 'model.name=SimGCL') + 'SimGCL=-n_layer 2 -lambda 0.5 -eps 0.1\n'
+    ref = SimGCL(ModelConf.from_string(conf), train, [])
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref.readConfiguration()
+        ref.initModel()
+    U, I = ref.num_users, ref.num_items
+    adj = ref.norm_adj
+    A_ui, A_iu, _ = parallel.shard_bipartite_by_user(adj.rowptr, adj.cols, adj.vals, U, I, 0, 1)
+    m = parallel.UserShardedSimGCL(A_ui, A_iu, ref.ego[:U].clone(), ref.ego[U:].clone(), ref.n_layers, ref.lRate, ref.regU, 0,
+                                   U, ref.cl_rate, ref.eps, noise_seed=ref.noise_seed, d_valid=ref.emb_size)
+    su, si, sj = g['shuffled_u'], g['shuffled_i'], g['pair_all_j']
+    for step in range(3):
+        sl = slice(step * 2048, (step + 1) * 2048)
+        b = [torch.from_numpy(np.ascontiguousarray(x[sl])).cuda() for x in (su, si, sj)]
+        ref.train_step(*b)
+        m.train_step(*b)
+        t_ref, rec_ref, cl_ref = ref.losses()
+        t, rec, cl = m.losses()
+        assert abs(rec - rec_ref) <= 1e-5 * abs(rec_ref) and abs(cl - cl_ref) <= 1e-5 * abs(cl_ref)
+        gref = ref._total
+        gtot = torch.cat([m.tot_u, m.tot_i])
+        assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max())
+        torch.testing.assert_close(torch.cat([m.Eu, m.Ei]), ref.ego, rtol=2e-3, atol=2e-4)
