@@ -44,13 +44,19 @@ class QRec(object):
         elif ev.contains('-predict'):
             self.trainingData = load(config['ratings'])
             self.testData = FileIO.loadUserList(ev['-predict'])
+        if config.contains('social'):                                       # QRec.py:44-46
+            self.socialConfig = OptionConf(self.config['social.setup'])
+            self.relation = FileIO.loadRelationship(config, self.config['social'])
         print('Reading data and preprocessing...')
 
     def execute(self):
         cls = _model_class(self.config['model.name'])
         ev = self.evaluation
         if not ev.contains('-cv'):
-            self.measure = cls(self.config, self.trainingData, self.testData).execute()
+            if self.config.contains('social'):                              # QRec.py:110-113
+                self.measure = cls(self.config, self.trainingData, self.testData, self.relation).execute()
+            else:
+                self.measure = cls(self.config, self.trainingData, self.testData).execute()
             return self.measure
         k = int(ev['-cv'])
         if k < 2 or k > 10:
@@ -58,7 +64,10 @@ class QRec(object):
             sys.exit(-1)
         folds = []
         for n, (train, test) in enumerate(DataSplit.crossValidation(self.trainingData, k, binarized=ev.contains('-b')), 1):
-            folds.append(cls(self.config, train, test, '[' + str(n) + ']').execute())   # one GPU: folds run in turn
+            fold = '[' + str(n) + ']'
+            model = (cls(self.config, train, test, self.relation, fold) if self.config.contains('social')
+                     else cls(self.config, train, test, fold))
+            folds.append(model.execute())                               # one GPU: folds run in turn
         self.measure = folds
         res = []
         for pos, line in enumerate(folds[0]):

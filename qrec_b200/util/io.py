@@ -54,3 +54,24 @@ class FileIO(object):
         print('loading user List...')
         with open(filepath) as fh:
             return [line.strip().split()[0] for line in fh]
+
+    @staticmethod
+    def loadRelationship(conf, filePath):
+        """-> [[user1, user2, weight], ...] (util/io.py:88-111 of the reference): `social.setup` gives `-columns a b [c]`
+        and `-header`; the weight defaults to 1."""
+        setup = OptionConf(conf['social.setup'])
+        print('loading social data...')
+        with open(filePath) as fh:
+            lines = fh.readlines()
+        if setup.contains('-header'):
+            lines = lines[1:]
+        cols = [int(c) for c in setup['-columns'].strip().split()]
+        splitter = re.compile(' |,|\t')
+        out = []
+        for lineno, line in enumerate(lines):
+            fields = splitter.split(line.strip())
+            if len(cols) < 2:
+                print('The social file is not in a correct format. Error: Line num %d' % lineno)
+                sys.exit(-1)
+            out.append([fields[cols[0]], fields[cols[1]], float(fields[cols[2]]) if len(cols) >= 3 else 1])
+        return out

@@ -300,3 +300,29 @@ def test_user_sharded_simgcl_world1_equals_dropin_step(golden_graph, tmp_path):
         gtot = torch.cat([m.tot_u, m.tot_i])
         assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max())
         torch.testing.assert_close(torch.cat([m.Eu, m.Ei]), ref.ego, rtol=2e-3, atol=2e-4)
+
+
+def test_tbpr_dropin_device_run_equals_oracle_run(golden_bpr, monkeypatch, tmp_path):
+    """f-4 sibling model TBPR (model/ranking/TBPR.py): the same seeded life cycle twice in this process -- once with
+    the K1 parity kernel on the GPU (float64), once with the kernel replaced by the pinned oracle on the CPU (the
+    configuration tests/test_tbpr_cpu.py proves equal to the unmodified reference class) -- gives the same losses,
+    learning rates and tables; fast mode (one user-major launch per epoch) lands in the same quality band."""
+    import test_tbpr_cpu as T
+    from test_bpr_model_cpu import _stub_engine
+    from qrec_b200.model.ranking.TBPR import TBPR
+    os.chdir(tmp_path)
+    train, test, rel = T._data(golden_bpr)
+    m_gpu, losses_gpu, measure_gpu = T._run(TBPR, train, test, rel, T.CONF)
+    m_fast, losses_fast, measure_fast = T._run(TBPR, train, test, rel, T.CONF.replace('num.max.epoch=3', 'num.max.epoch=12')
+                                               + 'engine=-mode fast\n')
+    with monkeypatch.context() as mp:
+        _stub_engine(mp, [])
+        m_cpu, losses_cpu, measure_cpu = T._run(TBPR, train, test, rel, T.CONF)
+    assert [l[1] for l in losses_gpu] == [l[1] for l in losses_cpu]
+    np.testing.assert_allclose([l[0] for l in losses_gpu], [l[0] for l in losses_cpu], rtol=1e-10)
+    np.testing.assert_allclose(m_gpu.P, m_cpu.P, rtol=1e-10, atol=1e-13)
+    np.testing.assert_allclose(m_gpu.Q, m_cpu.Q, rtol=1e-10, atol=1e-13)
+    assert [x.strip() for x in measure_gpu] == [x.strip() for x in measure_cpu]
+    prec = lambda meas: float([x for x in meas if x.startswith('Precision')][0].split(':')[1])   # noqa: E731
+    assert prec(measure_fast) >= 0.8 * prec(measure_cpu)
+    assert losses_fast[-1][0] < losses_fast[0][0]
