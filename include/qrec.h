@@ -266,6 +266,32 @@ int qrec_score_topn_f32(const float* dev_U, const float* dev_V, int32_t d, int32
                         const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,
                         float* dev_out_scores, void* stream);
 
+/* =====================================================================================
+ * f-2 -- the normalised joint adjacency and its per-epoch edge-dropout rebuild on the device
+ * (base/graphRecommender.py:10-29; model/ranking/SGL.py:113-155, aug_type 1).  The joint CSR of the full graph
+ * (rowptr int64[n_rows+1], cols int32 sorted per row) is built once; `pair` int32[nnz] maps every stored entry to
+ * its undirected edge so that (u,i) and (i,u) share a weight; pair_w fp32[n_pairs] is the edge multiplicity
+ * (number of kept interaction lines, duplicates summed like scipy's constructor; 0 = dropped).
+ * ===================================================================================== */
+/* deg[r] = sum of row r's weights; vals[e] = (deg_r^-1/2 * w) * deg_c^-1/2 in fp32 (isolated nodes: 0).
+ * pair / pair_w may both be NULL (all weights 1). */
+int qrec_adj_normalize_f32(int32_t n_rows, const int64_t* dev_rowptr, const int32_t* dev_cols, const int32_t* dev_pair,
+                           const float* dev_pair_w, float* dev_deg, float* dev_vals, void* stream);
+/* keep[k] = Philox-uniform(k; tag, epoch, seed) >= drop_rate, one flag per interaction line. */
+int qrec_edge_keep_philox(int64_t n_lines, float drop_rate, uint64_t seed, uint32_t tag, uint32_t epoch,
+                          uint8_t* dev_keep, void* stream);
+/* pair_w[p] = number of lines k with line_pair[k] == p and keep[k] != 0 (keep NULL: all lines). */
+int qrec_adj_line_weights_f32(int64_t n_lines, const int32_t* dev_line_pair, const uint8_t* dev_keep, int64_t n_pairs,
+                              float* dev_pair_w, void* stream);
+/* Sub-graph of the edges with pair_w > 0: degrees into dev_deg, the new row pointer into dev_new_rowptr
+ * (int64[n_rows+1], exclusive scan of the surviving entries per row).  scan_scratch: int64[ceil((n_rows+1)/1024)]. */
+int qrec_adj_subgraph_count(int32_t n_rows, const int64_t* dev_rowptr, const int32_t* dev_pair, const float* dev_pair_w,
+                            float* dev_deg, int64_t* dev_new_rowptr, int64_t* dev_scan_scratch, void* stream);
+/* Ordered compaction of the surviving entries (the CSR stays sorted) with the sub-graph's own D^-1/2 scaling. */
+int qrec_adj_subgraph_fill_f32(int32_t n_rows, const int64_t* dev_rowptr, const int32_t* dev_cols, const int32_t* dev_pair,
+                               const float* dev_pair_w, const float* dev_deg, const int64_t* dev_new_rowptr,
+                               int32_t* dev_new_cols, float* dev_new_vals, void* stream);
+
 /* Measurement aid for the K1 roofline (bench.py "row_op_peak"; not on the product path): issues
  * n_ops 256-byte row operations against random rows of dev_table [rows, 64] fp32 with nothing else in
  * the loop -- mode 0: LDG.E.128 gathers, 1: REDG.E.ADD.F32x4 scatter-adds (value 1e-9 alternating in

@@ -416,6 +416,54 @@ def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out
     return out_ids, out_scores
 
 
+def adj_normalize(rowptr, cols, pair, pair_w, deg, vals):
+    """deg = weighted row sums, vals = D^-1/2 A D^-1/2 entries (fp32, the reference's operand order)."""
+    torch = _torch()
+    check(lib.qrec_adj_normalize_f32(rowptr.shape[0] - 1, _dev(rowptr, torch.int64, 'rowptr'), _dev(cols, torch.int32, 'cols'),
+                                     _dev(pair, torch.int32, 'pair') if pair is not None else None,
+                                     _dev(pair_w, torch.float32, 'pair_w') if pair_w is not None else None,
+                                     _dev(deg, torch.float32, 'deg'), _dev(vals, torch.float32, 'vals'), _stream()),
+          'qrec_adj_normalize_f32')
+    return vals
+
+
+def edge_keep_philox(n_lines, drop_rate, seed, tag, epoch, device, out=None):
+    torch = _torch()
+    if out is None:
+        out = torch.empty(n_lines, dtype=torch.uint8, device=device)
+    check(lib.qrec_edge_keep_philox(int(n_lines), float(drop_rate), int(seed), int(tag), int(epoch), _dev(out, torch.uint8, 'keep'),
+                                    _stream()), 'qrec_edge_keep_philox')
+    return out
+
+
+def adj_line_weights(line_pair, keep, pair_w):
+    torch = _torch()
+    check(lib.qrec_adj_line_weights_f32(line_pair.shape[0], _dev(line_pair, torch.int32, 'line_pair'),
+                                        _dev(keep, torch.uint8, 'keep') if keep is not None else None, pair_w.shape[0],
+                                        _dev(pair_w, torch.float32, 'pair_w'), _stream()), 'qrec_adj_line_weights_f32')
+    return pair_w
+
+
+def adj_subgraph(rowptr, cols, pair, pair_w):
+    """CSR (rowptr, cols, vals) of the edges with pair_w > 0, re-normalised with the sub-graph's own degrees."""
+    torch = _torch()
+    n_rows = rowptr.shape[0] - 1
+    dev = rowptr.device
+    deg = torch.empty(n_rows, dtype=torch.float32, device=dev)
+    new_rowptr = torch.empty(n_rows + 1, dtype=torch.int64, device=dev)
+    scratch = torch.empty((n_rows + 1 + 1023) // 1024 + 1, dtype=torch.int64, device=dev)
+    args = (_dev(rowptr, torch.int64, 'rowptr'), _dev(pair, torch.int32, 'pair'), _dev(pair_w, torch.float32, 'pair_w'))
+    check(lib.qrec_adj_subgraph_count(n_rows, args[0], args[1], args[2], deg.data_ptr(), new_rowptr.data_ptr(), scratch.data_ptr(),
+                                      _stream()), 'qrec_adj_subgraph_count')
+    nnz = int(new_rowptr[-1].item())                          # the one host round trip: the size of the new arrays
+    new_cols = torch.empty(nnz, dtype=torch.int32, device=dev)
+    new_vals = torch.empty(nnz, dtype=torch.float32, device=dev)
+    check(lib.qrec_adj_subgraph_fill_f32(n_rows, args[0], _dev(cols, torch.int32, 'cols'), args[1], args[2], deg.data_ptr(),
+                                         new_rowptr.data_ptr(), new_cols.data_ptr(), new_vals.data_ptr(), _stream()),
+          'qrec_adj_subgraph_fill_f32')
+    return new_rowptr, new_cols, new_vals
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

@@ -67,3 +67,28 @@ def rows_and_sets(u, i, num_users):
     for uu, ii in zip(u.tolist(), i.tolist()):
         rows[uu][ii] = 1
     return [list(r.keys()) for r in rows], [set(r.keys()) for r in rows]
+
+
+def adjacency_kernel_stand_ins(monkeypatch):
+    """numpy restatements of the two value kernels of csrc/adj_kernels.cu (the GPU suite runs the real ones)."""
+    import torch
+    from qrec_b200 import engine as E
+
+    def line_weights(line_pair, keep, pair_w):
+        k = np.ones(len(line_pair), bool) if keep is None else keep.numpy().astype(bool)
+        pair_w.copy_(torch.from_numpy(np.bincount(line_pair.numpy()[k], minlength=len(pair_w)).astype(np.float32)))
+        return pair_w
+
+    def normalize(rowptr, cols, pair, pair_w, deg, vals):
+        rp, co = rowptr.numpy(), cols.numpy()
+        w = pair_w.numpy()[pair.numpy()]
+        row = np.repeat(np.arange(len(rp) - 1), np.diff(rp))
+        d = np.zeros(len(rp) - 1, np.float32)
+        np.add.at(d, row, w)
+        with np.errstate(divide='ignore'):
+            dinv = np.where(d > 0, (1.0 / np.sqrt(d.astype(np.float64))), 0.0).astype(np.float32)
+        deg.copy_(torch.from_numpy(d))
+        vals.copy_(torch.from_numpy((dinv[row] * w) * dinv[co]))
+        return vals
+    monkeypatch.setattr(E, 'adj_line_weights', line_weights)
+    monkeypatch.setattr(E, 'adj_normalize', normalize)

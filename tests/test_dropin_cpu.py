@@ -6,6 +6,8 @@ import random
 import numpy as np
 import pytest
 
+from conftest import adjacency_kernel_stand_ins
+
 from qrec_b200.util.config import ModelConf, OptionConf
 from qrec_b200.util.measure import Measure
 from qrec_b200.util.qmath import find_k_largest, _heap_top_k
@@ -117,12 +119,14 @@ def test_shuffle_training_data_equals_random_shuffle(golden_bpr):
     assert m.data.trainingData == expect and random.getstate() == st
 
 
-def test_device_adjacency_builder_equals_reference_matrix(golden_graph, graph_ids):
-    """graph_build.norm_adjacency_csr (sort + run-length, here on CPU tensors) reproduces the scipy
-    matrix of base/graphRecommender.py:10-29 recorded from the reference -- structure exactly, values
-    to fp32 rounding -- including summed duplicate interactions and an isolated node."""
+def test_device_adjacency_builder_equals_reference_matrix(golden_graph, graph_ids, monkeypatch):
+    """graph_build.norm_adjacency_csr (structure by sort + run-length, here on CPU tensors; the value kernels
+    replaced by numpy stand-ins) reproduces the scipy matrix of base/graphRecommender.py:10-29 recorded from
+    the reference -- structure exactly, values to fp32 rounding -- including summed duplicate interactions and
+    an isolated node."""
     import torch
     from qrec_b200.graph_build import norm_adjacency_csr
+    adjacency_kernel_stand_ins(monkeypatch)
     g = golden_graph
     u, i, nu, ni = graph_ids
     rowptr, cols, vals = norm_adjacency_csr(torch.from_numpy(u), torch.from_numpy(i), nu, ni)
@@ -165,6 +169,7 @@ def test_graph_recommender_adj_tensor_method_on_cpu_tensors(golden_graph, tmp_pa
     train = [[u, i, 1.0] for u, i in zip(g['train_users'].tolist(), g['train_items'].tolist())]
     m = GraphRecommender(_conf(str(g['conf'])), train, [])
     monkeypatch.setattr(GraphRecommender, '_device', lambda self: torch.device('cpu'))
+    adjacency_kernel_stand_ins(monkeypatch)
     adj = m.create_joint_sparse_adj_tensor()
     assert adj.shape == tuple(g['adj_shape']) and adj.nnz == len(g['adj_indices']) and adj.rowsplit
     assert np.array_equal(adj.rowptr.numpy(), g['adj_indptr']) and np.array_equal(adj.cols.numpy(), g['adj_indices'])

@@ -45,6 +45,8 @@ def _stub(monkeypatch, calls):
         loss += l
 
     monkeypatch.setattr(IterativeRecommender, '_device', lambda self: torch.device('cpu'))
+    from conftest import adjacency_kernel_stand_ins
+    adjacency_kernel_stand_ins(monkeypatch)
     monkeypatch.setattr(E, 'spmm_csr', spmm)
     monkeypatch.setattr(E, 'spmm_csr_scatter_rows', scatter_rows)
     monkeypatch.setattr(E, 'bpr_grad_scatter', grad_scatter)
