@@ -362,6 +362,76 @@ def _neumf_init(m):
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE config 1: the reference's own FilmTrust run through the drop-in class (parity mode)
+# ---------------------------------------------------------------------------------------------
+def filmtrust_section():
+    """configs[0]: BPR on FilmTrust, d=64, the seeded 3-epoch run recorded from the UNMODIFIED reference
+    (tests/golden/bpr_filmtrust_seed0.npz: split, MT19937 states, epoch losses, learning rates, metrics), replayed
+    through qrec_b200.model.ranking.BPR in parity mode (sequential semantics on the GPU, float64): the epoch losses
+    and the ranking measures must equal the reference's; trainModel() is timed.  The reference class itself
+    (pure-Python loop, measured in the build container, BASELINE.md section 2) does ~95 K triples/s on one core;
+    it cannot be run on this box (no reference checkout, no network)."""
+    import contextlib
+    import io
+    import random
+    import tempfile
+    from qrec_b200.util.config import ModelConf
+    from qrec_b200.model.ranking.BPR import BPR
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'bpr_filmtrust_seed0.npz'))
+    train = [[u, i, r] for u, i, r in zip(g['train_users'].tolist(), g['train_items'].tolist(), g['train_rating'].tolist())]
+    test = [[u, i, r] for u, i, r in zip(g['test_users'].tolist(), g['test_items'].tolist(), g['test_rating'].tolist())]
+    out = {'workload': 'BPR on FilmTrust (ratings.txt, -ap 0.2 -b 1, d=64, lr 0.01, 3 epochs, seeds 0/0): %d training pairs'
+                       % len(train), 'reference_python_triples_per_s_build_container': 95_500.0}
+    cwd = os.getcwd()
+    with tempfile.TemporaryDirectory() as tmp:
+        os.chdir(tmp)
+        try:
+            for mode, extra in (('parity_f64', ''), ('parity_f32', 'engine=-mode parity -precision f32\n'), ('fast_f32', 'engine=-mode fast\n')):
+                random.setstate((3, tuple(int(x) for x in g['mt_state_after_split']), None))
+                np.random.seed(0)
+                model = BPR(ModelConf.from_string(str(g['conf']) + extra), train, test)
+                losses = []
+                orig = model.isConverged
+                model.isConverged = lambda epoch, m=model, o=orig: (losses.append(m.loss), o(epoch))[1]
+                with contextlib.redirect_stdout(io.StringIO()):
+                    model.readConfiguration(); model.initializing_log(); model.initModel()
+                    t0 = time.perf_counter()
+                    model.trainModel()
+                    dt = time.perf_counter() - t0
+                    model.evalRanking()
+                ref_loss = g['loss'].tolist()
+                out[mode] = {'train_seconds': dt, 'epochs': len(losses), 'triples_per_s': len(losses) * len(g['triples_epoch'][0]) / dt,
+                             'epoch_losses': losses, 'reference_epoch_losses': ref_loss,
+                             'max_loss_rel_err': max(abs(a - b) / b for a, b in zip(losses, ref_loss)),
+                             'measure': [m.strip() for m in model.measure], 'reference_measure': g['measure'].tolist(),
+                             'measure_equal': [m.strip() for m in model.measure] == g['measure'].tolist()}
+        finally:
+            os.chdir(cwd)
+    return out
+
+
+def zipf_section(torch, E, synthetic, dev, steps=5):
+    """SURVEY 8(d) contention stress: the same 1M x 100K x 50M shape with Zipf-like item popularity
+    (item = floor(I x^2): the hottest item takes ~0.3 % of all positives), fused user-major epoch."""
+    data = synthetic.make_interactions(NUM_USERS, NUM_ITEMS, DEGREE, device=dev, zipf=True, seed=424242)
+    P, Q = synthetic.init_tables(NUM_USERS, NUM_ITEMS, D, seed=12, device=dev)
+    loss = torch.zeros(1, dtype=torch.float64, device=dev)
+    ep = [0]
+
+    def one():
+        ep[0] += 1
+        E.bpr_epoch_usermajor(P, Q, data['sorted_rowptr'], data['i'], data['sorted_rowptr'], data['sorted_cols'], NUM_ITEMS, 99, ep[0],
+                              LR, REG_U, REG_I, loss)
+    one(); one()
+    ms = _time_ms(torch, one, steps)
+    hot = int(torch.bincount(data['i'].long(), minlength=NUM_ITEMS).max().item())
+    assert np.isfinite(float(loss.item()))
+    return {'workload': 'BPR synthetic 1M x 100K x 50M, Zipf-like items (item = floor(I x^2)), d=64, fused user-major epoch',
+            'ms_per_epoch': ms, 'triples_per_s': NUM_USERS * DEGREE / (ms * 1e-3), 'hottest_item_positives': hot,
+            'parity': 'tests/test_gpu_parity_config2.py::test_fused_epoch_vs_sequential_reference_zipf_contended'}
+
+
+# ---------------------------------------------------------------------------------------------
 # second half of the headline metric: LightGCN epoch time on the same synthetic graph
 # ---------------------------------------------------------------------------------------------
 def local_bipartite_blocks(torch, dist, data, users_local, num_items, world):
@@ -690,7 +760,12 @@ def run_ours(args):
         epoch_on(P1, Q1, sync1, 0, l1, j_out=jx)
         getattr(sync1, 'finalize', lambda: None)()
         torch.cuda.synchronize()
+        replicas_equal = None
         if world > 1:
+            qs = [torch.empty_like(Q1) for _ in range(world)]
+            dist.all_gather(qs, Q1)
+            replicas_equal = all(torch.equal(qs[0], t) for t in qs)       # after the drain every rank holds the same item table
+            del qs
             dist.all_reduce(l1)
             gi = torch.empty(n_local * world, dtype=torch.int32, device=dev)
             gj = torch.empty(n_local * world, dtype=torch.int32, device=dev)
@@ -713,6 +788,8 @@ def run_ours(args):
                               '%d item-table syncs) from the initial tables, negatives exported through j_out, against the '
                               'sequential reference loop on the same stream' % (world, q_syncs))
             parity['bound_held_in_tests'] = 'loss rel_err <= 1e-3 (tests/test_gpu_parity_config2.py)'
+            if replicas_equal is not None:
+                parity['item_table_replicas_bit_identical_after_drain'] = bool(replicas_equal)
             del P0_host, hu_all
         del P1, Q1, jx, gi, gj, gP, sync1
         torch.cuda.empty_cache()
@@ -738,6 +815,18 @@ def run_ours(args):
             neumf = neumf_section(torch, E, data, dev, measured_hbm_peak()[0])
         except Exception as exc:                     # noqa: BLE001
             neumf = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        torch.cuda.empty_cache()
+
+    filmtrust, zipf = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        try:
+            filmtrust = filmtrust_section()
+        except Exception as exc:                     # noqa: BLE001
+            filmtrust = {'error': '%s: %s' % (type(exc).__name__, exc)}
+        try:
+            zipf = zipf_section(torch, E, synthetic, dev)
+        except Exception as exc:                     # noqa: BLE001
+            zipf = {'error': '%s: %s' % (type(exc).__name__, exc)}
         torch.cuda.empty_cache()
 
     roofs, hbm_cfg = None, None
@@ -836,6 +925,10 @@ def run_ours(args):
             out['lightgcn'] = lightgcn
         if neumf is not None:
             out['neumf'] = neumf
+        if filmtrust is not None:
+            out['config1_filmtrust'] = filmtrust
+        if zipf is not None:
+            out['zipf_contended'] = zipf
         if parity is not None:
             out['parity_check'] = parity
         if world == 1 and parity is not None and 'error' not in parity:
@@ -870,6 +963,7 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-lightgcn', action='store_true')
     ap.add_argument('--no-neumf', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the FilmTrust (config 1) and Zipf sections')
     ap.add_argument('--no-roofs', action='store_true', help='skip the row-op microbenchmark and the HBM-bound configuration')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-epoch parity check against the sequential oracle')
     args = ap.parse_args()
