@@ -478,6 +478,14 @@ int qrec_gather_rows_f32(const float* dev_T, const int32_t* dev_idx, int64_t n, 
 /* G[idx[b], :] += scale * src[b, 0:d] (IndexedSlices gradient, duplicates summed). */
 int qrec_scatter_add_rows_f32(float* dev_G, const int32_t* dev_idx, int64_t n, int32_t d,
                               const float* dev_src, int32_t ld_src, float scale, void* stream);
+/* K7 (SURVEY 8e, row-sharded item table): device-side bucketing of the 2n item requests of a minibatch by owner
+ * rank (owner = id / rows_per_rank) into FIXED-capacity buckets, so that the id / row / delta exchanges are
+ * equal-split all-to-alls with no host round trip.  send[world*cap] receives the owner-local row ids (-1 = empty
+ * slot; qrec_gather_rows_f32 returns zeros for it, qrec_scatter_add_rows_f32 skips it), pos[k] the slot of request
+ * k (= the row of the fetched block it will read and the delta block it will write).  *overflow is set when a
+ * bucket needs more than `cap` slots (the step is then invalid). */
+int qrec_bucket_requests(const int32_t* dev_ids, int64_t n, int32_t rows_per_rank, int32_t world, int32_t cap,
+                         int32_t* dev_count, int32_t* dev_send, int32_t* dev_pos, int32_t* dev_overflow, void* stream);
 /* mode 0 GMF | 1 MLP | 2 NeuMF head: y = sigmoid(wg*(UG*IG).h_mf + wm*H3.h_mlp); when training,
  * loss += BCE(r, y; +1e-9) [+ reg*l2_loss(UG)+reg*l2_loss(IG), modes 0/2], dz = dLoss/dz, and the
  * per-sample gradients GMF=UG*IG, dUG, dIG (incl. reg), dH3 (ReLU-masked).  The h-vector terms of

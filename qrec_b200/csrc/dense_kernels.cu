@@ -370,7 +370,8 @@ gather_rows_kernel(const float* __restrict__ T, const int* __restrict__ idx, lon
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n * nvec; k += stride) {
     const long long b = k / nvec;
     const int v = (int)(k % nvec);
-    const float4 x = __ldg(reinterpret_cast<const float4*>(T + (size_t)__ldg(idx + b) * nvec * 4) + v);
+    const int row = __ldg(idx + b);                      // row < 0: an empty slot of a fixed-capacity exchange -> zeros
+    const float4 x = row >= 0 ? __ldg(reinterpret_cast<const float4*>(T + (size_t)row * nvec * 4) + v) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(out + (size_t)b * ld_out + v * 4) = x;
   }
 }
@@ -383,10 +384,36 @@ scatter_add_rows_kernel(float* __restrict__ G, const int* __restrict__ idx, long
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n * nvec; k += stride) {
     const long long b = k / nvec;
     const int v = (int)(k % nvec);
+    const int row = __ldg(idx + b);
+    if (row < 0) continue;                                // empty slot
     float4 x = *reinterpret_cast<const float4*>(src + (size_t)b * ld_src + v * 4);
     x.x *= scale; x.y *= scale; x.z *= scale; x.w *= scale;
-    float* dst = G + (size_t)__ldg(idx + b) * nvec * 4 + v * 4;
+    float* dst = G + (size_t)row * nvec * 4 + v * 4;
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+  }
+}
+
+// K7 (row-sharded item table): request k asks for item ids[k]; its owner is ids[k] / rows_per_rank.  Every
+// (requester, owner) pair has a FIXED number of slots (cap), so the three exchanges are equal-split all-to-alls
+// whose sizes the host knows without looking at the data: slot = atomicAdd(count[owner]); send[owner*cap + slot] =
+// LOCAL row at the owner; pos[k] = owner*cap + slot (where the row will arrive and the delta must be left).
+// A bucket that overflows raises *overflow (the step is then invalid; the caller re-runs with a larger cap).
+__global__ void __launch_bounds__(256)
+bucket_requests_kernel(const int* __restrict__ ids, long long n, int rows_per_rank, int world, int cap,
+                       int* __restrict__ count, int* __restrict__ send, int* __restrict__ pos, int* __restrict__ overflow) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+    const int id = __ldg(ids + k);
+    int owner = id / rows_per_rank;
+    if (owner >= world) owner = world - 1;
+    const int slot = atomicAdd(count + owner, 1);
+    if (slot < cap) {
+      send[(long long)owner * cap + slot] = id - owner * rows_per_rank;
+      pos[k] = owner * cap + slot;
+    } else {
+      pos[k] = owner * cap;                                // stays in bounds; the step is flagged invalid
+      atomicExch(overflow, 1);
+    }
   }
 }
 
@@ -609,6 +636,19 @@ int qrec_scatter_add_rows_f32(float* G, const int32_t* idx, int64_t n, int32_t d
   if (n == 0) return QREC_OK;
   QREC_REQUIRE(G && idx && src, "qrec_scatter_add_rows_f32: null pointer");
   scatter_add_rows_kernel<<<grid_for(n * (d / 4), 256), 256, 0, (cudaStream_t)stream>>>(G, idx, n, d / 4, src, ld_src, scale);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bucket_requests(const int32_t* ids, int64_t n, int32_t rows_per_rank, int32_t world, int32_t cap, int32_t* count,
+                         int32_t* send, int32_t* pos, int32_t* overflow, void* stream) {
+  QREC_REQUIRE(n >= 0 && rows_per_rank >= 1 && world >= 1 && cap >= 1, "qrec_bucket_requests: bad argument");
+  QREC_REQUIRE(count && send && overflow && (n == 0 || (ids && pos)), "qrec_bucket_requests: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  QREC_CUDA(cudaMemsetAsync(count, 0, sizeof(int32_t) * world, st));
+  QREC_CUDA(cudaMemsetAsync(send, 0xff, sizeof(int32_t) * (size_t)world * cap, st));      // -1 = empty slot
+  if (n == 0) return QREC_OK;
+  bucket_requests_kernel<<<grid_for(n, 256), 256, 0, st>>>(ids, n, rows_per_rank, world, cap, count, send, pos, overflow);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

@@ -464,6 +464,14 @@ def adj_subgraph(rowptr, cols, pair, pair_w):
     return new_rowptr, new_cols, new_vals
 
 
+def bucket_requests(ids, rows_per_rank, world, cap, count, send, pos, overflow):
+    """K7: requests -> fixed-capacity per-owner buckets on the device (csrc/dense_kernels.cu)."""
+    torch = _torch()
+    check(lib.qrec_bucket_requests(_dev(ids, torch.int32, 'ids'), ids.shape[0], int(rows_per_rank), int(world), int(cap),
+                                   _dev(count, torch.int32, 'count'), _dev(send, torch.int32, 'send'), _dev(pos, torch.int32, 'pos'),
+                                   _dev(overflow, torch.int32, 'overflow'), _stream()), 'qrec_bucket_requests')
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

@@ -321,18 +321,29 @@ class ShardedItemTableBPR(object):
     """Throughput-mode BPR where rank r owns users [lo_u, hi_u) (P rows + their triples) and the item
     block [r*bi, (r+1)*bi) of Q.  Per minibatch of LOCAL triples (three exchanges):
 
-      ids    the 2n item ids (i then j) are bucketed by owner and exchanged      all-to-all (4 B/id)
-      rows   owners gather the requested rows (qrec_gather_rows_f32) and return   all-to-all (4d B/row)
-      step   qrec_bpr_sgd_staged_f32: BPR.py:45-52 on P (in place) and the staged rows -> item deltas
-      grads  deltas travel back the same way and are scatter-added by the owner   all-to-all + REDG
+      bucket the 2n item requests (i then j) go into FIXED-capacity per-owner buckets on the device
+             (qrec_bucket_requests): the exchanges below are equal-split all-to-alls whose sizes the host
+             knows without reading device data -- no .tolist(), no host synchronisation inside a step
+      ids    owner-local row ids travel to the owners                              all-to-all (4 B/slot)
+      rows   owners gather the requested rows (qrec_gather_rows_f32) and return      all-to-all (4d B/slot)
+      step   qrec_bpr_sgd_staged_f32: BPR.py:45-52 on P (atomic adds) and the staged rows -> item deltas
+      grads  deltas travel back the same way and are scatter-added by the owner      all-to-all + REDG
 
-    A rank's own item block takes the same path (the self-exchange never leaves the GPU).
-    Duplicate requests are not merged: every occurrence fetches its own copy and returns its own
-    delta, the owner's scatter-add sums them -- the same sum-of-deltas semantics as the single-GPU
-    kernel.  Collectives: torch.distributed all_to_all_single (NCCL over NVLink / gloo in tests)."""
+    A rank's own item block takes the same path (the self-exchange never leaves the GPU).  Duplicate requests are
+    not merged: every occurrence fetches its own copy and returns its own delta, the owner's scatter-add sums
+    them -- the same sum-of-deltas semantics as the single-GPU kernel.  Empty slots carry row id -1 (fetched as
+    zeros, skipped by the scatter).  `capacity_slack` sizes the buckets: mean + slack * sigma (+64) of a uniform
+    item distribution; a bucket that still overflows sets a device flag that `check()` turns into an error
+    (re-run with a larger slack -- popularity-skewed items need it).
+
+    `epoch()` runs the minibatches through TWO lanes (streams with their own buffers): while one lane's rows or
+    deltas are on NVLink the other lane's gather / staged-SGD / scatter kernels run, so communication overlaps
+    compute; a row fetched by one lane may miss the delta the other lane is about to return (one minibatch of
+    extra staleness, the same Hogwild reading as triples in flight inside one kernel).
+    Collectives: torch.distributed all_to_all_single (NCCL over NVLink / gloo in tests)."""
 
     def __init__(self, P_local, Q_local, num_items, rank, world, lr, reg_u, reg_i, group=None,
-                 gather=None, staged=None, scatter=None):
+                 gather=None, staged=None, scatter=None, bucket=None, max_batch=1 << 20, capacity_slack=6.0):
         from . import engine as E
         if num_items % world:
             raise ValueError('ShardedItemTableBPR: num_items must be a multiple of the world size')
@@ -340,44 +351,90 @@ class ShardedItemTableBPR(object):
         self.rank, self.world, self.group = rank, world, group
         self.bi = num_items // world
         self.lr, self.reg_u, self.reg_i = lr, reg_u, reg_i
-        self.loss = torch.zeros(1, dtype=torch.float64, device=P_local.device)
+        dev = P_local.device
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
         self._gather = gather or (lambda T, idx, out: E.gather_rows(T, idx, out))
         self._staged = staged or (lambda P, u, pi, pj, R, D, loss: E.bpr_sgd_staged(P, u, pi, pj, R, D, self.lr, self.reg_u,
                                                                                  self.reg_i, loss))
         self._scatter = scatter or (lambda G, idx, src: E.scatter_add_rows(G, idx, src))
+        self._bucket = bucket or (lambda ids, cap, count, send, pos, ovf: E.bucket_requests(ids, self.bi, self.world, cap, count,
+                                                                                           send, pos, ovf))
+        self.max_batch, self.slack = int(max_batch), float(capacity_slack)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.bytes_sent = 0
+        self._lanes = {}
 
-    def step(self, u_local, i_glob, j_glob):
-        """u_local: int32 local user ids; i_glob/j_glob: int32 global item ids (device tensors)."""
-        dev, d, n = self.P.device, self.P.shape[1], u_local.shape[0]
-        ids = torch.cat([i_glob, j_glob]).long()                       # request k -> item id
-        owner = torch.div(ids, self.bi, rounding_mode='floor')
-        order = torch.argsort(owner, stable=True)                      # requests grouped by owner
-        send_ids = ids[order].int().contiguous()
-        send_counts = torch.bincount(owner, minlength=self.world)
-        recv_counts = torch.empty_like(send_counts)
-        _all_to_all(recv_counts, send_counts, None, None, self.group)  # one count per peer
-        sc, rc = send_counts.tolist(), recv_counts.tolist()
-        n_recv = int(sum(rc))
-        recv_ids = torch.empty(n_recv, dtype=torch.int32, device=dev)
-        _all_to_all(recv_ids, send_ids, rc, sc, self.group)
-        # ---- owner side: gather the requested rows and send them back
-        local_rows = (recv_ids - self.rank * self.bi).contiguous()
-        rows_out = torch.empty(n_recv, d, device=dev)
-        self._gather(self.Q, local_rows, rows_out)
-        R = torch.empty(2 * n, d, device=dev)
-        _all_to_all(R, rows_out, sc, rc, self.group)
-        # ---- requester side: position of request k inside R is the inverse of `order`
-        pos = torch.empty(2 * n, dtype=torch.int32, device=dev)
-        pos[order] = torch.arange(2 * n, dtype=torch.int32, device=dev)
-        D = torch.zeros(2 * n, d, device=dev)
-        self._staged(self.P, u_local, pos[:n].contiguous(), pos[n:].contiguous(), R, D, self.loss)
-        # ---- deltas travel back; the owner scatter-adds them
-        back = torch.empty(n_recv, d, device=dev)
-        _all_to_all(back, D, rc, sc, self.group)
-        self._scatter(self.Q, local_rows, back)
-        self.bytes_sent += 4 * 2 * n + 2 * 4 * d * (2 * n - sc[self.rank])
+    def capacity(self, n):
+        """Slots per (requester, owner) bucket for a minibatch of n triples (2n requests)."""
+        m = 2.0 * n / self.world
+        sigma = (2.0 * n * (1.0 / self.world) * (1.0 - 1.0 / self.world)) ** 0.5
+        return min(2 * n, int(m + self.slack * sigma) + 64) if self.world > 1 else 2 * n
+
+    def _lane(self, key, n):
+        lane = self._lanes.get(key)
+        cap = self.capacity(n)
+        if lane is None or lane['cap'] < cap:
+            dev, d, W = self.P.device, self.P.shape[1], self.world
+            z = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)       # noqa: E731
+            lane = dict(cap=cap, count=z(W, dt=torch.int32), send=z(W * cap, dt=torch.int32), recv=z(W * cap, dt=torch.int32),
+                        pos=z(2 * self.max_batch, dt=torch.int32), rows=z(W * cap, d), R=z(W * cap, d), D=z(W * cap, d),
+                        back=z(W * cap, d),
+                        stream=(torch.cuda.Stream(device=dev) if dev.type == 'cuda' and key != 'main' else None))
+            self._lanes[key] = lane
+        return lane
+
+    def step(self, u_local, i_glob, j_glob, lane='main'):
+        """u_local: int32 local user ids; i_glob/j_glob: int32 global item ids (device tensors).  Asynchronous:
+        nothing here waits for the device."""
+        n = int(u_local.shape[0])
+        if n > self.max_batch:
+            raise ValueError('ShardedItemTableBPR: minibatch of %d triples exceeds max_batch=%d' % (n, self.max_batch))
+        L = self._lane(lane, n)
+        cap, W = L['cap'], self.world
+        ids = torch.cat([i_glob, j_glob]).contiguous()                  # request k -> item id (i then j)
+        pos = L['pos'][:2 * n]
+        self._bucket(ids, cap, L['count'], L['send'], pos, self.overflow)
+        _all_to_all(L['recv'], L['send'], None, None, self.group)       # equal split: cap slots per peer
+        self._gather(self.Q, L['recv'], L['rows'])                      # owner side; -1 -> zeros
+        _all_to_all(L['R'], L['rows'], None, None, self.group)          # slot p of R answers slot p of send
+        L['D'].zero_()
+        self._staged(self.P, u_local, pos[:n], pos[n:], L['R'], L['D'], self.loss)
+        _all_to_all(L['back'], L['D'], None, None, self.group)          # deltas return to the owners
+        self._scatter(self.Q, L['recv'], L['back'])                     # -1 slots skipped
+        d = self.P.shape[1]
+        self.bytes_sent += (W - 1) * cap * (4 + 2 * 4 * d)
         return self.loss
+
+    def epoch(self, u_local, i_glob, j_glob, batch, rowptr_host=None):
+        """All minibatches of the rank's triples (user-major order) through two alternating lanes."""
+        n = int(u_local.shape[0])
+        cuts = list(range(0, n, batch)) + [n]
+        cuda = self.P.device.type == 'cuda'
+        if not cuda:
+            for a, b in zip(cuts[:-1], cuts[1:]):
+                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b])
+            return self.loss
+        cur = torch.cuda.current_stream()
+        start = torch.cuda.Event(); start.record(cur)
+        done = []
+        for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
+            L = self._lane('lane%d' % (k & 1), b - a)
+            L['stream'].wait_event(start)
+            with torch.cuda.stream(L['stream']):
+                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b], lane='lane%d' % (k & 1))
+        for key in ('lane0', 'lane1'):
+            if key in self._lanes:
+                ev = torch.cuda.Event(); ev.record(self._lanes[key]['stream']); done.append(ev)
+        for ev in done:
+            cur.wait_event(ev)
+        return self.loss
+
+    def check(self):
+        """Host-side validity check (one device read): raises if any bucket overflowed since the last call."""
+        if int(self.overflow.item()):
+            self.overflow.zero_()
+            raise RuntimeError('ShardedItemTableBPR: a request bucket overflowed its fixed capacity; the affected steps are '
+                               'invalid -- raise capacity_slack (popularity-skewed items need more head-room)')
 
 
 # =============================================================================================

@@ -189,8 +189,19 @@ def _sharded_bpr_worker(rank, world, port, out):
         bi = I // world
         lu, li, lj = parallel.shard_triples_by_user(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j), rank, world, U)
 
-        def gather(T, idx, o):
-            o.copy_(T[idx.long()])
+        def gather(T, idx, o):                                   # row -1 = empty slot -> zeros (as the kernel does)
+            o.copy_(torch.where((idx >= 0)[:, None], T[idx.clamp(min=0).long()], torch.zeros(1)))
+
+        def bucket(ids, cap, count, send, pos, ovf):             # numpy restatement of bucket_requests_kernel
+            count.zero_(); send.fill_(-1)
+            for k, idv in enumerate(ids.tolist()):
+                owner = min(idv // bi, world - 1)
+                slot = int(count[owner]); count[owner] += 1
+                if slot < cap:
+                    send[owner * cap + slot] = idv - owner * bi
+                    pos[k] = owner * cap + slot
+                else:
+                    pos[k] = owner * cap; ovf.fill_(1)
 
         def staged(P, uu, pi, pj, R, D, loss):
             # the same arithmetic as the kernel, via the oracle's sequential step on private copies
@@ -206,10 +217,14 @@ def _sharded_bpr_worker(rank, world, port, out):
                 loss += l
 
         def scatter(G, idx, src):
-            G.index_add_(0, idx.long(), src)
+            keep = idx >= 0
+            G.index_add_(0, idx[keep].long(), src[keep])
         m = parallel.ShardedItemTableBPR(torch.from_numpy(P0[lo:hi].copy()), torch.from_numpy(Q0[rank * bi:(rank + 1) * bi].copy()),
-                                         I, rank, world, lr, reg, reg, gather=gather, staged=staged, scatter=scatter)
-        loss = m.step(lu, li, lj)
+                                         I, rank, world, lr, reg, reg, gather=gather, staged=staged, scatter=scatter, bucket=bucket,
+                                         max_batch=64)
+        assert m.capacity(12) == 24 and (1 << 20) < m.capacity(1 << 20) < 1.01 * (1 << 20)   # mean + slack*sigma + 64, capped at 2n
+        loss = m.epoch(lu, li, lj, batch=5)                          # several minibatches, ragged tail
+        m.check()                                                    # no bucket overflowed
         Pr, Qr = P0.copy(), Q0.copy()
         ref_loss = c_oracle.bpr_sgd_sequential(Pr, Qr, u, i, j, lr, reg, reg)
         tot = loss.clone()
@@ -217,6 +232,17 @@ def _sharded_bpr_worker(rank, world, port, out):
         assert abs(float(tot) - ref_loss) < 1e-5 * ref_loss
         assert np.allclose(m.P.numpy(), Pr[lo:hi], rtol=1e-6, atol=1e-7)
         assert np.allclose(m.Q.numpy(), Qr[rank * bi:(rank + 1) * bi], rtol=1e-6, atol=1e-7)
+        # a bucket that is too small is reported, not silently truncated
+        tiny = parallel.ShardedItemTableBPR(m.P, m.Q, I, rank, world, lr, reg, reg, gather=gather, staged=staged, scatter=scatter,
+                                            bucket=bucket, max_batch=64)
+        tiny.capacity = lambda n: 1
+        tiny.step(lu[:6], li[:6], lj[:6])
+        flag = tiny.overflow.clone()
+        dist.all_reduce(flag)
+        assert int(flag) >= 1
+        if int(tiny.overflow):
+            with pytest.raises(RuntimeError):
+                tiny.check()
         out[rank] = 1
     finally:
         dist.destroy_process_group()

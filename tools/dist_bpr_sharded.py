@@ -16,7 +16,8 @@ sys.path.insert(0, ROOT)
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--batch', type=int, default=1 << 21, help='triples per rank per step')
+    ap.add_argument('--batch', type=int, default=1 << 21, help='triples per rank per epoch() call')
+    ap.add_argument('--minibatch', type=int, default=1 << 18, help='triples per minibatch (one id/row/delta exchange each)')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -25,7 +26,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
+        dist.init_process_group('nccl', device_id=dev, pg_options=dist.ProcessGroupNCCL.Options(is_high_priority_stream=True))
     U, I, D, DEG = 1_000_000, 100_000, 64, 50
     lo, hi = parallel.user_range(rank, world, U)
     bi = I // world
@@ -40,9 +41,10 @@ def main():
     loss = torch.zeros(1, dtype=torch.float64, device=dev)
     E.bpr_sgd_batch(Pf, Qf, u, i, j, 0.05, 0.01, 0.01, loss)
     lu, li, lj = parallel.shard_triples_by_user(u, i, j, rank, world, U)
-    m = parallel.ShardedItemTableBPR(Pl, Ql, I, rank, world, 0.05, 0.01, 0.01)
-    m.step(lu, li, lj)
+    m = parallel.ShardedItemTableBPR(Pl, Ql, I, rank, world, 0.05, 0.01, 0.01, max_batch=max(args.minibatch, 1 << 16))
+    m.epoch(lu, li, lj, batch=7000)           # several minibatches through the two lanes
     torch.cuda.synchronize()
+    m.check()
     torch.testing.assert_close(Pl, Pf[lo:hi], rtol=1e-6, atol=1e-7)
     torch.testing.assert_close(Ql, Qf[rank * bi:(rank + 1) * bi], rtol=1e-6, atol=1e-7)
     if rank == 0:
@@ -54,23 +56,27 @@ def main():
     bu, bi_ = data['u'][perm].contiguous(), data['i'][perm].contiguous()
     bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 3, 0)
     m.lr, m.reg_u, m.reg_i = 0.01, 0.001, 0.001
+    # user-major order inside the sample, like an epoch of the rank's shard
+    order = torch.argsort(bu.long(), stable=True)
+    bu, bi_, bj = bu[order].contiguous(), bi_[order].contiguous(), bj[order].contiguous()
     for _ in range(3):
-        m.step(bu, bi_, bj)
+        m.epoch(bu, bi_, bj, args.minibatch)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        m.step(bu, bi_, bj)
+        m.epoch(bu, bi_, bj, args.minibatch)
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    m.check()
     if rank == 0:
         ms = float(t.item())
-        print(json.dumps({'sharded_q_step_ms': ms, 'world': world, 'triples_per_rank_per_step': args.batch,
+        print(json.dumps({'sharded_q_step_ms': ms, 'minibatch': args.minibatch, 'bucket_capacity': m.capacity(args.minibatch), 'world': world, 'triples_per_rank_per_step': args.batch,
                           'triples_per_s_total': args.batch * world / ms * 1e3,
                           'nvlink_bytes_per_triple_each_way': 2 * 4 * D * (world - 1) / world}))
     if world > 1:
