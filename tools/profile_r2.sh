@@ -12,8 +12,10 @@ for t in ${TARGETS:-k1 k1_hbm rowops spmm topn}; do
   [ "$t" = rowops ] && kre="regex:row_op_kernel"
   [ "$t" = spmm ] && kre="regex:spmm_csr"
   [ "$t" = topn ] && kre="regex:score_topn"
-  timeout 900 $NCU --set full --import-source on -k "$kre" -s 1 -c ${COUNT:-1} -o "$out/${t}_full_r2" -f \
-    python tools/ncu_targets.py "$t" 2 > "$out/ncu_$t.log" 2>&1
+  skip=1; count=1; reps=2
+  [ "$t" = rowops ] && { skip=0; count=3; reps=1; }          # the three modes, one launch each
+  timeout 900 $NCU --set full --import-source on -k "$kre" -s $skip -c $count -o "$out/${t}_full_r2" -f \
+    python tools/ncu_targets.py "$t" $reps > "$out/ncu_$t.log" 2>&1
   echo "$t: exit $?"
   ncu -i "$out/${t}_full_r2.ncu-rep" --page raw --csv > "$out/${t}_full_r2_raw.csv" 2>/dev/null
 done
