@@ -255,6 +255,10 @@ int qrec_table_reduce_scatter_p2p_f32(const float* const* peer_D, int32_t world,
                                       void* stream);
 int qrec_table_gather_merge_p2p_f32(const float* const* peer_S, int32_t world, float* dev_Q, float* dev_B,
                                     const float* dev_D, int64_t n, void* stream);
+/* Plain all-gather of the reduce-scattered sums (peer_S as above): out[k] = S_owner(k)[k].  With
+ * qrec_table_reduce_scatter_p2p_f32 and a barrier in between this is an all-reduce over peer memory (used for the
+ * [I, d] item block of the user-sharded LightGCN / SimGCL layers). */
+int qrec_table_all_gather_p2p_f32(const float* const* peer_S, int32_t world, float* dev_out, int64_t n, void* stream);
 
 /* K8: batched ranking evaluation, replaces the per-user loop of Recommender.evalRanking
  * (base/recommender.py:143-152) + find_k_largest (util/qmath.py:134-146).  For every row r of the block:

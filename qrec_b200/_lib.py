@@ -91,6 +91,7 @@ SIGNATURES = {
     'qrec_table_delta_f32': (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     'qrec_table_merge_f32': (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     'qrec_table_reduce_scatter_p2p_f32': (C.c_int, [C.POINTER(vp), C.c_int32, C.c_int32, vp, C.c_int64, vp]),
+    'qrec_table_all_gather_p2p_f32': (C.c_int, [C.POINTER(vp), C.c_int32, vp, C.c_int64, vp]),
     'qrec_table_gather_merge_p2p_f32': (C.c_int, [C.POINTER(vp), C.c_int32, vp, vp, vp, C.c_int64, vp]),
     'qrec_score_topn_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
     'qrec_adj_normalize_f32': (C.c_int, [C.c_int32, vp, vp, vp, vp, vp, vp, vp]),

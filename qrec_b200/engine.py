@@ -389,6 +389,13 @@ def table_reduce_scatter_p2p(peer_D_ptrs, rank, S, n):
           'qrec_table_reduce_scatter_p2p_f32')
 
 
+def table_all_gather_p2p(peer_S_ptrs, out):
+    """out[k] = the summed slice held by its owner (second half of the peer-memory all-reduce)."""
+    torch = _torch()
+    check(lib.qrec_table_all_gather_p2p_f32(_ptr_array(peer_S_ptrs), len(peer_S_ptrs), _dev(out, torch.float32, 'out'),
+                                            out.numel(), _stream()), 'qrec_table_all_gather_p2p_f32')
+
+
 def table_gather_merge_p2p(peer_S_ptrs, Q, B, D):
     """All-gather of the summed slices from their owners fused with the merge (Q += S - D; B += S)."""
     torch = _torch()
