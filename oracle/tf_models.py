@@ -123,3 +123,29 @@ def neumf_loss_and_grad(params, mode, u, i, r, reg):
         loss = bce(y) + mf_reg + reg * l2(hn)
     loss.backward()
     return float(loss), {k: (v.grad.numpy() if v.grad is not None else None) for k, v in P.items()}, y.detach().numpy()
+
+
+def sgl_loss_and_grad(adj_main, views, ego, num_users, u, i, j, n_layers, ssl_reg, temp, reg):
+    """model/ranking/SGL.py:56-76 (three LightGCN encoders, mean of E_0..E_n), :206-230 (calc_ssl_loss_v3: users and
+    items of the batch merged into one InfoNCE), :232-238 (BPR + batch L2 + ssl).  views[v][k]: scipy matrix of
+    view v (0/1), layer k.  Returns (rec, ssl, d total / d ego)."""
+    E0 = torch.tensor(ego, dtype=torch.float64, requires_grad=True)
+
+    def encoder(mats):
+        emb, outs = E0, [E0]
+        for k in range(n_layers):
+            emb = torch.sparse.mm(_sp(mats[k]), emb)
+            outs.append(emb)
+        return torch.stack(outs, 1).mean(1)
+    m0 = encoder([adj_main] * n_layers)
+    m1, m2 = encoder(views[0]), encoder(views[1])
+    ut, it, jt = (torch.as_tensor(np.asarray(x), dtype=torch.long) for x in (u, i, j))
+    ue, pe, ne = m0[ut], m0[num_users + it], m0[num_users + jt]
+    rec = _bpr_loss(ue, pe, ne, 10e-8) + reg * 0.5 * ((ue ** 2).sum() + (pe ** 2).sum() + (ne ** 2).sum())
+    idx = torch.cat([torch.unique(ut), torch.unique(it) + num_users])
+    z1, z2 = _l2n(m1[idx]), _l2n(m2[idx])
+    pos = torch.exp((z1 * z2).sum(1) / temp)
+    ttl = torch.exp(z1 @ z2.t() / temp).sum(1)
+    ssl = -torch.log(pos / ttl).sum()
+    (rec + ssl_reg * ssl).backward()
+    return float(rec), float(ssl_reg * ssl), E0.grad.numpy()

@@ -166,7 +166,8 @@ def test_ngcf_step_vs_autograd(torch, golden_graph, tmp_path):
         assert np.abs(m._gw['W_%d_2' % k].cpu().numpy() - rgW2[k]).max() <= 3e-3 * np.abs(rgW2[k]).max()
 
 
-@pytest.mark.parametrize('name,extra', [('SimGCL', 'SimGCL=-n_layer 2 -lambda 0.5 -eps 0.1\n'), ('NGCF', '')])
+@pytest.mark.parametrize('name,extra', [('SimGCL', 'SimGCL=-n_layer 2 -lambda 0.5 -eps 0.1\n'), ('NGCF', ''),
+                                        ('SGL', 'SGL=-n_layer 2 -lambda 0.1 -droprate 0.1 -augtype 1 -temp 0.2\n')])
 def test_graph_models_full_lifecycle(golden_bpr, tmp_path, name, extra):
     """execute() end to end on FilmTrust: trains, evaluates, and lands in a sane quality band."""
     import importlib
@@ -240,3 +241,42 @@ def test_neumf_full_lifecycle(golden_bpr, tmp_path):
         measure = NeuMF(ModelConf.from_string(conf), train, test).execute()
     got = {m.split(':')[0]: float(m.split(':')[1]) for m in measure[1:]}
     assert got['Precision'] > 0.12 and got['Recall'] > 0.25
+
+
+@pytest.mark.parametrize('aug', [1, 2, 0])
+def test_sgl_step_vs_autograd(torch, golden_graph, tmp_path, aug):
+    """One SGL minibatch (f-4 sibling model; model/ranking/SGL.py): three LightGCN encoders over the full graph and
+    the epoch's two augmented views (rebuilt on the device by the f-2 kernels), BPR + merged user/item InfoNCE,
+    per-view Horner backward -- against the float64 autograd restatement fed with the SAME view matrices (read back
+    from the device; their construction has its own test, test_gpu_adjacency.py)."""
+    import scipy.sparse as sp
+    from oracle import tf_models
+    from qrec_b200.model.ranking.SGL import SGL
+    g = golden_graph
+    m = _graph_model(SGL, g, tmp_path, 'SGL=-n_layer 2 -lambda 0.1 -droprate 0.3 -augtype %d -temp 0.2\n' % aug)
+    N, d = m.num_users + m.num_items, m.emb_size
+    m.ego.mul_(20.0)                                   # make the InfoNCE term visible next to the 0.005-sigma init
+    views = m.build_views(0)
+    assert len(views) == 2 and all(len(v) == 2 for v in views)
+    to_sp = lambda a: sp.csr_matrix((a.vals.cpu().numpy().astype(np.float64), a.cols.cpu().numpy(), a.rowptr.cpu().numpy()), shape=(N, N))  # noqa: E731
+    sp_views = [[to_sp(a) for a in v] for v in views]
+    full = to_sp(m.norm_adj)
+    for v in sp_views:                                 # a view keeps ~70 % of the edges (node dropout: ~49 %), never more
+        for a in v:
+            assert 0.3 * full.nnz < a.nnz < (0.85 if aug else 0.7) * full.nnz
+    if aug == 2:
+        assert views[0][0].nnz != views[0][1].nnz or not torch.equal(views[0][0].cols, views[0][1].cols)   # a fresh draw per layer
+    else:
+        assert views[0][0] is views[0][1]
+    ego0 = m.ego[:, :d].cpu().numpy().astype(np.float64)
+    sl = slice(0, 2048)
+    u, i, j = g['shuffled_u'][sl], g['shuffled_i'][sl], g['pair_all_j'][sl]
+    m.train_step(*(_dev(torch, x) for x in (u, i, j)))
+    rec, ssl = m.losses()
+    rrec, rssl, rgrad = tf_models.sgl_loss_and_grad(full, sp_views, ego0, m.num_users, u, i, j, 2, 0.1, 0.2, m.regU)
+    assert abs(rec - rrec) <= 1e-4 * abs(rrec) and abs(ssl - rssl) <= 1e-4 * abs(rssl)
+    got = m._total[:, :d].cpu().numpy()
+    assert np.abs(got - rgrad).max() <= 2e-3 * np.abs(rgrad).max()
+    moved = m.ego[:, :d].cpu().numpy() - ego0
+    big = np.abs(rgrad) > 1e-3 * np.abs(rgrad).max()
+    assert np.all(np.sign(moved[big]) == -np.sign(rgrad[big]))
