@@ -401,3 +401,80 @@ def test_overlapped_sync_single_process_is_identity():
     s = parallel.OverlappedTableSync(Q)
     Q += 1
     assert s.wave_done() is Q and s.finalize() is Q and bool((Q == 2).all()) and s.world == 1
+
+
+# ---------------------------------------------------------------------------------------------
+# SimGCL over a row-sharded user table (BASELINE config 5's decomposition), gloo world 2, kernel stand-ins
+# ---------------------------------------------------------------------------------------------
+class _Setattr(object):
+    """monkeypatch-like shim for the spawned worker processes."""
+    @staticmethod
+    def setattr(obj, name, value):
+        setattr(obj, name, value)
+
+    @staticmethod
+    def chdir(path):
+        os.chdir(path)
+
+
+def _simgcl_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import tf_models
+    from qrec_b200 import engine as E
+    import test_sgl_model_cpu as S
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        S._stub(_Setattr)                                       # numpy / torch restatements of the kernels' contracts
+        U, I, d, L, lr, reg, cl_rate, eps, seed = 9, 6, 8, 2, 0.01, 0.001, 0.5, 0.1, 0x5151
+        A = _toy_graph(U, I, seed=3)
+
+        def perturb(Emb, eps_, seed_, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
+            nz = tf_models.philox_uniform(row_offset + Emb.shape[0], Emb.shape[1], seed_, tag, step)[row_offset:]
+            nz = torch.from_numpy(nz).float()
+            Emb.add_(torch.sign(Emb) * nz / nz.norm(dim=1, keepdim=True).clamp(min=1e-6) * eps_)
+            if acc is not None:
+                acc.add_(Emb, alpha=acc_scale)
+            return Emb
+        E.simgcl_perturb = perturb
+        rp, co, va = (torch.from_numpy(x) for x in (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data))
+        A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, U, I, rank, world)
+        rng = np.random.default_rng(1)
+        ego = (rng.standard_normal((U + I, d)) * 0.3).astype(np.float32)
+        m = parallel.UserShardedSimGCL(A_ui, A_iu, torch.from_numpy(ego[lo:hi].copy()), torch.from_numpy(ego[U:].copy()), L, lr, reg,
+                                       lo, U, cl_rate, eps, noise_seed=seed, d_valid=d)
+        ego_ref = ego.astype(np.float64)
+        for step in range(1, 3):
+            u = rng.integers(0, U, 7).astype(np.int32); i = rng.integers(0, I, 7).astype(np.int32)
+            j = rng.integers(0, I, 7).astype(np.int32)
+            noise = [[tf_models.philox_uniform(U + I, d, seed, e * 16 + k, step) for k in range(L)] for e in (1, 2)]
+            rrec, rcl, rgrad = tf_models.simgcl_loss_and_grad(A, ego_ref, U, u, i, j, L, eps, cl_rate, reg, noise)
+            m.train_step(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            _, rec, cl = m.losses()
+            assert abs(rec - rrec) <= 1e-4 * abs(rrec) and abs(cl - rcl) <= 1e-4 * abs(rcl), (rank, step, rec, rrec, cl, rcl)
+            assert np.abs(m.tot_u.numpy() - rgrad[lo:hi]).max() <= 1e-3 * np.abs(rgrad).max(), (rank, step)
+            assert np.abs(m.tot_i.numpy() - rgrad[U:]).max() <= 1e-3 * np.abs(rgrad).max(), (rank, step)
+            # follow the engine's tables for the next step (Adam's first steps amplify rounding; the gradient is the check)
+            parts = [None] * world
+            dist.all_gather_object(parts, (lo, hi, m.Eu.numpy().copy()))
+            for a, b, blk in parts:
+                ego_ref[a:b] = blk
+            ego_ref[U:] = m.Ei.numpy()
+            # the replicated item rows are identical on every rank
+            others = [None] * world
+            dist.all_gather_object(others, m.Ei.numpy().copy())
+            assert all(np.array_equal(others[0], o) for o in others)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_user_sharded_simgcl_matches_autograd_world2():
+    """parallel.UserShardedSimGCL: noise keyed by the global row, item-block all-reduces per layer, InfoNCE over the
+    batch's users assembled from their owners, collapsed backward -- equal to the float64 autograd restatement of
+    model/ranking/SimGCL.py on every rank."""
+    port = 37500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_simgcl_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
