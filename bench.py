@@ -8,16 +8,26 @@ reference's own iteration order (model/ranking/BPR.py:31-33: users in id order, 
          row) fused into gather -> dots -> sigmoid -> SGD step -> scatter-add; P[u] register-resident
          inside a user, item rows REDG-added, j never written to HBM
   +   regU*|P|^2 + regI*|Q|^2 for the epoch loss                  (qrec_sumsq_f32, BPR.py:40)
-The same epoch with the triples in SHUFFLED order through the order-agnostic kernel
-(qrec_bpr_sgd_batch_f32) is timed too and reported under "shuffled_order".
 with the (u,i) pairs, the rated-item CSR and both tables already resident in HBM.  `e2e` is the
 same epoch entered through the host-buffer C-ABI call (qrec_bpr_epoch_usermajor_host): the step's
 positives (CSR: rowptr + item ids) start in pinned HOST memory and are copied to the device chunk by
 chunk inside the timed region, overlapped with the kernel; the loss comes back to the host.
 
 Multi-GPU (strong scaling of the fixed 50M set): users are range-partitioned, so P rows and each
-user's triples live on one rank; Q (25.6 MB) is replicated and its per-rank deltas are summed
-with an NCCL all-reduce `--q-syncs` times per step.
+user's triples live on one rank; Q (25.6 MB) is replicated and the ranks exchange the sum of their
+item-row deltas after each of `--q-syncs` launches per step -- asynchronously, hidden behind the next
+launch (parallel.OverlappedTableSync: peer-memory reduce-scatter / all-gather kernels, NCCL fallback).
+
+Further objects on the same JSON line (N=1 unless noted; each can be switched off, none can cost the headline):
+  parity_check       (any N) epoch 0 of this very path from the initial tables, negatives exported, against the
+                     sequential float64 oracle on the same stream -- also the CPU baseline (whole epoch, 1 core)
+  roofline           contract fields + row_op_peak (measured L2 / HBM row gather + scatter-add rates,
+                     csrc/microbench.cu) + hbm_bound_config (1M-item table: Q does not fit the L2)
+  shuffled_order     the same epoch with shuffled pairs through the order-agnostic kernel
+  lightgcn           (any N) LightGCN 3-layer minibatch steps, users sharded / items replicated; epoch time
+  neumf              BASELINE config 4: NeuMF steps, reference and [256,128,64] MLP widths, tcgen05 TF32
+  config1_filmtrust  BASELINE config 1: the recorded reference run replayed through the drop-in class
+  zipf_contended     the fused epoch on Zipf-distributed items
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 """
