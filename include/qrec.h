@@ -210,6 +210,16 @@ int qrec_bpr_epoch_usermajor_f32(float* dev_P, float* dev_Q, int32_t d, int32_t 
                                  int32_t num_items, uint64_t seed, uint32_t epoch, int32_t* dev_j_out,
                                  float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
 
+/* The fused epoch with the item rows staged through shared memory by the bulk-copy (TMA) engine: one
+ * cp.async.bulk (256 bytes) per row into a per-lane-group staging slot, completion on an mbarrier, lanes read their
+ * slices with LDS.128; two slots per group, so the next 4 triples' rows are in flight while 4 are computed.  Same
+ * step, order, sampler (identical negatives) and scatter-add as qrec_bpr_epoch_usermajor_f32.  d = 64 only. */
+int qrec_bpr_epoch_usermajor_tma_f32(float* dev_P, float* dev_Q, int32_t d, int32_t n_users, int64_t n,
+                                     const int64_t* dev_rowptr, const int32_t* dev_i,
+                                     const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
+                                     int32_t num_items, uint64_t seed, uint32_t epoch, int32_t* dev_j_out,
+                                     float lr, float reg_u, float reg_i, double* dev_loss, void* stream);
+
 /* The fused epoch with a pre-test in the sampler: rated_sig holds 16 words per user, bit (c & 511) set
  * for every rated column c (qrec_rated_signature_build; static per data set).  A clear bit proves a
  * draw is not rated, so about 1 - deg/512 of the draws skip the binary search -- the dependent-load

@@ -46,6 +46,10 @@ def main():
         fused.append(('fused sampling + signature pre-test',
                       lambda: E.bpr_epoch_usermajor_sig(P, Q, rowptr, data['i'], data['sorted_rowptr'], data['sorted_cols'], sig,
                                                         I, 1, next(seeds), 0.01, 0.001, 0.001, loss)))
+    if os.environ.get('QREC_TEST_UNVALIDATED') == '1':
+        fused.append(('fused sampling, item rows staged by bulk (TMA) copies',
+                      lambda: E.bpr_epoch_usermajor_tma(P, Q, rowptr, data['i'], data['sorted_rowptr'], data['sorted_cols'],
+                                                        I, 1, next(seeds), 0.01, 0.001, 0.001, loss)))
     for name, fn in fused:
         for _ in range(3):
             fn()

@@ -9,7 +9,7 @@ export QREC_TEST_UNVALIDATED=1
 out=gpurun_out/first_run
 mkdir -p "$out"
 python -c "import __graft_entry__ as g; g.build()" > "$out/build.log" 2>&1 || { echo "build failed"; tail -20 "$out/build.log"; exit 1; }
-for t in test_gpu_table_sync test_gpu_topn test_gpu_adjacency test_gpu_k1_sig test_gpu_rating test_gpu_lightgcn_blocked test_gpu_spmm_variants test_gpu_tcgemm_v2 test_gpu_parity_config2; do
+for t in test_gpu_table_sync test_gpu_topn test_gpu_adjacency test_gpu_k1_tma test_gpu_k1_sig test_gpu_rating test_gpu_lightgcn_blocked test_gpu_spmm_variants test_gpu_tcgemm_v2 test_gpu_parity_config2; do
   timeout 600 python -m pytest "tests/$t.py" -m gpu -q -s > "$out/$t.log" 2>&1
   echo "$t: exit $? -- $(tail -1 "$out/$t.log")"
 done
