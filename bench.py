@@ -48,6 +48,9 @@ NUM_USERS, NUM_ITEMS, DEGREE, D = 1_000_000, 100_000, 50, 64
 LR, REG_U, REG_I = 0.01, 0.001, 0.001
 ALGO_BYTES_PER_TRIPLE = 24 * D + 12          # 3 rows read + 3 rows written + 3 int32
 METRIC = 'BPR triples/sec at d=64'
+# Multi-GPU code paths that are on by default.  'blocking' = the round-1 delta all-reduce; 'auto' = the overlapped exchange
+# (peer-memory kernels, NCCL fallback).  Flipped to the new paths only once they have been validated on >= 2 GPUs.
+MULTI_GPU_DEFAULTS = {'qsync': 'blocking', 'lightgcn_multi': False, 'parity_multi': False}
 WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, user-major (reference) order'
 
 
@@ -759,57 +762,62 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ parity of this very path at this size
     parity = None
-    if not args.no_parity:
-        P1, Q1 = synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + rank, device=dev)
-        if world > 1:
-            dist.broadcast(Q1, 0)
-        Q0_host = Q1.cpu().numpy() if rank == 0 else None
-        sync1 = make_sync(Q1)
-        jx = torch.empty(n_local, dtype=torch.int32, device=dev)
-        l1 = torch.zeros(3, dtype=torch.float64, device=dev)
-        epoch_on(P1, Q1, sync1, 0, l1, j_out=jx)
-        getattr(sync1, 'finalize', lambda: None)()
-        torch.cuda.synchronize()
-        replicas_equal = None
-        if world > 1:
-            qs = [torch.empty_like(Q1) for _ in range(world)]
-            dist.all_gather(qs, Q1)
-            replicas_equal = all(torch.equal(qs[0], t) for t in qs)       # after the drain every rank holds the same item table
-            del qs
-            dist.all_reduce(l1)
-            gi = torch.empty(n_local * world, dtype=torch.int32, device=dev)
-            gj = torch.empty(n_local * world, dtype=torch.int32, device=dev)
-            gP = torch.empty(users_local * world, D, dtype=torch.float32, device=dev)
-            dist.all_gather_into_tensor(gi, i.contiguous())
-            dist.all_gather_into_tensor(gj, jx)
-            dist.all_gather_into_tensor(gP, P1)
-        else:
-            gi, gj, gP = i, jx, P1
-        if rank == 0:
-            P0_host = np.concatenate([synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + r, device=dev)[0].cpu().numpy()
-                                      for r in range(world)])
-            hu_all = np.repeat(np.arange(users_local * world, dtype=np.int32), DEGREE)
-            try:
-                parity = parity_against_sequential(P0_host, Q0_host, hu_all, gi.cpu().numpy(), gj.cpu().numpy(),
-                                                   gP.cpu().numpy(), Q1.cpu().numpy(), float(l1[0].item()), full=(world == 1))
-            except Exception as exc:                 # noqa: BLE001  (never costs the headline line)
-                parity = {'error': '%s: %s' % (type(exc).__name__, exc)}
-            parity['what'] = ('epoch 0 of the benchmarked path (qrec_bpr_epoch_usermajor_f32, fused Philox sampling, %d GPU(s), '
-                              '%d item-table syncs) from the initial tables, negatives exported through j_out, against the '
-                              'sequential reference loop on the same stream' % (world, q_syncs))
-            parity['bound_held_in_tests'] = 'loss rel_err <= 1e-3 (tests/test_gpu_parity_config2.py)'
-            if replicas_equal is not None:
-                parity['item_table_replicas_bit_identical_after_drain'] = bool(replicas_equal)
-            del P0_host, hu_all
-        del P1, Q1, jx, gi, gj, gP, sync1
-        torch.cuda.empty_cache()
-        if world > 1:
-            dist.barrier()
+    if not args.no_parity and (world == 1 or args.parity_multi):
+        try:
+            P1, Q1 = synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + rank, device=dev)
+            if world > 1:
+                dist.broadcast(Q1, 0)
+            Q0_host = Q1.cpu().numpy() if rank == 0 else None
+            sync1 = make_sync(Q1)
+            jx = torch.empty(n_local, dtype=torch.int32, device=dev)
+            l1 = torch.zeros(3, dtype=torch.float64, device=dev)
+            epoch_on(P1, Q1, sync1, 0, l1, j_out=jx)
+            getattr(sync1, 'finalize', lambda: None)()
+            torch.cuda.synchronize()
+            replicas_equal = None
+            if world > 1:
+                qs = [torch.empty_like(Q1) for _ in range(world)]
+                dist.all_gather(qs, Q1)
+                replicas_equal = all(torch.equal(qs[0], t) for t in qs)       # after the drain every rank holds the same item table
+                del qs
+                dist.all_reduce(l1)
+                gi = torch.empty(n_local * world, dtype=torch.int32, device=dev)
+                gj = torch.empty(n_local * world, dtype=torch.int32, device=dev)
+                gP = torch.empty(users_local * world, D, dtype=torch.float32, device=dev)
+                dist.all_gather_into_tensor(gi, i.contiguous())
+                dist.all_gather_into_tensor(gj, jx)
+                dist.all_gather_into_tensor(gP, P1)
+            else:
+                gi, gj, gP = i, jx, P1
+            if rank == 0:
+                P0_host = np.concatenate([synthetic.init_tables(users_local, NUM_ITEMS, D, seed=1 + r, device=dev)[0].cpu().numpy()
+                                          for r in range(world)])
+                hu_all = np.repeat(np.arange(users_local * world, dtype=np.int32), DEGREE)
+                try:
+                    parity = parity_against_sequential(P0_host, Q0_host, hu_all, gi.cpu().numpy(), gj.cpu().numpy(),
+                                                       gP.cpu().numpy(), Q1.cpu().numpy(), float(l1[0].item()), full=(world == 1))
+                except Exception as exc:                 # noqa: BLE001  (never costs the headline line)
+                    parity = {'error': '%s: %s' % (type(exc).__name__, exc)}
+                parity['what'] = ('epoch 0 of the benchmarked path (qrec_bpr_epoch_usermajor_f32, fused Philox sampling, %d GPU(s), '
+                                  '%d item-table syncs) from the initial tables, negatives exported through j_out, against the '
+                                  'sequential reference loop on the same stream' % (world, q_syncs))
+                parity['bound_held_in_tests'] = 'loss rel_err <= 1e-3 (tests/test_gpu_parity_config2.py)'
+                if replicas_equal is not None:
+                    parity['item_table_replicas_bit_identical_after_drain'] = bool(replicas_equal)
+                del P0_host, hu_all
+            del P1, Q1, jx, gi, gj, gP, sync1
+            torch.cuda.empty_cache()
+            if world > 1:
+                dist.barrier()
+        except Exception as exc:                         # noqa: BLE001
+            if world > 1:
+                raise                                    # a rank that drops out would hang the others' collectives
+            parity = {'error': '%s: %s' % (type(exc).__name__, exc)}
 
     # ------------------------------------------------------------------ second half of the metric: LightGCN
     # (all ranks; the secondary sections must never cost the headline line: report their failure instead)
     lightgcn = None
-    if not args.no_lightgcn:
+    if not args.no_lightgcn and (world == 1 or args.lightgcn_multi):
         del u, i, j, hu, hi, hj, su, si, sj
         torch.cuda.empty_cache()
         try:
@@ -966,13 +974,17 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--q-syncs', type=int, default=2, help='launches (waves) per step when N>1; the item-table deltas are exchanged after each')
-    ap.add_argument('--qsync', default='auto', choices=['auto', 'p2p', 'nccl', 'blocking'],
+    ap.add_argument('--qsync', default=MULTI_GPU_DEFAULTS['qsync'], choices=['auto', 'p2p', 'nccl', 'blocking'],
                     help='N>1 item-table exchange: overlapped peer-memory kernels (p2p), overlapped ncclAllReduce (nccl), auto = p2p with nccl fallback, blocking = round-1 path')
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
     ap.add_argument('--ref-sample', type=int, default=4_000_000)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-lightgcn', action='store_true')
     ap.add_argument('--no-neumf', action='store_true')
+    ap.add_argument('--parity-multi', action=argparse.BooleanOptionalAction, default=MULTI_GPU_DEFAULTS['parity_multi'],
+                    help='run the full-epoch parity check at N>1 too (rank 0 runs the 50M-triple oracle, ~20 s)')
+    ap.add_argument('--lightgcn-multi', action=argparse.BooleanOptionalAction, default=MULTI_GPU_DEFAULTS['lightgcn_multi'],
+                    help='run the LightGCN section at N>1 too (users sharded, items replicated)')
     ap.add_argument('--no-extras', action='store_true', help='skip the FilmTrust (config 1) and Zipf sections')
     ap.add_argument('--no-roofs', action='store_true', help='skip the row-op microbenchmark and the HBM-bound configuration')
     ap.add_argument('--no-parity', action='store_true', help='skip the full-epoch parity check against the sequential oracle')
