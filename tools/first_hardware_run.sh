@@ -13,6 +13,7 @@ for t in test_gpu_table_sync test_gpu_topn test_gpu_adjacency test_gpu_k1_tma te
   timeout 600 python -m pytest "tests/$t.py" -m gpu -q -s > "$out/$t.log" 2>&1
   echo "$t: exit $? -- $(tail -1 "$out/$t.log")"
 done
+timeout 900 compute-sanitizer --tool memcheck python tools/sanitize_all.py > "$out/sanitizer_r2_memcheck.log" 2>&1; echo "memcheck: exit $? -- $(grep -c "ERROR SUMMARY" "$out/sanitizer_r2_memcheck.log") $(grep "ERROR SUMMARY" "$out/sanitizer_r2_memcheck.log" | tail -1)"
 timeout 600 python tools/bench_k1.py      > "$out/bench_k1.jsonl"      2> "$out/bench_k1.err";      echo "bench_k1: exit $?"
 timeout 600 python tools/bench_rating.py  > "$out/bench_rating.jsonl"  2> "$out/bench_rating.err";  echo "bench_rating: exit $?"
 timeout 600 python tools/bench_graph.py --spmm-only > "$out/bench_spmm.jsonl" 2> "$out/bench_spmm.err"; echo "bench_spmm: exit $?"

@@ -108,6 +108,28 @@ def main():
                                   dev(csr.sorted_cols), sig, ni, 5, 0, 0.01, 0.001, 0.001, loss)
         torch.cuda.synchronize()
         print('sanitize_all: + K9, launched', E.launch_count(), 'kernels')
+        # round-2 kernels
+        from qrec_b200.graph_build import JointAdjacency
+        E.bpr_epoch_usermajor(P, Q, dev(csr.pos_rowptr), dev(csr.pos_cols), dev(csr.sorted_rowptr), dev(csr.sorted_cols), ni, 5, 0,
+                              0.01, 0.001, 0.001, loss)
+        E.bpr_epoch_usermajor_tma(P, Q, dev(csr.pos_rowptr), dev(csr.pos_cols), dev(csr.sorted_rowptr), dev(csr.sorted_cols), ni, 5, 0,
+                                  0.01, 0.001, 0.001, loss)
+        ids, vals = E.score_topn(P, Q, dev(np.arange(nu, dtype=np.int32)), dev(csr.sorted_rowptr), dev(csr.sorted_cols), 10)
+        J = JointAdjacency(dev(u.astype(np.int64)), dev(i.astype(np.int64)), nu, ni, device='cuda')
+        J.full(); J.edge_dropout(0.3, 1, 2, 3)
+        Bt, Dt, St = Q.clone(), torch.empty(Q.numel(), device='cuda'), torch.empty(Q.numel(), device='cuda')
+        E.table_delta(Q.view(-1), Bt.view(-1), Dt, St)
+        E.table_reduce_scatter_p2p([Dt.data_ptr(), Dt.data_ptr()], 1, St, Dt.numel())
+        E.table_gather_merge_p2p([St.data_ptr(), St.data_ptr()], Q.view(-1), Bt.view(-1), Dt)
+        E.table_all_gather_p2p([St.data_ptr(), St.data_ptr()], Dt)
+        E.table_merge(Q.view(-1), Bt.view(-1), Dt, St)
+        E.ubench_row_ops(torch.rand(1000, 64, device='cuda'), 5000, 2)
+        cnt, snd = torch.empty(2, dtype=torch.int32, device='cuda'), torch.empty(2 * 900, dtype=torch.int32, device='cuda')
+        pos, ovf = torch.empty(n, dtype=torch.int32, device='cuda'), torch.zeros(1, dtype=torch.int32, device='cuda')
+        E.bucket_requests(dev(i), ni // 2, 2, 900, cnt, snd, pos, ovf)
+        E.simgcl_perturb(X, 0.1, 7, 1, 1, acc=acc, acc_scale=0.5, d_valid=62, row_offset=12345)
+        torch.cuda.synchronize()
+        print('sanitize_all: + round 2, launched', E.launch_count(), 'kernels')
 
 
 if __name__ == '__main__':
