@@ -409,11 +409,11 @@ def filmtrust_section():
             for mode, extra in (('parity_f64', ''), ('fast_f32', 'engine=-mode fast\n')):
                 random.setstate((3, tuple(int(x) for x in g['mt_state_after_split']), None))
                 np.random.seed(0)
-                model = BPR(ModelConf.from_string(str(g['conf']) + extra), train, test)
                 losses = []
-                orig = model.isConverged
-                model.isConverged = lambda epoch, m=model, o=orig: (losses.append(m.loss), o(epoch))[1]
-                with contextlib.redirect_stdout(io.StringIO()):
+                with contextlib.redirect_stdout(io.StringIO()):       # the bench prints ONE line: keep the class quiet
+                    model = BPR(ModelConf.from_string(str(g['conf']) + extra), train, test)
+                    orig = model.isConverged
+                    model.isConverged = lambda epoch, m=model, o=orig: (losses.append(m.loss), o(epoch))[1]
                     model.readConfiguration(); model.initializing_log(); model.initModel()
                     t0 = time.perf_counter()
                     model.trainModel()
