@@ -767,16 +767,18 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
   FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
                      (uint32_t)(seed >> 32), epoch, j_out};
   const int nvec = d / 4;
-  // CTAs per SM the grid is capped at (3 are resident): 8 = each CTA walks ~1/1184 of the launch.  A larger cap
-  // makes CTAs shorter-lived, so a concurrent high-priority stream (the item-table exchange of
-  // parallel.OverlappedTableSync) finds free slots sooner.  QREC_K1_UM_CAP overrides (experiment switch).
+  // Grid = exactly the CTAs that are resident at once (occupancy API per instantiation), so that the launch is ONE
+  // sweep over the user-major stream: at any moment the lane groups work on a contiguous window of chunks
+  // (chunk = group + k * ngroups).  A larger grid makes later CTAs start again at the beginning of the stream --
+  // several interleaved sweeps, i.e. a much larger re-ordering against the reference loop (measured at config 2:
+  // P / Q error relative to the epoch's update 14.7 % / 37.6 % with 8 CTAs per SM vs a few % with one sweep;
+  // bench.py parity_check).  QREC_K1_UM_CAP=<CTAs per SM> overrides (experiment switch).
   static int cap_mult = -1;
   if (cap_mult < 0) {
     const char* e = getenv("QREC_K1_UM_CAP");
-    cap_mult = e ? atoi(e) : 8;
-    if (cap_mult < 1) cap_mult = 8;
+    cap_mult = e ? atoi(e) : 0;
+    if (cap_mult < 0) cap_mult = 0;
   }
-  const long long cap = (long long)sm_count() * cap_mult;
   constexpr int CH = 32;
   // experiment switch (d = 64 only), measured on 50 M triples: 0 = 3 CTAs/SM, 4 triples in flight
   // (default, 5.80 ms); 1 = 4 CTAs/SM at 64 registers (spills, 7.08 ms); 2 = 2 CTAs/SM, 8 triples in
@@ -786,25 +788,32 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
     const char* e = getenv("QREC_K1_UM_VARIANT");
     variant = e ? atoi(e) : 0;
   }
-#define QREC_UM2(LPR, FULLV, SAMPLEV)                                                            \
-  bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV><<<(int)blocks, 256, 0, st>>>(             \
-      P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr)
+#define QREC_UM_LAUNCH(KERNEL, SIGPTR)                                                           \
+  {                                                                                              \
+    int occ = 3;                                                                                 \
+    if (cap_mult > 0) occ = cap_mult;                                                            \
+    else if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, KERNEL, 256, 0) != cudaSuccess || occ < 1) occ = 3; \
+    const long long cap = (long long)sm_count() * occ;                                           \
+    if (blocks > cap) blocks = cap;                                                              \
+    KERNEL<<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, \
+                                        reg_u, reg_i, loss, fs, trip_off, SIGPTR);               \
+  }
+#define QREC_UM2(LPR, FULLV, SAMPLEV) QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<LPR, 4, CH, FULLV, SAMPLEV>), nullptr)
 #define QREC_UM(LPR)                                                                             \
   {                                                                                              \
     const long long per_block = 8 * (32 / LPR);                                                  \
     long long blocks = ((n + CH - 1) / CH + per_block - 1) / per_block;                          \
-    if (blocks > cap) blocks = cap;                                                              \
     if (nvec == LPR && sample && rated_sig != nullptr) {                                         \
-      bpr_sgd_usermajor_kernel<LPR, 4, CH, true, true, 3, true><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, rated_sig); \
+      QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<LPR, 4, CH, true, true, 3, true>), rated_sig)     \
     } else if (nvec == LPR && LPR == 16 && variant == 1) {                                       \
-      if (sample) bpr_sgd_usermajor_kernel<16, 4, CH, true, true, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
-      else bpr_sgd_usermajor_kernel<16, 4, CH, true, false, 4><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
+      if (sample) QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<16, 4, CH, true, true, 4>), nullptr)  \
+      else QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<16, 4, CH, true, false, 4>), nullptr)        \
     } else if (nvec == LPR && LPR == 16 && variant == 2) {                                       \
-      if (sample) bpr_sgd_usermajor_kernel<16, 8, CH, true, true, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
-      else bpr_sgd_usermajor_kernel<16, 8, CH, true, false, 2><<<(int)blocks, 256, 0, st>>>(P, Q, nvec, n_users, n, reinterpret_cast<const long long*>(rowptr), i, j, lr, reg_u, reg_i, loss, fs, trip_off, nullptr); \
+      if (sample) QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<16, 8, CH, true, true, 2>), nullptr)  \
+      else QREC_UM_LAUNCH((bpr_sgd_usermajor_kernel<16, 8, CH, true, false, 2>), nullptr)        \
     } else                                                                                       \
-    if (nvec == LPR) { if (sample) QREC_UM2(LPR, true, true); else QREC_UM2(LPR, true, false); } \
-    else { if (sample) QREC_UM2(LPR, false, true); else QREC_UM2(LPR, false, false); }           \
+    if (nvec == LPR) { if (sample) QREC_UM2(LPR, true, true) else QREC_UM2(LPR, true, false) }   \
+    else { if (sample) QREC_UM2(LPR, false, true) else QREC_UM2(LPR, false, false) }             \
   }
   if (nvec <= 4) QREC_UM(4)
   else if (nvec <= 8) QREC_UM(8)
@@ -812,6 +821,7 @@ int launch_usermajor(float* P, float* Q, int32_t d, int32_t n_users, int64_t n, 
   else QREC_UM(32)
 #undef QREC_UM
 #undef QREC_UM2
+#undef QREC_UM_LAUNCH
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

@@ -224,7 +224,9 @@ extern "C" int qrec_bpr_epoch_usermajor_tma_f32(float* P, float* Q, int32_t d, i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   long long blocks = ((n + CH - 1) / CH + GROUPS - 1) / GROUPS;
-  const long long cap = (long long)sms * 8;
+  int occ = 3;                                       // one sweep over the stream: grid = resident CTAs (see launch_usermajor)
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bpr_sgd_usermajor_tma_kernel<true>, 256, smem) != cudaSuccess || occ < 1) occ = 3;
+  const long long cap = (long long)sms * occ;
   if (blocks > cap) blocks = cap;
   FusedSampler fs = {reinterpret_cast<const long long*>(rated_rowptr), rated_cols, num_items, (uint32_t)seed,
                      (uint32_t)(seed >> 32), epoch, j_out};

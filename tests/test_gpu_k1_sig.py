@@ -58,7 +58,8 @@ def test_signature_build_matches_numpy(torch, E):
     torch.cuda.synchronize()
     got = sig.cpu().numpy().view(np.uint32)
     assert np.array_equal(got, _signature(csr.sorted_rowptr, csr.sorted_cols))
-    assert not got[3].any() and (got[7] == 0xFFFFFFFF).all()
+    # user 3 has no rated items; the heavy user's 1500 items set (nearly) every one of the 512 bits
+    assert not got[3].any() and sum(bin(int(w)).count('1') for w in got[7]) >= 0.9 * 512
 
 
 @pytest.mark.parametrize('d', [16, 32, 64, 128])

@@ -91,7 +91,7 @@ def main():
     print('sanitize_all: launched', E.launch_count(), 'kernels')
     if os.environ.get('QREC_TEST_UNVALIDATED') == '1':
         # K9 (rating-prediction MF): kept apart until its first hardware run has passed
-        n9 = 2000
+        n9 = n
         u9, i9 = np.ascontiguousarray(u[:n9]), np.ascontiguousarray(i[:n9])
         r9 = torch.rand(n9, device='cuda') * 4
         wu9, wi9 = E.mf_order_prepare(u9, i9, nu, ni)
