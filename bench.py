@@ -636,6 +636,18 @@ def run_ours(args):
     ub = parallel.sync_points(users_local, q_syncs)
     k1_events = []
 
+    # the sampler's rejection test: 512-bit rated-set signature per user before the bisection (identical negatives,
+    # tests/test_gpu_k1_sig.py; 6.27 vs 6.59 ms per 50 M triples) unless --sampler bisect
+    rated_sig = E.rated_signature(rowptr, cols) if args.sampler == 'sig' else None
+
+    def fused(Pt, Qt, pos_rowptr, pos_i, rated_rowptr, rated_cols, sig, seed, epoch, loss1, j_out):
+        if sig is not None:
+            E.bpr_epoch_usermajor_sig(Pt, Qt, pos_rowptr, pos_i, rated_rowptr, rated_cols, sig, NUM_ITEMS, seed, epoch, LR, REG_U,
+                                      REG_I, loss1, j_out=j_out)
+        else:
+            E.bpr_epoch_usermajor(Pt, Qt, pos_rowptr, pos_i, rated_rowptr, rated_cols, NUM_ITEMS, seed, epoch, LR, REG_U, REG_I,
+                                  loss1, j_out=j_out)
+
     def epoch_on(Pt, Qt, sync, epoch, loss_t, j_out=None, events=None):
         """One epoch of the rank's shard on tables (Pt, Qt): q_syncs fused launches, each followed by the
         item-table delta all-reduce when N>1.  j_out (int32[n_local]) receives the sampled negatives."""
@@ -646,13 +658,12 @@ def run_ours(args):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
             if q_syncs == 1:
-                E.bpr_epoch_usermajor(Pt, Qt, csr_rowptr, i, rowptr, cols, NUM_ITEMS, 2024, epoch, LR, REG_U, REG_I,
-                                      loss_t[0:1], j_out=j_out)
+                fused(Pt, Qt, csr_rowptr, i, rowptr, cols, rated_sig, 2024, epoch, loss_t[0:1], j_out)
             else:
                 rp = (csr_rowptr[ua:ub_ + 1] - a).contiguous()
-                E.bpr_epoch_usermajor(Pt[ua:ub_], Qt, rp, i[a:b], rowptr[ua:ub_ + 1].contiguous(), cols, NUM_ITEMS,
-                                      2024 + s, epoch, LR, REG_U, REG_I, loss_t[0:1],
-                                      j_out=None if j_out is None else j_out[a:b])
+                fused(Pt[ua:ub_], Qt, rp, i[a:b], rowptr[ua:ub_ + 1].contiguous(), cols,
+                      None if rated_sig is None else rated_sig[ua:ub_], 2024 + s, epoch, loss_t[0:1],
+                      None if j_out is None else j_out[a:b])
             if events is not None:
                 e1.record()
                 events.append((e0, e1, b - a))
@@ -893,7 +904,7 @@ def run_ours(args):
                 'epoch_loss': epoch_loss,
             },
             'roofline': {
-                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32,true,true> (fused Philox sampling)', 'achieved': achieved, 'peak': peak,
+                'bound': 'hbm', 'kernel': 'bpr_sgd_usermajor_kernel<16,4,32,true,true%s> (fused Philox sampling%s)' % ((',3,true', ', signature pre-test') if rated_sig is not None else ('', '')), 'achieved': achieved, 'peak': peak,
                 'unit': 'GB/s', 'frac': achieved / peak, 'peak_source': peak_src,
                 'algorithmic_bytes_per_triple': ALGO_BYTES_PER_TRIPLE,
                 'kernel_model_bytes_per_triple': kernel_model_bytes,
@@ -989,6 +1000,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-lightgcn', action='store_true')
     ap.add_argument('--no-neumf', action='store_true')
+    ap.add_argument('--sampler', default='sig', choices=['sig', 'bisect'],
+                    help='in-kernel rejection test: rated-set signature before the bisection (default) or bisection only')
     ap.add_argument('--parity-multi', action=argparse.BooleanOptionalAction, default=MULTI_GPU_DEFAULTS['parity_multi'],
                     help='run the full-epoch parity check at N>1 too (rank 0 runs the 50M-triple oracle, ~20 s)')
     ap.add_argument('--lightgcn-multi', action=argparse.BooleanOptionalAction, default=MULTI_GPU_DEFAULTS['lightgcn_multi'],

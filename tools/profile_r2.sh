@@ -7,7 +7,7 @@ mkdir -p "$out"
 NCU="ncu --clock-control none"
 timeout 900 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file "$out/launches_r2_bench.csv" \
   python bench.py --steps 2 --warmup 1 --no-parity --no-lightgcn --no-neumf --no-extras --no-roofs > "$out/bench_under_ncu.log" 2>&1
-for t in ${TARGETS:-k1 k1_hbm rowops spmm topn}; do
+for t in ${TARGETS:-k1_sig k1 k1_hbm rowops spmm topn}; do
   kre="regex:bpr_sgd_usermajor"
   [ "$t" = rowops ] && kre="regex:row_op_kernel"
   [ "$t" = spmm ] && kre="regex:spmm_csr"
