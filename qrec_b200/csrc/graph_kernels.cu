@@ -15,6 +15,8 @@
 //                                var -= m*alpha/(sqrt(v)+eps).
 #include <cmath>
 
+#include <cstdlib>
+
 #include "common.h"
 
 namespace {
@@ -486,8 +488,15 @@ int qrec_spmm_csr_rowsplit_f32(int32_t n_rows, int64_t nnz, const int64_t* rowpt
   QREC_REQUIRE(X != Y, "qrec_spmm_csr_rowsplit_f32: X and Y must not alias");
   // d = 64: the width-specialised instantiation at 4 CTAs/SM (spmm_variants.cu, variant 0) -- bit-identical results,
   // 2.15 ms instead of 2.49 ms on the 100 M-nnz benchmark graph (profiles/README.md, round 2)
-  if (d == 64 && X != nullptr && Y != nullptr)
-    return qrec_spmm_csr_rowsplit_var_f32(0, n_rows, rowptr, cols, vals, X, Y, d, acc, acc_scale, stream);
+  if (d == 64 && X != nullptr && Y != nullptr) {
+    static int var = -1;                                  // QREC_SPMM_VARIANT: experiment switch (spmm_variants.cu)
+    if (var < 0) {
+      const char* e = getenv("QREC_SPMM_VARIANT");
+      var = e ? atoi(e) : 0;
+      if (var < 0 || var > 6) var = 0;
+    }
+    return qrec_spmm_csr_rowsplit_var_f32(var, n_rows, rowptr, cols, vals, X, Y, d, acc, acc_scale, stream);
+  }
   const int nvec = d / 4;
   cudaStream_t st = (cudaStream_t)stream;
   const long long cap = (long long)sm_count() * 8;

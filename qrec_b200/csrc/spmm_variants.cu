@@ -11,6 +11,7 @@
 //   4  G=4 x 2 buffers, 3 CTAs/SM   software pipeline: the next group's gathers are issued before the
 //                                   current group is consumed (8 in flight continuously)
 //   5  G=8 x 2 buffers, 2 CTAs/SM   the same with 16 in flight
+//   6  variant 0 + L2 residency hints: (col, val) streamed (L2::evict_first, no L1 allocation), X rows evict_last
 // STATUS: written after round 1's GPU budget was spent -- compiled, not yet run on hardware; reached
 // only through qrec_spmm_csr_rowsplit_var_f32 (tests/test_gpu_spmm_variants.py, tools/bench_graph.py).
 #include "common.h"
@@ -36,12 +37,48 @@ __device__ __forceinline__ void store_row(float* __restrict__ Y, float* __restri
   }
 }
 
+// L2 residency hints (variant 6): the (col, val) arrays are read once and only pollute the L2, the gathered X rows are
+// what should stay -- stream the former (evict_first, no L1 allocation), pin the latter (evict_last).
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+template <bool HINT>
+__device__ __forceinline__ int ld_index(const int* p, unsigned long long pol) {
+  if (!HINT) return __ldg(p);
+  int v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <bool HINT>
+__device__ __forceinline__ float ld_value(const float* p, unsigned long long pol) {
+  if (!HINT) return __ldg(p);
+  float v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol));
+  return v;
+}
+template <bool HINT>
+__device__ __forceinline__ float4 ld_row(const float4* p, unsigned long long pol) {
+  if (!HINT) return __ldg(p);
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+  return v;
+}
+
 // lock-step batches of G gathers (the production structure with G and the occupancy as parameters)
-template <int G, int MINB>
+template <int G, int MINB, bool HINT = false>
 __global__ void __launch_bounds__(256, MINB)
 spmm_rowsplit_batch_kernel(int n_rows, const long long* __restrict__ rowptr, const int* __restrict__ cols,
                            const float* __restrict__ vals, const float* __restrict__ X, float* __restrict__ Y,
                            float* __restrict__ acc, float acc_scale) {
+  const unsigned long long pol_stream = HINT ? l2_policy_evict_first() : 0ULL, pol_keep = HINT ? l2_policy_evict_last() : 0ULL;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
   const unsigned gmask = ((1u << LPR) - 1u) << (sub * LPR);
@@ -53,16 +90,16 @@ spmm_rowsplit_batch_kernel(int n_rows, const long long* __restrict__ rowptr, con
     int c = 0;
     float w = 0.f;
     if (start + l < end) {
-      c = __ldg(cols + start + l);
-      w = __ldg(vals + start + l);
+      c = ld_index<HINT>(cols + start + l, pol_stream);
+      w = ld_value<HINT>(vals + start + l, pol_stream);
     }
     for (long long base = start; base < end; base += LPR) {
       const int m = (end - base) < LPR ? (int)(end - base) : LPR;
       int cn = 0;
       float wn = 0.f;
       if (base + LPR + l < end) {
-        cn = __ldg(cols + base + LPR + l);
-        wn = __ldg(vals + base + LPR + l);
+        cn = ld_index<HINT>(cols + base + LPR + l, pol_stream);
+        wn = ld_value<HINT>(vals + base + LPR + l, pol_stream);
       }
       for (int t = 0; t < m; t += G) {
         int cc[G];
@@ -76,7 +113,7 @@ spmm_rowsplit_batch_kernel(int n_rows, const long long* __restrict__ rowptr, con
         }
 #pragma unroll
         for (int q = 0; q < G; ++q)
-          x[q] = (t + q) < m ? __ldg(reinterpret_cast<const float4*>(X + (size_t)cc[q] * 64) + l)
+          x[q] = (t + q) < m ? ld_row<HINT>(reinterpret_cast<const float4*>(X + (size_t)cc[q] * 64) + l, pol_keep)
                              : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int q = 0; q < G; ++q) fma4(a, ww[q], x[q]);
@@ -173,7 +210,7 @@ int sm_count() {
 extern "C" int qrec_spmm_csr_rowsplit_var_f32(int32_t variant, int32_t n_rows, const int64_t* rowptr,
                                               const int32_t* cols, const float* vals, const float* X, float* Y,
                                               int32_t d, float* acc, float acc_scale, void* stream) {
-  QREC_REQUIRE(variant >= 0 && variant <= 5, "qrec_spmm_csr_rowsplit_var_f32: variant %d (0..5)", variant);
+  QREC_REQUIRE(variant >= 0 && variant <= 6, "qrec_spmm_csr_rowsplit_var_f32: variant %d (0..6)", variant);
   QREC_REQUIRE(d == 64, "qrec_spmm_csr_rowsplit_var_f32: experiments are d = 64 only (got %d)", d);
   QREC_REQUIRE(n_rows >= 0, "qrec_spmm_csr_rowsplit_var_f32: n_rows < 0");
   if (n_rows == 0) return QREC_OK;
@@ -193,6 +230,7 @@ extern "C" int qrec_spmm_csr_rowsplit_var_f32(int32_t variant, int32_t n_rows, c
     case 2: QREC_VAR((spmm_rowsplit_batch_kernel<8, 6>)); break;
     case 3: QREC_VAR((spmm_rowsplit_batch_kernel<16, 3>)); break;
     case 4: QREC_VAR((spmm_rowsplit_pipe_kernel<4, 3>)); break;
+    case 6: QREC_VAR((spmm_rowsplit_batch_kernel<8, 4, true>)); break;
     default: QREC_VAR((spmm_rowsplit_pipe_kernel<8, 2>)); break;
   }
 #undef QREC_VAR

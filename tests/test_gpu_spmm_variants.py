@@ -10,7 +10,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize('variant', range(6))
+@pytest.mark.parametrize('variant', range(7))
 def test_variant_reproduces_production_bits(variant):
     import scipy.sparse as sp
     import torch

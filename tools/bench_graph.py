@@ -63,7 +63,7 @@ def main():
                           'achieved_GBs': algo / ms / 1e6, 'frac_of_measured_hbm': algo / ms / 1e6 / peak,
                           'compulsory_GB': floor / 1e9, 'zipf': args.zipf}))
     if D == 64:   # experiment configurations, csrc/spmm_variants.cu
-        for variant in range(6):
+        for variant in range(7):
             ms = timed(lambda: E.spmm_csr_rowsplit_variant(variant, rowptr, cols, vals, X, Y, acc=acc, acc_scale=0.25),
                        args.steps, args.warmup)
             print(json.dumps({'kernel': 'spmm_csr_rowsplit_var_f32', 'variant': variant, 'ms': ms,
