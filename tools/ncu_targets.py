@@ -7,6 +7,7 @@
   python tools/ncu_targets.py rowops    the row gather / scatter-add microbenchmark (L2-resident table)
   python tools/ncu_targets.py spmm      one whole-graph SpMM (1.1M rows, 100M nnz, d=64)
   python tools/ncu_targets.py topn      K8 on 65536 users x 100K items, N=10
+  python tools/ncu_targets.py neumf | lightgcn   the bench sections (for launch lists)
 Numbers printed under ncu are never bench values."""
 import os
 import sys
@@ -54,6 +55,14 @@ def main():
         users = torch.arange(65536, dtype=torch.int32, device=dev)
         for _ in range(reps):
             E.score_topn(P, Q, users, data['sorted_rowptr'], data['sorted_cols'], 10)
+    elif what in ('neumf', 'lightgcn'):
+        import bench
+        data = synthetic.make_interactions(U, I, DEG, device=dev)
+        if what == 'neumf':
+            print(bench.neumf_section(torch, E, data, dev, 6540.5, steps=2, warmup=1))
+        else:
+            import torch.distributed as dist
+            print(bench.lightgcn_section(torch, dist, E, synthetic, data, dev, 6540.5, 0, 1, steps=2, warmup=1))
     else:
         raise SystemExit('unknown target ' + what)
     torch.cuda.synchronize()
