@@ -50,7 +50,7 @@ ALGO_BYTES_PER_TRIPLE = 24 * D + 12          # 3 rows read + 3 r
 METRIC = 'BPR triples/sec at d=64'
 # Multi-GPU code paths that are on by default.  'blocking' = the round-1 delta all-reduce; 'auto' = the overlapped exchange
 # (peer-memory kernels, NCCL fallback).  Flipped to the new paths only once they have been validated on >= 2 GPUs.
-MULTI_GPU_DEFAULTS = {'qsync': 'blocking', 'lightgcn_multi': False, 'parity_multi': False}
+MULTI_GPU_DEFAULTS = {'qsync': 'auto', 'lightgcn_multi': True, 'parity_multi': True}     # validated at N=2 (profiles/r2/multi_n2)
 WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, user-major (reference) order'
 
 

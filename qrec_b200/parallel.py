@@ -583,12 +583,13 @@ class UserShardedLightGCN(object):
         z = lambda n: torch.zeros(n, d, device=dev)           # noqa: E731
         self.bu, self.bi = [z(nu), z(nu)], [z(ni), z(ni)]
         # the item-side partial sums of a layer are written straight into peer-mapped buffers and summed over
-        # NVLink by our own kernels (PeerAllReduce); NCCL all-reduce when symmetric memory is unavailable (or
-        # QREC_PEER_ALLREDUCE=0), gloo / world 1: plain tensors
+        # NVLink by our own kernels (PeerAllReduce) when QREC_PEER_ALLREDUCE=1 -- validated, but at N=2 NCCL's all-reduce
+        # of the 25.6 MB block was the faster of the two at B=2048 (5.7 vs 7.1 ms/step), so NCCL is the default;
+        # gloo / world 1: plain tensors
         self.peer = None
         import os as _os
         if (dev.type == 'cuda' and dist.is_initialized() and dist.get_world_size(group) > 1 and spmm is None
-                and _os.environ.get('QREC_PEER_ALLREDUCE', '1') != '0'):
+                and _os.environ.get('QREC_PEER_ALLREDUCE', '0') == '1'):
             try:
                 self.peer = PeerAllReduce((ni, d), 2, dev, group)
                 self.bi = self.peer.bufs
