@@ -402,11 +402,28 @@ __global__ void __launch_bounds__(256)
 bucket_requests_kernel(const int* __restrict__ ids, long long n, int rows_per_rank, int world, int cap,
                        int* __restrict__ count, int* __restrict__ send, int* __restrict__ pos, int* __restrict__ overflow) {
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
-    const int id = __ldg(ids + k);
-    int owner = id / rows_per_rank;
-    if (owner >= world) owner = world - 1;
-    const int slot = atomicAdd(count + owner, 1);
+  const int lane = threadIdx.x & 31;
+  const long long first = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // uniform trip count per warp so that the warp-aggregated reservation below sees all 32 lanes
+  for (long long k0 = first - lane; k0 < n; k0 += stride) {
+    const long long k = k0 + lane;
+    const bool valid = k < n;
+    int id = 0, owner = 0;
+    if (valid) {
+      id = __ldg(ids + k);
+      owner = id / rows_per_rank;
+      if (owner >= world) owner = world - 1;
+    }
+    // one atomicAdd per (warp, owner) instead of one per request: with few owners every request of a minibatch
+    // would otherwise hit the same handful of counters
+    const unsigned act = __ballot_sync(0xffffffffu, valid);
+    if (!valid) continue;
+    const unsigned peers = __match_any_sync(act, owner);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count + owner, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    const int slot = base + __popc(peers & ((1u << lane) - 1u));
     if (slot < cap) {
       send[(long long)owner * cap + slot] = id - owner * rows_per_rank;
       pos[k] = owner * cap + slot;
