@@ -500,6 +500,10 @@ int qrec_scatter_add_rows_f32(float* dev_G, const int32_t* dev_idx, int64_t n, i
  * bucket needs more than `cap` slots (the step is then invalid). */
 int qrec_bucket_requests(const int32_t* dev_ids, int64_t n, int32_t rows_per_rank, int32_t world, int32_t cap,
                          int32_t* dev_count, int32_t* dev_send, int32_t* dev_pos, int32_t* dev_overflow, void* stream);
+/* out[c] = beta*out[c] + alpha * sum_b A[b, c] * v[b] (v NULL: column sums; beta 0 or 1): the bias gradients
+ * (tf.reduce_sum over the batch) and head-vector gradients of NeuMF.py:39-57 without a tiled GEMM. */
+int qrec_gemv_t_f32(const float* dev_A, int32_t lda, int64_t rows, int32_t cols, const float* dev_v, float alpha,
+                    float beta, float* dev_out, void* stream);
 /* mode 0 GMF | 1 MLP | 2 NeuMF head: y = sigmoid(wg*(UG*IG).h_mf + wm*H3.h_mlp); when training,
  * loss += BCE(r, y; +1e-9) [+ reg*l2_loss(UG)+reg*l2_loss(IG), modes 0/2], dz = dLoss/dz, and the
  * per-sample gradients GMF=UG*IG, dUG, dIG (incl. reg), dH3 (ReLU-masked).  The h-vector terms of

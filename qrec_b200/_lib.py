@@ -134,6 +134,7 @@ SIGNATURES = {
     'qrec_gather_rows_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int32, vp]),
     'qrec_scatter_add_rows_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int32, vp, C.c_int32, C.c_float, vp]),
     'qrec_bucket_requests': (C.c_int, [vp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, vp, vp, vp, vp, vp]),
+    'qrec_gemv_t_f32': (C.c_int, [vp, C.c_int32, C.c_int64, C.c_int32, vp, C.c_float, C.c_float, vp, vp]),
     'qrec_neumf_head_f32': (C.c_int, [C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int32, C.c_float,
                                       vp, vp, vp, vp, vp, vp, vp, vp]),
     'qrec_mask_rated_f32': (C.c_int, [vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float, vp]),

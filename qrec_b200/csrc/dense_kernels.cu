@@ -434,6 +434,35 @@ bucket_requests_kernel(const int* __restrict__ ids, long long n, int rows_per_ra
   }
 }
 
+// out[c] += alpha * sum_b A[b, c] * v[b]   (v == nullptr: column sums).  The bias / head-vector gradients of NeuMF
+// (NeuMF.py:39-57: d b_k = column sums of dH_k, d h = X^T dz) are matrix^T-vector products over the B samples of a
+// minibatch; through the tiled sgemm they cost a 64x64 tile per useful column.  Here a block owns a slab of rows,
+// threads own columns (coalesced row reads), partial sums meet in shared memory and leave with one atomic per
+// column and block.
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const float* __restrict__ A, int lda, long long rows, int cols, const float* __restrict__ v, float alpha,
+              float* __restrict__ out, int rows_per_block) {
+  __shared__ float part[256];
+  const int cw = cols < 256 ? (cols <= 32 ? 32 : (cols <= 64 ? 64 : (cols <= 128 ? 128 : 256))) : 256;   // threads per row
+  const int ry = threadIdx.x / cw, cx = threadIdx.x % cw, rstep = 256 / cw;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = (r0 + rows_per_block) < rows ? (r0 + rows_per_block) : rows;
+  for (int c0 = 0; c0 < cols; c0 += cw) {
+    const int c = c0 + cx;
+    float acc = 0.f;
+    if (c < cols)
+      for (long long r = r0 + ry; r < r1; r += rstep) acc = fmaf(__ldg(A + (size_t)r * lda + c), v ? __ldg(v + r) : 1.0f, acc);
+    part[threadIdx.x] = acc;
+    __syncthreads();
+    if (ry == 0 && c < cols) {
+      float t = 0.f;
+      for (int q = 0; q < rstep; ++q) t += part[q * cw + cx];
+      atomicAdd(out + c, alpha * t);
+    }
+    __syncthreads();
+  }
+}
+
 // Prediction heads and their gradients.  mode 0 = GMF (NeuMF.py:52-58), 1 = MLP (:60-65),
 // 2 = fused NeuMF (:67-73).  One warp per sample.
 //   z = wg * (UG*IG).h_mf + wm * H3.h_mlp,  (wg, wm) = (1,0) | (0,1) | (.5,.5);  y = sigmoid(z)
@@ -666,6 +695,21 @@ int qrec_bucket_requests(const int32_t* ids, int64_t n, int32_t rows_per_rank, i
   QREC_CUDA(cudaMemsetAsync(send, 0xff, sizeof(int32_t) * (size_t)world * cap, st));      // -1 = empty slot
   if (n == 0) return QREC_OK;
   bucket_requests_kernel<<<grid_for(n, 256), 256, 0, st>>>(ids, n, rows_per_rank, world, cap, count, send, pos, overflow);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_gemv_t_f32(const float* A, int32_t lda, int64_t rows, int32_t cols, const float* v, float alpha, float beta, float* out,
+                    void* stream) {
+  QREC_REQUIRE(rows >= 0 && cols >= 1 && lda >= cols, "qrec_gemv_t_f32: bad shape");
+  QREC_REQUIRE(out && (A || rows == 0), "qrec_gemv_t_f32: null pointer");
+  QREC_REQUIRE(beta == 0.f || beta == 1.f, "qrec_gemv_t_f32: beta must be 0 (overwrite) or 1 (accumulate)");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (beta == 0.f) QREC_CUDA(cudaMemsetAsync(out, 0, sizeof(float) * (size_t)cols, st));
+  if (rows == 0) return QREC_OK;
+  const int rows_per_block = 128;
+  const long long blocks = (rows + rows_per_block - 1) / rows_per_block;
+  gemv_t_kernel<<<(int)blocks, 256, 0, st>>>(A, lda, rows, cols, v, alpha, out, rows_per_block);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

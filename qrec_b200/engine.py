@@ -493,6 +493,16 @@ def bucket_requests(ids, rows_per_rank, world, cap, count, send, pos, overflow):
                                    _dev(overflow, torch.int32, 'overflow'), _stream()), 'qrec_bucket_requests')
 
 
+def gemv_t(A, v, out, alpha=1.0, beta=0.0):
+    """out = beta*out + alpha * A^T v (v None: column sums of A); A [rows, cols] fp32 with unit column stride (a
+    row slice of a workspace is fine), out [cols]."""
+    torch = _torch()
+    ptr, ld = _strided_rows(A, 'A')
+    check(lib.qrec_gemv_t_f32(ptr, max(ld, A.shape[1]), A.shape[0], A.shape[1], _dev(v, torch.float32, 'v') if v is not None else None,
+                              float(alpha), float(beta), _dev(out, torch.float32, 'out'), _stream()), 'qrec_gemv_t_f32')
+    return out
+
+
 def sumsq(x, out):
     torch = _torch()
     fn = lib.qrec_sumsq_f64 if x.dtype == torch.float64 else lib.qrec_sumsq_f32

@@ -117,22 +117,22 @@ class NeuMF(DeepRecommender):
             E.scatter_add_rows(g['PG'], u, self._dUG[:B])
             E.scatter_add_rows(g['QG'], i, self._dIG[:B])
             # d h_mf = wg * GMF^T dz + reg*h_mf (mf_reg) [+ reg*0.25*h_mf: l2_loss(h_NeuMF), mode 2]
-            E.sgemm(self._GMF[:B], dz, g['h_mf'].unsqueeze(1), trans_a=True, alpha=wg)
+            E.gemv_t(self._GMF[:B], self._dz[:B], g['h_mf'], alpha=wg)
             E.axpby(g['h_mf'], g['h_mf'], p['h_mf'], 1.0, self.regU * (1.25 if mode == 2 else 1.0))
         if ml:
             # d h_mlp = wm * relu(H3)^T dz : dH3 already carries wm*dz*h_mlp masked, so use H3 directly
-            E.sgemm(self._H3[:B], dz, g['h_mlp'].unsqueeze(1), trans_a=True, alpha=wm)
+            E.gemv_t(self._H3[:B], self._dz[:B], g['h_mlp'], alpha=wm)
             if mode == 2:
                 E.axpby(g['h_mlp'], g['h_mlp'], p['h_mlp'], 1.0, self.regU * 0.25)
             ones = self._ones[:B]
             E.sgemm(self._H2[:B], self._dH3[:B], g['W3'], trans_a=True)
-            E.sgemm(self._dH3[:B], ones, g['b3'].unsqueeze(1), trans_a=True)
+            E.gemv_t(self._dH3[:B], None, g['b3'])
             E.tc_gemm(self._dH3[:B], p['W3'], self._dH2[:B], b_is_nk=True, epilogue=E.EPI_RELU_MASK, mask=self._H2[:B])
             E.sgemm(self._H1[:B], self._dH2[:B], g['W2'], trans_a=True)
-            E.sgemm(self._dH2[:B], ones, g['b2'].unsqueeze(1), trans_a=True)
+            E.gemv_t(self._dH2[:B], None, g['b2'])
             E.tc_gemm(self._dH2[:B], p['W2'], self._dH1[:B], b_is_nk=True, epilogue=E.EPI_RELU_MASK, mask=self._H1[:B])
             E.sgemm(self._X0[:B], self._dH1[:B], g['W1'], trans_a=True)
-            E.sgemm(self._dH1[:B], ones, g['b1'].unsqueeze(1), trans_a=True)
+            E.gemv_t(self._dH1[:B], None, g['b1'])
             E.tc_gemm(self._dH1[:B], p['W1'], self._dX0[:B], b_is_nk=True)
             E.scatter_add_rows(g['PM'], u, self._dX0[:B, :d])
             E.scatter_add_rows(g['QM'], i, self._dX0[:B, d:])

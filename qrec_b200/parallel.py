@@ -370,9 +370,9 @@ class ShardedItemTableBPR(object):
         sigma = (2.0 * n * (1.0 / self.world) * (1.0 - 1.0 / self.world)) ** 0.5
         return min(2 * n, int(m + self.slack * sigma) + 64) if self.world > 1 else 2 * n
 
-    def _lane(self, key, n):
+    def _lane(self, key, n, cap=None):
         lane = self._lanes.get(key)
-        cap = self.capacity(n)
+        cap = cap if cap is not None else self.capacity(n)
         if lane is None or lane['cap'] < cap:
             dev, d, W = self.P.device, self.P.shape[1], self.world
             z = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)       # noqa: E731
@@ -383,13 +383,17 @@ class ShardedItemTableBPR(object):
             self._lanes[key] = lane
         return lane
 
-    def step(self, u_local, i_glob, j_glob, lane='main'):
+    def step(self, u_local, i_glob, j_glob, lane='main', cap=None):
         """u_local: int32 local user ids; i_glob/j_glob: int32 global item ids (device tensors).  Asynchronous:
-        nothing here waits for the device."""
+        nothing here waits for the device.  Every rank of the group must call step() the same number of times with
+        the same bucket capacity `cap` (the exchanges are equal-split collectives); a rank that has run out of
+        triples passes empty tensors -- epoch() takes care of both."""
         n = int(u_local.shape[0])
         if n > self.max_batch:
             raise ValueError('ShardedItemTableBPR: minibatch of %d triples exceeds max_batch=%d' % (n, self.max_batch))
-        L = self._lane(lane, n)
+        if n == 0 and self.world == 1:
+            return self.loss
+        L = self._lane(lane, n, cap)
         cap, W = L['cap'], self.world
         ids = torch.cat([i_glob, j_glob]).contiguous()                  # request k -> item id (i then j)
         pos = L['pos'][:2 * n]
@@ -408,20 +412,26 @@ class ShardedItemTableBPR(object):
     def epoch(self, u_local, i_glob, j_glob, batch, rowptr_host=None):
         """All minibatches of the rank's triples (user-major order) through two alternating lanes."""
         n = int(u_local.shape[0])
-        cuts = list(range(0, n, batch)) + [n]
+        cap = self.capacity(batch)                                  # one capacity for every rank and minibatch
+        steps = -(-n // batch)
+        if self.world > 1:                                          # ranks own different numbers of triples: agree on the
+            t = torch.tensor([steps], dtype=torch.int64, device=self.P.device)     # number of exchanges (one small
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)             # all-reduce per epoch)
+            steps = int(t.item())
+        cuts = [min(n, k * batch) for k in range(steps + 1)]
         cuda = self.P.device.type == 'cuda'
         if not cuda:
             for a, b in zip(cuts[:-1], cuts[1:]):
-                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b])
+                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b], cap=cap)
             return self.loss
         cur = torch.cuda.current_stream()
         start = torch.cuda.Event(); start.record(cur)
         done = []
         for k, (a, b) in enumerate(zip(cuts[:-1], cuts[1:])):
-            L = self._lane('lane%d' % (k & 1), b - a)
+            L = self._lane('lane%d' % (k & 1), b - a, cap)
             L['stream'].wait_event(start)
             with torch.cuda.stream(L['stream']):
-                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b], lane='lane%d' % (k & 1))
+                self.step(u_local[a:b], i_glob[a:b], j_glob[a:b], lane='lane%d' % (k & 1), cap=cap)
         for key in ('lane0', 'lane1'):
             if key in self._lanes:
                 ev = torch.cuda.Event(); ev.record(self._lanes[key]['stream']); done.append(ev)

@@ -280,3 +280,20 @@ def test_sgl_step_vs_autograd(torch, golden_graph, tmp_path, aug):
     moved = m.ego[:, :d].cpu().numpy() - ego0
     big = np.abs(rgrad) > 1e-3 * np.abs(rgrad).max()
     assert np.all(np.sign(moved[big]) == -np.sign(rgrad[big]))
+
+
+@pytest.mark.parametrize('rows,cols', [(10240, 320), (10240, 64), (77, 5), (1, 128), (3000, 300), (0, 16)])
+def test_gemv_t(torch, E, rows, cols):
+    """qrec_gemv_t_f32: A^T v and plain column sums (NeuMF's head-vector / bias gradients), on a row slice of a wider
+    workspace too, overwrite and accumulate."""
+    g = torch.Generator(device='cuda'); g.manual_seed(rows + cols)
+    W = torch.randn(rows + 3, cols, device='cuda', generator=g)
+    A = W[:rows]
+    v = torch.randn(rows, device='cuda', generator=g)
+    out = torch.full((cols,), float('nan'), device='cuda')
+    E.gemv_t(A, v, out, alpha=0.5)
+    ref = 0.5 * (A.double().t() @ v.double())
+    assert float((out.double() - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
+    E.gemv_t(A, None, out, alpha=2.0, beta=1.0)
+    ref = ref + 2.0 * A.double().sum(0)
+    assert float((out.double() - ref).abs().max()) <= 1e-4 * max(1.0, float(ref.abs().max()))
