@@ -10,7 +10,7 @@ timeout 900 $NCU --metrics gpu__time_duration.sum -c 400 --csv --log-file "$out/
 for t in ${TARGETS:-k1_sig k1 k1_hbm rowops spmm topn}; do
   kre="regex:bpr_sgd_usermajor"
   [ "$t" = rowops ] && kre="regex:row_op_kernel"
-  [ "$t" = spmm ] && kre="regex:spmm_csr"
+  [ "$t" = spmm ] && kre="regex:spmm_"
   [ "$t" = topn ] && kre="regex:score_topn"
   skip=1; count=1; reps=2
   [ "$t" = rowops ] && { skip=0; count=3; reps=1; }          # the three modes, one launch each
