@@ -24,8 +24,7 @@ def pytest_collection_modifyitems(config, items):
     if has_cuda:
         # `pytest -x` stops at the first failure: run the suites with the longest hardware record first and the ones
         # added most recently last, so that a regression in new code cannot hide the evidence for the old
-        late = ['test_gpu_k7_bucket', 'test_gpu_k1_tma', 'test_gpu_table_sync', 'test_gpu_topn', 'test_gpu_adjacency', 'test_user_sharded_simgcl', 'test_tbpr_dropin', 'test_sgl_step', 'lifecycle[SGL',
-                'test_gpu_parity_config2']
+        late = ['test_gpu_k7_bucket', 'test_gemv_t', 'test_user_sharded_simgcl', 'test_tbpr_dropin', 'test_sgl_step', 'lifecycle[SGL']
         rank = lambda it: next((k + 1 for k, name in enumerate(late) if name in it.nodeid), 0)   # noqa: E731
         items.sort(key=rank)                         # stable: everything else keeps its order
         return
