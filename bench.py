@@ -750,6 +750,7 @@ def run_ours(args):
     hi = i.cpu().pin_memory()                                  # this epoch's positives, CSR order
     hrp = csr_rowptr.cpu().pin_memory()
     pipe = E.HostPipeline(local, chunk_triples=1 << 22)
+    pipe.set_rated_signature(rated_sig)                       # same sampler as the device-resident path
     e2e_epoch = [1000]
 
     def e2e_step():

@@ -321,6 +321,10 @@ int qrec_ubench_row_ops_f32(float* dev_table, int64_t rows, int64_t n_ops, int32
 typedef struct qrec_ctx qrec_ctx;
 int qrec_ctx_create(int device, int64_t chunk_triples, qrec_ctx** out);
 int qrec_ctx_destroy(qrec_ctx* ctx);
+/* Optional: the rated-set signatures of ALL users ([n_users, 16] words, qrec_rated_signature_build) for the fused
+ * sampler's pre-test in qrec_bpr_epoch_usermajor_host (same negatives, fewer dependent loads); NULL switches it off.
+ * The array must stay alive while the ctx uses it. */
+int qrec_ctx_set_rated_signature(qrec_ctx* ctx, const uint32_t* dev_rated_sig);
 /* host u/i/j: pinned memory gives true overlap; pageable memory works but serialises.
  * *host_loss receives sum_k -ln(s_k) of this call.  Synchronous on return. */
 int qrec_bpr_epoch_host(qrec_ctx* ctx, float* dev_P, float* dev_Q, int32_t d, int64_t n,

@@ -105,6 +105,7 @@ SIGNATURES = {
     'qrec_sumsq_f64': (C.c_int, [vp, C.c_int64, vp, vp]),
     'qrec_ctx_create': (C.c_int, [C.c_int, C.c_int64, C.POINTER(vp)]),
     'qrec_ctx_destroy': (C.c_int, [vp]),
+    'qrec_ctx_set_rated_signature': (C.c_int, [vp, vp]),
     'qrec_bpr_epoch_host': (C.c_int, [vp, vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                       C.c_float, C.c_float, c_f64p]),
     'qrec_bpr_epoch_usermajor_host': (C.c_int, [vp, vp, vp, C.c_int32, C.c_int32, vp, vp, vp, vp, C.c_int32, C.c_uint64,

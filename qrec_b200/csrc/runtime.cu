@@ -32,6 +32,7 @@ struct qrec_ctx {
   cudaStream_t copy = nullptr, compute = nullptr;
   double* dev_loss = nullptr;
   double* pinned_loss = nullptr;
+  const uint32_t* rated_sig = nullptr;   // optional [n_users, 16] rated-set signatures (qrec_rated_signature_build)
 };
 
 extern "C" {
@@ -114,6 +115,12 @@ int qrec_bpr_epoch_host(qrec_ctx* c, float* P, float* Q, int32_t d, int64_t n,
 // stream while the fused sampling+SGD kernel runs chunk c.  The rejection CSR stays resident on the
 // device; negatives are drawn in the kernel (Philox counter = global triple index, so the result does
 // not depend on the chunking).
+int qrec_ctx_set_rated_signature(qrec_ctx* c, const uint32_t* dev_sig) {
+  QREC_REQUIRE(c != nullptr, "qrec_ctx_set_rated_signature: null ctx");
+  c->rated_sig = dev_sig;
+  return QREC_OK;
+}
+
 int qrec_bpr_epoch_usermajor_host(qrec_ctx* c, float* P, float* Q, int32_t d, int32_t n_users,
                                   const int64_t* host_rowptr, const int32_t* host_i,
                                   const int64_t* dev_rated_rowptr, const int32_t* dev_rated_cols,
@@ -148,7 +155,8 @@ int qrec_bpr_epoch_usermajor_host(qrec_ctx* c, float* P, float* Q, int32_t d, in
     if (m > 0) {
       const int rc = qrec::launch_usermajor(P + (size_t)ua * d, Q, d, ub - ua, m, c->rp_slot[r], c->slot[r], nullptr, lr,
                                             reg_u, reg_i, c->dev_loss, true, dev_rated_rowptr + ua, dev_rated_cols,
-                                            num_items, seed, epoch, nullptr, t0, c->compute);
+                                            num_items, seed, epoch, nullptr, t0, c->compute,
+                                            c->rated_sig ? c->rated_sig + (size_t)ua * 16 : nullptr);
       if (rc != QREC_OK) return rc;
     }
     QREC_CUDA(cudaEventRecord(c->freed[r], c->compute));

@@ -517,6 +517,13 @@ class HostPipeline(object):
         self._ctx = C.c_void_p()
         check(lib.qrec_ctx_create(int(device), int(chunk_triples), C.byref(self._ctx)), 'qrec_ctx_create')
 
+    def set_rated_signature(self, sig):
+        """sig: rated_signature(...) of ALL users ([n_users, 16] int32 CUDA) or None; kept alive by the pipeline."""
+        torch = _torch()
+        self._sig = sig
+        check(lib.qrec_ctx_set_rated_signature(self._ctx, _dev(sig, torch.int32, 'rated_sig') if sig is not None else None),
+              'qrec_ctx_set_rated_signature')
+
     def close(self):
         if self._ctx:
             check(lib.qrec_ctx_destroy(self._ctx), 'qrec_ctx_destroy')

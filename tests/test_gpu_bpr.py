@@ -507,6 +507,15 @@ def test_usermajor_host_pipeline_matches_single_launch(torch, E):
     assert float(((Pa - P0t) - (Pb - P0t)).abs().max()) <= 0.02 * float((Pa - P0t).abs().max())
     assert float(((Qa - Q0t) - (Qb - Q0t)).abs().max()) <= 0.02 * float((Qa - Q0t).abs().max())
     assert abs(hl - la.item()) <= 1e-4 * abs(hl)
+    # the same pipeline with the rated-set signatures attached: identical negatives, so the same loss and tables
+    Pc, Qc = _dev(torch, P0), _dev(torch, Q0)
+    pipe.set_rated_signature(E.rated_signature(rrp, rc))
+    hl_sig = pipe.bpr_epoch_usermajor(Pc, Qc, torch.from_numpy(rowptr).pin_memory(), torch.from_numpy(i).pin_memory(),
+                                      rrp, rc, ni, 77, 2, lr, REG, REG)
+    pipe.set_rated_signature(None)
+    torch.cuda.synchronize()
+    assert abs(hl_sig - hl) <= 1e-4 * abs(hl)
+    assert float(((Pc - P0t) - (Pb - P0t)).abs().max()) <= 0.02 * float((Pb - P0t).abs().max())
     # a user with more positives than the staging chunk is reported, not silently split
     small = E.HostPipeline(0, chunk_triples=100)
     with pytest.raises(E.QRecError):
