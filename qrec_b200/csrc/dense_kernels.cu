@@ -166,8 +166,8 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
              const float* __restrict__ B, int ldb, float beta, float* __restrict__ C, int ldc,
              int ksplit) {
   constexpr int BM = 64, BN = 64, BK = 16;
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Bs[BK][BN + 4];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   const long long ntiles = (long long)((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int kslab = ((K + ksplit - 1) / ksplit + BK - 1) / BK * BK;
@@ -198,9 +198,10 @@ sgemm_kernel(int M, int N, int K, float alpha, const float* __restrict__ A, int 
       __syncthreads();
 #pragma unroll
       for (int k = 0; k < BK; ++k) {
-        float a[4], b[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) { a[q] = As[k][ty * 4 + q]; b[q] = Bs[k][tx * 4 + q]; }
+        // rows of As / Bs are 68 floats apart (272 B): 16-byte aligned, so one LDS.128 each instead of four LDS.32
+        const float4 av = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
