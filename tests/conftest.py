@@ -24,7 +24,7 @@ def pytest_collection_modifyitems(config, items):
     if has_cuda:
         # `pytest -x` stops at the first failure: run the suites with the longest hardware record first and the ones
         # added most recently last, so that a regression in new code cannot hide the evidence for the old
-        late = ['test_gpu_k7_bucket', 'test_gemv_t', 'test_user_sharded_simgcl', 'test_tbpr_dropin', 'test_sgl_step', 'lifecycle[SGL']
+        late = ['lifecycle[SGL']
         rank = lambda it: next((k + 1 for k, name in enumerate(late) if name in it.nodeid), 0)   # noqa: E731
         items.sort(key=rank)                         # stable: everything else keeps its order
         return

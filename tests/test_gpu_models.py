@@ -167,7 +167,8 @@ def test_ngcf_step_vs_autograd(torch, golden_graph, tmp_path):
 
 
 @pytest.mark.parametrize('name,extra', [('SimGCL', 'SimGCL=-n_layer 2 -lambda 0.5 -eps 0.1\n'), ('NGCF', ''),
-                                        ('SGL', 'SGL=-n_layer 2 -lambda 0.1 -droprate 0.1 -augtype 1 -temp 0.2\n')])
+                                        ('SGL', 'SGL=-n_layer 2 -lambda 0.01 -droprate 0.1 -augtype 1 -temp 0.2\n')])   # lambda 0.1 (the yelp2018 conf) lets
+                                       # the InfoNCE term swamp BPR on a graph this small: P@10 0.006 vs 0.34 (also with the CPU stand-ins)
 def test_graph_models_full_lifecycle(golden_bpr, tmp_path, name, extra):
     """execute() end to end on FilmTrust: trains, evaluates, and lands in a sane quality band."""
     import importlib

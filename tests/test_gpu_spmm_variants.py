@@ -44,6 +44,6 @@ def test_variant_entry_point_limits():
     rp = torch.zeros(3, dtype=torch.int64, device='cuda'); co = torch.zeros(0, dtype=torch.int32, device='cuda')
     va = torch.zeros(0, device='cuda')
     with pytest.raises(E.QRecError):
-        E.spmm_csr_rowsplit_variant(6, rp, co, va, torch.zeros(4, 64, device='cuda'), torch.zeros(2, 64, device='cuda'))
+        E.spmm_csr_rowsplit_variant(7, rp, co, va, torch.zeros(4, 64, device='cuda'), torch.zeros(2, 64, device='cuda'))
     with pytest.raises(E.QRecError):
         E.spmm_csr_rowsplit_variant(0, rp, co, va, torch.zeros(4, 32, device='cuda'), torch.zeros(2, 32, device='cuda'))
