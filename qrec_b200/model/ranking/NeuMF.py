@@ -95,6 +95,11 @@ class NeuMF(DeepRecommender):
 
     def train_step(self, mode, u, i, r):
         """One minibatch of phase `mode` (0 GMF, 1 MLP, 2 NeuMF).  u,i: int32 CUDA, r: fp32 CUDA."""
+        self._backward(mode, u, i, r)
+        return self._update(mode)
+
+    def _backward(self, mode, u, i, r):
+        """Forward + loss + the gradient SUMS over the minibatch's samples into self.grads."""
         from ... import engine as E
         p, g, d = self.params, self.grads, self.emb_size
         B = u.shape[0]
@@ -107,7 +112,6 @@ class NeuMF(DeepRecommender):
                      self._H3[:B] if ml else None, p['h_mf'] if gm else None, p['h_mlp'] if ml else None, r,
                      self.regU, self._loss, self._y[:B], self._dz[:B], self._GMF[:B] if gm else None,
                      self._dUG[:B] if gm else None, self._dIG[:B] if gm else None, self._dH3[:B] if ml else None)
-        dz = self._dz[:B].unsqueeze(1)
         wg = 1.0 if mode == 0 else 0.5
         wm = 1.0 if mode == 1 else 0.5
         for k in self.opt_vars[mode]:
@@ -118,13 +122,9 @@ class NeuMF(DeepRecommender):
             E.scatter_add_rows(g['QG'], i, self._dIG[:B])
             # d h_mf = wg * GMF^T dz + reg*h_mf (mf_reg) [+ reg*0.25*h_mf: l2_loss(h_NeuMF), mode 2]
             E.gemv_t(self._GMF[:B], self._dz[:B], g['h_mf'], alpha=wg)
-            E.axpby(g['h_mf'], g['h_mf'], p['h_mf'], 1.0, self.regU * (1.25 if mode == 2 else 1.0))
         if ml:
             # d h_mlp = wm * relu(H3)^T dz : dH3 already carries wm*dz*h_mlp masked, so use H3 directly
             E.gemv_t(self._H3[:B], self._dz[:B], g['h_mlp'], alpha=wm)
-            if mode == 2:
-                E.axpby(g['h_mlp'], g['h_mlp'], p['h_mlp'], 1.0, self.regU * 0.25)
-            ones = self._ones[:B]
             E.sgemm(self._H2[:B], self._dH3[:B], g['W3'], trans_a=True)
             E.gemv_t(self._dH3[:B], None, g['b3'])
             E.tc_gemm(self._dH3[:B], p['W3'], self._dH2[:B], b_is_nk=True, epilogue=E.EPI_RELU_MASK, mask=self._H2[:B])
@@ -136,11 +136,26 @@ class NeuMF(DeepRecommender):
             E.tc_gemm(self._dH1[:B], p['W1'], self._dX0[:B], b_is_nk=True)
             E.scatter_add_rows(g['PM'], u, self._dX0[:B, :d])
             E.scatter_add_rows(g['QM'], i, self._dX0[:B, d:])
+
+    def _update(self, mode):
+        """Parameter-only regularisers + TF1 Adam.  self.grads holds sums over samples: a data-parallel run adds the
+        ranks' buffers first (parallel.UserShardedNeuMF._reduce_gradients); the terms added here are applied once."""
+        from ... import engine as E
+        p, g = self.params, self.grads
+        gm, ml = mode != 1, mode != 0
+        self._reduce_gradients(mode)
+        if gm:
+            E.axpby(g['h_mf'], g['h_mf'], p['h_mf'], 1.0, self.regU * (1.25 if mode == 2 else 1.0))
+        if ml and mode == 2:
+            E.axpby(g['h_mlp'], g['h_mlp'], p['h_mlp'], 1.0, self.regU * 0.25)
         self.opt_step[mode] += 1
         for k in self.opt_vars[mode]:
             m, v = self.opt_state[mode][k]
             E.adam_dense_tf1(p[k], m, v, g[k], self.lRate, self.opt_step[mode])
         return self._loss
+
+    def _reduce_gradients(self, mode):
+        """Hook between the per-sample gradient sums and the optimiser; a single process has nothing to add."""
 
     def loss_value(self, mode):
         """Python float of the last step's loss incl. the h-vector regularisers (NeuMF.py:56-57,72)."""
