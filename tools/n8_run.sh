@@ -33,3 +33,4 @@ QREC_PEER_ALLREDUCE=1 run_bench lgcn_peer "--qsync p2p --no-parity --lightgcn-mu
 port=$((port+1)); timeout 900 $TR --master-port $port tools/dist_simgcl.py --steps 5 --skip-parity > "$out/dist_simgcl.log" 2>&1; echo "dist_simgcl (config 5): exit $? -- $(grep -h '^{' "$out/dist_simgcl.log" | cut -c1-900)"
 port=$((port+1)); QREC_PEER_ALLREDUCE=1 timeout 900 $TR --master-port $port tools/dist_simgcl.py --steps 5 --skip-parity > "$out/dist_simgcl_peer.log" 2>&1; echo "dist_simgcl peer (config 5): exit $? -- $(grep -h '^{' "$out/dist_simgcl_peer.log" | cut -c1-400)"
 port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_bpr_sharded.py --steps 5 --minibatch 1048576 --batch 4194304 > "$out/dist_bpr_sharded.log" 2>&1; echo "dist_bpr_sharded: exit $? -- $(grep -h '^{' "$out/dist_bpr_sharded.log" | cut -c1-400)"
+port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_neumf.py --steps 10 > "$out/dist_neumf.log" 2>&1; echo "dist_neumf: exit $? -- $(grep -h '^{' "$out/dist_neumf.log" | cut -c1-700)"; tail -3 "$out/dist_neumf.log" | grep -v '^{' | tail -2
