@@ -757,7 +757,9 @@ def run_ours(args):
         e2e_epoch[0] += 1
         l = pipe.bpr_epoch_usermajor(P, Q, hrp, hi, rowptr, cols, NUM_ITEMS, 2024, e2e_epoch[0], LR, REG_U, REG_I)
         qsync.sync()
-        torch.cuda.synchronize()
+        if not hasattr(qsync, 'finalize'):
+            torch.cuda.synchronize()      # blocking exchange rewrites Q: the next epoch's kernels (own streams) must wait
+        # overlapped exchange: delta is taken on this stream, the sum and the atomic merge run beside the next epoch
         return l
 
     for w in range(max(1, args.warmup // 2)):
