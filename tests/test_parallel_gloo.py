@@ -478,3 +478,128 @@ def test_user_sharded_simgcl_matches_autograd_world2():
     out = mgr.dict()
     mp.spawn(_simgcl_worker, args=(2, port, out), nprocs=2, join=True)
     assert dict(out) == {0: 1, 1: 1}
+
+
+# ---------------------------------------------------------------------------------------------
+# NeuMF data parallel (8e): user tables sharded, item tables + MLP replicated; gloo world 2, kernel stand-ins
+# ---------------------------------------------------------------------------------------------
+def _neumf_stand_ins():
+    """torch restatements of the contracts of the kernels NeuMF.train_step composes (include/qrec.h)."""
+    import numpy as np
+    from oracle import bpr_oracle as O
+    from qrec_b200 import engine as E
+
+    def tc_gemm(A, B, C, b_is_nk=False, epilogue=0, bias=None, mask=None):
+        out = A @ (B.t() if b_is_nk else B)
+        if epilogue in (E.EPI_BIAS_RELU, E.EPI_BIAS):
+            out = out + bias
+        if epilogue == E.EPI_BIAS_RELU:
+            out = torch.relu(out)
+        if epilogue == E.EPI_RELU_MASK:
+            out = out * (mask > 0)
+        C.copy_(out)
+
+    def head(mode, training, UG, IG, H3, h_mf, h_mlp, r, reg, loss, y, dz, GMF, dUG, dIG, dH3):
+        wg, wm = (1.0, 0.0) if mode == 0 else ((0.0, 1.0) if mode == 1 else (0.5, 0.5))
+        z = 0
+        if mode != 1:
+            z = z + wg * ((UG * IG) * h_mf).sum(1)
+        if mode != 0:
+            z = z + wm * (H3 * h_mlp).sum(1)
+        yy = torch.sigmoid(z)
+        y.copy_(yy)
+        if not training:
+            return
+        e = 10e-10
+        d_y = -r / (yy + e) + (1 - r) / (1 - yy + e)
+        dzz = d_y * yy * (1 - yy)
+        dz.copy_(dzz)
+        l = -(r * torch.log(yy + e) + (1 - r) * torch.log(1 - yy + e)).sum()
+        if mode != 1:
+            l = l + 0.5 * reg * ((UG * UG).sum() + (IG * IG).sum())
+            GMF.copy_(UG * IG)
+            dUG.copy_(wg * dzz[:, None] * h_mf * IG + reg * UG)
+            dIG.copy_(wg * dzz[:, None] * h_mf * UG + reg * IG)
+        if mode != 0:
+            dH3.copy_((H3 > 0) * (wm * dzz[:, None] * h_mlp))
+        loss += float(l)
+
+    def gemv_t(A, v, out, alpha=1.0, beta=0.0):
+        res = alpha * (A.t() @ (v if v is not None else torch.ones(A.shape[0])))
+        out.copy_(res if beta == 0.0 else out + res)
+
+    def sgemm(A, B, C, trans_a=False, trans_b=False, alpha=1.0, beta=0.0):
+        prod = alpha * ((A.t() if trans_a else A) @ (B.t() if trans_b else B))
+        C.copy_(prod if beta == 0.0 else prod + beta * C)
+    E.tc_gemm, E.neumf_head, E.gemv_t, E.sgemm = tc_gemm, head, gemv_t, sgemm
+    E.gather_rows = lambda T, idx, out: out.copy_(T[idx.long()])
+    E.scatter_add_rows = lambda G, idx, src, scale=1.0: G.index_add_(0, idx.long(), scale * src)
+    E.axpby = lambda dst, a, b, alpha, beta: dst.copy_(alpha * a + beta * b)
+    E.adam_dense_tf1 = lambda var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8: O.adam_tf1(var.numpy(), m.numpy(), v.numpy(), g.numpy(), lr, t)
+
+
+def _neumf_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import tf_models
+    from qrec_b200.base.deepRecommender import DeepRecommender
+    from qrec_b200.model.ranking.NeuMF import NeuMF
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        _neumf_stand_ins()
+        DeepRecommender.initModel = lambda self: None           # synthetic ids: no data plumbing
+        U, I, d, reg = 12, 9, 8, 0.01
+        Sharded = parallel.make_user_sharded_neumf(NeuMF)
+
+        def build(cls, nu):
+            class FakeData(object):
+                user, item = range(nu), range(I)
+            m = cls.__new__(cls)
+            m.data, m.num_users, m.num_items, m.emb_size, m.batch_size = FakeData(), nu, I, d, 4
+            m.lRate, m.regU, m.regI, m.engine_device, m.engine_seed, m.device = 0.01, reg, reg, 0, 0, torch.device('cpu')
+            m.initModel()
+            return m
+        full = build(NeuMF, U)
+        rng = np.random.default_rng(3)
+        for k, v in full.params.items():
+            v.copy_(torch.from_numpy(rng.standard_normal(tuple(v.shape)).astype(np.float32) * 0.4))
+        lo, hi = parallel.user_range(rank, world, U)
+        m = build(Sharded, hi - lo).shard(lo)
+        for k, v in full.params.items():
+            m.params[k].copy_(v[lo:hi] if k in ('PG', 'PM') else v)
+        for mode in (0, 1, 2):
+            before = {k: v.numpy().astype(np.float64).copy() for k, v in full.params.items()}
+            u = rng.integers(0, U, 20).astype(np.int32); i = rng.integers(0, I, 20).astype(np.int32)
+            r = (rng.random(20) < 0.3).astype(np.float32)
+            if mode == 1:
+                u[:] = rng.integers(0, parallel.user_range(0, world, U)[1], 20)      # rank 1 owns none of this minibatch
+            ref_loss, ref_g, _ = tf_models.neumf_loss_and_grad(before, mode, u, i, r, reg)
+            full.train_step(mode, torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(r))
+            loss = m.train_step(mode, torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(r))
+            # the sharded gradients (after the reduction, with the parameter-only regularisers) equal autograd of the
+            # reference's loss on the WHOLE minibatch ...
+            for k in m.opt_vars[mode]:
+                want = ref_g[k][lo:hi] if k in ('PG', 'PM') else ref_g[k]
+                assert np.abs(m.grads[k].numpy() - want).max() <= 1e-4 * max(1e-3, np.abs(ref_g[k]).max()), (rank, mode, k)
+            # ... and the parameters follow the single-process class
+            for k, v in full.params.items():
+                mine = v[lo:hi] if k in ('PG', 'PM') else v
+                assert torch.allclose(m.params[k], mine, rtol=1e-4, atol=1e-6), (rank, mode, k)
+            # kernel loss = BCE + per-sample L2; the h-vector terms are added by loss_value()
+            extra = 0.0 if mode == 1 else reg * 0.5 * float((before['h_mf'] ** 2).sum())
+            extra += reg * 0.5 * 0.25 * float((before['h_mf'] ** 2).sum() + (before['h_mlp'] ** 2).sum()) if mode == 2 else 0.0
+            assert abs(float(loss) + extra - ref_loss) <= 1e-4 * abs(ref_loss), (rank, mode, float(loss), ref_loss)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_user_sharded_neumf_matches_autograd_world2():
+    """parallel.make_user_sharded_neumf: samples routed to their user's owner, replicated gradients summed between
+    backward and Adam, head-vector regularisers applied once -- gradients equal float64 autograd of
+    model/ranking/NeuMF.py's three losses on the whole minibatch, parameters follow the single-process class."""
+    port = 39500 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_neumf_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
