@@ -267,6 +267,7 @@ spmm_scatter_rows_kernel(int n_src, const int* __restrict__ src_rows, const long
     if (si >= n_src) break;
     const int slice = (int)(w % 64);
     const int r = __ldg(src_rows + si);
+    if (r < 0) continue;                           // padding entry of a de-duplicated, fixed-length row list
     const long long start = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
     for (long long lo = start + (long long)slice * SLICE; lo < end; lo += 64LL * SLICE) {
       const long long hi = (lo + SLICE) < end ? (lo + SLICE) : end;
@@ -325,7 +326,7 @@ bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V
         const int uu = __shfl_sync(0xffffffffu, mu, t & 31);
         const int ii = __shfl_sync(0xffffffffu, mi, t & 31);
         const int jj = __shfl_sync(0xffffffffu, mj, t & 31);
-        ok[r] = t < cnt;
+        ok[r] = t < cnt && uu >= 0;                     // u < 0: not this rank's triple (sharded callers pad instead of compacting)
         ou[r] = (size_t)uu * d + l * 4;
         oi[r] = (size_t)ii * d + l * 4;
         oj[r] = (size_t)jj * d + l * 4;

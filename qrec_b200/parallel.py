@@ -564,6 +564,14 @@ def blocked_spmm(spmm, blocks, X, Y, scratch, acc, s):
         acc.add_(Y, alpha=s)
 
 
+def _sorted_unique_padded(x):
+    """The distinct values of an int32 vector as a same-length vector: sorted, every repeat replaced by -1.  Unlike
+    torch.unique the length does not depend on the data, so nothing has to be read back by the host."""
+    s, _ = torch.sort(x)
+    s[1:] = torch.where(s[1:] == s[:-1], torch.full_like(s[1:], -1), s[1:])
+    return s.int().contiguous()
+
+
 class UserShardedLightGCN(object):
     """LightGCN minibatch step (model/ranking/LightGCN.py:13-39 semantics) with the USER rows of the ego
     table partitioned over the ranks and the (25.6 MB at the benchmark scale) ITEM rows replicated.
@@ -668,16 +676,19 @@ class UserShardedLightGCN(object):
     def train_step(self, u, i, j):
         """u, i, j: the WHOLE minibatch (global ids, int32 device tensors) on every rank."""
         self._propagate(self.Eu, self.Ei, self.mean_u, self.mean_i)
-        mine = (u >= self.lo) & (u < self.lo + self.Eu.shape[0])
-        lu, li, lj = (u[mine] - self.lo).contiguous(), i[mine].contiguous(), j[mine].contiguous()
+        # no compaction, hence no host synchronisation inside a step: triples of other ranks' users keep their slot
+        # with u = -1 (K3 skips them), and the row lists of the sparse first backward layer are sorted, with
+        # repeated entries replaced by -1 (the scatter kernel skips those)
+        nloc = self.Eu.shape[0]
+        lu = u - self.lo
+        lu = torch.where((lu >= 0) & (lu < nloc), lu, torch.full_like(lu, -1)).contiguous()
         self.gu.zero_(); self.gi.zero_(); self.loss.zero_()
-        if lu.numel():
-            self._grad(self.mean_u, self.mean_i, lu, li, lj, self.gu, self.gi, self.loss)
+        self._grad(self.mean_u, self.mean_i, lu, i, j, self.gu, self.gi, self.loss)
         self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
         self._allreduce(self.loss)
         if u.shape[0] <= 8192 and self._scatter is not None and self.Eu.shape[1] <= 128:
-            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=torch.unique(lu).int(),
-                            nz_i=torch.unique(torch.cat([i, j])).int())
+            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=_sorted_unique_padded(lu),
+                            nz_i=_sorted_unique_padded(torch.cat([i, j])))
         else:
             self._propagate(self.gu, self.gi, self.tot_u, self.tot_i)
         self.step += 1

@@ -284,7 +284,10 @@ def _user_sharded_worker(rank, world, port, out, blocks=1):
                 acc.add_(Y, alpha=s)
 
         def grad(Ue, Ve, u, i, j, gU, gV, loss):
-            l, a, b = O.bpr_loss_grad(Ue.numpy(), Ve.numpy(), u.numpy(), i.numpy(), j.numpy(), 10e-8, reg)
+            keep = (u >= 0).numpy()                       # u = -1: another rank's triple (K3 skips it)
+            if not keep.any():
+                return
+            l, a, b = O.bpr_loss_grad(Ue.numpy(), Ve.numpy(), u.numpy()[keep], i.numpy()[keep], j.numpy()[keep], 10e-8, reg)
             gU.add_(torch.from_numpy(a).float()); gV.add_(torch.from_numpy(b).float())
             loss += l
         m = parallel.UserShardedLightGCN(

@@ -68,17 +68,24 @@ def main():
             l_ref = float(ref.train_step(mode, u, i, r).item())
             l = float(m.train_step(mode, u, i, r).item())
             assert abs(l - l_ref) <= 1e-4 * abs(l_ref), (mode, step, l, l_ref)
+            # gradients (after the reduction): the sums over samples are regrouped by rank, so fp32 / TF32 rounding
+            # differs -- compare against the largest entry; then the parameters: Adam turns a gradient that rounds
+            # to the other side of zero into a step of the other sign, so a parameter may differ by up to 2 lr
+            for k in m.opt_vars[mode]:
+                gr = ref.grads[k][lo:hi] if k in ('PG', 'PM') else ref.grads[k]
+                assert float((m.grads[k] - gr).abs().max()) <= 2e-3 * float(ref.grads[k].abs().max()) + 1e-7, (k, mode, step)
             for k, v in ref.params.items():
                 mine = v[lo:hi] if k in ('PG', 'PM') else v
-                torch.testing.assert_close(m.params[k], mine, rtol=2e-3, atol=2e-5, msg=lambda s, k=k: '%s (mode %d step %d): %s' % (k, mode, step, s))
+                assert float((m.params[k] - mine).abs().max()) <= 2.1 * ref.lRate, (k, mode, step)
+                assert float((m.params[k] - mine).abs().mean()) <= 0.05 * ref.lRate, (k, mode, step)
     if world > 1:                                          # replicated parameters stay bit-identical across ranks
         for k in ('QG', 'W1', 'h_mlp'):
             parts = [torch.empty_like(m.params[k]) for _ in range(world)]
             dist.all_gather(parts, m.params[k])
             assert all(torch.equal(parts[0], t) for t in parts), k
     if rank == 0:
-        print(json.dumps({'parity': 'UserShardedNeuMF == single-GPU NeuMF over 3 phases x 3 steps (losses 1e-4, parameters 2e-3; '
-                                    'replicas bit-identical)', 'world': world, 'problem': [U, I]}))
+        print(json.dumps({'parity': 'UserShardedNeuMF == single-GPU NeuMF over 3 phases x 3 steps (losses 1e-4, reduced gradients 2e-3 of max, '
+                                    'parameters within Adam sign noise; replicas bit-identical)', 'world': world, 'problem': [U, I]}))
     del ref, m
     torch.cuda.empty_cache()
 

@@ -1,0 +1,25 @@
+#!/usr/bin/env bash
+# quick multi-GPU re-check after the sync-free LightGCN step and the NeuMF data-parallel class (N from env)
+set -u
+N=${N:-2}
+out=gpurun_out/multi_check_n$N
+mkdir -p "$out"
+python -c "import __graft_entry__ as g; g.build()" > "$out/build.log" 2>&1 || { echo "build failed"; exit 1; }
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
+port=29900
+port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_neumf.py --steps 10 > "$out/dist_neumf.log" 2>&1; echo "dist_neumf: exit $? -- $(grep -h '^{' "$out/dist_neumf.log" | cut -c1-900)"; grep -E "AssertionError|Error" "$out/dist_neumf.log" | head -3
+port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 > "$out/dist_lightgcn.log" 2>&1; echo "dist_lightgcn: exit $? -- $(grep -h '^{' "$out/dist_lightgcn.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn.log" | head -3
+for w in ${WAVES:-1 2}; do
+port=$((port+1)); timeout 600 $TR --master-port $port bench.py --gpus $N --steps 20 --warmup 5 --q-syncs $w > "$out/bench_w$w.json" 2> "$out/bench_w$w.err"
+python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('$out/bench_w$w.json') if l.startswith('{')][-1])
+    pc=d.get('parity_check') or {}; lg=d.get('lightgcn') or {}
+    print('bench w$w: value %.3e e2e %.3e ms/step %.3f k1 %.3f | loss %.0f' % (d['value'], d['e2e']['value'], d['ms_per_step'], d['roofline']['launch_ms'], d['config']['epoch_loss']))
+    if pc: print('   parity loss %.2e P %.3f Q %.3f' % (pc['loss_sum_neg_log_sigmoid']['rel_err'], pc['P']['rms_err_over_rms_update'], pc['Q']['rms_err_over_rms_update']))
+    if lg: print('   lightgcn', {k:round(v['ms_per_step'],3) for k,v in lg.items() if k.startswith('batch')})
+except Exception as e:
+    print('bench w$w FAILED', e); print(open('$out/bench_w$w.err').read()[-1200:])
+PY
+done
