@@ -995,7 +995,9 @@ def main():
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--q-syncs', type=int, default=2, help='launches (waves) per step when N>1; the item-table deltas are exchanged after each')
+    ap.add_argument('--q-syncs', type=int, default=1, help='launches (waves) per step when N>1; the item-table deltas are exchanged after each (overlapped with the next '
+                         'launch).  1 = one exchange per epoch: 53 G triples/s at N=8, epoch loss after 25 epochs 1.7 %% above one GPU; '
+                         '2: 45 G, 0.9 %%; 4: 35 G (profiles/README.md)')
     ap.add_argument('--qsync', default=MULTI_GPU_DEFAULTS['qsync'], choices=['auto', 'p2p', 'nccl', 'blocking'],
                     help='N>1 item-table exchange: overlapped peer-memory kernels (p2p), overlapped ncclAllReduce (nccl), auto = p2p with nccl fallback, blocking = round-1 path')
     ap.add_argument('--cpu-sample', type=int, default=20_000_000)
