@@ -9,6 +9,7 @@ grep -E "^(FAILED|ERROR)" "$out/pytest_gpu.log" | head
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; echo "smoke: exit $? -- $(tail -1 "$out/smoke.log")"
 /usr/bin/time -v timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > "$out/bench.json" 2> "$out/bench.err"; echo "bench: exit $? wall $(grep 'Elapsed (wall' "$out/bench.err" | awk '{print $NF}')"
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > "$out/bench_reference.json" 2> "$out/bench_reference.err"; echo "reference arm: exit $?"
+timeout 600 python tools/bench_models.py --steps 5 > "$out/bench_models.jsonl" 2> "$out/bench_models.err"; echo "bench_models: exit $?"; cut -c1-200 "$out/bench_models.jsonl"
 python - <<PY
 import json
 d=json.loads([l for l in open('$out/bench.json') if l.startswith('{')][-1])
