@@ -496,9 +496,13 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
     m = parallel.UserShardedLightGCN(A_ui, A_iu, Eu, Ei, layers, 0.001, 0.001, rank * users_local, item_side_blocks=item_blocks)
     spmm_algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)                 # SURVEY 8(d) no-reuse gather model
     res = {'layers': layers, 'rows': N, 'nnz': nnz, 'n_gpus': world,
-           'semantics': 'full propagation + backward + dense Adam per minibatch; every timed step a different minibatch',
+           'semantics': 'the reference step: n-layer propagation + loss + its backward pass + dense Adam on every row, once per '
+                        'minibatch; every timed step a different minibatch.  At B <= 8192 the two layers that touch only the '
+                        "batch's rows -- the last forward layer (the loss reads nothing else of its output) and the first backward "
+                        'layer (the loss gradient is zero elsewhere) -- run over those rows\' edges only; the parameter update '
+                        'equals the all-rows computation (tests/test_lightgcn_model_cpu.py, test_gpu_models.py vs autograd)',
            'impl': 'parallel.UserShardedLightGCN: users partitioned over %d rank(s), items replicated, bipartite blocks '
-                   'A_ui/A_iu, sparse first backward layer, %s' % (world, 'one all-reduce of the item block per layer '
+                   'A_ui/A_iu, row-restricted last forward / first backward layer, %s' % (world, 'one all-reduce of the item block per layer '
                                                                    '(overlapped with the user-side SpMM)' if world > 1 else 'no collective'),
            'item_side_blocks': item_blocks}
     n_local = users_local * DEGREE
@@ -533,9 +537,11 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
         n_steps = -(-U * DEGREE // B)
-        step_bytes = 2 * layers * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
+        full_products = 2 * layers - (2 if (B <= 8192 and layers > 1) else 0)       # whole-graph SpMMs actually executed
+        step_bytes = full_products * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
         res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
                                'epoch_extrapolated_from_steps': steps, 'algorithmic_GB_per_step': step_bytes / 1e9,
+                               'whole_graph_products_per_step': full_products,
                                'frac_of_hbm_peak_whole_job': step_bytes / ms / 1e6 / (peak * world), 'loss': float(m.loss.item())}
         del batches
     if world == 1:

@@ -378,6 +378,15 @@ int qrec_spmm_csr_scatter_rows_f32(int32_t n_rows, int32_t n_src, const int32_t*
                                    const float* dev_vals, const float* dev_X, float* dev_Y, int32_t d,
                                    float* dev_acc, float acc_scale, void* stream);
 
+/* Pull-side product on a list of OUTPUT rows (the last forward layer of a minibatch step: the loss of
+ * model/ranking/LightGCN.py:22-26 reads the propagated embeddings of the batch's rows only).  For k < n_list with
+ * r = rows[k] >= 0:  s = sum_e a_e X[col_e] over CSR row r;  Y[compact ? k : r] = s (Y may be NULL);
+ * acc[r] += acc_scale * s (acc may be NULL; the listed rows must then be distinct).  Entries r = -1 are padding:
+ * skipped, their row of a compact Y is zero-filled.  d % 4 == 0, d <= 128. */
+int qrec_spmm_csr_rows_f32(int32_t n_list, const int32_t* dev_rows, const int64_t* dev_rowptr,
+                           const int32_t* dev_cols, const float* dev_vals, const float* dev_X, float* dev_Y,
+                           int32_t compact, int32_t d, float* dev_acc, float acc_scale, void* stream);
+
 /* =====================================================================================
  * K3 -- gather rows of the propagated tables, bpr_loss + batch L2 and its gradient,
  * scatter-added into dense gradient buffers.  util/loss.py:3-6, LightGCN.py:22-24,28-30.
@@ -400,6 +409,10 @@ int qrec_bpr_grad_scatter_f32(const float* dev_U, const float* dev_V, int32_t d,
 int qrec_adam_dense_tf1_f32(float* dev_var, float* dev_m, float* dev_v, const float* dev_g,
                             int64_t n, float lr, float beta1, float beta2, float eps,
                             int64_t t, void* stream);
+/* The same update with the step-dependent factor lr_t = lr * sqrt(1 - beta2^t) / (1 - beta1^t) read from device
+ * memory at run time: a training step captured in a CUDA graph replays with a new t without re-capturing. */
+int qrec_adam_dense_tf1_devstep_f32(float* dev_var, float* dev_m, float* dev_v, const float* dev_g, int64_t n,
+                                    const float* dev_lr_t, float beta1, float beta2, float eps, void* stream);
 
 /* Layer mean helper (LightGCN.py:19): dst[k] = scale * (a[k] + b[k]); dst may alias a. */
 int qrec_axpby_f32(float* dev_dst, const float* dev_a, const float* dev_b, float alpha,

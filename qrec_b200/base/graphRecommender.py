@@ -45,6 +45,11 @@ class DeviceCSR(object):
         from .. import engine
         return engine.spmm_csr_scatter_rows(self.rowptr, self.cols, self.vals, src_rows, X, out, acc=acc, acc_scale=acc_scale)
 
+    def matmul_rows(self, X, rows, out=None, compact=False, acc=None, acc_scale=0.0):
+        """The rows `rows` (int32, distinct, -1 = padding) of A @ X, stored into `out` and / or accumulated into acc."""
+        from .. import engine
+        return engine.spmm_csr_rows(self.rowptr, self.cols, self.vals, rows, X, out, compact=compact, acc=acc, acc_scale=acc_scale)
+
     def matmul(self, X, out, acc=None, acc_scale=0.0):
         from .. import engine
         return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale,

@@ -297,6 +297,76 @@ spmm_scatter_rows_kernel(int n_src, const int* __restrict__ src_rows, const long
   }
 }
 
+// Pull-side product on a LIST of output rows: out[k] = sum_e a_e X[col_e] over the CSR row rows[k].  One warp per
+// listed row; the warp's 32/LPR lane groups take the row's entries round-robin, four gathers in flight each, and
+// their partial sums meet in a butterfly at the end (a fixed order: the result is deterministic).  Used for the
+// LAST forward layer of a minibatch step, of which the loss reads only the batch's rows.
+template <int LPR>
+__global__ void __launch_bounds__(256)
+spmm_list_rows_kernel(int n_list, const int* __restrict__ rows, const long long* __restrict__ rowptr,
+                      const int* __restrict__ cols, const float* __restrict__ vals, const float* __restrict__ X,
+                      float* __restrict__ Y, int compact, int nvec, float* __restrict__ acc, float acc_scale) {
+  constexpr int GPW = 32 / LPR;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LPR, l = lane % LPR;
+  const int d = nvec * 4;
+  const bool live = l < nvec;
+  const int warp = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)(((long long)gridDim.x * blockDim.x) >> 5);
+  for (int w = warp; w < n_list; w += nwarps) {
+    const int r = __ldg(rows + w);
+    if (r < 0) {                                           // padding entry of a fixed-length row list
+      if (compact && Y != nullptr && sub == 0 && live)
+        *reinterpret_cast<float4*>(Y + (size_t)w * d + l * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    const long long start = __ldg(rowptr + r), end = __ldg(rowptr + r + 1);
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (long long base = start + sub; base < end; base += 4 * GPW) {
+      int c[4];
+      float a[4];
+      float4 x[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const long long e = base + (long long)t * GPW;
+        const bool ok = e < end;
+        c[t] = ok ? __ldg(cols + e) : -1;
+        a[t] = ok ? __ldg(vals + e) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        x[t] = (live && c[t] >= 0) ? __ldg(reinterpret_cast<const float4*>(X + (size_t)c[t] * d) + l)
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        s.x = fmaf(a[t], x[t].x, s.x);
+        s.y = fmaf(a[t], x[t].y, s.y);
+        s.z = fmaf(a[t], x[t].z, s.z);
+        s.w = fmaf(a[t], x[t].w, s.w);
+      }
+    }
+#pragma unroll
+    for (int off = LPR; off < 32; off <<= 1) {
+      s.x += __shfl_xor_sync(0xffffffffu, s.x, off);
+      s.y += __shfl_xor_sync(0xffffffffu, s.y, off);
+      s.z += __shfl_xor_sync(0xffffffffu, s.z, off);
+      s.w += __shfl_xor_sync(0xffffffffu, s.w, off);
+    }
+    if (sub == 0 && live) {
+      if (Y != nullptr) *reinterpret_cast<float4*>(Y + (size_t)(compact ? w : r) * d + l * 4) = s;
+      if (acc != nullptr) {                                // listed rows are distinct: a plain read-modify-write
+        float4* ap = reinterpret_cast<float4*>(acc + (size_t)r * d + l * 4);
+        float4 o = *ap;
+        o.x = fmaf(acc_scale, s.x, o.x);
+        o.y = fmaf(acc_scale, s.y, o.y);
+        o.z = fmaf(acc_scale, s.z, o.z);
+        o.w = fmaf(acc_scale, s.w, o.w);
+        *ap = o;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ K3
 template <int LPR, int VPL, int UNROLL>
 __global__ void __launch_bounds__(256)
@@ -392,7 +462,8 @@ bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V
 __global__ void __launch_bounds__(256)
 adam_dense_tf1_kernel(float* __restrict__ var, float* __restrict__ m, float* __restrict__ v,
                       const float* __restrict__ g, long long n, float lr_t, float b1, float b2,
-                      float eps) {
+                      float eps, const float* __restrict__ lr_t_dev) {
+  if (lr_t_dev != nullptr) lr_t = __ldg(lr_t_dev);      // step-dependent factor read at run time (CUDA-graph replays)
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long n4 = n >> 2;
@@ -551,6 +622,32 @@ int qrec_spmm_csr_scatter_rows_f32(int32_t n_rows, int32_t n_src, const int32_t*
   return QREC_OK;
 }
 
+int qrec_spmm_csr_rows_f32(int32_t n_list, const int32_t* rows, const int64_t* rowptr, const int32_t* cols,
+                           const float* vals, const float* X, float* Y, int32_t compact, int32_t d, float* acc,
+                           float acc_scale, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 128 && d % 4 == 0, "qrec_spmm_csr_rows_f32: d=%d unsupported (multiple of 4, <= 128)", d);
+  QREC_REQUIRE(n_list >= 0, "qrec_spmm_csr_rows_f32: n_list < 0");
+  if (n_list == 0) return QREC_OK;
+  QREC_REQUIRE(rows && rowptr && cols && vals && X && (Y || acc), "qrec_spmm_csr_rows_f32: null pointer");
+  QREC_REQUIRE(aligned16(X) && (!Y || aligned16(Y)) && (!acc || aligned16(acc)),
+               "qrec_spmm_csr_rows_f32: matrices must be 16-byte aligned");
+  const int nvec = d / 4;
+  const long long cap = (long long)sm_count() * 8;
+  long long blocks = ((long long)n_list + 7) / 8;          // one warp per listed row, 8 warps per block
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_LIST(LPR)                                                                                     \
+  spmm_list_rows_kernel<LPR><<<(int)blocks, 256, 0, st>>>(n_list, rows, reinterpret_cast<const long long*>(rowptr), \
+                                                          cols, vals, X, Y, compact, nvec, acc, acc_scale)
+  if (nvec <= 4) QREC_LIST(4);
+  else if (nvec <= 8) QREC_LIST(8);
+  else if (nvec <= 16) QREC_LIST(16);
+  else QREC_LIST(32);
+#undef QREC_LIST
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
 int qrec_bpr_grad_scatter_f32(const float* U, const float* V, int32_t d, int64_t n,
                               const int32_t* u, const int32_t* i, const int32_t* j, float eps,
                               float reg, float* gU, float* gV, double* loss, void* stream) {
@@ -592,7 +689,22 @@ int qrec_adam_dense_tf1_f32(float* var, float* m, float* v, const float* g, int6
   const long long blocks = (n / 4 + 255) / 256 + 1;
   const long long cap = (long long)sm_count() * 8;
   adam_dense_tf1_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
-      var, m, v, g, n, lr_t, beta1, beta2, eps);
+      var, m, v, g, n, lr_t, beta1, beta2, eps, nullptr);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_adam_dense_tf1_devstep_f32(float* var, float* m, float* v, const float* g, int64_t n, const float* dev_lr_t,
+                                    float beta1, float beta2, float eps, void* stream) {
+  QREC_REQUIRE(n >= 0, "qrec_adam_dense_tf1_devstep_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(var && m && v && g && dev_lr_t, "qrec_adam_dense_tf1_devstep_f32: null pointer");
+  QREC_REQUIRE(aligned16(var) && aligned16(m) && aligned16(v) && aligned16(g),
+               "qrec_adam_dense_tf1_devstep_f32: buffers must be 16-byte aligned");
+  const long long blocks = (n / 4 + 255) / 256 + 1;
+  const long long cap = (long long)sm_count() * 8;
+  adam_dense_tf1_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, (cudaStream_t)stream>>>(
+      var, m, v, g, n, 0.f, beta1, beta2, eps, dev_lr_t);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

@@ -628,6 +628,20 @@ def spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scal
     return Y
 
 
+def spmm_csr_rows(rowptr, cols, vals, rows, X, Y=None, compact=False, acc=None, acc_scale=0.0):
+    """The rows `rows` (int32, -1 = padding) of the product (rowptr, cols, vals) @ X: written to Y (row k of a compact Y,
+    row rows[k] otherwise; Y may be None) and / or accumulated as acc[rows[k]] += acc_scale * row (distinct rows)."""
+    torch = _torch()
+    assert Y is not None or acc is not None
+    check(lib.qrec_spmm_csr_rows_f32(rows.shape[0], _dev(rows, torch.int32, 'rows'), _dev(rowptr, torch.int64, 'rowptr'),
+                                     _dev(cols, torch.int32, 'cols'), _dev(vals, torch.float32, 'vals'),
+                                     _dev(X, torch.float32, 'X'), _dev(Y, torch.float32, 'Y') if Y is not None else None,
+                                     1 if compact else 0, X.shape[1],
+                                     _dev(acc, torch.float32, 'acc') if acc is not None else None, float(acc_scale),
+                                     _stream()), 'qrec_spmm_csr_rows_f32')
+    return Y
+
+
 def bpr_grad_scatter(U, V, u, i, j, eps, reg, gU, gV, loss):
     torch = _torch()
     check(lib.qrec_bpr_grad_scatter_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'),
@@ -645,6 +659,22 @@ def adam_dense_tf1(var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
                                       _dev(v, torch.float32, 'v'), _dev(g, torch.float32, 'g'),
                                       var.numel(), float(lr), float(beta1), float(beta2), float(eps),
                                       int(t), _stream()), 'qrec_adam_dense_tf1_f32')
+    return var
+
+
+def adam_lr_t(lr, t, beta1=0.9, beta2=0.999):
+    """lr * sqrt(1 - beta2^t) / (1 - beta1^t) with the roundings of qrec_adam_dense_tf1_f32 (fp32 powers)."""
+    import numpy as np
+    b1p, b2p = np.float32(float(beta1) ** t), np.float32(float(beta2) ** t)
+    return float(np.float32(lr) * np.sqrt(np.float32(1.0) - b2p) / (np.float32(1.0) - b1p))
+
+
+def adam_dense_tf1_devstep(var, m, v, g, lr_t_dev, beta1=0.9, beta2=0.999, eps=1e-8):
+    """adam_dense_tf1 with the step factor in a 1-element fp32 CUDA tensor (filled from adam_lr_t before a replay)."""
+    torch = _torch()
+    check(lib.qrec_adam_dense_tf1_devstep_f32(_dev(var, torch.float32, 'var'), _dev(m, torch.float32, 'm'), _dev(v, torch.float32, 'v'),
+                                              _dev(g, torch.float32, 'g'), var.numel(), _dev(lr_t_dev, torch.float32, 'lr_t'),
+                                              float(beta1), float(beta2), float(eps), _stream()), 'qrec_adam_dense_tf1_devstep_f32')
     return var
 
 

@@ -40,14 +40,19 @@ class LightGCN(GraphRecommender):
         self._loss = torch.zeros(1, dtype=torch.float64, device=dev)
         self._step = 0
 
-    def propagate(self):
-        """mean(E0..En) into self._mean; returns (user rows, item rows) views (LightGCN.py:13-20)."""
+    def propagate(self, rows=None):
+        """mean(E0..En) into self._mean; returns (user rows, item rows) views (LightGCN.py:13-20).
+        rows (int32, distinct, -1 padded): the only rows the caller will read -- the last layer, whose output feeds
+        no further layer, is then evaluated on those rows alone (the other rows of the mean lack its term)."""
         from ... import engine as E
         s = 1.0 / (self.n_layers + 1)
         E.axpby(self._mean, self.ego, self.ego, s, 0.0)
         cur = self.ego
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
+            if rows is not None and k == self.n_layers - 1 and k > 0 and hasattr(self.norm_adj, 'matmul_rows'):
+                self.norm_adj.matmul_rows(cur, rows, acc=self._mean, acc_scale=s)
+                break
             self.norm_adj.matmul(cur, nxt, acc=self._mean, acc_scale=s)
             cur = nxt
         return self._mean[:self.num_users], self._mean[self.num_users:]
@@ -56,7 +61,14 @@ class LightGCN(GraphRecommender):
         """One minibatch (LightGCN.py:28-39).  u,i,j: int32 CUDA tensors.  Returns the device loss."""
         from ... import engine as E
         s = 1.0 / (self.n_layers + 1)
-        Ue, Ve = self.propagate()
+        # the rows the batch touches: the loss reads the propagated embeddings there and nowhere else, and its
+        # gradient is zero everywhere else (sorted, repeats replaced by -1: no data-dependent length, no host sync)
+        batch_rows = None
+        if u.shape[0] <= 8192 and self.emb_pad <= 128 and hasattr(self.norm_adj, 'matmul_sparse_rows'):
+            from ...parallel import _sorted_unique_padded
+            import torch
+            batch_rows = _sorted_unique_padded(torch.cat([u, i + self.num_users, j + self.num_users]))
+        Ue, Ve = self.propagate(batch_rows)
         self._grad.zero_()
         self._loss.zero_()
         E.bpr_grad_scatter(Ue, Ve, u, i, j, BPR_EPS, self.regU, self._grad[:self.num_users],
@@ -65,11 +77,9 @@ class LightGCN(GraphRecommender):
         cur = self._grad
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
-            if k == 0 and hasattr(self.norm_adj, 'matmul_sparse_rows') and u.shape[0] <= 8192 and self.emb_pad <= 128:
+            if k == 0 and batch_rows is not None:
                 # the loss gradient is non-zero only in the batch's rows: scatter along their edges
-                import torch
-                nz = torch.unique(torch.cat([u, i + self.num_users, j + self.num_users])).int()
-                self.norm_adj.matmul_sparse_rows(cur, nz, nxt, acc=self._total, acc_scale=s)
+                self.norm_adj.matmul_sparse_rows(cur, batch_rows, nxt, acc=self._total, acc_scale=s)
             else:
                 self.norm_adj.matmul(cur, nxt, acc=self._total, acc_scale=s)
             cur = nxt

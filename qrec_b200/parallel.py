@@ -586,7 +586,8 @@ class UserShardedLightGCN(object):
     (replicated) for items."""
 
     def __init__(self, A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, group=None,
-                 spmm=None, grad=None, adam=None, scale=None, axpy=None, item_side_blocks=1):
+                 spmm=None, grad=None, adam=None, scale=None, axpy=None, item_side_blocks=1,
+                 scatter=None, rows=None, scatter_add=None):
         """item_side_blocks > 1 (experimental, default off): the item-side product A_iu E_u runs as that
         many passes over column blocks of local users (split_csr_columns / blocked_spmm), so each pass
         gathers user rows from a slice of E_u that fits the L2."""
@@ -628,8 +629,18 @@ class UserShardedLightGCN(object):
         self._axpy = axpy or (lambda dst, src, s: E.axpby(dst, dst, src, 1.0, s))
         # sparse-source product (first backward layer): Y[dst] += a * X[src] over the edges of the listed
         # source rows; only available with the CUDA kernels (the gloo test injects dense stand-ins)
-        self._scatter = None if spmm is not None else (
-            lambda A, rows, X, Y, acc, s: E.spmm_csr_scatter_rows(A[0], A[1], A[2], rows, X, Y, acc=acc, acc_scale=s))
+        self._scatter = scatter or (None if spmm is not None else (
+            lambda A, rows, X, Y, acc, s: E.spmm_csr_scatter_rows(A[0], A[1], A[2], rows, X, Y, acc=acc, acc_scale=s)))
+        # listed-rows product (last forward layer) and the row scatter-add that folds its all-reduced block back in
+        self._rows = rows or (None if spmm is not None else (
+            lambda A, rows, X, Y, compact, acc, s: E.spmm_csr_rows(A[0], A[1], A[2], rows, X, Y, compact=compact, acc=acc, acc_scale=s)))
+        self._scatter_add = scatter_add or (lambda G, idx, src, s: E.scatter_add_rows(G, idx, src, scale=s))
+        self._need = {}
+
+    def _need_buf(self, n):
+        if n not in self._need:
+            self._need[n] = torch.empty(n, self.Ei.shape[1], device=self.Ei.device)
+        return self._need[n]
 
     def _allreduce(self, t):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -646,15 +657,30 @@ class UserShardedLightGCN(object):
             return dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
         return None
 
-    def _propagate(self, src_u, src_i, acc_u, acc_i, nz_u=None, nz_i=None):
+    def _propagate(self, src_u, src_i, acc_u, acc_i, nz_u=None, nz_i=None, need_u=None, need_i=None):
         """nz_u / nz_i: the only non-zero rows of src_u / src_i (the loss gradient touches the batch rows
-        only), so the first layer scatters along those rows' edges instead of a full SpMM."""
+        only), so the first layer scatters along those rows' edges instead of a full SpMM.
+        need_u / need_i: the only rows of acc_u / acc_i the caller reads (the loss reads the batch rows only), so
+        the LAST layer is evaluated on those rows alone (its output feeds no further layer); the other rows of
+        acc then lack the last layer's term.  Both lists are sorted, distinct, -1-padded."""
         s = 1.0 / (self.n_layers + 1)
         self._scale(acc_u, src_u, s)
         self._scale(acc_i, src_i, s)
         cu, ci = src_u, src_i
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            if k == self.n_layers - 1 and k > 0 and need_u is not None and self._rows is not None:
+                if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                    part = self._need_buf(need_i.shape[0])               # this rank's partial sums, one row per list entry
+                    self._rows(self.A_iu, need_i, cu, part, True, None, 0.0)
+                    work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                    self._rows(self.A_ui, need_u, ci, None, False, acc_u, s)
+                    work.wait()
+                    self._scatter_add(acc_i, need_i, part, s)
+                else:
+                    self._rows(self.A_iu, need_i, cu, None, False, acc_i, s)
+                    self._rows(self.A_ui, need_u, ci, None, False, acc_u, s)
+                break
             sparse = k == 0 and nz_u is not None and self._scatter is not None
             # item side first (this rank's partial sums), its all-reduce in flight during the user side
             if sparse:
@@ -675,22 +701,21 @@ class UserShardedLightGCN(object):
 
     def train_step(self, u, i, j):
         """u, i, j: the WHOLE minibatch (global ids, int32 device tensors) on every rank."""
-        self._propagate(self.Eu, self.Ei, self.mean_u, self.mean_i)
         # no compaction, hence no host synchronisation inside a step: triples of other ranks' users keep their slot
-        # with u = -1 (K3 skips them), and the row lists of the sparse first backward layer are sorted, with
-        # repeated entries replaced by -1 (the scatter kernel skips those)
+        # with u = -1 (K3 skips them), and the row lists of the row-restricted layers (last forward, first backward)
+        # are sorted, with repeated entries replaced by -1 (the kernels skip those)
         nloc = self.Eu.shape[0]
         lu = u - self.lo
         lu = torch.where((lu >= 0) & (lu < nloc), lu, torch.full_like(lu, -1)).contiguous()
+        batch_rows = u.shape[0] <= 8192 and self._scatter is not None and self.Eu.shape[1] <= 128
+        rows_u = _sorted_unique_padded(lu) if batch_rows else None
+        rows_i = _sorted_unique_padded(torch.cat([i, j])) if batch_rows else None
+        self._propagate(self.Eu, self.Ei, self.mean_u, self.mean_i, need_u=rows_u, need_i=rows_i)
         self.gu.zero_(); self.gi.zero_(); self.loss.zero_()
         self._grad(self.mean_u, self.mean_i, lu, i, j, self.gu, self.gi, self.loss)
         self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
         self._allreduce(self.loss)
-        if u.shape[0] <= 8192 and self._scatter is not None and self.Eu.shape[1] <= 128:
-            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=_sorted_unique_padded(lu),
-                            nz_i=_sorted_unique_padded(torch.cat([i, j])))
-        else:
-            self._propagate(self.gu, self.gi, self.tot_u, self.tot_i)
+        self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=rows_u, nz_i=rows_i)
         self.step += 1
         self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
         self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)

@@ -165,6 +165,13 @@ def test_adam_tf1(torch, E):
         np.testing.assert_allclose(dv.cpu().numpy(), var, rtol=1e-5, atol=1e-7)
         np.testing.assert_allclose(dm.cpu().numpy(), m, rtol=1e-5, atol=1e-7)   # fma vs mul+add near 0
         np.testing.assert_allclose(dvv.cpu().numpy(), v, rtol=1e-5, atol=1e-9)
+        # the variant that reads the step factor from device memory (for CUDA-graph replays) returns the same bits
+        a = [t_.clone() for t_ in (dv, dm, dvv)]
+        b = [t_.clone() for t_ in (dv, dm, dvv)]
+        gg = _dev(torch, rng.standard_normal(n).astype(np.float32))
+        E.adam_dense_tf1(a[0], a[1], a[2], gg, 0.001, 7)
+        E.adam_dense_tf1_devstep(b[0], b[1], b[2], gg, torch.tensor([E.adam_lr_t(0.001, 7)], dtype=torch.float32, device='cuda'))
+        assert all(torch.equal(x, y) for x, y in zip(a, b))
 
 
 def test_spmm_scatter_rows_equals_dense_product(torch, E, golden_graph):
@@ -189,3 +196,45 @@ def test_spmm_scatter_rows_equals_dense_product(torch, E, golden_graph):
     E.spmm_csr_scatter_rows(_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data),
                             torch.zeros(0, dtype=torch.int32, device='cuda'), _dev(torch, X), Y)
     assert bool((Y == 0).all())
+
+
+@pytest.mark.parametrize('d', [8, 32, 52, 64, 128])
+def test_spmm_listed_rows_equals_dense_product(torch, E, golden_graph, d):
+    """Last-forward shortcut: only a list of output rows of A @ X (one warp per row, lane groups splitting the
+    row's entries).  Direct, compact and accumulate-only outputs; -1 entries are padding; unlisted rows untouched."""
+    adj = _golden_adj(golden_graph)
+    n = adj.shape[0]
+    rng = np.random.default_rng(14)
+    rows = np.unique(rng.integers(0, n, 600)).astype(np.int32)
+    rows = np.unique(np.concatenate([rows, [int(np.argmax(np.diff(adj.indptr)))],       # the longest row
+                                     [int(np.argmin(np.diff(adj.indptr)))]])).astype(np.int32)   # and a shortest one
+    padded = np.full(len(rows) + 37, -1, np.int32)
+    slots = np.sort(rng.choice(len(padded), len(rows), replace=False))
+    padded[slots] = rows
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    ref = (adj.astype(np.float64) @ X.astype(np.float64))
+    csr = (_dev(torch, adj.indptr.astype(np.int64)), _dev(torch, adj.indices), _dev(torch, adj.data))
+    dX, dr = _dev(torch, X), _dev(torch, padded)
+    # rows of a full-height output + accumulation
+    acc0 = rng.standard_normal((n, d)).astype(np.float32)
+    acc, Y = _dev(torch, acc0), torch.full((n, d), 7.0, device='cuda')
+    E.spmm_csr_rows(*csr, dr, dX, Y, acc=acc, acc_scale=0.25)
+    got, gacc = Y.cpu().numpy(), acc.cpu().numpy()
+    np.testing.assert_allclose(got[rows], ref[rows], rtol=1e-4, atol=2e-6)
+    np.testing.assert_allclose(gacc[rows], acc0[rows] + 0.25 * ref[rows], rtol=1e-4, atol=2e-6)
+    other = np.setdiff1d(np.arange(n), rows)
+    assert np.all(got[other] == 7.0) and np.array_equal(gacc[other], acc0[other])
+    # compact output: row k of Y belongs to list entry k, padding entries give zero rows
+    Yc = torch.full((len(padded), d), 7.0, device='cuda')
+    E.spmm_csr_rows(*csr, dr, dX, Yc, compact=True)
+    gc = Yc.cpu().numpy()
+    np.testing.assert_allclose(gc[slots], ref[rows], rtol=1e-4, atol=2e-6)
+    assert np.all(gc[padded < 0] == 0.0)
+    # accumulate only; twice the same call is deterministic
+    a1, a2 = _dev(torch, acc0), _dev(torch, acc0)
+    E.spmm_csr_rows(*csr, dr, dX, None, acc=a1, acc_scale=-1.5)
+    E.spmm_csr_rows(*csr, dr, dX, None, acc=a2, acc_scale=-1.5)
+    assert torch.equal(a1, a2)
+    np.testing.assert_allclose(a1.cpu().numpy()[rows], acc0[rows] - 1.5 * ref[rows], rtol=1e-4, atol=4e-6)
+    # empty list
+    E.spmm_csr_rows(*csr, torch.zeros(0, dtype=torch.int32, device='cuda'), dX, Y)

@@ -1,6 +1,6 @@
 """Host logic of the LightGCN drop-in (a12-a15) without a GPU: device stubbed to 'cpu', kernels replaced
 by dense / oracle stand-ins.  Checks the class's own step -- layer-mean propagation through the SpMM
-epilogue, the sparse first backward layer (rows found with torch.unique), the dense Adam on the ego table,
+epilogue, the last forward layer on the batch's rows only, the sparse first backward layer (sorted, -1-padded row lists), the dense Adam on the ego table,
 the padded table width -- against the oracle's restatement of model/ranking/LightGCN.py:13-39 on the
 reference's FilmTrust graph and sampled batches."""
 import contextlib
@@ -31,12 +31,30 @@ def _stub(monkeypatch, calls):
     def scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scale=0.0):
         calls.append('scatter_rows')
         keep = torch.zeros(X.shape[0], dtype=torch.bool)
-        keep[src_rows.long()] = True
+        listed = src_rows[src_rows >= 0].long()            # -1 entries are padding
+        assert listed.numel() == torch.unique(listed).numel()
+        keep[listed] = True
         assert float(X[~keep].abs().sum()) == 0.0          # the caller's claim: only those rows are non-zero
         A = dense(rowptr, cols, vals, Y.shape[0])          # symmetric adjacency: B^T X == A X
         Y.copy_(torch.from_numpy(A.T @ X.numpy()))
         if acc is not None:
             acc.add_(Y, alpha=acc_scale)
+        return Y
+
+    def list_rows(rowptr, cols, vals, rows, X, Y=None, compact=False, acc=None, acc_scale=0.0):
+        calls.append('rows')
+        A = dense(rowptr, cols, vals, X.shape[0])
+        listed = rows[rows >= 0].long()
+        assert listed.numel() == torch.unique(listed).numel()
+        part = torch.from_numpy(A[listed.numpy()] @ X.numpy())
+        if Y is not None:
+            if compact:
+                Y.zero_()
+                Y[(rows >= 0).nonzero().ravel()] = part
+            else:
+                Y[listed] = part
+        if acc is not None:
+            acc[listed] += acc_scale * part                # ONLY the listed rows receive the layer's term
         return Y
 
     def grad_scatter(U, V, u, i, j, eps, reg, gU, gV, loss):
@@ -49,6 +67,7 @@ def _stub(monkeypatch, calls):
     adjacency_kernel_stand_ins(monkeypatch)
     monkeypatch.setattr(E, 'spmm_csr', spmm)
     monkeypatch.setattr(E, 'spmm_csr_scatter_rows', scatter_rows)
+    monkeypatch.setattr(E, 'spmm_csr_rows', list_rows)
     monkeypatch.setattr(E, 'bpr_grad_scatter', grad_scatter)
     monkeypatch.setattr(E, 'axpby', lambda dst, a, b, alpha, beta: dst.copy_(alpha * a + beta * b))
     monkeypatch.setattr(E, 'adam_dense_tf1', lambda var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8:
@@ -85,9 +104,10 @@ def test_lightgcn_step_equals_oracle_restatement(golden_graph, graph_ids, monkey
         np.testing.assert_allclose(m.ego[:U_, :50].numpy(), Ur, rtol=2e-3, atol=2e-5)
         np.testing.assert_allclose(m.ego[U_:, :50].numpy(), Vr, rtol=2e-3, atol=2e-5)
         assert float(m.ego[:, 50:].abs().sum()) == 0.0                     # padding columns never move
-    # per step: n forward SpMMs, one sparse-source product + (n - 1) SpMMs backward
+    # per step: (n - 1) forward SpMMs + the last layer on the batch's rows only; one sparse-source product
+    # + (n - 1) SpMMs backward
     n = m.n_layers
-    assert calls == (['spmm'] * n + ['scatter_rows'] + ['spmm'] * (n - 1)) * 3
+    assert calls == (['spmm'] * (n - 1) + ['rows', 'scatter_rows'] + ['spmm'] * (n - 1)) * 3
     Ue, Ve = m.propagate()
     fu, fv, _ = O.lightgcn_forward(adj, Ur, Vr, n)
     np.testing.assert_allclose(Ue[:, :50].numpy(), fu, rtol=2e-3, atol=2e-5)

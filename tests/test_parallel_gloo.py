@@ -259,7 +259,7 @@ def test_sharded_item_table_bpr_world2():
 # ---------------------------------------------------------------------------------------------
 # LightGCN, user-partitioned / item-replicated: one all-reduce of the item block per layer
 # ---------------------------------------------------------------------------------------------
-def _user_sharded_worker(rank, world, port, out, blocks=1):
+def _user_sharded_worker(rank, world, port, out, blocks=1, row_lists=False):
     import numpy as np
     from oracle import bpr_oracle as O
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
@@ -290,11 +290,41 @@ def _user_sharded_worker(rank, world, port, out, blocks=1):
             l, a, b = O.bpr_loss_grad(Ue.numpy(), Ve.numpy(), u.numpy()[keep], i.numpy()[keep], j.numpy()[keep], 10e-8, reg)
             gU.add_(torch.from_numpy(a).float()); gV.add_(torch.from_numpy(b).float())
             loss += l
+        calls = []
+
+        def dense(Ablk, n_cols):
+            return torch.sparse_csr_tensor(Ablk[0], Ablk[1].long(), Ablk[2], size=(Ablk[0].numel() - 1, n_cols)).to_dense()
+
+        def scatter(Ablk, rows, X, Y, acc, s):               # Y = B^T X over the edge lists of the listed source rows
+            calls.append('scatter')
+            listed = rows[rows >= 0].long()
+            assert listed.numel() == torch.unique(listed).numel()
+            keep = torch.zeros(X.shape[0], dtype=torch.bool); keep[listed] = True
+            assert float(X[~keep].abs().sum()) == 0.0        # the caller's claim
+            Y.copy_(dense(Ablk, Y.shape[0]).t() @ X)
+            if acc is not None:
+                acc.add_(Y, alpha=s)
+
+        def list_rows(Ablk, rows, X, Y, compact, acc, s):    # the listed rows of A X, nothing else
+            calls.append('rows')
+            listed = rows[rows >= 0].long()
+            assert listed.numel() == torch.unique(listed).numel()
+            part = dense(Ablk, X.shape[0])[listed] @ X
+            if Y is not None:
+                assert compact
+                Y.zero_(); Y[(rows >= 0).nonzero().ravel()] = part
+            if acc is not None:
+                acc[listed] += s * part
+
+        def scatter_add(G, idx, src, s):
+            ok = idx >= 0
+            G.index_add_(0, idx[ok].long(), s * src[ok])
+        extra = dict(scatter=scatter, rows=list_rows, scatter_add=scatter_add) if row_lists else {}
         m = parallel.UserShardedLightGCN(
             A_ui, A_iu, torch.from_numpy(ego[lo:hi].copy()), torch.from_numpy(ego[U:].copy()), L, lr, reg, lo,
             spmm=spmm, grad=grad, adam=lambda var, mm, v, g, t: O.adam_tf1(var.numpy(), mm.numpy(), v.numpy(), g.numpy(), lr, t),
             scale=lambda dst, src, s: dst.copy_(src * s), axpy=lambda dst, src, s: dst.add_(src, alpha=s),
-            item_side_blocks=blocks)
+            item_side_blocks=blocks, **extra)
         Ur, Vr = ego[:U].copy(), ego[U:].copy()
         mU, vU, mV, vV = (np.zeros_like(x) for x in (Ur, Ur, Vr, Vr))
         for step in range(3):
@@ -305,9 +335,22 @@ def _user_sharded_worker(rank, world, port, out, blocks=1):
             assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
             assert np.allclose(m.Eu.numpy(), Ur[lo:hi], rtol=1e-3, atol=1e-6), (rank, step)
             assert np.allclose(m.Ei.numpy(), Vr, rtol=1e-3, atol=1e-6), (rank, step)
+        if row_lists:       # per step: last forward layer = 2 listed-row products, first backward layer = 2 scatters
+            assert calls == (['rows', 'rows', 'scatter', 'scatter']) * 3, calls
         out[rank] = 1
     finally:
         dist.destroy_process_group()
+
+
+def test_user_sharded_lightgcn_row_restricted_layers_world2():
+    """The row-restricted layers of the sharded step (last forward layer evaluated on the batch's rows only, with
+    the ranks' [rows, d] partial blocks all-reduced instead of the whole item block; first backward layer
+    scattered from the batch's rows): same trajectory as the single-process oracle, which propagates every row."""
+    port = 35900 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_user_sharded_worker, args=(2, port, out, 1, True), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
 
 
 def test_user_sharded_lightgcn_matches_single_process_world2():

@@ -4,10 +4,10 @@ set -u
 out=gpurun_out/final_run
 mkdir -p "$out"
 python -c "import __graft_entry__ as g; g.build()" > "$out/build.log" 2>&1 || { echo "build failed"; tail -20 "$out/build.log"; exit 1; }
-timeout 1800 python -m pytest tests/ -x -q -m gpu > "$out/pytest_gpu.log" 2>&1; echo "pytest -x -m gpu: exit $? -- $(tail -1 "$out/pytest_gpu.log")"
+timeout 1800 python -m pytest tests/ -q -m gpu > "$out/pytest_gpu.log" 2>&1; echo "pytest -x -m gpu: exit $? -- $(tail -1 "$out/pytest_gpu.log")"
 grep -E "^(FAILED|ERROR)" "$out/pytest_gpu.log" | head
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > "$out/smoke.log" 2>&1; echo "smoke: exit $? -- $(tail -1 "$out/smoke.log")"
-/usr/bin/time -v timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > "$out/bench.json" 2> "$out/bench.err"; echo "bench: exit $? wall $(grep 'Elapsed (wall' "$out/bench.err" | awk '{print $NF}')"
+t0=$(date +%s); timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > "$out/bench.json" 2> "$out/bench.err"; echo "bench: exit $? wall $(( $(date +%s) - t0 )) s"
 timeout 600 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > "$out/bench_reference.json" 2> "$out/bench_reference.err"; echo "reference arm: exit $?"
 timeout 600 python tools/bench_models.py --steps 5 > "$out/bench_models.jsonl" 2> "$out/bench_models.err"; echo "bench_models: exit $?"; cut -c1-200 "$out/bench_models.jsonl"
 python - <<PY
