@@ -538,10 +538,13 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
         ms = float(tms.item())
         n_steps = -(-U * DEGREE // B)
         full_products = 2 * layers - (2 if (B <= 8192 and layers > 1) else 0)       # whole-graph SpMMs actually executed
-        step_bytes = full_products * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
+        rest_bytes = (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
+        executed_bytes = full_products * spmm_algo + rest_bytes
+        step_bytes = 2 * layers * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
         res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
                                'epoch_extrapolated_from_steps': steps, 'algorithmic_GB_per_step': step_bytes / 1e9,
-                               'whole_graph_products_per_step': full_products,
+                               'whole_graph_products_per_step': full_products, 'executed_GB_per_step': executed_bytes / 1e9,
+                               'frac_of_hbm_peak_executed': executed_bytes / ms / 1e6 / (peak * world),
                                'frac_of_hbm_peak_whole_job': step_bytes / ms / 1e6 / (peak * world), 'loss': float(m.loss.item())}
         del batches
     if world == 1:

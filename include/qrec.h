@@ -437,6 +437,13 @@ int qrec_simgcl_perturb_f32(float* dev_E, int64_t n_rows, int32_t d, int32_t d_v
 int qrec_simgcl_perturb_rows_f32(float* dev_E, int64_t n_rows, int64_t row_offset, int32_t d, int32_t d_valid,
                                  float eps, uint64_t seed, uint32_t tag, uint32_t step, float* dev_acc,
                                  float acc_scale, void* stream);
+/* The same perturbation for a LIST of rows held compactly: row k of dev_Ec ([n_list, d], e.g. the compact output of
+ * qrec_spmm_csr_rows_f32) stands for table row dev_rows[k] (global row row_offset + dev_rows[k]); entries -1 are
+ * skipped.  Ec[k] is perturbed in place and acc[dev_rows[k]] += acc_scale * Ec[k] (the last encoder layer of a
+ * minibatch step, of which the losses of model/ranking/SimGCL.py:60-78,92-96 read the batch's rows only). */
+int qrec_simgcl_perturb_listed_f32(float* dev_Ec, const int32_t* dev_rows, int64_t n_list, int64_t row_offset,
+                                   int32_t d, int32_t d_valid, float eps, uint64_t seed, uint32_t tag, uint32_t step,
+                                   float* dev_acc, float acc_scale, void* stream);
 
 /* Z[r,:] = l2_normalize(T[idx[r],:]) (tf.nn.l2_normalize, epsilon 1e-12 on the squared norm);
  * norms[r] = the divisor.  SimGCL.py:61-69. */

@@ -124,6 +124,8 @@ SIGNATURES = {
                                           C.c_uint32, vp, C.c_float, vp]),
     'qrec_simgcl_perturb_rows_f32': (C.c_int, [vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32,
                                                C.c_uint32, vp, C.c_float, vp]),
+    'qrec_simgcl_perturb_listed_f32': (C.c_int, [vp, vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_float, C.c_uint64, C.c_uint32,
+                                                  C.c_uint32, vp, C.c_float, vp]),
     'qrec_gather_normalize_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, vp, vp]),
     'qrec_infonce_rows_f32': (C.c_int, [vp, C.c_int32, C.c_float, vp, vp]),
     'qrec_normalize_bwd_scatter_f32': (C.c_int, [vp, vp, vp, vp, C.c_int32, C.c_int32, C.c_float, vp, vp]),

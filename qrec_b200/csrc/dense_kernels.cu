@@ -32,13 +32,19 @@ int sm_count() {
 __global__ void __launch_bounds__(256)
 simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, int d_valid, float eps, uint32_t k0,
                       uint32_t k1, uint32_t tag, uint32_t step, float* __restrict__ acc,
-                      float acc_scale, long long row_off) {   // row_off: global id of row 0 (row-sharded tables)
+                      float acc_scale, long long row_off,     // row_off: global id of row 0 (row-sharded tables)
+                      const int* __restrict__ row_list) {     // non-null: E is compact, row k belongs to table row row_list[k]
   const int lane = threadIdx.x & 31;
   const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
   for (long long r = warp; r < n_rows; r += nwarps) {
     float4* row = reinterpret_cast<float4*>(E) + r * nvec;
-    const unsigned long long gr = (unsigned long long)(r + row_off);   // the noise is a function of the GLOBAL row
+    long long tr = r;                                         // row of the table (and of acc) this row of E stands for
+    if (row_list != nullptr) {
+      tr = __ldg(row_list + r);
+      if (tr < 0) continue;                                   // padding entry of a fixed-length row list
+    }
+    const unsigned long long gr = (unsigned long long)(tr + row_off);   // the noise is a function of the GLOBAL row
     float ss = 0.f;
     // first pass: squared norm of the row's noise (regenerated below; Philox is cheaper than HBM)
     for (int v = lane; v < nvec; v += 32) {
@@ -62,7 +68,7 @@ simgcl_perturb_kernel(float* __restrict__ E, long long n_rows, int nvec, int d_v
       e.w += sgn(e.w) * u01(w[3]) * inv;
       row[v] = e;
       if (acc != nullptr) {
-        float4* ap = reinterpret_cast<float4*>(acc) + r * nvec + v;
+        float4* ap = reinterpret_cast<float4*>(acc) + tr * nvec + v;
         float4 o = *ap;
         o.x += acc_scale * e.x; o.y += acc_scale * e.y; o.z += acc_scale * e.z; o.w += acc_scale * e.w;
         *ap = o;
@@ -557,7 +563,20 @@ int qrec_simgcl_perturb_rows_f32(float* E, int64_t n_rows, int64_t row_offset, i
   QREC_REQUIRE(E != nullptr, "qrec_simgcl_perturb_f32: null table");
   simgcl_perturb_kernel<<<grid_for(n_rows, 8), 256, 0, (cudaStream_t)stream>>>(
       E, n_rows, d / 4, (d_valid > 0 && d_valid < d) ? d_valid : d, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc,
-      acc_scale, row_offset);
+      acc_scale, row_offset, nullptr);
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_simgcl_perturb_listed_f32(float* Ec, const int32_t* rows, int64_t n_list, int64_t row_offset, int32_t d,
+                                   int32_t d_valid, float eps, uint64_t seed, uint32_t tag, uint32_t step, float* acc,
+                                   float acc_scale, void* stream) {
+  QREC_REQUIRE(n_list >= 0 && row_offset >= 0 && d >= 4 && d % 4 == 0, "qrec_simgcl_perturb_listed_f32: bad shape (d multiple of 4)");
+  if (n_list == 0) return QREC_OK;
+  QREC_REQUIRE(Ec != nullptr && rows != nullptr, "qrec_simgcl_perturb_listed_f32: null pointer");
+  simgcl_perturb_kernel<<<grid_for(n_list, 8), 256, 0, (cudaStream_t)stream>>>(
+      Ec, n_list, d / 4, (d_valid > 0 && d_valid < d) ? d_valid : d, eps, (uint32_t)seed, (uint32_t)(seed >> 32), tag, step, acc,
+      acc_scale, row_offset, rows);
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

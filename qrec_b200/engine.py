@@ -700,6 +700,17 @@ def simgcl_perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0
     return Emb
 
 
+def simgcl_perturb_listed(Ec, rows, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
+    """simgcl_perturb for a compact block: row k of Ec stands for table row rows[k] (-1 = padding, skipped);
+    acc[rows[k]] += acc_scale * perturbed row."""
+    torch = _torch()
+    check(lib.qrec_simgcl_perturb_listed_f32(_dev(Ec, torch.float32, 'Ec'), _dev(rows, torch.int32, 'rows'), rows.shape[0],
+                                             int(row_offset), Ec.shape[1], int(d_valid), float(eps), int(seed), int(tag),
+                                             int(step), _dev(acc, torch.float32, 'acc') if acc is not None else None,
+                                             float(acc_scale), _stream()), 'qrec_simgcl_perturb_listed_f32')
+    return Ec
+
+
 def gather_normalize(T, idx, Z, norms):
     torch = _torch()
     check(lib.qrec_gather_normalize_f32(_dev(T, torch.float32, 'T'), _dev(idx, torch.int32, 'idx'), idx.shape[0],

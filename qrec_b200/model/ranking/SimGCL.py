@@ -66,14 +66,25 @@ class SimGCL(GraphRecommender):
         self.noise_seed = self.engine_seed + 0x5151
 
     # ------------------------------------------------------------------ encoders
-    def encode(self, out, perturbed=0):
-        """mean(E_1..E_n) into `out` (E0 excluded: SimGCL.py:23-28).  perturbed = 0 | 1 | 2."""
+    def encode(self, out, perturbed=0, rows=None):
+        """mean(E_1..E_n) into `out` (E0 excluded: SimGCL.py:23-28).  perturbed = 0 | 1 | 2.
+        rows (int32, distinct, -1 padded): the only rows of `out` the caller reads -- the last layer (product and
+        noise) is then evaluated on those rows alone; the other rows of `out` lack its term."""
         from ... import engine as E
         s = 1.0 / self.n_layers
         out.zero_()
         cur = self.ego
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
+            if rows is not None and k == self.n_layers - 1 and k > 0:
+                if perturbed:
+                    part = self._rows_block(rows.shape[0])
+                    self.norm_adj.matmul_rows(cur, rows, out=part, compact=True)
+                    E.simgcl_perturb_listed(part, rows, self.eps, self.noise_seed, perturbed * 16 + k, self._step, acc=out,
+                                            acc_scale=s, d_valid=self.emb_size)
+                else:
+                    self.norm_adj.matmul_rows(cur, rows, acc=out, acc_scale=s)
+                break
             if perturbed:
                 self.norm_adj.matmul(cur, nxt)
                 E.simgcl_perturb(nxt, self.eps, self.noise_seed, perturbed * 16 + k, self._step, acc=out, acc_scale=s,
@@ -82,6 +93,12 @@ class SimGCL(GraphRecommender):
                 self.norm_adj.matmul(cur, nxt, acc=out, acc_scale=s)
             cur = nxt
         return out[:self.num_users], out[self.num_users:]
+
+    def _rows_block(self, n):
+        import torch
+        if getattr(self, '_rows_buf', None) is None or self._rows_buf.shape[0] < n:
+            self._rows_buf = torch.empty(n, self.emb_pad, device=self.device)
+        return self._rows_buf[:n]
 
     def _infonce(self, tab1, tab2, idx, grad_rows):
         import torch
@@ -108,9 +125,15 @@ class SimGCL(GraphRecommender):
         from ... import engine as E
         nu = self.num_users
         self._step += 1
-        mU, mV = self.encode(self._main, 0)
-        p1U, p1V = self.encode(self._pert[0], 1)
-        p2U, p2V = self.encode(self._pert[1], 2)
+        # the rows the batch touches: every loss term reads the encoders' outputs there and nowhere else, and the
+        # summed loss gradient is zero everywhere else (sorted, repeats replaced by -1: no data-dependent length)
+        rows = None
+        if u.shape[0] <= 8192 and self.emb_pad <= 128 and self.n_layers > 1 and hasattr(self.norm_adj, 'matmul_rows'):
+            from ...parallel import _sorted_unique_padded
+            rows = _sorted_unique_padded(torch.cat([u, i + nu, j + nu]))
+        mU, mV = self.encode(self._main, 0, rows)
+        p1U, p1V = self.encode(self._pert[0], 1, rows)
+        p2U, p2V = self.encode(self._pert[1], 2, rows)
         self._grad.zero_()
         self._loss.zero_()
         E.bpr_grad_scatter(mU, mV, u, i, j, BPR_EPS, self.regU, self._grad[:nu], self._grad[nu:], self._loss[0:1])
@@ -123,7 +146,11 @@ class SimGCL(GraphRecommender):
         cur = self._grad
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
-            self.norm_adj.matmul(cur, nxt, acc=self._total, acc_scale=1.0 / self.n_layers)
+            if k == 0 and rows is not None:
+                # the gradient is non-zero only in the batch's rows: scatter along their edges
+                self.norm_adj.matmul_sparse_rows(cur, rows, nxt, acc=self._total, acc_scale=1.0 / self.n_layers)
+            else:
+                self.norm_adj.matmul(cur, nxt, acc=self._total, acc_scale=1.0 / self.n_layers)
             cur = nxt
         E.adam_dense_tf1(self.ego, self._adam_m, self._adam_v, self._total, self.lRate, self._step)
         return self._loss

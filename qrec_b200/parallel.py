@@ -637,10 +637,10 @@ class UserShardedLightGCN(object):
         self._scatter_add = scatter_add or (lambda G, idx, src, s: E.scatter_add_rows(G, idx, src, scale=s))
         self._need = {}
 
-    def _need_buf(self, n):
-        if n not in self._need:
-            self._need[n] = torch.empty(n, self.Ei.shape[1], device=self.Ei.device)
-        return self._need[n]
+    def _need_buf(self, n, slot=0):
+        if (n, slot) not in self._need:
+            self._need[(n, slot)] = torch.empty(n, self.Ei.shape[1], device=self.Ei.device)
+        return self._need[(n, slot)]
 
     def _allreduce(self, t):
         if dist.is_initialized() and dist.get_world_size(self.group) > 1:
@@ -755,13 +755,37 @@ class UserShardedSimGCL(UserShardedLightGCN):
         self.losses_dev = torch.zeros(2, dtype=torch.float64, device=dev)       # [rec, cl (unscaled)]
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
 
-    def _encode(self, out_u, out_i, view):
-        """out <- mean(E_1..E_n) of encoder `view` (0 clean, 1 / 2 perturbed); SimGCL.py:22-38."""
+    def _encode(self, out_u, out_i, view, need_u=None, need_i=None):
+        """out <- mean(E_1..E_n) of encoder `view` (0 clean, 1 / 2 perturbed); SimGCL.py:22-38.
+        need_u / need_i (sorted, distinct, -1 padded): the only rows of out_u / out_i the losses read -- the last
+        layer (product, noise, and the exchange: a [rows, d] block instead of the whole item block) is then
+        evaluated on those rows alone."""
         E, s = self.E, 1.0 / self.n_layers
         out_u.zero_(); out_i.zero_()
         cu, ci = self.Eu, self.Ei
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            if need_u is not None and k == self.n_layers - 1 and k > 0:
+                part_i = self._need_buf(need_i.shape[0])
+                self._rows(self.A_iu, need_i, cu, part_i, True, None, 0.0)      # this rank's partial sums of the listed item rows
+                work = None
+                if self.world > 1:
+                    work = dist.all_reduce(part_i, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+                if view == 0:
+                    self._rows(self.A_ui, need_u, ci, None, False, out_u, s)
+                else:
+                    part_u = self._need_buf(need_u.shape[0], 1)
+                    self._rows(self.A_ui, need_u, ci, part_u, True, None, 0.0)
+                    E.simgcl_perturb_listed(part_u, need_u, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_u,
+                                            acc_scale=s, d_valid=self.d_valid, row_offset=self.lo)
+                if work is not None:
+                    work.wait()
+                if view == 0:
+                    self._scatter_add(out_i, need_i, part_i, s)
+                else:                                                           # sign() of the FULL sum: after the all-reduce
+                    E.simgcl_perturb_listed(part_i, need_i, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_i,
+                                            acc_scale=s, d_valid=self.d_valid, row_offset=self.U_total)
+                break
             self._spmm(self.A_iu, cu, ni_, None, 0.0)                       # item side: this rank's partial sums
             work = self._allreduce_async(ni_)
             if view == 0:
@@ -779,16 +803,24 @@ class UserShardedSimGCL(UserShardedLightGCN):
                                  d_valid=self.d_valid, row_offset=self.U_total)
             cu, ci = nu_, ni_
 
-    def _backward(self, gu, gi, tot_u, tot_i):
-        """tot <- 1/n * sum_{k=1..n} A^k G (the encoders' common backward map; E_0 is not in the mean)."""
+    def _backward(self, gu, gi, tot_u, tot_i, nz_u=None, nz_i=None):
+        """tot <- 1/n * sum_{k=1..n} A^k G (the encoders' common backward map; E_0 is not in the mean).
+        nz_u / nz_i: the only non-zero rows of gu / gi -- the first layer scatters along those rows' edges."""
         s = 1.0 / self.n_layers
         tot_u.zero_(); tot_i.zero_()
         cu, ci = gu, gi
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
-            self._spmm(self.A_iu, cu, ni_, None, 0.0)
+            sparse = k == 0 and nz_u is not None
+            if sparse:
+                self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)     # A_iu G_u through the users' edge lists
+            else:
+                self._spmm(self.A_iu, cu, ni_, None, 0.0)
             work = self._allreduce_async(ni_)
-            self._spmm(self.A_ui, ci, nu_, tot_u, s)
+            if sparse:
+                self._scatter(self.A_iu, nz_i, ci, nu_, tot_u, s)      # A_ui G_i through the items' edge lists
+            else:
+                self._spmm(self.A_ui, ci, nu_, tot_u, s)
             if work is not None:
                 work.wait()
             self._axpy(tot_i, ni_, s)
@@ -833,9 +865,16 @@ class UserShardedSimGCL(UserShardedLightGCN):
         E = self.E
         self.step += 1
         nloc = self.Eu.shape[0]
-        self._encode(self.mean_u, self.mean_i, 0)
-        self._encode(self.p_u[0], self.p_i[0], 1)
-        self._encode(self.p_u[1], self.p_i[1], 2)
+        # the rows the batch touches (local users; items): all the losses read of the encoders' outputs, and the only
+        # rows where the summed loss gradient is non-zero
+        rows_u = rows_i = None
+        if u.shape[0] <= 8192 and self.Eu.shape[1] <= 128 and self.n_layers > 1 and self._rows is not None:
+            lu_all = u - self.lo
+            lu_all = torch.where((lu_all >= 0) & (lu_all < nloc), lu_all, torch.full_like(lu_all, -1))
+            rows_u, rows_i = _sorted_unique_padded(lu_all), _sorted_unique_padded(torch.cat([i, j]))
+        self._encode(self.mean_u, self.mean_i, 0, rows_u, rows_i)
+        self._encode(self.p_u[0], self.p_i[0], 1, rows_u, rows_i)
+        self._encode(self.p_u[1], self.p_i[1], 2, rows_u, rows_i)
         mine = (u >= self.lo) & (u < self.lo + nloc)
         lu, li, lj = (u[mine] - self.lo).contiguous(), i[mine].contiguous(), j[mine].contiguous()
         self.gu.zero_(); self.gi.zero_(); self.losses_dev.zero_()
@@ -849,7 +888,7 @@ class UserShardedSimGCL(UserShardedLightGCN):
         self._infonce(self.p_u[0], self.p_u[1], uu.shape[0], own, (uu[own] - self.lo).int().contiguous(), self.gu, False)
         allpos = torch.arange(ii.shape[0], device=ii.device)
         self._infonce(self.p_i[0], self.p_i[1], ii.shape[0], allpos, ii.contiguous(), self.gi, True)
-        self._backward(self.gu, self.gi, self.tot_u, self.tot_i)
+        self._backward(self.gu, self.gi, self.tot_u, self.tot_i, rows_u, rows_i)
         self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
         self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
         return self.losses_dev

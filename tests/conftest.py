@@ -97,3 +97,80 @@ def adjacency_kernel_stand_ins(monkeypatch):
         return vals
     monkeypatch.setattr(E, 'adj_line_weights', line_weights)
     monkeypatch.setattr(E, 'adj_normalize', normalize)
+
+
+def row_list_kernel_stand_ins(monkeypatch):
+    """numpy / torch restatements of the contracts of the row-list kernels (include/qrec.h: qrec_spmm_csr_rows_f32,
+    qrec_spmm_csr_scatter_rows_f32, qrec_simgcl_perturb_{rows,listed}_f32, qrec_scatter_add_rows_f32) for the CPU
+    tests of the classes that compose them.  Each stand-in asserts the caller's side of the contract (distinct
+    listed rows; the source is zero outside the listed rows)."""
+    import numpy as np
+    import scipy.sparse as sp
+    import torch
+    from oracle import tf_models
+    from qrec_b200 import engine as E
+    calls = []
+
+    def dense(rowptr, cols, vals, n_cols):
+        return sp.csr_matrix((vals.numpy(), cols.numpy(), rowptr.numpy()), shape=(rowptr.numel() - 1, n_cols))
+
+    def listed(rows):
+        got = rows[rows >= 0].long()
+        assert got.numel() == torch.unique(got).numel(), 'listed rows must be distinct'
+        return got
+
+    def spmm_rows(rowptr, cols, vals, rows, X, Y=None, compact=False, acc=None, acc_scale=0.0):
+        calls.append('rows')
+        got = listed(rows)
+        part = torch.from_numpy(np.asarray(dense(rowptr, cols, vals, X.shape[0])[got.numpy()] @ X.numpy())).float()
+        if Y is not None:
+            if compact:
+                Y.zero_()
+                Y[(rows >= 0).nonzero().ravel()] = part
+            else:
+                Y[got] = part
+        if acc is not None:
+            acc[got] += acc_scale * part
+        return Y
+
+    def scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scale=0.0):
+        calls.append('scatter_rows')
+        keep = torch.zeros(X.shape[0], dtype=torch.bool)
+        keep[listed(src_rows)] = True
+        assert float(X[~keep].abs().sum()) == 0.0, 'the source must be zero outside the listed rows'
+        Y.copy_(torch.from_numpy(np.asarray(dense(rowptr, cols, vals, Y.shape[0]).T @ X.numpy())).float())
+        if acc is not None:
+            acc.add_(Y, alpha=acc_scale)
+        return Y
+
+    def _noise(n_rows, d, seed, tag, step, d_valid):
+        nz = torch.from_numpy(tf_models.philox_uniform(n_rows, d, seed, tag, step)).float()
+        if 0 < d_valid < d:
+            nz[:, d_valid:] = 0.0
+        return nz / nz.norm(dim=1, keepdim=True).clamp(min=1e-6)
+
+    def perturb(Emb, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
+        nz = _noise(row_offset + Emb.shape[0], Emb.shape[1], seed, tag, step, d_valid)[row_offset:]
+        Emb.add_(torch.sign(Emb) * nz * eps)
+        if acc is not None:
+            acc.add_(Emb, alpha=acc_scale)
+        return Emb
+
+    def perturb_listed(Ec, rows, eps, seed, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
+        calls.append('perturb_listed')
+        got, slots = listed(rows), (rows >= 0).nonzero().ravel()
+        nz = _noise(row_offset + int(got.max()) + 1 if got.numel() else 1, Ec.shape[1], seed, tag, step, d_valid)
+        Ec[slots] = Ec[slots] + torch.sign(Ec[slots]) * nz[row_offset + got] * eps
+        if acc is not None:
+            acc[got] += acc_scale * Ec[slots]
+        return Ec
+
+    def scatter_add_rows(G, idx, src, scale=1.0):
+        ok = idx >= 0
+        G.index_add_(0, idx[ok].long(), scale * src[ok])
+        return G
+
+    for name, fn in (('spmm_csr_rows', spmm_rows), ('spmm_csr_scatter_rows', scatter_rows), ('simgcl_perturb', perturb),
+                     ('simgcl_perturb_listed', perturb_listed), ('scatter_add_rows', scatter_add_rows)):
+        monkeypatch.setattr(E, name, fn)
+    return calls

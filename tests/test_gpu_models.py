@@ -63,6 +63,22 @@ def test_perturb_matches_definition(torch, E):
     delta = Xd.cpu().numpy() - X
     np.testing.assert_allclose(np.linalg.norm(delta[10:], axis=1), eps, rtol=1e-4)
     assert np.all(np.sign(Xd.cpu().numpy()) == np.sign(X))
+    # the listed-rows form (compact block + row list with padding, rows of a row-sharded table at offset 100):
+    # bit-identical to the whole-table call on those rows, acc touched at the listed rows only
+    rows = np.array([7, -1, 150, 3, -1, 199], np.int32)
+    Xs = X[100:]                                                      # the "shard": global rows 100..299
+    whole, acc_w = _dev(torch, Xs), _dev(torch, acc0[100:])
+    E.simgcl_perturb(whole, eps, 0xabcdef0123, 17, 3, acc=acc_w, acc_scale=0.5, row_offset=100)
+    block = np.zeros((len(rows), d), np.float32)
+    block[rows >= 0] = Xs[rows[rows >= 0]]
+    blk, acc_l = _dev(torch, block), _dev(torch, acc0[100:])
+    E.simgcl_perturb_listed(blk, _dev(torch, rows), eps, 0xabcdef0123, 17, 3, acc=acc_l, acc_scale=0.5, row_offset=100)
+    sel = rows[rows >= 0]
+    assert np.array_equal(blk.cpu().numpy()[rows >= 0], whole.cpu().numpy()[sel])
+    assert np.all(blk.cpu().numpy()[rows < 0] == 0.0)
+    assert np.array_equal(acc_l.cpu().numpy()[sel], acc_w.cpu().numpy()[sel])
+    other = np.setdiff1d(np.arange(200), sel)
+    assert np.array_equal(acc_l.cpu().numpy()[other], acc0[100:][other])
 
 
 def test_infonce_block_vs_autograd(torch, E):

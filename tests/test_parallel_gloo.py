@@ -475,14 +475,8 @@ def _simgcl_worker(rank, world, port, out):
         U, I, d, L, lr, reg, cl_rate, eps, seed = 9, 6, 8, 2, 0.01, 0.001, 0.5, 0.1, 0x5151
         A = _toy_graph(U, I, seed=3)
 
-        def perturb(Emb, eps_, seed_, tag, step, acc=None, acc_scale=0.0, d_valid=0, row_offset=0):
-            nz = tf_models.philox_uniform(row_offset + Emb.shape[0], Emb.shape[1], seed_, tag, step)[row_offset:]
-            nz = torch.from_numpy(nz).float()
-            Emb.add_(torch.sign(Emb) * nz / nz.norm(dim=1, keepdim=True).clamp(min=1e-6) * eps_)
-            if acc is not None:
-                acc.add_(Emb, alpha=acc_scale)
-            return Emb
-        E.simgcl_perturb = perturb
+        from conftest import row_list_kernel_stand_ins
+        calls = row_list_kernel_stand_ins(_Setattr)             # incl. the noise, keyed by the GLOBAL row
         rp, co, va = (torch.from_numpy(x) for x in (A.indptr.astype(np.int64), A.indices.astype(np.int32), A.data))
         A_ui, A_iu, (lo, hi) = parallel.shard_bipartite_by_user(rp, co, va, U, I, rank, world)
         rng = np.random.default_rng(1)
@@ -510,6 +504,10 @@ def _simgcl_worker(rank, world, port, out):
             others = [None] * world
             dist.all_gather_object(others, m.Ei.numpy().copy())
             assert all(np.array_equal(others[0], o) for o in others)
+        # per step: three encoders whose last layer runs on the batch's rows (2 listed-row products each, + the noise on
+        # both blocks for the two perturbed views), and a backward pass whose first layer is 2 scatters
+        per_step = ['rows', 'rows'] + ['rows', 'rows', 'perturb_listed', 'perturb_listed'] * 2 + ['scatter_rows'] * 2
+        assert calls == per_step * 2, calls
         out[rank] = 1
     finally:
         dist.destroy_process_group()
