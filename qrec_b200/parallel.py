@@ -587,7 +587,7 @@ class UserShardedLightGCN(object):
 
     def __init__(self, A_ui, A_iu, E_u_local, E_i, n_layers, lr, reg, user_lo, group=None,
                  spmm=None, grad=None, adam=None, scale=None, axpy=None, item_side_blocks=1,
-                 scatter=None, rows=None, scatter_add=None):
+                 scatter=None, rows=None, scatter_add=None, gather=None):
         """item_side_blocks > 1 (experimental, default off): the item-side product A_iu E_u runs as that
         many passes over column blocks of local users (split_csr_columns / blocked_spmm), so each pass
         gathers user rows from a slice of E_u that fits the L2."""
@@ -635,6 +635,7 @@ class UserShardedLightGCN(object):
         self._rows = rows or (None if spmm is not None else (
             lambda A, rows, X, Y, compact, acc, s: E.spmm_csr_rows(A[0], A[1], A[2], rows, X, Y, compact=compact, acc=acc, acc_scale=s)))
         self._scatter_add = scatter_add or (lambda G, idx, src, s: E.scatter_add_rows(G, idx, src, scale=s))
+        self._gather = gather or (None if spmm is not None else (lambda T, idx, out: E.gather_rows(T, idx, out)))
         self._need = {}
 
     def _need_buf(self, n, slot=0):
@@ -713,7 +714,16 @@ class UserShardedLightGCN(object):
         self._propagate(self.Eu, self.Ei, self.mean_u, self.mean_i, need_u=rows_u, need_i=rows_i)
         self.gu.zero_(); self.gi.zero_(); self.loss.zero_()
         self._grad(self.mean_u, self.mean_i, lu, i, j, self.gu, self.gi, self.loss)
-        self._allreduce(self.gi)                              # item gradients: sum of the ranks' partials
+        if rows_i is not None and self._gather is not None and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            # item gradients are non-zero in the batch's item rows only: the ranks' partial sums travel as one
+            # [rows, d] block (1 MB at B = 2048) instead of the whole [I, d] table
+            part = self._need_buf(rows_i.shape[0], 2)
+            self._gather(self.gi, rows_i, part)
+            self._allreduce(part)
+            self.gi.zero_()
+            self._scatter_add(self.gi, rows_i, part, 1.0)
+        else:
+            self._allreduce(self.gi)                          # item gradients: sum of the ranks' partials
         self._allreduce(self.loss)
         self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=rows_u, nz_i=rows_i)
         self.step += 1
@@ -880,7 +890,14 @@ class UserShardedSimGCL(UserShardedLightGCN):
         self.gu.zero_(); self.gi.zero_(); self.losses_dev.zero_()
         if lu.numel():
             E.bpr_grad_scatter(self.mean_u, self.mean_i, lu, li, lj, 10e-8, self.reg, self.gu, self.gi, self.losses_dev[0:1])
-        self._allreduce(self.gi)                               # BPR item gradients: sum of the ranks' partials
+        if rows_i is not None and self.world > 1:              # BPR item gradients: sum of the ranks' partials,
+            part = self._need_buf(rows_i.shape[0], 2)          # exchanged as the batch's [rows, d] block
+            self._gather(self.gi, rows_i, part)
+            self._allreduce(part)
+            self.gi.zero_()
+            self._scatter_add(self.gi, rows_i, part, 1.0)
+        else:
+            self._allreduce(self.gi)
         self._allreduce(self.losses_dev[0:1])
         uu = torch.unique(u)                                    # tf.unique (order is irrelevant to the sums)
         ii = torch.unique(i).int()

@@ -170,7 +170,13 @@ def row_list_kernel_stand_ins(monkeypatch):
         G.index_add_(0, idx[ok].long(), scale * src[ok])
         return G
 
+    def gather_rows(T, idx, out):
+        ok = idx >= 0
+        out.zero_()
+        out[ok] = T[idx[ok].long()]
+        return out
+
     for name, fn in (('spmm_csr_rows', spmm_rows), ('spmm_csr_scatter_rows', scatter_rows), ('simgcl_perturb', perturb),
-                     ('simgcl_perturb_listed', perturb_listed), ('scatter_add_rows', scatter_add_rows)):
+                     ('simgcl_perturb_listed', perturb_listed), ('scatter_add_rows', scatter_add_rows), ('gather_rows', gather_rows)):
         monkeypatch.setattr(E, name, fn)
     return calls

@@ -319,7 +319,11 @@ def _user_sharded_worker(rank, world, port, out, blocks=1, row_lists=False):
         def scatter_add(G, idx, src, s):
             ok = idx >= 0
             G.index_add_(0, idx[ok].long(), s * src[ok])
-        extra = dict(scatter=scatter, rows=list_rows, scatter_add=scatter_add) if row_lists else {}
+        def gather(T, idx, out_):                            # rows of T at idx; zeros for the -1 padding entries
+            calls.append('gather')
+            out_.zero_(); ok = idx >= 0
+            out_[ok] = T[idx[ok].long()]
+        extra = dict(scatter=scatter, rows=list_rows, scatter_add=scatter_add, gather=gather) if row_lists else {}
         m = parallel.UserShardedLightGCN(
             A_ui, A_iu, torch.from_numpy(ego[lo:hi].copy()), torch.from_numpy(ego[U:].copy()), L, lr, reg, lo,
             spmm=spmm, grad=grad, adam=lambda var, mm, v, g, t: O.adam_tf1(var.numpy(), mm.numpy(), v.numpy(), g.numpy(), lr, t),
@@ -335,8 +339,8 @@ def _user_sharded_worker(rank, world, port, out, blocks=1, row_lists=False):
             assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
             assert np.allclose(m.Eu.numpy(), Ur[lo:hi], rtol=1e-3, atol=1e-6), (rank, step)
             assert np.allclose(m.Ei.numpy(), Vr, rtol=1e-3, atol=1e-6), (rank, step)
-        if row_lists:       # per step: last forward layer = 2 listed-row products, first backward layer = 2 scatters
-            assert calls == (['rows', 'rows', 'scatter', 'scatter']) * 3, calls
+        if row_lists:       # per step: last forward layer = 2 listed-row products, the item gradients exchanged as a gathered [rows, d] block, first backward layer = 2 scatters
+            assert calls == (['rows', 'rows', 'gather', 'scatter', 'scatter']) * 3, calls
         out[rank] = 1
     finally:
         dist.destroy_process_group()
