@@ -86,26 +86,35 @@ class SGL(GraphRecommender):
         return views
 
     # ------------------------------------------------------------------ encoders
-    def encode(self, mats, out):
-        """out <- mean(E_0, A_1 E_0, A_2 A_1 E_0, ...) (SGL.py:56-76)."""
+    def encode(self, mats, out, rows=None):
+        """out <- mean(E_0, A_1 E_0, A_2 A_1 E_0, ...) (SGL.py:56-76).
+        rows (int32, distinct, -1 padded): the only rows of `out` the caller reads -- the last layer is then
+        evaluated on those rows alone (the other rows of `out` lack its term)."""
         from ... import engine as E
         s = 1.0 / (self.n_layers + 1)
         E.axpby(out, self.ego, self.ego, s, 0.0)
         cur = self.ego
         for k in range(self.n_layers):
             nxt = self._buf[k % 2]
+            if rows is not None and k == self.n_layers - 1 and k > 0:
+                mats[k].matmul_rows(cur, rows, acc=out, acc_scale=s)
+                break
             mats[k].matmul(cur, nxt, acc=out, acc_scale=s)
             cur = nxt
         return out
 
-    def _backprop(self, mats, G):
-        """self._total += 1/(n+1) (G + A_1 (G + A_2 (... + A_n G))): the encoder's transpose (A symmetric)."""
+    def _backprop(self, mats, G, rows=None):
+        """self._total += 1/(n+1) (G + A_1 (G + A_2 (... + A_n G))): the encoder's transpose (A symmetric).
+        rows: the only non-zero rows of G -- the innermost product scatters along those rows' edges."""
         from ... import engine as E
         s = 1.0 / (self.n_layers + 1)
         cur = G
         for k in range(self.n_layers - 1, -1, -1):
             nxt = self._buf[k % 2]
-            mats[k].matmul(cur, nxt)
+            if rows is not None and k == self.n_layers - 1:
+                mats[k].matmul_sparse_rows(cur, rows, nxt)
+            else:
+                mats[k].matmul(cur, nxt)
             E.axpby(nxt, nxt, G, 1.0, 1.0)
             cur = nxt
         E.axpby(self._total, self._total, cur, 1.0, s)
@@ -117,9 +126,15 @@ class SGL(GraphRecommender):
         nu, d = self.num_users, self.emb_pad
         main_mats = [self.norm_adj] * self.n_layers
         self._step += 1
-        m0 = self.encode(main_mats, self._mean[0])
-        m1 = self.encode(self.views[0], self._mean[1])
-        m2 = self.encode(self.views[1], self._mean[2])
+        # the rows the batch touches: all the losses read of the encoders' outputs, and the only rows where their
+        # gradients are non-zero (sorted, repeats replaced by -1: no data-dependent length)
+        rows = None
+        if u.shape[0] <= 8192 and d <= 128 and self.n_layers > 1:
+            from ...parallel import _sorted_unique_padded
+            rows = _sorted_unique_padded(torch.cat([u, i + nu, j + nu]))
+        m0 = self.encode(main_mats, self._mean[0], rows)
+        m1 = self.encode(self.views[0], self._mean[1], rows)
+        m2 = self.encode(self.views[1], self._mean[2], rows)
         for g in self._grad:
             g.zero_()
         self._loss.zero_()
@@ -140,9 +155,9 @@ class SGL(GraphRecommender):
         E.normalize_bwd_scatter(dZ1, Z1, n1, idx, self.ssl_reg, self._grad[1])
         E.normalize_bwd_scatter(dZ2, Z2, n2, idx, self.ssl_reg, self._grad[2])
         self._total.zero_()
-        self._backprop(main_mats, self._grad[0])
-        self._backprop(self.views[0], self._grad[1])
-        self._backprop(self.views[1], self._grad[2])
+        self._backprop(main_mats, self._grad[0], rows)
+        self._backprop(self.views[0], self._grad[1], rows)
+        self._backprop(self.views[1], self._grad[2], rows)
         E.adam_dense_tf1(self.ego, self._adam_m, self._adam_v, self._total, self.lRate, self._step)
         return self._loss
 

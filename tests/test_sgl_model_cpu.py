@@ -86,6 +86,8 @@ def test_sgl_step_equals_autograd_restatement(golden_graph, monkeypatch, tmp_pat
     from qrec_b200.model.ranking.SGL import SGL
     g = golden_graph
     _stub(monkeypatch)
+    from conftest import row_list_kernel_stand_ins
+    calls = row_list_kernel_stand_ins(monkeypatch)
     monkeypatch.chdir(tmp_path)
     n_tr = 6000
     train = [[u, i, 1.0] for u, i in zip(g['train_users'][:n_tr].tolist(), g['train_items'][:n_tr].tolist())]
@@ -120,4 +122,6 @@ def test_sgl_step_equals_autograd_restatement(golden_graph, monkeypatch, tmp_pat
     assert abs(rec - rrec) <= 1e-5 * abs(rrec) and abs(ssl - rssl) <= 1e-5 * abs(rssl)
     got = m._total[:, :d].numpy()
     assert np.abs(got - rgrad).max() <= 1e-4 * np.abs(rgrad).max()
+    # the last layer of each of the three encoders ran on the batch's rows, the innermost backward product of each as a scatter
+    assert calls == ['rows'] * 3 + ['scatter_rows'] * 3, calls
     assert float(m._total[:, d:].abs().sum()) == 0.0 and float(m.ego[:, d:].abs().sum()) == 0.0   # padding columns never move

@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
-# quick multi-GPU re-check after the sync-free LightGCN step and the NeuMF data-parallel class (N from env)
+# quick multi-GPU re-check (N from env): data-parallel NeuMF, sharded LightGCN / SimGCL with the row-restricted layers, bench line
 set -u
 N=${N:-2}
 out=gpurun_out/multi_check_n$N
@@ -9,6 +9,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 port=29900
 port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_neumf.py --steps 10 > "$out/dist_neumf.log" 2>&1; echo "dist_neumf: exit $? -- $(grep -h '^{' "$out/dist_neumf.log" | cut -c1-900)"; grep -E "AssertionError|Error" "$out/dist_neumf.log" | head -3
 [ "${SKIP_DIST_LGCN:-0}" = 1 ] || { port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 > "$out/dist_lightgcn.log" 2>&1; echo "dist_lightgcn: exit $? -- $(grep -h '^{' "$out/dist_lightgcn.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn.log" | head -3; }
+[ "${SKIP_DIST_SIMGCL:-0}" = 1 ] || { port=$((port+1)); timeout 900 $TR --master-port $port tools/dist_simgcl.py --steps 5 > "$out/dist_simgcl.log" 2>&1; echo "dist_simgcl: exit $? -- $(grep -h '^{' "$out/dist_simgcl.log" | cut -c1-600)"; grep -E "AssertionError|Error" "$out/dist_simgcl.log" | head -3; }
 for w in ${WAVES:-1 2}; do
 port=$((port+1)); timeout 600 $TR --master-port $port bench.py --gpus $N --steps 20 --warmup 5 --q-syncs $w > "$out/bench_w$w.json" 2> "$out/bench_w$w.err"
 python - <<PY
