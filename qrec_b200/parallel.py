@@ -665,40 +665,56 @@ class UserShardedLightGCN(object):
         the LAST layer is evaluated on those rows alone (its output feeds no further layer); the other rows of
         acc then lack the last layer's term.  Both lists are sorted, distinct, -1-padded."""
         s = 1.0 / (self.n_layers + 1)
+        multi = dist.is_initialized() and dist.get_world_size(self.group) > 1
         self._scale(acc_u, src_u, s)
         self._scale(acc_i, src_i, s)
         cu, ci = src_u, src_i
+        pending = None                 # (handle, block) of the previous layer's item-side exchange, still in flight
+
+        def settle():
+            # the previous layer's item block must be the sum over the ranks before anything reads it
+            if pending is not None:
+                if pending[0] is not None:
+                    pending[0].wait()
+                self._axpy(acc_i, pending[1], s)
+
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
+            # Order inside a layer: (1) the item side -- this rank's partial sums, computed from LOCAL user rows only, so it
+            # does not wait for the previous layer's exchange; (2) settle that exchange; (3) start this layer's exchange;
+            # (4) the user side, which reads the previous layer's (now complete) item block.  Every exchange is thus in
+            # flight during two products: the user side of its own layer and the item side of the next.
             if k == self.n_layers - 1 and k > 0 and need_u is not None and self._rows is not None:
-                if dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                if multi:
                     part = self._need_buf(need_i.shape[0])               # this rank's partial sums, one row per list entry
                     self._rows(self.A_iu, need_i, cu, part, True, None, 0.0)
+                    settle()
                     work = dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
                     self._rows(self.A_ui, need_u, ci, None, False, acc_u, s)
                     work.wait()
                     self._scatter_add(acc_i, need_i, part, s)
                 else:
                     self._rows(self.A_iu, need_i, cu, None, False, acc_i, s)
+                    settle()
                     self._rows(self.A_ui, need_u, ci, None, False, acc_u, s)
+                pending = None
                 break
             sparse = k == 0 and nz_u is not None and self._scatter is not None
-            # item side first (this rank's partial sums), its all-reduce in flight during the user side
             if sparse:
                 self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)    # A_iu G_u through the users' edge lists
             elif self.A_iu_blocks is not None:
                 blocked_spmm(self._spmm, self.A_iu_blocks, cu, ni_, self._scratch_i, None, 0.0)
             else:
                 self._spmm(self.A_iu, cu, ni_, None, 0.0)
+            settle()
             work = self._allreduce_async(ni_)
             if sparse:
                 self._scatter(self.A_iu, nz_i, ci, nu_, acc_u, s)     # A_ui G_i through the items' edge lists
             else:
                 self._spmm(self.A_ui, ci, nu_, acc_u, s)      # users: local, no communication
-            if work is not None:
-                work.wait()
-            self._axpy(acc_i, ni_, s)
+            pending = (work, ni_)
             cu, ci = nu_, ni_
+        settle()
 
     def train_step(self, u, i, j):
         """u, i, j: the WHOLE minibatch (global ids, int32 device tensors) on every rank."""
@@ -773,11 +789,30 @@ class UserShardedSimGCL(UserShardedLightGCN):
         E, s = self.E, 1.0 / self.n_layers
         out_u.zero_(); out_i.zero_()
         cu, ci = self.Eu, self.Ei
+        pending = None                 # (handle, block, layer) of the previous layer's item-side exchange
+
+        def settle():
+            # the previous layer's item block becomes the sum over the ranks; sign() of a perturbed view is taken of
+            # that FULL sum, hence after the all-reduce
+            if pending is None:
+                return
+            if pending[0] is not None:
+                pending[0].wait()
+            if view == 0:
+                self._axpy(out_i, pending[1], s)
+            else:
+                E.simgcl_perturb(pending[1], self.eps, self.noise_seed, view * 16 + pending[2], self.step, acc=out_i, acc_scale=s,
+                                 d_valid=self.d_valid, row_offset=self.U_total)
+
+        # order inside a layer as in UserShardedLightGCN._propagate: item side (local inputs only), settle the previous
+        # exchange, start this one, user side -- every exchange is in flight during two products
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
             if need_u is not None and k == self.n_layers - 1 and k > 0:
                 part_i = self._need_buf(need_i.shape[0])
                 self._rows(self.A_iu, need_i, cu, part_i, True, None, 0.0)      # this rank's partial sums of the listed item rows
+                settle()
+                pending = None
                 work = None
                 if self.world > 1:
                     work = dist.all_reduce(part_i, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
@@ -792,11 +827,12 @@ class UserShardedSimGCL(UserShardedLightGCN):
                     work.wait()
                 if view == 0:
                     self._scatter_add(out_i, need_i, part_i, s)
-                else:                                                           # sign() of the FULL sum: after the all-reduce
+                else:
                     E.simgcl_perturb_listed(part_i, need_i, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_i,
                                             acc_scale=s, d_valid=self.d_valid, row_offset=self.U_total)
                 break
             self._spmm(self.A_iu, cu, ni_, None, 0.0)                       # item side: this rank's partial sums
+            settle()
             work = self._allreduce_async(ni_)
             if view == 0:
                 self._spmm(self.A_ui, ci, nu_, out_u, s)                    # users: local; layer mean fused
@@ -804,14 +840,9 @@ class UserShardedSimGCL(UserShardedLightGCN):
                 self._spmm(self.A_ui, ci, nu_, None, 0.0)
                 E.simgcl_perturb(nu_, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_u, acc_scale=s,
                                  d_valid=self.d_valid, row_offset=self.lo)
-            if work is not None:
-                work.wait()
-            if view == 0:
-                self._axpy(out_i, ni_, s)
-            else:                                                           # sign() of the FULL sum: after the all-reduce
-                E.simgcl_perturb(ni_, self.eps, self.noise_seed, view * 16 + k, self.step, acc=out_i, acc_scale=s,
-                                 d_valid=self.d_valid, row_offset=self.U_total)
+            pending = (work, ni_, k)
             cu, ci = nu_, ni_
+        settle()
 
     def _backward(self, gu, gi, tot_u, tot_i, nz_u=None, nz_i=None):
         """tot <- 1/n * sum_{k=1..n} A^k G (the encoders' common backward map; E_0 is not in the mean).
@@ -819,6 +850,14 @@ class UserShardedSimGCL(UserShardedLightGCN):
         s = 1.0 / self.n_layers
         tot_u.zero_(); tot_i.zero_()
         cu, ci = gu, gi
+        pending = None
+
+        def settle():
+            if pending is not None:
+                if pending[0] is not None:
+                    pending[0].wait()
+                self._axpy(tot_i, pending[1], s)
+
         for k in range(self.n_layers):
             nu_, ni_ = self.bu[k % 2], self.bi[k % 2]
             sparse = k == 0 and nz_u is not None
@@ -826,15 +865,15 @@ class UserShardedSimGCL(UserShardedLightGCN):
                 self._scatter(self.A_ui, nz_u, cu, ni_, None, 0.0)     # A_iu G_u through the users' edge lists
             else:
                 self._spmm(self.A_iu, cu, ni_, None, 0.0)
+            settle()
             work = self._allreduce_async(ni_)
             if sparse:
                 self._scatter(self.A_iu, nz_i, ci, nu_, tot_u, s)      # A_ui G_i through the items' edge lists
             else:
                 self._spmm(self.A_ui, ci, nu_, tot_u, s)
-            if work is not None:
-                work.wait()
-            self._axpy(tot_i, ni_, s)
+            pending = (work, ni_)
             cu, ci = nu_, ni_
+        settle()
 
     def _infonce(self, tab1, tab2, idx_rows, own_pos, own_local, grad_rows, replicated):
         """InfoNCE between two views on the batch's unique rows.  idx_rows: b global-batch positions; own_pos:
