@@ -96,6 +96,7 @@ SIGNATURES = {
     'qrec_table_all_gather_p2p_f32': (C.c_int, [C.POINTER(vp), C.c_int32, vp, C.c_int64, vp]),
     'qrec_table_gather_merge_p2p_f32': (C.c_int, [C.POINTER(vp), C.c_int32, vp, vp, vp, C.c_int64, vp]),
     'qrec_score_topn_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
+    'qrec_score_topn_tc_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int32, vp, C.c_int32, vp, vp, C.c_float, C.c_int32, vp, vp, vp]),
     'qrec_adj_normalize_f32': (C.c_int, [C.c_int32, vp, vp, vp, vp, vp, vp, vp]),
     'qrec_edge_keep_philox': (C.c_int, [C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp]),
     'qrec_adj_line_weights_f32': (C.c_int, [C.c_int64, vp, vp, C.c_int64, vp, vp]),

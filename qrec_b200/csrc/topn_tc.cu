@@ -1,0 +1,362 @@
+// K8 on the tensor cores ("tiled P_tile . Q^T on tensor cores -> rated positions := 0 -> per-row
+// top-N").  Same contract and same selection rule as csrc/topn_kernels.cu (the reference flow of
+// base/recommender.py:143-152 + util/qmath.py:134-146); what changes is where the scores come from:
+//
+//   * a CTA owns 128 users.  Their rows of U are split once into two TF32 operands, hi = rna_tf32(x) and
+//     lo = rna_tf32(x - hi), stored K-major / SWIZZLE_128B in shared memory (the layout of csrc/tc_gemm.cu);
+//   * the item table streams through in tiles of 128 items, split the same way into a 2-stage ring (global ->
+//     registers one tile ahead -> shared);
+//   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) three times per k-step --
+//     hi.hi + lo.hi + hi.lo, the classical 3xTF32 error-compensated product: the dropped lo.lo term is 2^-22
+//     relative, i.e. fp32-level scores, which is what keeps the index lists equal to an fp32 GEMV's wherever
+//     scores are distinct (plain TF32's 10-bit mantissa reorders close scores) -- into one of two 128-column TMEM
+//     accumulators;
+//   * while the tensor cores work on tile t, the 128 threads (thread r = TMEM lane r = user r) read tile t-1's
+//     accumulator with tcgen05.ld and run the selection of topn_kernels.cu with the row's count and cut-off in
+//     REGISTERS: compare, rated test (bisection) only for scores that pass, append to the row's 256-key list in an
+//     L2-resident scratch; a warp sorts a row (bitonic, shared memory) whenever its list could overflow.
+// Nothing of the [users x items] matrix is written.  d must be 32 or 64 (one or two 128-byte k-blocks).
+#include "common.h"
+
+namespace {
+
+constexpr int CAP = 256;   // candidate slots per user (>= N_max + items per tile)
+constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
+constexpr int TM = 128, TN = 128;
+constexpr int KBLK = TM * 128;                       // bytes of one k-block (32 fp32 = 128 B per row) of a 128-row operand
+
+__device__ __forceinline__ uint32_t ord_of(float s) {          // monotone float -> uint
+  const uint32_t u = __float_as_uint(s);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float score_of(uint32_t o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ bool is_rated(const int* __restrict__ cols, long long lo, long long hi, int item) {
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    const int c = __ldg(cols + mid);
+    if (c == item) return true;
+    if (c < item) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+// one warp sorts the CAP keys of one row, descending (bitonic network in shared memory)
+__device__ __forceinline__ void warp_sort_desc(unsigned long long* k, int lane) {
+#pragma unroll 1
+  for (int size = 2; size <= CAP; size <<= 1) {
+#pragma unroll 1
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      __syncwarp();
+      for (int t = lane; t < CAP / 2; t += 32) {
+        const int lo = 2 * t - (t & (stride - 1));
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;
+        const unsigned long long a = k[lo], b = k[hi];
+        if ((a < b) == desc) { k[lo] = b; k[hi] = a; }
+      }
+    }
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (csrc/tc_gemm.cu): start>>4 | SBO = 1024 B | version 1 | swizzle 128B
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor, kind::tf32: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+__device__ __forceinline__ uint32_t make_idesc() {
+  uint32_t i = 0;
+  i |= 1u << 4;
+  i |= 2u << 7;
+  i |= 2u << 10;
+  i |= (uint32_t)(TN >> 3) << 17;
+  i |= (uint32_t)(TM >> 4) << 24;
+  return i;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+// Bounded wait: a protocol error traps (the launch fails with an error) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spins = 0;; ++spins) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (spins > (1u << 22)) __trap();
+  }
+}
+// byte offset of element (row, k) inside one K-major SWIZZLE_128B k-block (k in [0,32) fp32)
+__device__ __forceinline__ uint32_t sw_off(int row, int k) {
+  const int chunk = (k >> 2) ^ (row & 7);
+  return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + chunk * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ float rna_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// x = hi + lo with hi, lo representable in TF32 (up to 2^-22 |x|)
+__device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& lo) {
+  hi = make_float4(rna_tf32(v.x), rna_tf32(v.y), rna_tf32(v.z), rna_tf32(v.w));
+  lo = make_float4(rna_tf32(v.x - hi.x), rna_tf32(v.y - hi.y), rna_tf32(v.z - hi.z), rna_tf32(v.w - hi.w));
+}
+
+// KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
+// then one 2 KB sort buffer per warp.
+template <int KB>
+__global__ void __launch_bounds__(128, 1)
+score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, int n_items,
+                     const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
+                     const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
+                     float* __restrict__ out_scores, unsigned long long* __restrict__ workspace) {
+  constexpr int D = KB * 32;
+  constexpr int OPER = KB * KBLK;                     // bytes of one 128-row operand (hi or lo)
+  constexpr int VPT = TN * D / 4 / 128;               // float4 per thread per 128-row tile (8 or 16)
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ uint64_t mma_done[2];
+  __shared__ uint32_t tmem_base_slot;
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* const sA_hi = smem;
+  uint8_t* const sA_lo = smem + OPER;
+  uint8_t* const sB = smem + 2 * OPER;                // stage s: hi at sB + s * 2 * OPER, lo right behind it
+  unsigned long long* const sort_buf = reinterpret_cast<unsigned long long*>(smem + 6 * OPER);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int row0 = blockIdx.x * TM;
+  const int my_row = row0 + tid;
+  const int u = (my_row < n_rows) ? __ldg(user_ids + my_row) : -1;
+  unsigned long long* const cand = workspace + (size_t)blockIdx.x * TM * CAP;       // this CTA's 128 lists
+  unsigned long long* const my_cand = cand + (size_t)tid * CAP;
+  unsigned long long* const my_sort = sort_buf + (size_t)warp * CAP;
+  long long rlo = 0, rhi = 0;
+  if (u >= 0) { rlo = __ldg(rated_rowptr + u); rhi = __ldg(rated_rowptr + u + 1); }
+  const unsigned long long rated_key_hi = (unsigned long long)ord_of(rated_value) << 32;
+
+  if (tid == 0) {
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(2 * TN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  // ---- the users' rows, split and stored once: float4 number q of the tile is (row q / (D/4), columns 4 * (q % (D/4)))
+#pragma unroll
+  for (int p = 0; p < VPT; ++p) {
+    const int q = tid + 128 * p;
+    const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
+    const int ur = (row0 + row < n_rows) ? __ldg(user_ids + row0 + row) : -1;
+    const float4 v = (ur >= 0) ? __ldg(reinterpret_cast<const float4*>(U + (size_t)ur * D + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    const uint32_t off = (uint32_t)(c4 >> 5) * KBLK + sw_off(row, c4 & 31);
+    *reinterpret_cast<float4*>(sA_hi + off) = hi;
+    *reinterpret_cast<float4*>(sA_lo + off) = lo;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_acc = tmem_base_slot;
+  const uint32_t idesc = make_idesc();
+
+  const int n_tiles = (n_items + TN - 1) / TN;
+  float4 rb[VPT];
+  auto load_tile = [&](int t) {                       // global -> registers (tile t of the item table)
+    const int c0 = t * TN;
+#pragma unroll
+    for (int p = 0; p < VPT; ++p) {
+      const int q = tid + 128 * p;
+      const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
+      rb[p] = (c0 + row < n_items) ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(c0 + row) * D + c4))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int cnt = 0;                                        // this thread's row: candidates in its list, current cut-off
+  unsigned long long thr = 0ULL;
+
+  // selection over one finished accumulator (tile t, TMEM buffer t & 1)
+  auto select_tile = [&](int t) {
+    // a row that could overflow during this tile goes back to its N best first (the warp sorts it together)
+    unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - TN);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      const int c = __shfl_sync(0xffffffffu, cnt, src);
+      const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+      __syncwarp();
+      for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
+      warp_sort_desc(my_sort, lane);
+      unsigned long long* wl = cand + (size_t)(warp * 32 + src) * CAP;
+      for (int k = lane; k < N; k += 32) __stcg(wl + k, my_sort[k]);
+      if (lane == src) { cnt = N; thr = my_sort[N - 1]; }
+      __syncwarp();
+    }
+    mbar_wait(&mma_done[t & 1], (uint32_t)((t >> 1) & 1));
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int c0 = t * TN;
+#pragma unroll 1
+    for (int cc = 0; cc < TN; cc += 16) {
+      uint32_t r[16];
+      __syncwarp();                                   // the rare path below diverges; tcgen05.ld is warp-collective
+      const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)((t & 1) * TN + cc);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+            "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (u < 0) continue;
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        const int c = c0 + cc + q;
+        if (c >= n_items) continue;
+        const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
+        unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
+        // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
+        if (key > thr || (rated_key_hi | low) > thr) {
+          if (is_rated(rated_cols, rlo, rhi, c)) key = rated_key_hi | low;
+          if (key > thr) {
+            __stcg(my_cand + cnt, key);               // cnt < CAP by the compaction rule
+            ++cnt;
+          }
+        }
+      }
+    }
+    // the accumulator may be overwritten once every thread is past its loads: ordered by the barrier that precedes
+    // the next MMA issue into this buffer
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  };
+
+  load_tile(0);
+  for (int t = 0; t < n_tiles; ++t) {
+    const int s = t & 1;
+    uint8_t* const sB_hi = sB + s * 2 * OPER;
+    uint8_t* const sB_lo = sB_hi + OPER;
+    // stage s was read by the MMAs of tile t-2, whose completion select_tile(t-2) has waited for (iteration t-1)
+#pragma unroll
+    for (int p = 0; p < VPT; ++p) {
+      const int q = tid + 128 * p;
+      const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
+      float4 hi, lo;
+      split_tf32(rb[p], hi, lo);
+      const uint32_t off = (uint32_t)(c4 >> 5) * KBLK + sw_off(row, c4 & 31);
+      *reinterpret_cast<float4*>(sB_hi + off) = hi;
+      *reinterpret_cast<float4*>(sB_lo + off) = lo;
+    }
+    if (t + 1 < n_tiles) load_tile(t + 1);            // in flight during the MMAs and the selection below
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
+    __syncthreads();                                  // also: every thread is done reading TMEM buffer s (tile t-2)
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t acc_addr = tmem_acc + (uint32_t)(s * TN);
+      bool first = true;
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t a_hi = make_desc(smem_u32(sA_hi + kb * KBLK)), a_lo = make_desc(smem_u32(sA_lo + kb * KBLK));
+        const uint64_t b_hi = make_desc(smem_u32(sB_hi + kb * KBLK)), b_lo = make_desc(smem_u32(sB_lo + kb * KBLK));
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+          const uint64_t step = (uint64_t)(k4 * 2);   // +2 = 32 bytes (8 tf32) along K inside the 128-byte span
+#pragma unroll
+          for (int term = 0; term < 3; ++term) {      // small terms first: lo.hi, hi.lo, then hi.hi
+            const uint64_t da = (term == 0 ? a_lo : a_hi) + step;
+            const uint64_t db = (term == 1 ? b_lo : b_hi) + step;
+            const uint32_t accf = first ? 0u : 1u;
+            first = false;
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(acc_addr), "l"(da), "l"(db), "r"(idesc),
+                "r"(accf)
+                : "memory");
+          }
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[s]))
+                   : "memory");
+    }
+    if (t >= 1) select_tile(t - 1);
+  }
+  select_tile(n_tiles - 1);
+
+  // ---- final order and output: each warp sorts its 32 rows in turn
+  __syncwarp();
+  for (int src = 0; src < 32; ++src) {
+    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    const int ur = __shfl_sync(0xffffffffu, u, src);
+    if (ur < 0) continue;
+    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+    __syncwarp();
+    for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
+    warp_sort_desc(my_sort, lane);
+    const size_t orow = (size_t)(row0 + warp * 32 + src) * N;
+    for (int k = lane; k < N; k += 32) {
+      const unsigned long long key = my_sort[k];
+      out_ids[orow + k] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffULL));
+      out_scores[orow + k] = score_of((uint32_t)(key >> 32));
+    }
+    __syncwarp();
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(2 * TN));
+  }
+}
+
+template <int KB>
+int launch_tc(const float* U, const float* V, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
+              const int* cols, float rated_value, int N, int* out_ids, float* out_scores, cudaStream_t st) {
+  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + 1024;     // operands + sort buffers + alignment
+  static bool attr_set = false;
+  if (!attr_set) {
+    QREC_CUDA(cudaFuncSetAttribute(score_topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_set = true;
+  }
+  const int grid = (n_rows + TM - 1) / TM;
+  unsigned long long* ws = nullptr;                       // candidate lists: 2 KB per user, stream-ordered scratch
+  QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)grid * TM * CAP * sizeof(unsigned long long), st));
+  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, V, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
+                                                    out_scores, ws);
+  const cudaError_t launch_err = cudaGetLastError();
+  QREC_CUDA(cudaFreeAsync(ws, st));
+  if (launch_err != cudaSuccess) return qrec::cuda_fail(launch_err, "kernel launch", __FILE__, __LINE__);
+  qrec::count_launch();
+  return QREC_OK;
+}
+
+}  // namespace
+
+extern "C" int qrec_score_topn_tc_f32(const float* dev_U, const float* dev_V, int32_t d, int32_t n_items,
+                                      const int32_t* dev_user_ids, int32_t n_rows, const int64_t* dev_rated_rowptr,
+                                      const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,
+                                      float* dev_out_scores, void* stream) {
+  QREC_REQUIRE(n_rows >= 0 && n_items >= 1, "qrec_score_topn_tc_f32: bad size");
+  QREC_REQUIRE(d == 32 || d == 64, "qrec_score_topn_tc_f32: d=%d unsupported (32 or 64; use qrec_score_topn_f32)", d);
+  QREC_REQUIRE(N >= 1 && N <= NMAX && N <= n_items, "qrec_score_topn_tc_f32: N=%d must be in 1..min(%d, n_items)", N, NMAX);
+  if (n_rows == 0) return QREC_OK;
+  QREC_REQUIRE(dev_U && dev_V && dev_user_ids && dev_rated_rowptr && dev_rated_cols && dev_out_ids && dev_out_scores,
+               "qrec_score_topn_tc_f32: null pointer");
+  QREC_REQUIRE((reinterpret_cast<uintptr_t>(dev_U) & 15) == 0 && (reinterpret_cast<uintptr_t>(dev_V) & 15) == 0,
+               "qrec_score_topn_tc_f32: tables must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long* rp = reinterpret_cast<const long long*>(dev_rated_rowptr);
+  if (d == 32)
+    return launch_tc<1>(dev_U, dev_V, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
+  return launch_tc<2>(dev_U, dev_V, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
+}

@@ -6,6 +6,7 @@ sm_100a kernels.  There is no CPU path here: device entry points raise if a tens
 CUDA device.
 """
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -418,10 +419,19 @@ def table_gather_merge_p2p(peer_S_ptrs, Q, B, D):
           'qrec_table_gather_merge_p2p_f32')
 
 
-def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None):
+SCORE_TOPN_TENSOR_CORES = False      # default of score_topn(tensor_cores=None); QREC_TOPN_TC=0/1 overrides
+
+
+def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None, tensor_cores=None):
     """K8: the N best items of every listed user in one kernel (scores, rated -> rated_value, top-N; nothing
-    materialised).  Returns (ids int32 [n, N], scores fp32 [n, N]), best first, ties by ascending item id."""
+    materialised).  Returns (ids int32 [n, N], scores fp32 [n, N]), best first, ties by ascending item id.
+    tensor_cores: True = the tcgen05 3xTF32 kernel (csrc/topn_tc.cu; d must be 32 or 64), False = the fp32 SIMT kernel
+    (csrc/topn_kernels.cu), None = the module default where the width allows it."""
     torch = _torch()
+    if tensor_cores is None:
+        env = os.environ.get('QREC_TOPN_TC')
+        tensor_cores = (SCORE_TOPN_TENSOR_CORES if env is None else env == '1') and U.shape[1] in (32, 64)
+    fn, name = (lib.qrec_score_topn_tc_f32, 'qrec_score_topn_tc_f32') if tensor_cores else (lib.qrec_score_topn_f32, 'qrec_score_topn_f32')
     n = int(user_ids.shape[0])
     if U.shape[1] != V.shape[1]:
         raise QRecError('score_topn: U and V must have the same width')
@@ -429,11 +439,10 @@ def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out
         out_ids = torch.empty(n, N, dtype=torch.int32, device=U.device)
     if out_scores is None:
         out_scores = torch.empty(n, N, dtype=torch.float32, device=U.device)
-    check(lib.qrec_score_topn_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'), U.shape[1], V.shape[0],
-                                  _dev(user_ids, torch.int32, 'user_ids'), n, _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
-                                  _dev(rated_cols, torch.int32, 'rated_cols'), float(rated_value), int(N),
-                                  _dev(out_ids, torch.int32, 'out_ids'), _dev(out_scores, torch.float32, 'out_scores'),
-                                  _stream()), 'qrec_score_topn_f32')
+    check(fn(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'), U.shape[1], V.shape[0],
+             _dev(user_ids, torch.int32, 'user_ids'), n, _dev(rated_rowptr, torch.int64, 'rated_rowptr'),
+             _dev(rated_cols, torch.int32, 'rated_cols'), float(rated_value), int(N),
+             _dev(out_ids, torch.int32, 'out_ids'), _dev(out_scores, torch.float32, 'out_scores'), _stream()), name)
     return out_ids, out_scores
 
 
