@@ -205,6 +205,10 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
       if (lane == src) { cnt = N; thr = my_sort[N - 1]; }
       __syncwarp();
     }
+    // cheap pre-filter for the 128 scores of this tile (the cut-off only moves in the compaction above): a score below
+    // the cut-off's score cannot pass, unless the list is not full yet or a rated item's fixed value could pass
+    const bool open_row = thr == 0ULL || (uint32_t)(thr >> 32) <= (uint32_t)(rated_key_hi >> 32);
+    const float thr_f = open_row ? 0.f : score_of((uint32_t)(thr >> 32));
     mbar_wait(&mma_done[t & 1], (uint32_t)((t >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int c0 = t * TN;
@@ -225,6 +229,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
       for (int q = 0; q < 16; ++q) {
         const int c = c0 + cc + q;
         if (c >= n_items) continue;
+        if (!(open_row || __uint_as_float(r[q]) >= thr_f)) continue;
         const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
         unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
         // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
