@@ -50,6 +50,7 @@ ALGO_BYTES_PER_TRIPLE = 24 * D + 12          # 3 rows read + 3 r
 METRIC = 'BPR triples/sec at d=64'
 # Multi-GPU code paths that are on by default.  'blocking' = the round-1 delta all-reduce; 'auto' = the overlapped exchange
 # (peer-memory kernels, NCCL fallback).  Flipped to the new paths only once they have been validated on >= 2 GPUs.
+LIGHTGCN_MULTI_SCHEME = 'user'        # 'cols' once its N>1 numbers are in (QREC_LGCN_SCHEME overrides)
 MULTI_GPU_DEFAULTS = {'qsync': 'auto', 'lightgcn_multi': True, 'parity_multi': True}     # validated at N=2 (profiles/r2/multi_n2)
 WORKLOAD = 'BPR synthetic 1M users x 100K items x 50M interactions, d=64, fp32, user-major (reference) order'
 
@@ -485,15 +486,37 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
     from qrec_b200 import parallel
     users_local = NUM_USERS // world
     U, I, N = NUM_USERS, NUM_ITEMS, NUM_USERS + NUM_ITEMS
-    A_ui, A_iu = local_bipartite_blocks(torch, dist, data, users_local, I, world)
     nnz = 2 * NUM_USERS * DEGREE
     g = torch.Generator(device=dev); g.manual_seed(5)
-    Ei = torch.randn(I, D, device=dev, generator=g) * 0.005               # same seed on every rank: replicated items
-    g.manual_seed(50 + rank)
-    Eu = torch.randn(users_local, D, device=dev, generator=g) * 0.005
-    # experiment switch (default 1 = the measured path): column-blocked item-side SpMM, DESIGN.md section 10
-    item_blocks = int(os.environ.get('QREC_LGCN_ITEM_BLOCKS', '1'))
-    m = parallel.UserShardedLightGCN(A_ui, A_iu, Eu, Ei, layers, 0.001, 0.001, rank * users_local, item_side_blocks=item_blocks)
+    # N > 1: 'user' = users partitioned over the ranks, items replicated (all-reduces of the item block);
+    #        'cols' = embedding columns partitioned, adjacency replicated (one [B] all-reduce per step)
+    scheme = os.environ.get('QREC_LGCN_SCHEME', LIGHTGCN_MULTI_SCHEME) if world > 1 else 'user'
+    if scheme == 'cols' and D % (4 * world):
+        scheme = 'user'
+    item_blocks = 1
+    if scheme == 'cols':
+        from qrec_b200.base.graphRecommender import DeviceCSR
+        # every rank needs the whole graph: the ranks' user ranges are consecutive, so the all-gathered column lists
+        # are the global user-major CSR (setup code)
+        parts = [torch.empty_like(data['sorted_cols']) for _ in range(world)]
+        dist.all_gather(parts, data['sorted_cols'].contiguous())
+        full = {'sorted_cols': torch.cat(parts), 'u': torch.arange(U, device=dev, dtype=torch.int32).repeat_interleave(DEGREE)}
+        del parts
+        rowptr, cols, vals = synthetic.build_norm_adj(full, U, I, dev)
+        del full
+        torch.cuda.empty_cache()
+        dw = D // world
+        ego_cols = (torch.randn(N, D, device=dev, generator=g) * 0.005)[:, rank * dw:(rank + 1) * dw].contiguous()   # same seed: one table
+        m = parallel.ColumnShardedLightGCN(DeviceCSR.from_tensors((N, N), rowptr, cols, vals), ego_cols, U, layers, 0.001, 0.001)
+        g.manual_seed(50 + rank)                       # the ranks draw different parts of the (all-gathered) minibatch
+    else:
+        A_ui, A_iu = local_bipartite_blocks(torch, dist, data, users_local, I, world)
+        Ei = torch.randn(I, D, device=dev, generator=g) * 0.005               # same seed on every rank: replicated items
+        g.manual_seed(50 + rank)
+        Eu = torch.randn(users_local, D, device=dev, generator=g) * 0.005
+        # experiment switch (default 1 = the measured path): column-blocked item-side SpMM, DESIGN.md section 10
+        item_blocks = int(os.environ.get('QREC_LGCN_ITEM_BLOCKS', '1'))
+        m = parallel.UserShardedLightGCN(A_ui, A_iu, Eu, Ei, layers, 0.001, 0.001, rank * users_local, item_side_blocks=item_blocks)
     spmm_algo = nnz * (8 + 4 * D) + N * (4 + 4 * D)                 # SURVEY 8(d) no-reuse gather model
     res = {'layers': layers, 'rows': N, 'nnz': nnz, 'n_gpus': world,
            'semantics': 'the reference step: n-layer propagation + loss + its backward pass + dense Adam on every row, once per '
@@ -501,7 +524,11 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
                         "batch's rows -- the last forward layer (the loss reads nothing else of its output) and the first backward "
                         'layer (the loss gradient is zero elsewhere) -- run over those rows\' edges only; the parameter update '
                         'equals the all-rows computation (tests/test_lightgcn_model_cpu.py, test_gpu_models.py vs autograd)',
-           'impl': 'parallel.UserShardedLightGCN: users partitioned over %d rank(s), items replicated, bipartite blocks '
+           'scheme': scheme,
+           'impl': ('parallel.ColumnShardedLightGCN: the %d embedding columns partitioned over %d ranks (every rank runs the '
+                    'single-GPU step at width %d on the whole, replicated adjacency); the only data-path collective of a step is '
+                    'the all-reduce of the [B] partial scores' % (D, world, D // world)) if scheme == 'cols' else
+                   'parallel.UserShardedLightGCN: users partitioned over %d rank(s), items replicated, bipartite blocks '
                    'A_ui/A_iu, row-restricted last forward / first backward layer, %s' % (world, 'one all-reduce of the item block per layer '
                                                                    '(overlapped with the user-side SpMM)' if world > 1 else 'no collective'),
            'item_side_blocks': item_blocks}

@@ -408,6 +408,22 @@ int qrec_bpr_grad_scatter_f32(const float* dev_U, const float* dev_V, int32_t d,
                               float eps, float reg, float* dev_gU, float* dev_gV,
                               double* dev_loss, void* stream);
 
+/* The same step for ranks that each hold a COLUMN block of the tables (feature-parallel LightGCN: the propagation
+ * A X is independent per column, so d/world columns of every row live on each rank and the only exchange of a
+ * minibatch step is the sum of these partial scores).  d = the LOCAL width.
+ *   partial scores: y_part[k] = sum over the local columns of U[u_k].(V[i_k] - V[j_k]); the local part of the batch L2
+ *                   term (reg/2 * squared norms) is added to *loss.
+ *   gradients     : given y_full = the ranks' y_part summed, scatter-adds the gradient of the local columns into gU / gV
+ *                   exactly like qrec_bpr_grad_scatter_f32 and adds log_weight * sum_k -ln(sigmoid(y_k) + eps) to *loss
+ *                   (log_weight = 1 on one rank, 0 on the others: the term is a function of the full score). */
+int qrec_bpr_partial_scores_f32(const float* dev_U, const float* dev_V, int32_t d, int64_t n, const int32_t* dev_u,
+                                const int32_t* dev_i, const int32_t* dev_j, float reg, float* dev_y_part,
+                                double* dev_loss, void* stream);
+int qrec_bpr_grad_from_scores_f32(const float* dev_U, const float* dev_V, int32_t d, int64_t n, const int32_t* dev_u,
+                                  const int32_t* dev_i, const int32_t* dev_j, const float* dev_y_full, float eps,
+                                  float reg, float log_weight, float* dev_gU, float* dev_gV, double* dev_loss,
+                                  void* stream);
+
 /* =====================================================================================
  * K4 -- tf.train.AdamOptimizer (TF 1.14) dense update over a whole variable:
  * LightGCN.py:31-32, NGCF.py:54, SimGCL.py:99, BPR.py:84.

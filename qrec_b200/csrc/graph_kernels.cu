@@ -368,12 +368,17 @@ spmm_list_rows_kernel(int n_list, const int* __restrict__ rows, const long long*
 }
 
 // ------------------------------------------------------------------------------------------ K3
-template <int LPR, int VPL, int UNROLL>
+// MODE 0: the fused kernel.  MODE 1 / 2: the same step for a COLUMN block of the tables (feature-parallel ranks, each
+// holding d/world columns of every row): 1 = partial scores y_k = sum over the local columns (+ the local part of the
+// batch L2 term into `loss`), no gradients; 2 = gradients of the local columns from the FULL scores (the ranks' partial
+// scores summed), the -ln term weighted by log_weight (1 on one rank, 0 elsewhere: it is a function of the full score).
+template <int LPR, int VPL, int UNROLL, int MODE = 0>
 __global__ void __launch_bounds__(256)
 bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V, int nvec,
                         long long n, const int* __restrict__ u, const int* __restrict__ i,
                         const int* __restrict__ j, float eps, float reg, float* __restrict__ gU,
-                        float* __restrict__ gV, double* loss) {
+                        float* __restrict__ gV, double* loss, float* __restrict__ y_buf = nullptr,
+                        float log_weight = 1.f) {
   constexpr int TPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -421,11 +426,23 @@ bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V
         }
         y = group_sum<LPR>(y);
         sq = group_sum<LPR>(sq);
+        if (MODE == 1) {                                  // partial score out, local part of the L2 term, nothing else
+          const int t = s0 + r * TPW + sub;
+          if (t < cnt && l == 0) {
+            y_buf[base + t] = ok[r] ? y : 0.f;
+            if (ok[r]) lsum += reg * 0.5f * sq;
+          }
+          continue;
+        }
+        if (MODE == 2) {
+          const int t = s0 + r * TPW + sub;
+          y = (t < cnt) ? __ldg(y_buf + base + t) : 0.f;  // the full score (sum of the ranks' partial scores)
+        }
         const float s = 1.0f / (1.0f + expf(-y));
         // d/dy of -ln(s+eps) = -s(1-s)/(s+eps)      
         const float gy = -s * (1.0f - s) / (s + eps);
         if (ok[r]) {
-          if (l == 0) lsum += -logf(s + eps) + reg * 0.5f * sq;
+          if (l == 0) lsum += (MODE == 2) ? log_weight * -logf(s + eps) : (-logf(s + eps) + reg * 0.5f * sq);
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             if ((l + v * LPR) < nvec) {
@@ -671,6 +688,57 @@ int qrec_bpr_grad_scatter_f32(const float* U, const float* V, int32_t d, int64_t
   else if (nvec <= 32) QREC_K3(32, 1, 4);
   else QREC_K3(32, 2, 2);
 #undef QREC_K3
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_partial_scores_f32(const float* U, const float* V, int32_t d, int64_t n, const int32_t* u, const int32_t* i,
+                                const int32_t* j, float reg, float* y_part, double* loss, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_bpr_partial_scores_f32: d=%d unsupported", d);
+  QREC_REQUIRE(n >= 0, "qrec_bpr_partial_scores_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(U && V && u && i && j && y_part && loss, "qrec_bpr_partial_scores_f32: null pointer");
+  QREC_REQUIRE(aligned16(U) && aligned16(V), "qrec_bpr_partial_scores_f32: tables must be 16-byte aligned");
+  const int nvec = d / 4;
+  const long long blocks_needed = ((n + 31) / 32 + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_K3P(LPR, VPL, UN)                                                                   \
+  bpr_grad_scatter_kernel<LPR, VPL, UN, 1><<<grid, 256, 0, st>>>(U, V, nvec, n, u, i, j, 0.f, reg, nullptr, nullptr, loss, y_part, 0.f)
+  if (nvec <= 4) QREC_K3P(4, 1, 2);
+  else if (nvec <= 8) QREC_K3P(8, 1, 4);
+  else if (nvec <= 16) QREC_K3P(16, 1, 4);
+  else if (nvec <= 32) QREC_K3P(32, 1, 4);
+  else QREC_K3P(32, 2, 2);
+#undef QREC_K3P
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_grad_from_scores_f32(const float* U, const float* V, int32_t d, int64_t n, const int32_t* u, const int32_t* i,
+                                  const int32_t* j, const float* y_full, float eps, float reg, float log_weight, float* gU,
+                                  float* gV, double* loss, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_bpr_grad_from_scores_f32: d=%d unsupported", d);
+  QREC_REQUIRE(n >= 0, "qrec_bpr_grad_from_scores_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(U && V && u && i && j && y_full && gU && gV && loss, "qrec_bpr_grad_from_scores_f32: null pointer");
+  QREC_REQUIRE(aligned16(U) && aligned16(V) && aligned16(gU) && aligned16(gV),
+               "qrec_bpr_grad_from_scores_f32: tables must be 16-byte aligned");
+  const int nvec = d / 4;
+  const long long blocks_needed = ((n + 31) / 32 + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+  float* yb = const_cast<float*>(y_full);
+#define QREC_K3A(LPR, VPL, UN)                                                                   \
+  bpr_grad_scatter_kernel<LPR, VPL, UN, 2><<<grid, 256, 0, st>>>(U, V, nvec, n, u, i, j, eps, reg, gU, gV, loss, yb, log_weight)
+  if (nvec <= 4) QREC_K3A(4, 1, 2);
+  else if (nvec <= 8) QREC_K3A(8, 1, 4);
+  else if (nvec <= 16) QREC_K3A(16, 1, 4);
+  else if (nvec <= 32) QREC_K3A(32, 1, 4);
+  else QREC_K3A(32, 2, 2);
+#undef QREC_K3A
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

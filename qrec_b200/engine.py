@@ -637,6 +637,27 @@ def spmm_csr_scatter_rows(rowptr, cols, vals, src_rows, X, Y, acc=None, acc_scal
     return Y
 
 
+def bpr_partial_scores(U, V, u, i, j, reg, y_part, loss):
+    """Column-block step, part 1: y_part[k] = U[u_k] . (V[i_k] - V[j_k]) over the LOCAL columns; local L2 part into loss."""
+    torch = _torch()
+    check(lib.qrec_bpr_partial_scores_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'), U.shape[1], u.shape[0],
+                                          _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'), float(reg),
+                                          _dev(y_part, torch.float32, 'y_part'), _dev(loss, torch.float64, 'loss'), _stream()),
+          'qrec_bpr_partial_scores_f32')
+    return y_part
+
+
+def bpr_grad_from_scores(U, V, u, i, j, y_full, eps, reg, log_weight, gU, gV, loss):
+    """Column-block step, part 2: gradients of the local columns from the full scores (the ranks' partial scores summed)."""
+    torch = _torch()
+    check(lib.qrec_bpr_grad_from_scores_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'), U.shape[1], u.shape[0],
+                                            _dev(u, torch.int32, 'u'), _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'),
+                                            _dev(y_full, torch.float32, 'y_full'), float(eps), float(reg), float(log_weight),
+                                            _dev(gU, torch.float32, 'gU'), _dev(gV, torch.float32, 'gV'),
+                                            _dev(loss, torch.float64, 'loss'), _stream()), 'qrec_bpr_grad_from_scores_f32')
+    return loss
+
+
 def spmm_csr_rows(rowptr, cols, vals, rows, X, Y=None, compact=False, acc=None, acc_scale=0.0):
     """The rows `rows` (int32, -1 = padding) of the product (rowptr, cols, vals) @ X: written to Y (row k of a compact Y,
     row rows[k] otherwise; Y may be None) and / or accumulated as acc[rows[k]] += acc_scale * row (distinct rows)."""

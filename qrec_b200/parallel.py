@@ -749,6 +749,100 @@ class UserShardedLightGCN(object):
 
 
 # =============================================================================================
+# LightGCN, feature parallel: the embedding COLUMNS are partitioned over the ranks
+# =============================================================================================
+class ColumnShardedLightGCN(object):
+    """LightGCN minibatch step (model/ranking/LightGCN.py:13-39 semantics) with the d embedding columns partitioned
+    over the ranks: rank r holds columns [r*d/w, (r+1)*d/w) of EVERY row of the ego table (and of its Adam slots) and
+    the whole normalised adjacency.
+
+    The propagation E_{k+1} = A E_k acts on every column independently, and so do the layer mean, the backward
+    pass (the same operator) and Adam (element-wise): none of them needs another rank's data.  The only quantity
+    that couples the columns is the score of a triple, y = e_u . (e_i - e_j), a sum over columns: each rank computes
+    its partial scores (qrec_bpr_partial_scores_f32), ONE all-reduce of the [B] vector (8 KB at B = 2048) makes them
+    whole, and each rank forms the gradient of its own columns from the full scores (qrec_bpr_grad_from_scores_f32).
+    So a step moves 4 B bytes per rank through NVLink instead of 5-7 all-reduces of the [I, d] item block (the
+    row-sharded scheme above), and every rank runs the single-GPU step at width d/w.  The loss value (the -ln terms
+    counted on rank 0, the batch L2 term in column parts) needs a second, 8-byte all-reduce.
+
+    Cost: the adjacency is replicated (0.8 GB at the benchmark scale, 8 GB at config 5's), and the narrow rows
+    (32 B at d/w = 8) make the SpMM request-bound rather than byte-bound.  Row-restricted last forward / first backward
+    layers as in the single-GPU class."""
+
+    def __init__(self, adj, ego_cols, num_users, n_layers, lr, reg, group=None):
+        from . import engine as E
+        self.E = E
+        self.adj, self.ego, self.nu = adj, ego_cols, int(num_users)
+        self.n_layers, self.lr, self.reg, self.group = n_layers, lr, reg, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        n, dw = ego_cols.shape
+        dev = ego_cols.device
+        z = lambda: torch.zeros(n, dw, device=dev)            # noqa: E731
+        self.buf = [z(), z()]
+        self.mean, self.grad, self.total = z(), z(), z()
+        self.m, self.v = z(), z()
+        self.loss = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._y = {}
+        self.step = 0
+
+    def _propagate(self, src, acc, need=None, nz=None):
+        """acc <- s * sum_{k=0..n} A^k src on this rank's columns; need / nz: row lists of the restricted layers."""
+        E, s = self.E, 1.0 / (self.n_layers + 1)
+        E.axpby(acc, src, src, s, 0.0)
+        cur = src
+        for k in range(self.n_layers):
+            nxt = self.buf[k % 2]
+            if need is not None and k == self.n_layers - 1 and k > 0:
+                self.adj.matmul_rows(cur, need, acc=acc, acc_scale=s)
+                break
+            if nz is not None and k == 0:
+                self.adj.matmul_sparse_rows(cur, nz, nxt, acc=acc, acc_scale=s)
+            else:
+                self.adj.matmul(cur, nxt, acc=acc, acc_scale=s)
+            cur = nxt
+        return acc
+
+    def train_step(self, u, i, j):
+        """u, i, j: the WHOLE minibatch (global ids, int32 device tensors), identical on every rank."""
+        E, nu = self.E, self.nu
+        B = u.shape[0]
+        rows = None
+        if B <= 8192 and self.ego.shape[1] <= 128 and hasattr(self.adj, 'matmul_rows'):
+            rows = _sorted_unique_padded(torch.cat([u, i + nu, j + nu]))
+        self._propagate(self.ego, self.mean, need=rows)
+        if B not in self._y:
+            self._y[B] = torch.empty(B, dtype=torch.float32, device=self.ego.device)
+        y = self._y[B]
+        self.loss.zero_()
+        E.bpr_partial_scores(self.mean[:nu], self.mean[nu:], u, i, j, self.reg, y, self.loss)
+        if self.world > 1:
+            dist.all_reduce(y, op=dist.ReduceOp.SUM, group=self.group)       # the step's only data-path collective
+        self.grad.zero_()
+        E.bpr_grad_from_scores(self.mean[:nu], self.mean[nu:], u, i, j, y, 10e-8, self.reg, 1.0 if self.rank == 0 else 0.0,
+                               self.grad[:nu], self.grad[nu:], self.loss)
+        if self.world > 1:                                   # 8 bytes; nothing on the device depends on it but the next zero_()
+            dist.all_reduce(self.loss, op=dist.ReduceOp.SUM, group=self.group)
+        self._propagate(self.grad, self.total, nz=rows)
+        self.step += 1
+        E.adam_dense_tf1(self.ego, self.m, self.v, self.total, self.lr, self.step)
+        return self.loss
+
+    def gather_columns(self, block=None):
+        """[N, d] on every rank from the ranks' column blocks (default: the ego table) -- for export / evaluation."""
+        block = self.ego if block is None else block
+        if self.world == 1:
+            return block
+        parts = [torch.empty_like(block) for _ in range(self.world)]
+        dist.all_gather(parts, block.contiguous(), group=self.group)
+        return torch.cat(parts, dim=1)
+
+    def propagated(self):
+        """mean(E_0..E_n) of this rank's columns from the FULL propagation (every row is read by the caller)."""
+        return self._propagate(self.ego, self.mean)
+
+
+# =============================================================================================
 # SimGCL over a row-sharded user table (SURVEY.md 8e, BASELINE config 5: 10M users x 1M items on 8 GPUs)
 # =============================================================================================
 class UserShardedSimGCL(UserShardedLightGCN):

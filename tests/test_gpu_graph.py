@@ -238,3 +238,38 @@ def test_spmm_listed_rows_equals_dense_product(torch, E, golden_graph, d):
     np.testing.assert_allclose(a1.cpu().numpy()[rows], acc0[rows] - 1.5 * ref[rows], rtol=1e-4, atol=4e-6)
     # empty list
     E.spmm_csr_rows(*csr, torch.zeros(0, dtype=torch.int32, device='cuda'), dX, Y)
+
+
+@pytest.mark.parametrize('d,world,n', [(64, 8, 2048), (64, 2, 777), (128, 4, 5000), (16, 4, 33), (256, 2, 100)])
+def test_bpr_column_block_step_equals_fused_kernel(torch, E, d, world, n):
+    """Feature-parallel K3: partial scores per column block, summed (the all-reduce), then the gradient of each block
+    from the full scores -- together the fused kernel's gradient and loss (the -ln terms counted once, the L2 term in
+    column parts), for every block width down to 8 columns."""
+    rng = np.random.default_rng(d + world + n)
+    nu, ni = 300, 170
+    U = (rng.standard_normal((nu, d)) * 0.2).astype(np.float32)
+    V = (rng.standard_normal((ni, d)) * 0.2).astype(np.float32)
+    u, i, j = (rng.integers(0, hi, n).astype(np.int32) for hi in (nu, ni, ni))
+    du, di, dj = _dev(torch, u), _dev(torch, i), _dev(torch, j)
+    gU, gV = torch.zeros(nu, d, device='cuda'), torch.zeros(ni, d, device='cuda')
+    loss = torch.zeros(1, dtype=torch.float64, device='cuda')
+    E.bpr_grad_scatter(_dev(torch, U), _dev(torch, V), du, di, dj, 10e-8, 0.001, gU, gV, loss)
+    dw = d // world
+    blocks = [(_dev(torch, np.ascontiguousarray(U[:, r * dw:(r + 1) * dw])), _dev(torch, np.ascontiguousarray(V[:, r * dw:(r + 1) * dw])))
+              for r in range(world)]
+    losses = torch.zeros(world, dtype=torch.float64, device='cuda')
+    parts = torch.full((world, n), 7.0, device='cuda')
+    for r, (Ub, Vb) in enumerate(blocks):
+        E.bpr_partial_scores(Ub, Vb, du, di, dj, 0.001, parts[r], losses[r:r + 1])
+    y = parts.sum(0).contiguous()
+    ref_y = (U[u].astype(np.float64) * (V[i].astype(np.float64) - V[j].astype(np.float64))).sum(1)
+    np.testing.assert_allclose(y.cpu().numpy(), ref_y, rtol=1e-4, atol=1e-6)
+    got_U, got_V = torch.zeros(nu, d, device='cuda'), torch.zeros(ni, d, device='cuda')
+    for r, (Ub, Vb) in enumerate(blocks):
+        gu, gv = torch.zeros(nu, dw, device='cuda'), torch.zeros(ni, dw, device='cuda')
+        E.bpr_grad_from_scores(Ub, Vb, du, di, dj, y, 10e-8, 0.001, 1.0 if r == 0 else 0.0, gu, gv, losses[r:r + 1])
+        got_U[:, r * dw:(r + 1) * dw] = gu
+        got_V[:, r * dw:(r + 1) * dw] = gv
+    torch.testing.assert_close(got_U, gU, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(got_V, gV, rtol=1e-4, atol=1e-6)
+    assert abs(losses.sum().item() - loss.item()) <= 1e-6 * abs(loss.item())

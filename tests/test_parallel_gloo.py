@@ -346,6 +346,70 @@ def _user_sharded_worker(rank, world, port, out, blocks=1, row_lists=False):
         dist.destroy_process_group()
 
 
+def _column_sharded_worker(rank, world, port, out):
+    import numpy as np
+    from oracle import bpr_oracle as O
+    from qrec_b200 import engine as E
+    from qrec_b200.base.graphRecommender import DeviceCSR
+    from conftest import row_list_kernel_stand_ins
+    import test_sgl_model_cpu as S
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        S._stub(_Setattr)                                       # spmm / axpby / adam restatements
+        calls = row_list_kernel_stand_ins(_Setattr)
+
+        def partial_scores(U_, V_, u, i, j, reg, y_part, loss):  # the contract of qrec_bpr_partial_scores_f32
+            uu, ii, jj = (x.long() for x in (u, i, j))
+            y_part.copy_((U_[uu] * (V_[ii] - V_[jj])).sum(1))
+            loss += reg * 0.5 * float((U_[uu] ** 2).sum() + (V_[ii] ** 2).sum() + (V_[jj] ** 2).sum())
+
+        def grad_from_scores(U_, V_, u, i, j, y_full, eps, reg, log_weight, gU, gV, loss):
+            uu, ii, jj = (x.long() for x in (u, i, j))
+            sg = torch.sigmoid(y_full.double())
+            gy = (-sg * (1 - sg) / (sg + eps)).float()[:, None]
+            gU.index_add_(0, uu, gy * (V_[ii] - V_[jj]) + reg * U_[uu])
+            gV.index_add_(0, ii, gy * U_[uu] + reg * V_[ii])
+            gV.index_add_(0, jj, -gy * U_[uu] + reg * V_[jj])
+            loss += log_weight * float((-torch.log(sg + eps)).sum())
+        E.bpr_partial_scores, E.bpr_grad_from_scores = partial_scores, grad_from_scores
+        U, I, d, L, lr, reg = 9, 6, 8, 3, 0.01, 0.001
+        A = _toy_graph(U, I, seed=3)
+        adj = DeviceCSR(A, 'cpu')
+        rng = np.random.default_rng(1)
+        ego = (rng.standard_normal((U + I, d)) * 0.1).astype(np.float32)
+        dw = d // world
+        m = parallel.ColumnShardedLightGCN(adj, torch.from_numpy(ego[:, rank * dw:(rank + 1) * dw].copy()), U, L, lr, reg)
+        Ur, Vr = ego[:U].copy(), ego[U:].copy()
+        mU, vU, mV, vV = (np.zeros_like(x) for x in (Ur, Ur, Vr, Vr))
+        for step in range(3):
+            u = rng.integers(0, U, 7).astype(np.int32); i = rng.integers(0, I, 7).astype(np.int32)
+            j = rng.integers(0, I, 7).astype(np.int32)
+            ref_loss = O.lightgcn_step(A, Ur, Vr, mU, vU, mV, vV, u, i, j, L, lr, reg, step + 1)
+            loss = m.train_step(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6, (rank, step, float(loss), ref_loss)
+            full = m.gather_columns().numpy()                   # every rank assembles the whole table
+            assert np.allclose(full[:U], Ur, rtol=1e-3, atol=1e-6) and np.allclose(full[U:], Vr, rtol=1e-3, atol=1e-6), (rank, step)
+        # the restricted layers ran: last forward on the row list, first backward as a scatter -- per step
+        assert calls == ['rows', 'scatter_rows'] * 3, calls
+        fu, fv, _ = O.lightgcn_forward(A, Ur, Vr, L)
+        prop = m.gather_columns(m.propagated()).numpy()
+        assert np.allclose(prop[:U], fu, rtol=1e-3, atol=1e-6) and np.allclose(prop[U:], fv, rtol=1e-3, atol=1e-6)
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_column_sharded_lightgcn_matches_single_process_world2():
+    """parallel.ColumnShardedLightGCN (feature parallel: every rank holds d/2 columns of every row, the whole
+    adjacency, and exchanges only the [B] partial scores): same trajectory as the single-process oracle."""
+    port = 36300 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_column_sharded_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+
+
 def test_user_sharded_lightgcn_row_restricted_layers_world2():
     """The row-restricted layers of the sharded step (last forward layer evaluated on the batch's rows only, with
     the ranks' [rows, d] partial blocks all-reduced instead of the whole item block; first backward layer

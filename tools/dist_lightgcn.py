@@ -19,9 +19,10 @@ def main():
     ap.add_argument('--layers', type=int, default=3)
     ap.add_argument('--batch', type=int, default=2048)
     ap.add_argument('--item-blocks', type=int, default=1, help='column blocks of the item-side SpMM (experimental)')
-    ap.add_argument('--scheme', default='user', choices=['user', 'rows'],
+    ap.add_argument('--scheme', default='user', choices=['user', 'rows', 'cols'],
                     help='user: users partitioned + items replicated (all-reduce of the item block per layer); '
-                         'rows: all rows partitioned (all-gather of the whole table per layer)')
+                         'rows: all rows partitioned (all-gather of the whole table per layer); '
+                         'cols: embedding columns partitioned, adjacency replicated (one [B] all-reduce per step)')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -38,7 +39,14 @@ def main():
         rp, co, va = synthetic.build_norm_adj(data, U, I, dev)
         g = torch.Generator(device=dev); g.manual_seed(3)
         ego = torch.randn(U + I, D, device=dev, generator=g) * 0.005
-        if args.scheme == 'rows':
+        if args.scheme == 'cols':
+            from qrec_b200.base.graphRecommender import DeviceCSR
+            dw = D // world
+            part, mine = None, None
+            m = parallel.ColumnShardedLightGCN(DeviceCSR.from_tensors((U + I, U + I), rp, co, va),
+                                               ego[:, rank * dw:(rank + 1) * dw].contiguous(), U, args.layers, 0.001, 0.001)
+            m.local_nnz = int(co.numel())
+        elif args.scheme == 'rows':
             part = parallel.NodePartition(U, I, world)
             lrp, lco, lva = parallel.shard_adjacency(rp, co, va, part, rank)
             mine = part.local_nodes(rank).to(dev)
@@ -80,13 +88,18 @@ def main():
         l_ref = ref.train_step(bu, bi, bj).item()
         l = m.train_step(bu, bi, bj).item()
         assert abs(l - l_ref) <= 1e-5 * abs(l_ref), (l, l_ref)
-        got = m.ego if args.scheme == 'rows' else torch.cat([m.Eu, m.Ei])
+        if args.scheme == 'cols':
+            lo_c = rank * (D // world)
+            got, gtot = m.ego, m.total
+            gref, eref = ref._total[:, lo_c:lo_c + D // world], ref.ego[:, lo_c:lo_c + D // world]
+        else:
+            got = m.ego if args.scheme == 'rows' else torch.cat([m.Eu, m.Ei])
+            gtot = m.total if args.scheme == 'rows' else torch.cat([m.tot_u, m.tot_i])
+            gref, eref = ref._total[mine], ref.ego[mine]
         # gradients first (Adam's first steps turn a tiny gradient difference into a visible table
         # difference wherever |g| ~ eps, so the tables get a looser absolute tolerance)
-        gtot = m.total if args.scheme == 'rows' else torch.cat([m.tot_u, m.tot_i])
-        gref = ref._total[mine]
         assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max()), 'gradient mismatch'
-        torch.testing.assert_close(got, ref.ego[mine], rtol=2e-3, atol=2e-4)
+        torch.testing.assert_close(got, eref, rtol=2e-3, atol=2e-4)
     if rank == 0:
         print(json.dumps({'parity': 'sharded (%s) == single-GPU LightGCN step' % args.scheme, 'world': world, 'graph': [U, I, U * DEG]}))
     del data, rp, co, va, ego, m, ref
@@ -97,6 +110,7 @@ def main():
     data, (rp, co, va), ego, part, mine, m = build(U, I)
     del rp, co, va, ego
     torch.cuda.empty_cache()
+    g.manual_seed(12)                                  # every rank draws the same minibatch (the cols scheme requires it)
     idx = torch.randint(0, U * DEG, (args.batch,), device=dev, generator=g)
     bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
     bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
