@@ -13,14 +13,17 @@
 //     accumulators;
 //   * while the tensor cores work on tile t, the 128 threads (thread r = TMEM lane r = user r) read tile t-1's
 //     accumulator with tcgen05.ld and run the selection of topn_kernels.cu with the row's count and cut-off in
-//     REGISTERS: compare, rated test (bisection) only for scores that pass, append to the row's 256-key list in an
-//     L2-resident scratch; a warp sorts a row (bitonic, shared memory) whenever its list could overflow.
+//     REGISTERS: a score that beats the cut-off is appended RAW to the row's 512-key list (L2-resident scratch) --
+//     one store, no rated test in the hot loop; whenever a list could overflow, its warp resolves the rated items of
+//     the whole list together (the user's rated row staged in shared memory, 16 keys per lane searched in parallel:
+//     no divergent chains of dependent global loads), sorts it (bitonic, shared memory) and keeps the N best.
 // Nothing of the [users x items] matrix is written.  d must be 32 or 64 (one or two 128-byte k-blocks).
 #include "common.h"
 
 namespace {
 
-constexpr int CAP = 256;   // candidate slots per user (>= N_max + items per tile)
+constexpr int CAP = 512;   // candidate slots per user (>= N_max + items per tile; large, so that a row is sorted rarely)
+constexpr int RBUF = 512;  // rated items of one user staged in shared memory for the (lazy) rated test; longer lists: global bisection
 constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
 constexpr int TM = 128, TN = 128;
 constexpr int KBLK = TM * 128;                       // bytes of one k-block (32 fp32 = 128 B per row) of a 128-row operand
@@ -116,7 +119,7 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& l
 }
 
 // KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
-// then one 2 KB sort buffer per warp.
+// then one 4 KB sort buffer and one 2 KB rated-row buffer per warp.
 template <int KB>
 __global__ void __launch_bounds__(128, 1)
 score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, int n_items,
@@ -134,6 +137,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   uint8_t* const sA_lo = smem + OPER;
   uint8_t* const sB = smem + 2 * OPER;                // stage s: hi at sB + s * 2 * OPER, lo right behind it
   unsigned long long* const sort_buf = reinterpret_cast<unsigned long long*>(smem + 6 * OPER);
+  int* const rated_buf = reinterpret_cast<int*>(smem + 6 * OPER + 4 * CAP * sizeof(unsigned long long));
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TM;
   const int my_row = row0 + tid;
@@ -141,6 +145,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   unsigned long long* const cand = workspace + (size_t)blockIdx.x * TM * CAP;       // this CTA's 128 lists
   unsigned long long* const my_cand = cand + (size_t)tid * CAP;
   unsigned long long* const my_sort = sort_buf + (size_t)warp * CAP;
+  int* const my_rated = rated_buf + warp * RBUF;
   long long rlo = 0, rhi = 0;
   if (u >= 0) { rlo = __ldg(rated_rowptr + u); rhi = __ldg(rated_rowptr + u + 1); }
   const unsigned long long rated_key_hi = (unsigned long long)ord_of(rated_value) << 32;
@@ -188,18 +193,48 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   int cnt = 0;                                        // this thread's row: candidates in its list, current cut-off
   unsigned long long thr = 0ULL;
 
+  // Row `src` of this warp: its candidate list into my_sort with the rated items resolved (a rated item scores
+  // `rated_value` whatever its dot product -- recommender.py:147-149), sorted descending.  Resolving twice is harmless.
+  auto resolve_and_sort = [&](int src) {
+    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    const long long lo = __shfl_sync(0xffffffffu, rlo, src), hi = __shfl_sync(0xffffffffu, rhi, src);
+    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+    const int len = (int)(hi - lo);
+    const bool staged = len <= RBUF;
+    __syncwarp();
+    if (staged)
+      for (int k = lane; k < len; k += 32) my_rated[k] = __ldg(rated_cols + lo + k);
+    __syncwarp();
+    for (int k = lane; k < CAP; k += 32) {
+      unsigned long long key = k < c ? __ldcg(list + k) : 0ULL;
+      if (k < c && len > 0) {
+        const int item = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffULL));
+        bool rated;
+        if (staged) {
+          int a = 0, b = len;
+          while (a < b) {
+            const int mid = (a + b) >> 1;
+            if (my_rated[mid] < item) a = mid + 1; else b = mid;
+          }
+          rated = a < len && my_rated[a] == item;
+        } else {
+          rated = is_rated(rated_cols, lo, hi, item);
+        }
+        if (rated) key = rated_key_hi | (key & 0xffffffffULL);
+      }
+      my_sort[k] = key;
+    }
+    warp_sort_desc(my_sort, lane);
+  };
+
   // selection over one finished accumulator (tile t, TMEM buffer t & 1)
   auto select_tile = [&](int t) {
-    // a row that could overflow during this tile goes back to its N best first (the warp sorts it together)
+    // a row that could overflow during this tile goes back to its N best first (its warp works on it together)
     unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - TN);
     while (need) {
       const int src = __ffs(need) - 1;
       need &= need - 1;
-      const int c = __shfl_sync(0xffffffffu, cnt, src);
-      const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
-      __syncwarp();
-      for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
-      warp_sort_desc(my_sort, lane);
+      resolve_and_sort(src);
       unsigned long long* wl = cand + (size_t)(warp * 32 + src) * CAP;
       for (int k = lane; k < N; k += 32) __stcg(wl + k, my_sort[k]);
       if (lane == src) { cnt = N; thr = my_sort[N - 1]; }
@@ -231,14 +266,11 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
         if (c >= n_items) continue;
         if (!(open_row || __uint_as_float(r[q]) >= thr_f)) continue;
         const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
-        unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
-        // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
+        const unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
+        // appended raw; a rated item can pass on its fixed value even when its dot product does not (resolved later)
         if (key > thr || (rated_key_hi | low) > thr) {
-          if (is_rated(rated_cols, rlo, rhi, c)) key = rated_key_hi | low;
-          if (key > thr) {
-            __stcg(my_cand + cnt, key);               // cnt < CAP by the compaction rule
-            ++cnt;
-          }
+          __stcg(my_cand + cnt, key);                 // cnt < CAP by the compaction rule
+          ++cnt;
         }
       }
     }
@@ -299,16 +331,12 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   }
   select_tile(n_tiles - 1);
 
-  // ---- final order and output: each warp sorts its 32 rows in turn
+  // ---- final order and output: each warp resolves and sorts its 32 rows in turn
   __syncwarp();
   for (int src = 0; src < 32; ++src) {
-    const int c = __shfl_sync(0xffffffffu, cnt, src);
     const int ur = __shfl_sync(0xffffffffu, u, src);
     if (ur < 0) continue;
-    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
-    __syncwarp();
-    for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
-    warp_sort_desc(my_sort, lane);
+    resolve_and_sort(src);
     const size_t orow = (size_t)(row0 + warp * 32 + src) * N;
     for (int k = lane; k < N; k += 32) {
       const unsigned long long key = my_sort[k];
@@ -327,7 +355,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
 template <int KB>
 int launch_tc(const float* U, const float* V, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
               const int* cols, float rated_value, int N, int* out_ids, float* out_scores, cudaStream_t st) {
-  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + 1024;     // operands + sort buffers + alignment
+  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + 4 * RBUF * (int)sizeof(int) + 1024;   // operands + sort / rated buffers + alignment
   static bool attr_set = false;
   if (!attr_set) {
     QREC_CUDA(cudaFuncSetAttribute(score_topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));

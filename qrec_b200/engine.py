@@ -695,7 +695,8 @@ def adam_dense_tf1(var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
 def adam_lr_t(lr, t, beta1=0.9, beta2=0.999):
     """lr * sqrt(1 - beta2^t) / (1 - beta1^t) with the roundings of qrec_adam_dense_tf1_f32 (fp32 powers)."""
     import numpy as np
-    b1p, b2p = np.float32(float(beta1) ** t), np.float32(float(beta2) ** t)
+    b1p = np.float32(float(np.float32(beta1)) ** float(t))        # (float)pow((double)beta1_f32, (double)t)
+    b2p = np.float32(float(np.float32(beta2)) ** float(t))
     return float(np.float32(lr) * np.sqrt(np.float32(1.0) - b2p) / (np.float32(1.0) - b1p))
 
 
