@@ -282,7 +282,7 @@ int qrec_score_topn_f32(const float* dev_U, const float* dev_V, int32_t d, int32
 /* The same contract with the scores computed on the tensor cores: tcgen05.mma kind::tf32, error-compensated
  * (3xTF32: hi.hi + lo.hi + hi.lo of operands split into two TF32 values), fp32 accumulators in TMEM read back with
  * tcgen05.ld by the selection code -- fp32-level scores (2^-22 relative per product), ~20x the SIMT kernel's rate.
- * d must be 32 or 64; tables 16-byte aligned.  csrc/topn_tc.cu. */
+ * d <= 64 and a multiple of 4; tables 16-byte aligned.  csrc/topn_tc.cu. */
 int qrec_score_topn_tc_f32(const float* dev_U, const float* dev_V, int32_t d, int32_t n_items,
                            const int32_t* dev_user_ids, int32_t n_rows, const int64_t* dev_rated_rowptr,
                            const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,

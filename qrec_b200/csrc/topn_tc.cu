@@ -17,7 +17,7 @@
 //     one store, no rated test in the hot loop; whenever a list could overflow, its warp resolves the rated items of
 //     the whole list together (the user's rated row staged in shared memory, 16 keys per lane searched in parallel:
 //     no divergent chains of dependent global loads), sorts it (bitonic, shared memory) and keeps the N best.
-// Nothing of the [users x items] matrix is written.  d must be 32 or 64 (one or two 128-byte k-blocks).
+// Nothing of the [users x items] matrix is written.  d <= 64, a multiple of 4 (one or two 128-byte k-blocks, zero-padded).
 #include "common.h"
 
 namespace {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& l
 // then one 4 KB sort buffer and one 2 KB rated-row buffer per warp.
 template <int KB>
 __global__ void __launch_bounds__(128, 1)
-score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, int n_items,
+score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, int d, int n_items,
                      const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
                      const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
                      float* __restrict__ out_scores, unsigned long long* __restrict__ workspace) {
@@ -165,7 +165,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
     const int q = tid + 128 * p;
     const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
     const int ur = (row0 + row < n_rows) ? __ldg(user_ids + row0 + row) : -1;
-    const float4 v = (ur >= 0) ? __ldg(reinterpret_cast<const float4*>(U + (size_t)ur * D + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 v = (ur >= 0 && c4 < d) ? __ldg(reinterpret_cast<const float4*>(U + (size_t)ur * d + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
     float4 hi, lo;
     split_tf32(v, hi, lo);
     const uint32_t off = (uint32_t)(c4 >> 5) * KBLK + sw_off(row, c4 & 31);
@@ -186,8 +186,8 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
     for (int p = 0; p < VPT; ++p) {
       const int q = tid + 128 * p;
       const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
-      rb[p] = (c0 + row < n_items) ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(c0 + row) * D + c4))
-                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[p] = (c0 + row < n_items && c4 < d) ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(c0 + row) * d + c4))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   };
   int cnt = 0;                                        // this thread's row: candidates in its list, current cut-off
@@ -353,7 +353,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
 }
 
 template <int KB>
-int launch_tc(const float* U, const float* V, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
+int launch_tc(const float* U, const float* V, int d, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
               const int* cols, float rated_value, int N, int* out_ids, float* out_scores, cudaStream_t st) {
   constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + 4 * RBUF * (int)sizeof(int) + 1024;   // operands + sort / rated buffers + alignment
   static bool attr_set = false;
@@ -364,7 +364,7 @@ int launch_tc(const float* U, const float* V, int n_items, const int* user_ids, 
   const int grid = (n_rows + TM - 1) / TM;
   unsigned long long* ws = nullptr;                       // candidate lists: 2 KB per user, stream-ordered scratch
   QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)grid * TM * CAP * sizeof(unsigned long long), st));
-  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, V, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
+  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, V, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
                                                     out_scores, ws);
   const cudaError_t launch_err = cudaGetLastError();
   QREC_CUDA(cudaFreeAsync(ws, st));
@@ -380,7 +380,7 @@ extern "C" int qrec_score_topn_tc_f32(const float* dev_U, const float* dev_V, in
                                       const int32_t* dev_rated_cols, float rated_value, int32_t N, int32_t* dev_out_ids,
                                       float* dev_out_scores, void* stream) {
   QREC_REQUIRE(n_rows >= 0 && n_items >= 1, "qrec_score_topn_tc_f32: bad size");
-  QREC_REQUIRE(d == 32 || d == 64, "qrec_score_topn_tc_f32: d=%d unsupported (32 or 64; use qrec_score_topn_f32)", d);
+  QREC_REQUIRE(d >= 4 && d <= 64 && d % 4 == 0, "qrec_score_topn_tc_f32: d=%d unsupported (multiple of 4, <= 64; use qrec_score_topn_f32)", d);
   QREC_REQUIRE(N >= 1 && N <= NMAX && N <= n_items, "qrec_score_topn_tc_f32: N=%d must be in 1..min(%d, n_items)", N, NMAX);
   if (n_rows == 0) return QREC_OK;
   QREC_REQUIRE(dev_U && dev_V && dev_user_ids && dev_rated_rowptr && dev_rated_cols && dev_out_ids && dev_out_scores,
@@ -389,7 +389,7 @@ extern "C" int qrec_score_topn_tc_f32(const float* dev_U, const float* dev_V, in
                "qrec_score_topn_tc_f32: tables must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const long long* rp = reinterpret_cast<const long long*>(dev_rated_rowptr);
-  if (d == 32)
-    return launch_tc<1>(dev_U, dev_V, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
-  return launch_tc<2>(dev_U, dev_V, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
+  if (d <= 32)                                            // columns beyond d are zero-filled up to the 32-wide k-block
+    return launch_tc<1>(dev_U, dev_V, d, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
+  return launch_tc<2>(dev_U, dev_V, d, n_items, dev_user_ids, n_rows, rp, dev_rated_cols, rated_value, N, dev_out_ids, dev_out_scores, st);
 }

@@ -425,12 +425,12 @@ SCORE_TOPN_TENSOR_CORES = False      # default of score_topn(tensor_cores=None);
 def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None, tensor_cores=None):
     """K8: the N best items of every listed user in one kernel (scores, rated -> rated_value, top-N; nothing
     materialised).  Returns (ids int32 [n, N], scores fp32 [n, N]), best first, ties by ascending item id.
-    tensor_cores: True = the tcgen05 3xTF32 kernel (csrc/topn_tc.cu; d must be 32 or 64), False = the fp32 SIMT kernel
+    tensor_cores: True = the tcgen05 3xTF32 kernel (csrc/topn_tc.cu; d <= 64, multiple of 4), False = the fp32 SIMT kernel
     (csrc/topn_kernels.cu), None = the module default where the width allows it."""
     torch = _torch()
     if tensor_cores is None:
         env = os.environ.get('QREC_TOPN_TC')
-        tensor_cores = (SCORE_TOPN_TENSOR_CORES if env is None else env == '1') and U.shape[1] in (32, 64)
+        tensor_cores = (SCORE_TOPN_TENSOR_CORES if env is None else env == '1') and U.shape[1] <= 64 and U.shape[1] % 4 == 0
     fn, name = (lib.qrec_score_topn_tc_f32, 'qrec_score_topn_tc_f32') if tensor_cores else (lib.qrec_score_topn_f32, 'qrec_score_topn_f32')
     n = int(user_ids.shape[0])
     if U.shape[1] != V.shape[1]:

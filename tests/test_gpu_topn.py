@@ -46,9 +46,9 @@ def _csr(rng, nu, ni, max_deg):
 
 @pytest.mark.parametrize('nu,ni,d,N,signed,tc', [(130, 1000, 64, 10, False, False), (77, 333, 52, 100, True, False), (5, 150, 8, 50, True, False),
                                                  (300, 20000, 64, 20, False, False), (64, 129, 128, 100, True, False),
-                                                 # the tcgen05 3xTF32 kernel (d = 32 | 64): same bounds -- fp32-level scores
+                                                 # the tcgen05 3xTF32 kernel (d <= 64): same bounds -- fp32-level scores
                                                  (130, 1000, 64, 10, False, True), (77, 333, 32, 100, True, True), (5, 150, 64, 50, True, True),
-                                                 (300, 20000, 64, 20, False, True), (129, 257, 32, 100, True, True),
+                                                 (300, 20000, 64, 20, False, True), (129, 257, 32, 100, True, True), (90, 700, 52, 30, True, True), (40, 300, 8, 20, False, True),
                                                  (1000, 5000, 64, 100, True, True)])
 def test_topn_equals_reference_flow(torch, E, nu, ni, d, N, signed, tc):
     _maybe_skip_tc(tc)
@@ -107,7 +107,7 @@ def test_topn_bad_arguments(torch, E):
     ids, _ = E.score_topn(U, V, u[:0], rp, co, 3)          # empty block
     assert ids.shape == (0, 3)
     with pytest.raises(E.QRecError):
-        E.score_topn(U, V, u, rp, co, 3, tensor_cores=True)   # d = 8: the tensor-core kernel takes 32 or 64
+        E.score_topn(torch.ones(4, 128, device='cuda'), torch.ones(5, 128, device='cuda'), u, rp, co, 3, tensor_cores=True)   # d > 64
 
 
 def test_topn_tensor_core_kernel_agrees_with_simt_kernel(torch, E):
