@@ -48,9 +48,10 @@ def main():
     data = synthetic.make_interactions(U, I, DEG, device=dev)
     rp, co, va = synthetic.build_norm_adj(data, U, I, dev)
 
-    class Adj(object):
-        def matmul(self, X, out, acc=None, acc_scale=0.0):
-            return E.spmm_csr(rp, co, va, X, out, acc=acc, acc_scale=acc_scale, rowsplit=True)
+    from qrec_b200.base.graphRecommender import DeviceCSR
+
+    def Adj():                       # the operand class the drop-in models build in initModel (matmul + the row-list products)
+        return DeviceCSR.from_tensors((U + I, U + I), rp, co, va)
     g = torch.Generator(device=dev); g.manual_seed(0)
     idx = torch.randperm(U * DEG, device=dev, generator=g)[:2048]
     bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
@@ -68,7 +69,8 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / args.steps
     steps_per_epoch = -(-U * DEG // 2048)
-    # ---- SimGCL (n_layer 2: 6 forward + 2 backward SpMM, noise, InfoNCE on the batch's unique rows)
+    # ---- SimGCL (n_layer 2: 3 whole-graph + 3 row-list products forward, 1 scatter + 1 whole-graph backward, noise,
+    #      InfoNCE on the batch's unique rows)
     m = shell(SimGCL, U, I, D, dev, Adj(), cl_rate=0.5, eps=0.1, n_layers=2)
     m.initModel()
     ms = timed(lambda: m.train_step(bu, bi, bj))

@@ -9,6 +9,7 @@ TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr
 port=29900
 port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_neumf.py --steps 10 > "$out/dist_neumf.log" 2>&1; echo "dist_neumf: exit $? -- $(grep -h '^{' "$out/dist_neumf.log" | cut -c1-900)"; grep -E "AssertionError|Error" "$out/dist_neumf.log" | head -3
 [ "${SKIP_DIST_LGCN:-0}" = 1 ] || { port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 > "$out/dist_lightgcn.log" 2>&1; echo "dist_lightgcn: exit $? -- $(grep -h '^{' "$out/dist_lightgcn.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn.log" | head -3; }
+[ "${SKIP_DIST_LGCN:-0}" = 1 ] || { port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 --scheme cols > "$out/dist_lightgcn_cols.log" 2>&1; echo "dist_lightgcn cols: exit $? -- $(grep -h '^{' "$out/dist_lightgcn_cols.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn_cols.log" | head -3; }
 [ "${SKIP_DIST_SIMGCL:-0}" = 1 ] || { port=$((port+1)); timeout 900 $TR --master-port $port tools/dist_simgcl.py --steps 5 > "$out/dist_simgcl.log" 2>&1; echo "dist_simgcl: exit $? -- $(grep -h '^{' "$out/dist_simgcl.log" | cut -c1-600)"; grep -E "AssertionError|Error" "$out/dist_simgcl.log" | head -3; }
 for w in ${WAVES:-1 2}; do
 port=$((port+1)); timeout 600 $TR --master-port $port bench.py --gpus $N --steps 20 --warmup 5 --q-syncs $w > "$out/bench_w$w.json" 2> "$out/bench_w$w.err"
@@ -24,3 +25,15 @@ except Exception as e:
     print('bench w$w FAILED', e); print(open('$out/bench_w$w.err').read()[-1200:])
 PY
 done
+
+# LightGCN section alone with the feature-parallel scheme
+port=$((port+1)); QREC_LGCN_SCHEME=cols timeout 600 $TR --master-port $port bench.py --gpus $N --steps 5 --warmup 3 --no-parity --no-roofs > "$out/bench_cols.json" 2> "$out/bench_cols.err"
+python - <<PY
+import json
+try:
+    d=json.loads([l for l in open('$out/bench_cols.json') if l.startswith('{')][-1])
+    lg=d.get('lightgcn') or {}
+    print('bench (lightgcn scheme %s): value %.3e | lightgcn' % (lg.get('scheme'), d['value']), {k:round(v['ms_per_step'],3) for k,v in lg.items() if k.startswith('batch')})
+except Exception as e:
+    print('bench cols FAILED', e); print(open('$out/bench_cols.err').read()[-1200:])
+PY
