@@ -4,8 +4,10 @@
 //
 //   * a CTA owns 128 users.  Their rows of U are split once into two TF32 operands, hi = rna_tf32(x) and
 //     lo = rna_tf32(x - hi), stored K-major / SWIZZLE_128B in shared memory (the layout of csrc/tc_gemm.cu);
-//   * the item table streams through in tiles of 128 items, split the same way into a 2-stage ring (global ->
-//     registers one tile ahead -> shared);
+//   * the item table is split the same way ONCE per call by a small pre-pass (split_items_kernel) that writes each
+//     128-item tile as one contiguous block already in the shared-memory layout; the main kernel streams those blocks
+//     through a 2-stage ring with cp.async.bulk (one 64 KB bulk copy per tile, completion on an mbarrier) -- no
+//     thread touches the item operands;
 //   * one thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8) three times per k-step --
 //     hi.hi + lo.hi + hi.lo, the classical 3xTF32 error-compensated product: the dropped lo.lo term is 2^-22
 //     relative, i.e. fp32-level scores, which is what keeps the index lists equal to an fp32 GEMV's wherever
@@ -102,6 +104,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spins > (1u << 22)) __trap();
   }
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk copy global -> shared (TMA engine), completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 // byte offset of element (row, k) inside one K-major SWIZZLE_128B k-block (k in [0,32) fp32)
 __device__ __forceinline__ uint32_t sw_off(int row, int k) {
   const int chunk = (k >> 2) ^ (row & 7);
@@ -118,11 +128,36 @@ __device__ __forceinline__ void split_tf32(const float4 v, float4& hi, float4& l
   lo = make_float4(rna_tf32(v.x - hi.x), rna_tf32(v.y - hi.y), rna_tf32(v.z - hi.z), rna_tf32(v.w - hi.w));
 }
 
+// Pre-pass: tile t of the item table (items [128 t, 128 t + 128), zero rows past the end, zero columns past d) as one
+// block of 2 * KB * 16 KB in the workspace: hi operand, then lo operand, each K-major SWIZZLE_128B -- byte for byte what
+// the main kernel wants in shared memory.
+template <int KB>
+__global__ void __launch_bounds__(128)
+split_items_kernel(const float* __restrict__ V, int d, int n_items, uint8_t* __restrict__ blocks) {
+  constexpr int D = KB * 32;
+  constexpr int OPER = KB * KBLK;
+  constexpr int VPT = TN * D / 4 / 128;
+  const int c0 = blockIdx.x * TN;
+  uint8_t* const out = blocks + (size_t)blockIdx.x * 2 * OPER;
+#pragma unroll
+  for (int p = 0; p < VPT; ++p) {
+    const int q = threadIdx.x + 128 * p;
+    const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
+    const float4 v = (c0 + row < n_items && c4 < d) ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(c0 + row) * d + c4))
+                                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    const uint32_t off = (uint32_t)(c4 >> 5) * KBLK + sw_off(row, c4 & 31);
+    *reinterpret_cast<float4*>(out + off) = hi;
+    *reinterpret_cast<float4*>(out + OPER + off) = lo;
+  }
+}
+
 // KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
 // then one 4 KB sort buffer and one 2 KB rated-row buffer per warp.
 template <int KB>
 __global__ void __launch_bounds__(128, 1)
-score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, int d, int n_items,
+score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ item_blocks, int d, int n_items,
                      const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
                      const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
                      float* __restrict__ out_scores, unsigned long long* __restrict__ workspace) {
@@ -131,6 +166,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   constexpr int VPT = TN * D / 4 / 128;               // float4 per thread per 128-row tile (8 or 16)
   extern __shared__ uint8_t smem_raw[];
   __shared__ uint64_t mma_done[2];
+  __shared__ uint64_t full[2];                        // stage s holds a whole tile (bulk-copy bytes counted)
   __shared__ uint32_t tmem_base_slot;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* const sA_hi = smem;
@@ -153,6 +189,8 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
@@ -172,6 +210,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
     *reinterpret_cast<float4*>(sA_hi + off) = hi;
     *reinterpret_cast<float4*>(sA_lo + off) = lo;
   }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");        // the A operands: generic-proxy writes -> async proxy (UMMA)
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -179,17 +218,6 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
   const uint32_t idesc = make_idesc();
 
   const int n_tiles = (n_items + TN - 1) / TN;
-  float4 rb[VPT];
-  auto load_tile = [&](int t) {                       // global -> registers (tile t of the item table)
-    const int c0 = t * TN;
-#pragma unroll
-    for (int p = 0; p < VPT; ++p) {
-      const int q = tid + 128 * p;
-      const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
-      rb[p] = (c0 + row < n_items && c4 < d) ? __ldg(reinterpret_cast<const float4*>(V + (size_t)(c0 + row) * d + c4))
-                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
   int cnt = 0;                                        // this thread's row: candidates in its list, current cut-off
   unsigned long long thr = 0ULL;
 
@@ -240,13 +268,14 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
       if (lane == src) { cnt = N; thr = my_sort[N - 1]; }
       __syncwarp();
     }
-    // cheap pre-filter for the 128 scores of this tile (the cut-off only moves in the compaction above): a score below
-    // the cut-off's score cannot pass, unless the list is not full yet or a rated item's fixed value could pass
+    // pre-filter for the 128 scores of this tile (the cut-off only moves in the compaction above): a score below the
+    // cut-off's score cannot pass, unless the list is not full yet or a rated item's fixed value could pass
     const bool open_row = thr == 0ULL || (uint32_t)(thr >> 32) <= (uint32_t)(rated_key_hi >> 32);
-    const float thr_f = open_row ? 0.f : score_of((uint32_t)(thr >> 32));
+    const float thr_f = open_row ? -INFINITY : score_of((uint32_t)(thr >> 32));
     mbar_wait(&mma_done[t & 1], (uint32_t)((t >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int c0 = t * TN;
+    const int valid = (n_items - c0) < TN ? (n_items - c0) : TN;      // columns of this tile that are items
 #pragma unroll 1
     for (int cc = 0; cc < TN; cc += 16) {
       uint32_t r[16];
@@ -259,14 +288,21 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
             "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (u < 0) continue;
+      // 16 compares without a branch: bit q of `pass` <=> score q is at or above the cut-off's score
+      uint32_t pass = 0;
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
+      for (int q = 0; q < 16; ++q) pass |= (__uint_as_float(r[q]) >= thr_f ? 1u : 0u) << q;
+      if (valid - cc < 16) pass &= (valid - cc) <= 0 ? 0u : ((1u << (valid - cc)) - 1u);
+      if (u < 0) pass = 0;
+      while (pass) {                                  // the few that pass: exact 64-bit test, raw append
+        const int q = __ffs(pass) - 1;
+        pass &= pass - 1;
+        uint32_t bits = r[0];                         // r[q] without dynamic register indexing
+#pragma unroll
+        for (int w = 1; w < 16; ++w) bits = (q == w) ? r[w] : bits;
         const int c = c0 + cc + q;
-        if (c >= n_items) continue;
-        if (!(open_row || __uint_as_float(r[q]) >= thr_f)) continue;
         const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
-        const unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
+        const unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(bits)) << 32) | low;
         // appended raw; a rated item can pass on its fixed value even when its dot product does not (resolved later)
         if (key > thr || (rated_key_hi | low) > thr) {
           __stcg(my_cand + cnt, key);                 // cnt < CAP by the compaction rule
@@ -279,27 +315,30 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   };
 
-  load_tile(0);
+  // ---- main loop.  Thread 0 drives the two engines: bulk copies (tile t+1 into the stage that MMA(t-1) has released) and
+  // the MMAs of tile t; then all 128 threads select from tile t-1's accumulator while the tensor cores work on tile t.
+  constexpr uint32_t TILE_BYTES = 2 * OPER;
+  if (tid == 0) {
+    for (int t0 = 0; t0 < 2 && t0 < n_tiles; ++t0) {
+      mbar_expect_tx(&full[t0], TILE_BYTES);
+      bulk_g2s(sB + t0 * TILE_BYTES, item_blocks + (size_t)t0 * TILE_BYTES, TILE_BYTES, &full[t0]);
+    }
+  }
   for (int t = 0; t < n_tiles; ++t) {
     const int s = t & 1;
-    uint8_t* const sB_hi = sB + s * 2 * OPER;
-    uint8_t* const sB_lo = sB_hi + OPER;
-    // stage s was read by the MMAs of tile t-2, whose completion select_tile(t-2) has waited for (iteration t-1)
-#pragma unroll
-    for (int p = 0; p < VPT; ++p) {
-      const int q = tid + 128 * p;
-      const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
-      float4 hi, lo;
-      split_tf32(rb[p], hi, lo);
-      const uint32_t off = (uint32_t)(c4 >> 5) * KBLK + sw_off(row, c4 & 31);
-      *reinterpret_cast<float4*>(sB_hi + off) = hi;
-      *reinterpret_cast<float4*>(sB_lo + off) = lo;
-    }
-    if (t + 1 < n_tiles) load_tile(t + 1);            // in flight during the MMAs and the selection below
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> async proxy (UMMA)
-    __syncthreads();                                  // also: every thread is done reading TMEM buffer s (tile t-2)
+    __syncthreads();                                  // every thread is done reading TMEM buffer s (tile t-2)
     if (tid == 0) {
+      if (t >= 1) {
+        mbar_wait(&mma_done[s ^ 1], (uint32_t)(((t - 1) >> 1) & 1));           // MMA(t-1) done: its operand stage is free
+        if (t + 1 < n_tiles) {
+          mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
+          bulk_g2s(sB + (s ^ 1) * TILE_BYTES, item_blocks + (size_t)(t + 1) * TILE_BYTES, TILE_BYTES, &full[s ^ 1]);
+        }
+      }
+      mbar_wait(&full[s], (uint32_t)((t >> 1) & 1));                           // tile t has landed
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      uint8_t* const sB_hi = sB + s * TILE_BYTES;
+      uint8_t* const sB_lo = sB_hi + OPER;
       const uint32_t acc_addr = tmem_acc + (uint32_t)(s * TN);
       bool first = true;
 #pragma unroll
@@ -327,6 +366,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const float* __restrict__ V, i
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[s]))
                    : "memory");
     }
+    __syncwarp();
     if (t >= 1) select_tile(t - 1);
   }
   select_tile(n_tiles - 1);
@@ -362,14 +402,19 @@ int launch_tc(const float* U, const float* V, int d, int n_items, const int* use
     attr_set = true;
   }
   const int grid = (n_rows + TM - 1) / TM;
-  unsigned long long* ws = nullptr;                       // candidate lists: 2 KB per user, stream-ordered scratch
-  QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), (size_t)grid * TM * CAP * sizeof(unsigned long long), st));
-  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, V, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
-                                                    out_scores, ws);
+  const int n_tiles = (n_items + TN - 1) / TN;
+  const size_t list_bytes = (size_t)grid * TM * CAP * sizeof(unsigned long long);    // candidate lists: 4 KB per user
+  const size_t block_bytes = (size_t)n_tiles * 2 * KB * KBLK;                         // the split item table, tile by tile
+  uint8_t* ws = nullptr;                                                              // stream-ordered scratch
+  QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), list_bytes + block_bytes, st));
+  uint8_t* const blocks = ws + list_bytes;                                            // (list_bytes is a multiple of 512 KB)
+  split_items_kernel<KB><<<n_tiles, 128, 0, st>>>(V, d, n_items, blocks);
+  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, blocks, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
+                                                    out_scores, reinterpret_cast<unsigned long long*>(ws));
   const cudaError_t launch_err = cudaGetLastError();
   QREC_CUDA(cudaFreeAsync(ws, st));
   if (launch_err != cudaSuccess) return qrec::cuda_fail(launch_err, "kernel launch", __FILE__, __LINE__);
-  qrec::count_launch();
+  qrec::count_launch(2);
   return QREC_OK;
 }
 
