@@ -168,7 +168,9 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   __shared__ uint64_t mma_done[2];
   __shared__ uint64_t full[2];                        // stage s holds a whole tile (bulk-copy bytes counted)
   __shared__ uint32_t tmem_base_slot;
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment by an offset from the array itself (not an integer round trip): the compiler keeps the
+  // shared address space, so the sort / rated buffers are read with LDS / written with STS
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* const sA_hi = smem;
   uint8_t* const sA_lo = smem + OPER;
   uint8_t* const sB = smem + 2 * OPER;                // stage s: hi at sB + s * 2 * OPER, lo right behind it
