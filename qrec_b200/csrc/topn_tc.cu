@@ -15,17 +15,18 @@
 //     accumulators;
 //   * while the tensor cores work on tile t, the 128 threads (thread r = TMEM lane r = user r) read tile t-1's
 //     accumulator with tcgen05.ld and run the selection of topn_kernels.cu with the row's count and cut-off in
-//     REGISTERS: a score that beats the cut-off is appended RAW to the row's 512-key list (L2-resident scratch) --
-//     one store, no rated test in the hot loop; whenever a list could overflow, its warp resolves the rated items of
-//     the whole list together (the user's rated row staged in shared memory, 16 keys per lane searched in parallel:
-//     no divergent chains of dependent global loads), sorts it (bitonic, shared memory) and keeps the N best.
+//     REGISTERS: 16 scores are compared without a branch; the few that beat the cut-off look up the row's 512-bit
+//     rated-set signature (built in shared memory when the kernel starts), run the exact rated test (bisection) only
+//     on a signature hit, and are appended to the row's 512-key list (L2-resident scratch).  Whenever a list could
+//     overflow, its warp finds the list's N-th largest key by a bit-wise search (16 keys per lane in registers, one
+//     warp reduction per bit -- no sort) and keeps the N keys at or above it; rows are sorted once, at the end.
 // Nothing of the [users x items] matrix is written.  d <= 64, a multiple of 4 (one or two 128-byte k-blocks, zero-padded).
 #include "common.h"
 
 namespace {
 
 constexpr int CAP = 512;   // candidate slots per user (>= N_max + items per tile; large, so that a row is sorted rarely)
-constexpr int RBUF = 512;  // rated items of one user staged in shared memory for the (lazy) rated test; longer lists: global bisection
+constexpr int SIGW = 16;   // 32-bit words of a row's rated-set signature (512 bits) kept in shared memory
 constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
 constexpr int TM = 128, TN = 128;
 constexpr int KBLK = TM * 128;                       // bytes of one k-block (32 fp32 = 128 B per row) of a 128-row operand
@@ -154,7 +155,7 @@ split_items_kernel(const float* __restrict__ V, int d, int n_items, uint8_t* __r
 }
 
 // KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
-// then one 4 KB sort buffer and one 2 KB rated-row buffer per warp.
+// then one 4 KB sort buffer per warp and the 128 rows' 512-bit rated-set signatures (8 KB).
 template <int KB>
 __global__ void __launch_bounds__(128, 1)
 score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ item_blocks, int d, int n_items,
@@ -175,7 +176,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   uint8_t* const sA_lo = smem + OPER;
   uint8_t* const sB = smem + 2 * OPER;                // stage s: hi at sB + s * 2 * OPER, lo right behind it
   unsigned long long* const sort_buf = reinterpret_cast<unsigned long long*>(smem + 6 * OPER);
-  int* const rated_buf = reinterpret_cast<int*>(smem + 6 * OPER + 4 * CAP * sizeof(unsigned long long));
+  uint32_t* const sig = reinterpret_cast<uint32_t*>(smem + 6 * OPER + 4 * CAP * sizeof(unsigned long long));   // [SIGW][TM], word-major
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int row0 = blockIdx.x * TM;
   const int my_row = row0 + tid;
@@ -183,10 +184,16 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   unsigned long long* const cand = workspace + (size_t)blockIdx.x * TM * CAP;       // this CTA's 128 lists
   unsigned long long* const my_cand = cand + (size_t)tid * CAP;
   unsigned long long* const my_sort = sort_buf + (size_t)warp * CAP;
-  int* const my_rated = rated_buf + warp * RBUF;
   long long rlo = 0, rhi = 0;
   if (u >= 0) { rlo = __ldg(rated_rowptr + u); rhi = __ldg(rated_rowptr + u + 1); }
   const unsigned long long rated_key_hi = (unsigned long long)ord_of(rated_value) << 32;
+  // this row's rated-set signature: bit hash(item) of 512 (the owning thread is the only writer of its column)
+#pragma unroll
+  for (int w = 0; w < SIGW; ++w) sig[w * TM + tid] = 0u;
+  for (long long k = rlo; k < rhi; ++k) {
+    const uint32_t h = ((uint32_t)__ldg(rated_cols + k) * 0x9E3779B1u) >> 23;
+    sig[(h >> 5) * TM + tid] |= 1u << (h & 31);
+  }
 
   if (tid == 0) {
     mbar_init(&mma_done[0], 1);
@@ -223,37 +230,72 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   int cnt = 0;                                        // this thread's row: candidates in its list, current cut-off
   unsigned long long thr = 0ULL;
 
-  // Row `src` of this warp: its candidate list into my_sort with the rated items resolved (a rated item scores
-  // `rated_value` whatever its dot product -- recommender.py:147-149), sorted descending.  Resolving twice is harmless.
-  auto resolve_and_sort = [&](int src) {
+  // Row `src` of this warp goes back to its N best: the N-th largest of its c keys by a bit-wise search on the keys
+  // held in registers (keys are distinct: the item id is part of the key), then the keys at or above it move to the
+  // front of the list.  The owner's count and cut-off are updated.
+  auto compact_row = [&](int src) {
     const int c = __shfl_sync(0xffffffffu, cnt, src);
-    const long long lo = __shfl_sync(0xffffffffu, rlo, src), hi = __shfl_sync(0xffffffffu, rhi, src);
-    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
-    const int len = (int)(hi - lo);
-    const bool staged = len <= RBUF;
-    __syncwarp();
-    if (staged)
-      for (int k = lane; k < len; k += 32) my_rated[k] = __ldg(rated_cols + lo + k);
-    __syncwarp();
-    for (int k = lane; k < CAP; k += 32) {
-      unsigned long long key = k < c ? __ldcg(list + k) : 0ULL;
-      if (k < c && len > 0) {
-        const int item = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffULL));
-        bool rated;
-        if (staged) {
-          int a = 0, b = len;
-          while (a < b) {
-            const int mid = (a + b) >> 1;
-            if (my_rated[mid] < item) a = mid + 1; else b = mid;
-          }
-          rated = a < len && my_rated[a] == item;
-        } else {
-          rated = is_rated(rated_cols, lo, hi, item);
-        }
-        if (rated) key = rated_key_hi | (key & 0xffffffffULL);
-      }
-      my_sort[k] = key;
+    unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+    unsigned long long k[CAP / 32];
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) k[i] = (lane + 32 * i < c) ? __ldcg(list + lane + 32 * i) : 0ULL;
+    // high words first (the score): the largest T with at least N keys whose high word is >= T
+    uint32_t th = 0;
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+      const uint32_t t1 = th | (1u << b);
+      int n = 0;
+#pragma unroll
+      for (int i = 0; i < CAP / 32; ++i) n += ((uint32_t)(k[i] >> 32) >= t1) ? 1 : 0;
+      if (__reduce_add_sync(0xffffffffu, n) >= N) th = t1;
     }
+    int above = 0, equal = 0;
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) {
+      above += ((uint32_t)(k[i] >> 32) > th) ? 1 : 0;
+      equal += ((uint32_t)(k[i] >> 32) == th) ? 1 : 0;
+    }
+    above = __reduce_add_sync(0xffffffffu, above);
+    equal = __reduce_add_sync(0xffffffffu, equal);
+    uint32_t tl = 0;                                   // low word (inverted item id) of the N-th key among the ties
+    if (equal > N - above) {                           // more keys tie on the score than fit: the smallest item ids win
+#pragma unroll 1
+      for (int b = 31; b >= 0; --b) {
+        const uint32_t t1 = tl | (1u << b);
+        int n = 0;
+#pragma unroll
+        for (int i = 0; i < CAP / 32; ++i) n += ((uint32_t)(k[i] >> 32) == th && (uint32_t)k[i] >= t1) ? 1 : 0;
+        if (__reduce_add_sync(0xffffffffu, n) >= N - above) tl = t1;
+      }
+    }
+    const unsigned long long cut = ((unsigned long long)th << 32) | tl;     // keys >= cut: exactly N of them
+    unsigned long long low = ~0ULL;
+    int base = 0;
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < CAP / 32; ++i) {
+      const bool keep = k[i] >= cut && k[i] != 0ULL;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) {
+        __stcg(list + base + __popc(m & ((1u << lane) - 1u)), k[i]);
+        low = k[i] < low ? k[i] : low;
+      }
+      base += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, low, o);
+      low = other < low ? other : low;
+    }
+    if (lane == src) { cnt = base; thr = low; }        // base == N; low = the N-th best key
+    __syncwarp();
+  };
+  // Row `src`: its list into my_sort, sorted descending (once per row, for the output).
+  auto sort_row = [&](int src) {
+    const int c = __shfl_sync(0xffffffffu, cnt, src);
+    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+    __syncwarp();
+    for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
     warp_sort_desc(my_sort, lane);
   };
 
@@ -264,11 +306,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
     while (need) {
       const int src = __ffs(need) - 1;
       need &= need - 1;
-      resolve_and_sort(src);
-      unsigned long long* wl = cand + (size_t)(warp * 32 + src) * CAP;
-      for (int k = lane; k < N; k += 32) __stcg(wl + k, my_sort[k]);
-      if (lane == src) { cnt = N; thr = my_sort[N - 1]; }
-      __syncwarp();
+      compact_row(src);
     }
     // pre-filter for the 128 scores of this tile (the cut-off only moves in the compaction above): a score below the
     // cut-off's score cannot pass, unless the list is not full yet or a rated item's fixed value could pass
@@ -304,11 +342,15 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
         for (int w = 1; w < 16; ++w) bits = (q == w) ? r[w] : bits;
         const int c = c0 + cc + q;
         const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
-        const unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(bits)) << 32) | low;
-        // appended raw; a rated item can pass on its fixed value even when its dot product does not (resolved later)
+        unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(bits)) << 32) | low;
+        // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
         if (key > thr || (rated_key_hi | low) > thr) {
-          __stcg(my_cand + cnt, key);                 // cnt < CAP by the compaction rule
-          ++cnt;
+          const uint32_t h = ((uint32_t)c * 0x9E3779B1u) >> 23;
+          if (((sig[(h >> 5) * TM + tid] >> (h & 31)) & 1u) && is_rated(rated_cols, rlo, rhi, c)) key = rated_key_hi | low;
+          if (key > thr) {
+            __stcg(my_cand + cnt, key);               // cnt < CAP by the compaction rule
+            ++cnt;
+          }
         }
       }
     }
@@ -373,12 +415,12 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   }
   select_tile(n_tiles - 1);
 
-  // ---- final order and output: each warp resolves and sorts its 32 rows in turn
+  // ---- final order and output: each warp sorts its 32 rows in turn
   __syncwarp();
   for (int src = 0; src < 32; ++src) {
     const int ur = __shfl_sync(0xffffffffu, u, src);
     if (ur < 0) continue;
-    resolve_and_sort(src);
+    sort_row(src);
     const size_t orow = (size_t)(row0 + warp * 32 + src) * N;
     for (int k = lane; k < N; k += 32) {
       const unsigned long long key = my_sort[k];
@@ -397,7 +439,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
 template <int KB>
 int launch_tc(const float* U, const float* V, int d, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
               const int* cols, float rated_value, int N, int* out_ids, float* out_scores, cudaStream_t st) {
-  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + 4 * RBUF * (int)sizeof(int) + 1024;   // operands + sort / rated buffers + alignment
+  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + SIGW * TM * (int)sizeof(uint32_t) + 1024;   // operands + sort buffers + signatures + alignment
   static bool attr_set = false;
   if (!attr_set) {
     QREC_CUDA(cudaFuncSetAttribute(score_topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
