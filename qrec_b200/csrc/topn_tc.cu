@@ -13,8 +13,10 @@
 //     relative, i.e. fp32-level scores, which is what keeps the index lists equal to an fp32 GEMV's wherever
 //     scores are distinct (plain TF32's 10-bit mantissa reorders close scores) -- into one of two 128-column TMEM
 //     accumulators;
-//   * while the tensor cores work on tile t, the 128 threads (thread r = TMEM lane r = user r) read tile t-1's
-//     accumulator with tcgen05.ld and run the selection of topn_kernels.cu with the row's count and cut-off in
+//   * while the tensor cores work on tile t, 256 threads read tile t-1's accumulator with tcgen05.ld -- two threads
+//     per user row (warps w and w+4 own TMEM lanes 32 (w%4)..; one takes columns 0-63 of the tile, the other 64-127),
+//     each with its OWN candidate list and cut-off (the N best overall are among the N best of the two halves; the
+//     lists are merged at the end) -- and run the selection of topn_kernels.cu with the count and cut-off in
 //     REGISTERS: 16 scores are compared without a branch; the few that beat the cut-off look up the row's 512-bit
 //     rated-set signature (built in shared memory when the kernel starts), run the exact rated test (bisection) only
 //     on a signature hit, and are appended to the row's 512-key list (L2-resident scratch).  Whenever a list could
@@ -25,7 +27,10 @@
 
 namespace {
 
-constexpr int CAP = 512;   // candidate slots per user (>= N_max + items per tile; large, so that a row is sorted rarely)
+constexpr int CAP = 320;   // candidate slots per half-row list (>= N_max + TRIG_EXTRA + the 64 items a tile can add)
+constexpr int TRIG_EXTRA = 96;   // a list is cut back to its N best once it holds more than N + TRIG_EXTRA keys
+constexpr int SORTN = 256; // keys of the final per-row sort (two lists of at most N_max keys)
+constexpr int NT = 256;    // threads per CTA: 8 warps, two per TMEM lane quarter
 constexpr int SIGW = 16;   // 32-bit words of a row's rated-set signature (512 bits) kept in shared memory
 constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
 constexpr int TM = 128, TN = 128;
@@ -47,14 +52,15 @@ __device__ __forceinline__ bool is_rated(const int* __restrict__ cols, long long
   }
   return false;
 }
-// one warp sorts the CAP keys of one row, descending (bitonic network in shared memory)
+// one warp sorts SZ keys, descending (bitonic network in shared memory)
+template <int SZ>
 __device__ __forceinline__ void warp_sort_desc(unsigned long long* k, int lane) {
 #pragma unroll 1
-  for (int size = 2; size <= CAP; size <<= 1) {
+  for (int size = 2; size <= SZ; size <<= 1) {
 #pragma unroll 1
     for (int stride = size >> 1; stride > 0; stride >>= 1) {
       __syncwarp();
-      for (int t = lane; t < CAP / 2; t += 32) {
+      for (int t = lane; t < SZ / 2; t += 32) {
         const int lo = 2 * t - (t & (stride - 1));
         const int hi = lo + stride;
         const bool desc = (lo & size) == 0;
@@ -155,17 +161,18 @@ split_items_kernel(const float* __restrict__ V, int d, int n_items, uint8_t* __r
 }
 
 // KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
-// then one 4 KB sort buffer per warp and the 128 rows' 512-bit rated-set signatures (8 KB).
+// then one 2 KB sort buffer per warp (8 warps) and the 128 rows' 512-bit rated-set signatures (8 KB).
 template <int KB>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(NT, 1)
 score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ item_blocks, int d, int n_items,
                      const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
                      const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
                      float* __restrict__ out_scores, unsigned long long* __restrict__ workspace) {
   constexpr int D = KB * 32;
   constexpr int OPER = KB * KBLK;                     // bytes of one 128-row operand (hi or lo)
-  constexpr int VPT = TN * D / 4 / 128;               // float4 per thread per 128-row tile (8 or 16)
+  constexpr int APT = TM * D / 4 / NT;                // float4 per thread of the users' 128-row operand (4 or 8)
   extern __shared__ uint8_t smem_raw[];
+  __shared__ int cnt_sh[2][TM];
   __shared__ uint64_t mma_done[2];
   __shared__ uint64_t full[2];                        // stage s holds a whole tile (bulk-copy bytes counted)
   __shared__ uint32_t tmem_base_slot;
@@ -176,23 +183,27 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   uint8_t* const sA_lo = smem + OPER;
   uint8_t* const sB = smem + 2 * OPER;                // stage s: hi at sB + s * 2 * OPER, lo right behind it
   unsigned long long* const sort_buf = reinterpret_cast<unsigned long long*>(smem + 6 * OPER);
-  uint32_t* const sig = reinterpret_cast<uint32_t*>(smem + 6 * OPER + 4 * CAP * sizeof(unsigned long long));   // [SIGW][TM], word-major
+  uint32_t* const sig = reinterpret_cast<uint32_t*>(smem + 6 * OPER + 8 * SORTN * sizeof(unsigned long long));   // [SIGW][TM], word-major
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wq = warp & 3, half = warp >> 2;          // TMEM lane quarter; which 64 columns of a tile this thread selects from
+  const int rowl = wq * 32 + lane;                    // the thread's user row inside the CTA (= its TMEM lane)
   const int row0 = blockIdx.x * TM;
-  const int my_row = row0 + tid;
+  const int my_row = row0 + rowl;
   const int u = (my_row < n_rows) ? __ldg(user_ids + my_row) : -1;
-  unsigned long long* const cand = workspace + (size_t)blockIdx.x * TM * CAP;       // this CTA's 128 lists
-  unsigned long long* const my_cand = cand + (size_t)tid * CAP;
-  unsigned long long* const my_sort = sort_buf + (size_t)warp * CAP;
+  unsigned long long* const cand = workspace + (size_t)blockIdx.x * TM * 2 * CAP;   // this CTA's 2 x 128 lists
+  unsigned long long* const my_cand = cand + ((size_t)rowl * 2 + half) * CAP;
+  unsigned long long* const my_sort = sort_buf + (size_t)warp * SORTN;
   long long rlo = 0, rhi = 0;
   if (u >= 0) { rlo = __ldg(rated_rowptr + u); rhi = __ldg(rated_rowptr + u + 1); }
   const unsigned long long rated_key_hi = (unsigned long long)ord_of(rated_value) << 32;
   // this row's rated-set signature: bit hash(item) of 512 (the owning thread is the only writer of its column)
+  if (half == 0) {
 #pragma unroll
-  for (int w = 0; w < SIGW; ++w) sig[w * TM + tid] = 0u;
-  for (long long k = rlo; k < rhi; ++k) {
-    const uint32_t h = ((uint32_t)__ldg(rated_cols + k) * 0x9E3779B1u) >> 23;
-    sig[(h >> 5) * TM + tid] |= 1u << (h & 31);
+    for (int w = 0; w < SIGW; ++w) sig[w * TM + rowl] = 0u;
+    for (long long k = rlo; k < rhi; ++k) {
+      const uint32_t h = ((uint32_t)__ldg(rated_cols + k) * 0x9E3779B1u) >> 23;
+      sig[(h >> 5) * TM + rowl] |= 1u << (h & 31);
+    }
   }
 
   if (tid == 0) {
@@ -208,8 +219,8 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   }
   // ---- the users' rows, split and stored once: float4 number q of the tile is (row q / (D/4), columns 4 * (q % (D/4)))
 #pragma unroll
-  for (int p = 0; p < VPT; ++p) {
-    const int q = tid + 128 * p;
+  for (int p = 0; p < APT; ++p) {
+    const int q = tid + NT * p;
     const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
     const int ur = (row0 + row < n_rows) ? __ldg(user_ids + row0 + row) : -1;
     const float4 v = (ur >= 0 && c4 < d) ? __ldg(reinterpret_cast<const float4*>(U + (size_t)ur * d + c4)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,7 +246,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   // front of the list.  The owner's count and cut-off are updated.
   auto compact_row = [&](int src) {
     const int c = __shfl_sync(0xffffffffu, cnt, src);
-    unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
+    unsigned long long* list = cand + ((size_t)(wq * 32 + src) * 2 + half) * CAP;
     unsigned long long k[CAP / 32];
 #pragma unroll
     for (int i = 0; i < CAP / 32; ++i) k[i] = (lane + 32 * i < c) ? __ldcg(list + lane + 32 * i) : 0ULL;
@@ -290,19 +301,10 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
     if (lane == src) { cnt = base; thr = low; }        // base == N; low = the N-th best key
     __syncwarp();
   };
-  // Row `src`: its list into my_sort, sorted descending (once per row, for the output).
-  auto sort_row = [&](int src) {
-    const int c = __shfl_sync(0xffffffffu, cnt, src);
-    const unsigned long long* list = cand + (size_t)(warp * 32 + src) * CAP;
-    __syncwarp();
-    for (int k = lane; k < CAP; k += 32) my_sort[k] = k < c ? __ldcg(list + k) : 0ULL;
-    warp_sort_desc(my_sort, lane);
-  };
-
   // selection over one finished accumulator (tile t, TMEM buffer t & 1)
   auto select_tile = [&](int t) {
     // a row that could overflow during this tile goes back to its N best first (its warp works on it together)
-    unsigned need = __ballot_sync(0xffffffffu, cnt > CAP - TN);
+    unsigned need = __ballot_sync(0xffffffffu, cnt > N + TRIG_EXTRA);
     while (need) {
       const int src = __ffs(need) - 1;
       need &= need - 1;
@@ -314,13 +316,13 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
     const float thr_f = open_row ? -INFINITY : score_of((uint32_t)(thr >> 32));
     mbar_wait(&mma_done[t & 1], (uint32_t)((t >> 1) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int c0 = t * TN;
-    const int valid = (n_items - c0) < TN ? (n_items - c0) : TN;      // columns of this tile that are items
+    const int c0 = t * TN + half * 64;                                // first item of this thread's 64 columns
+    const int valid = n_items - c0;                                    // columns of them that are items (may be <= 0 or > 64)
 #pragma unroll 1
-    for (int cc = 0; cc < TN; cc += 16) {
+    for (int cc = 0; cc < 64; cc += 16) {
       uint32_t r[16];
       __syncwarp();                                   // the rare path below diverges; tcgen05.ld is warp-collective
-      const uint32_t taddr = tmem_acc + ((uint32_t)(warp * 32) << 16) + (uint32_t)((t & 1) * TN + cc);
+      const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)((t & 1) * TN + half * 64 + cc);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -334,22 +336,22 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
       for (int q = 0; q < 16; ++q) pass |= (__uint_as_float(r[q]) >= thr_f ? 1u : 0u) << q;
       if (valid - cc < 16) pass &= (valid - cc) <= 0 ? 0u : ((1u << (valid - cc)) - 1u);
       if (u < 0) pass = 0;
-      while (pass) {                                  // the few that pass: exact 64-bit test, raw append
-        const int q = __ffs(pass) - 1;
-        pass &= pass - 1;
-        uint32_t bits = r[0];                         // r[q] without dynamic register indexing
+      if (pass) {                                     // the few that pass: exact 64-bit test, rated test on a signature hit
 #pragma unroll
-        for (int w = 1; w < 16; ++w) bits = (q == w) ? r[w] : bits;
-        const int c = c0 + cc + q;
-        const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
-        unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(bits)) << 32) | low;
-        // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
-        if (key > thr || (rated_key_hi | low) > thr) {
-          const uint32_t h = ((uint32_t)c * 0x9E3779B1u) >> 23;
-          if (((sig[(h >> 5) * TM + tid] >> (h & 31)) & 1u) && is_rated(rated_cols, rlo, rhi, c)) key = rated_key_hi | low;
-          if (key > thr) {
-            __stcg(my_cand + cnt, key);               // cnt < CAP by the compaction rule
-            ++cnt;
+        for (int q = 0; q < 16; ++q) {
+          if (pass & (1u << q)) {
+            const int c = c0 + cc + q;
+            const unsigned long long low = (unsigned long long)(0xffffffffu - (uint32_t)c);
+            unsigned long long key = ((unsigned long long)ord_of(__uint_as_float(r[q])) << 32) | low;
+            // a rated item scores `rated_value` whatever its dot product: it can pass even when the raw score does not
+            if (key > thr || (rated_key_hi | low) > thr) {
+              const uint32_t h = ((uint32_t)c * 0x9E3779B1u) >> 23;
+              if (((sig[(h >> 5) * TM + rowl] >> (h & 31)) & 1u) && is_rated(rated_cols, rlo, rhi, c)) key = rated_key_hi | low;
+              if (key > thr) {
+                __stcg(my_cand + cnt, key);           // cnt < CAP by the compaction rule
+                ++cnt;
+              }
+            }
           }
         }
       }
@@ -415,13 +417,29 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   }
   select_tile(n_tiles - 1);
 
-  // ---- final order and output: each warp sorts its 32 rows in turn
+  // ---- final: every list down to at most N keys, then the two lists of a row merged, sorted and written
   __syncwarp();
-  for (int src = 0; src < 32; ++src) {
+  {
+    unsigned need = __ballot_sync(0xffffffffu, cnt > N);
+    while (need) {
+      const int src = __ffs(need) - 1;
+      need &= need - 1;
+      compact_row(src);
+    }
+  }
+  cnt_sh[half][rowl] = cnt;
+  __syncthreads();                                    // both halves' lists (global, st.cg) and counts are visible
+  for (int src = half; src < 32; src += 2) {          // the two warps of a lane quarter share its 32 rows
+    const int r = wq * 32 + src;
     const int ur = __shfl_sync(0xffffffffu, u, src);
     if (ur < 0) continue;
-    sort_row(src);
-    const size_t orow = (size_t)(row0 + warp * 32 + src) * N;
+    const int ca = cnt_sh[0][r], cb = cnt_sh[1][r];   // <= N each
+    const unsigned long long* la = cand + (size_t)r * 2 * CAP;
+    const unsigned long long* lb = la + CAP;
+    __syncwarp();
+    for (int k = lane; k < SORTN; k += 32) my_sort[k] = k < ca ? __ldcg(la + k) : (k - ca < cb ? __ldcg(lb + (k - ca)) : 0ULL);
+    warp_sort_desc<SORTN>(my_sort, lane);
+    const size_t orow = (size_t)(row0 + r) * N;
     for (int k = lane; k < N; k += 32) {
       const unsigned long long key = my_sort[k];
       out_ids[orow + k] = (int)(0xffffffffu - (uint32_t)(key & 0xffffffffULL));
@@ -439,7 +457,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
 template <int KB>
 int launch_tc(const float* U, const float* V, int d, int n_items, const int* user_ids, int n_rows, const long long* rowptr,
               const int* cols, float rated_value, int N, int* out_ids, float* out_scores, cudaStream_t st) {
-  constexpr int SMEM = 6 * KB * KBLK + 4 * CAP * (int)sizeof(unsigned long long) + SIGW * TM * (int)sizeof(uint32_t) + 1024;   // operands + sort buffers + signatures + alignment
+  constexpr int SMEM = 6 * KB * KBLK + 8 * SORTN * (int)sizeof(unsigned long long) + SIGW * TM * (int)sizeof(uint32_t) + 1024;   // operands + sort buffers + signatures + alignment
   static bool attr_set = false;
   if (!attr_set) {
     QREC_CUDA(cudaFuncSetAttribute(score_topn_tc_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -447,13 +465,13 @@ int launch_tc(const float* U, const float* V, int d, int n_items, const int* use
   }
   const int grid = (n_rows + TM - 1) / TM;
   const int n_tiles = (n_items + TN - 1) / TN;
-  const size_t list_bytes = (size_t)grid * TM * CAP * sizeof(unsigned long long);    // candidate lists: 4 KB per user
+  const size_t list_bytes = (size_t)grid * TM * 2 * CAP * sizeof(unsigned long long);   // candidate lists: 2 x 2.5 KB per user
   const size_t block_bytes = (size_t)n_tiles * 2 * KB * KBLK;                         // the split item table, tile by tile
   uint8_t* ws = nullptr;                                                              // stream-ordered scratch
   QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), list_bytes + block_bytes, st));
-  uint8_t* const blocks = ws + list_bytes;                                            // (list_bytes is a multiple of 512 KB)
+  uint8_t* const blocks = ws + list_bytes;                                            // (list_bytes is a multiple of 640 KB)
   split_items_kernel<KB><<<n_tiles, 128, 0, st>>>(V, d, n_items, blocks);
-  score_topn_tc_kernel<KB><<<grid, 128, SMEM, st>>>(U, blocks, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
+  score_topn_tc_kernel<KB><<<grid, NT, SMEM, st>>>(U, blocks, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
                                                     out_scores, reinterpret_cast<unsigned long long*>(ws));
   const cudaError_t launch_err = cudaGetLastError();
   QREC_CUDA(cudaFreeAsync(ws, st));
