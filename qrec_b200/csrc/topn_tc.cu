@@ -30,7 +30,8 @@ namespace {
 constexpr int CAP = 320;   // candidate slots per half-row list (>= N_max + TRIG_EXTRA + the 64 items a tile can add)
 constexpr int TRIG_EXTRA = 96;   // a list is cut back to its N best once it holds more than N + TRIG_EXTRA keys
 constexpr int SORTN = 256; // keys of the final per-row sort (two lists of at most N_max keys)
-constexpr int NT = 256;    // threads per CTA: 8 warps, two per TMEM lane quarter
+constexpr int NT = 256;    // selecting threads per CTA: 8 warps, two per TMEM lane quarter (a 9th warp drives TMA and the MMAs)
+constexpr int NBUF = 4;    // TMEM accumulators of 128 columns: the tensor cores may run up to 3 tiles ahead of the slowest warp
 constexpr int SIGW = 16;   // 32-bit words of a row's rated-set signature (512 bits) kept in shared memory
 constexpr int NMAX = 100;  // base/recommender.py:131-134 clamps N to <= 100
 constexpr int TM = 128, TN = 128;
@@ -163,7 +164,7 @@ split_items_kernel(const float* __restrict__ V, int d, int n_items, uint8_t* __r
 // KB = d / 32 k-blocks.  Shared memory: A hi | A lo (KB x 16 KB each), then two B stages (hi | lo, KB x 16 KB each),
 // then one 2 KB sort buffer per warp (8 warps) and the 128 rows' 512-bit rated-set signatures (8 KB).
 template <int KB>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT + 32, 1)
 score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ item_blocks, int d, int n_items,
                      const int* __restrict__ user_ids, int n_rows, const long long* __restrict__ rated_rowptr,
                      const int* __restrict__ rated_cols, float rated_value, int N, int* __restrict__ out_ids,
@@ -173,8 +174,9 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   constexpr int APT = TM * D / 4 / NT;                // float4 per thread of the users' 128-row operand (4 or 8)
   extern __shared__ uint8_t smem_raw[];
   __shared__ int cnt_sh[2][TM];
-  __shared__ uint64_t mma_done[2];
-  __shared__ uint64_t full[2];                        // stage s holds a whole tile (bulk-copy bytes counted)
+  __shared__ uint64_t mma_done[NBUF];                 // accumulator b holds a finished tile (tcgen05.commit)
+  __shared__ uint64_t acc_free[NBUF];                 // all 8 selecting warps are done with accumulator b
+  __shared__ uint64_t full[2];                        // operand stage s holds a whole tile (bulk-copy bytes counted)
   __shared__ uint32_t tmem_base_slot;
   // 1024-byte alignment by an offset from the array itself (not an integer round trip): the compiler keeps the
   // shared address space, so the sort / rated buffers are read with LDS / written with STS
@@ -207,19 +209,22 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   }
 
   if (tid == 0) {
-    mbar_init(&mma_done[0], 1);
-    mbar_init(&mma_done[1], 1);
+    for (int b = 0; b < NBUF; ++b) {
+      mbar_init(&mma_done[b], 1);
+      mbar_init(&acc_free[b], NT / 32);
+    }
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(2 * TN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "n"(NBUF * TN));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   // ---- the users' rows, split and stored once: float4 number q of the tile is (row q / (D/4), columns 4 * (q % (D/4)))
 #pragma unroll
   for (int p = 0; p < APT; ++p) {
+    if (tid >= NT) break;                             // the 9th warp stages nothing
     const int q = tid + NT * p;
     const int row = q / (D / 4), c4 = (q % (D / 4)) * 4;
     const int ur = (row0 + row < n_rows) ? __ldg(user_ids + row0 + row) : -1;
@@ -314,7 +319,8 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
     // cut-off's score cannot pass, unless the list is not full yet or a rated item's fixed value could pass
     const bool open_row = thr == 0ULL || (uint32_t)(thr >> 32) <= (uint32_t)(rated_key_hi >> 32);
     const float thr_f = open_row ? -INFINITY : score_of((uint32_t)(thr >> 32));
-    mbar_wait(&mma_done[t & 1], (uint32_t)((t >> 1) & 1));
+    const int buf = t % NBUF;
+    mbar_wait(&mma_done[buf], (uint32_t)((t / NBUF) & 1));
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int c0 = t * TN + half * 64;                                // first item of this thread's 64 columns
     const int valid = n_items - c0;                                    // columns of them that are items (may be <= 0 or > 64)
@@ -322,7 +328,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
     for (int cc = 0; cc < 64; cc += 16) {
       uint32_t r[16];
       __syncwarp();                                   // the rare path below diverges; tcgen05.ld is warp-collective
-      const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)((t & 1) * TN + half * 64 + cc);
+      const uint32_t taddr = tmem_acc + ((uint32_t)(wq * 32) << 16) + (uint32_t)(buf * TN + half * 64 + cc);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
           "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -356,70 +362,64 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
         }
       }
     }
-    // the accumulator may be overwritten once every thread is past its loads: ordered by the barrier that precedes
-    // the next MMA issue into this buffer
+    // the accumulator may be overwritten once all 8 warps are past their loads: each warp says so on acc_free
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_free[buf])) : "memory");
   };
 
-  // ---- main loop.  Thread 0 drives the two engines: bulk copies (tile t+1 into the stage that MMA(t-1) has released) and
-  // the MMAs of tile t; then all 128 threads select from tile t-1's accumulator while the tensor cores work on tile t.
+  // ---- main loop.  The 9th warp's lane 0 drives the two engines -- bulk copies (tile j into the operand stage that
+  // MMA(j-2) has released) and the 24 MMAs of tile j into accumulator j % 4 once the 8 selecting warps have released
+  // it -- and never selects; the selecting warps follow at their own pace (no CTA-wide barrier per tile: a warp that
+  // compacts a list only holds back the accumulator it has not released yet).
   constexpr uint32_t TILE_BYTES = 2 * OPER;
-  if (tid == 0) {
-    for (int t0 = 0; t0 < 2 && t0 < n_tiles; ++t0) {
-      mbar_expect_tx(&full[t0], TILE_BYTES);
-      bulk_g2s(sB + t0 * TILE_BYTES, item_blocks + (size_t)t0 * TILE_BYTES, TILE_BYTES, &full[t0]);
-    }
-  }
-  for (int t = 0; t < n_tiles; ++t) {
-    const int s = t & 1;
-    __syncthreads();                                  // every thread is done reading TMEM buffer s (tile t-2)
-    if (tid == 0) {
-      if (t >= 1) {
-        mbar_wait(&mma_done[s ^ 1], (uint32_t)(((t - 1) >> 1) & 1));           // MMA(t-1) done: its operand stage is free
-        if (t + 1 < n_tiles) {
-          mbar_expect_tx(&full[s ^ 1], TILE_BYTES);
-          bulk_g2s(sB + (s ^ 1) * TILE_BYTES, item_blocks + (size_t)(t + 1) * TILE_BYTES, TILE_BYTES, &full[s ^ 1]);
-        }
-      }
-      mbar_wait(&full[s], (uint32_t)((t >> 1) & 1));                           // tile t has landed
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      uint8_t* const sB_hi = sB + s * TILE_BYTES;
-      uint8_t* const sB_lo = sB_hi + OPER;
-      const uint32_t acc_addr = tmem_acc + (uint32_t)(s * TN);
-      bool first = true;
+  if (warp == NT / 32) {
+    if (lane == 0) {
+      for (int j = 0; j < n_tiles; ++j) {
+        const int s = j & 1, b = j % NBUF;
+        if (j >= 2) mbar_wait(&mma_done[(j - 2) % NBUF], (uint32_t)(((j - 2) / NBUF) & 1));   // MMA(j-2) done: stage s is free
+        mbar_expect_tx(&full[s], TILE_BYTES);
+        bulk_g2s(sB + s * TILE_BYTES, item_blocks + (size_t)j * TILE_BYTES, TILE_BYTES, &full[s]);
+        if (j >= NBUF) mbar_wait(&acc_free[b], (uint32_t)((j / NBUF - 1) & 1));              // select(j-4) done everywhere
+        mbar_wait(&full[s], (uint32_t)((j >> 1) & 1));                                        // tile j has landed
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint8_t* const sB_hi = sB + s * TILE_BYTES;
+        uint8_t* const sB_lo = sB_hi + OPER;
+        const uint32_t acc_addr = tmem_acc + (uint32_t)(b * TN);
+        bool first = true;
 #pragma unroll
-      for (int kb = 0; kb < KB; ++kb) {
-        const uint64_t a_hi = make_desc(smem_u32(sA_hi + kb * KBLK)), a_lo = make_desc(smem_u32(sA_lo + kb * KBLK));
-        const uint64_t b_hi = make_desc(smem_u32(sB_hi + kb * KBLK)), b_lo = make_desc(smem_u32(sB_lo + kb * KBLK));
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t a_hi = make_desc(smem_u32(sA_hi + kb * KBLK)), a_lo = make_desc(smem_u32(sA_lo + kb * KBLK));
+          const uint64_t b_hi = make_desc(smem_u32(sB_hi + kb * KBLK)), b_lo = make_desc(smem_u32(sB_lo + kb * KBLK));
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const uint64_t step = (uint64_t)(k4 * 2);   // +2 = 32 bytes (8 tf32) along K inside the 128-byte span
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t step = (uint64_t)(k4 * 2);   // +2 = 32 bytes (8 tf32) along K inside the 128-byte span
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {      // small terms first: lo.hi, hi.lo, then hi.hi
-            const uint64_t da = (term == 0 ? a_lo : a_hi) + step;
-            const uint64_t db = (term == 1 ? b_lo : b_hi) + step;
-            const uint32_t accf = first ? 0u : 1u;
-            first = false;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\t"
-                "setp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(acc_addr), "l"(da), "l"(db), "r"(idesc),
-                "r"(accf)
-                : "memory");
+            for (int term = 0; term < 3; ++term) {      // small terms first: lo.hi, hi.lo, then hi.hi
+              const uint64_t da = (term == 0 ? a_lo : a_hi) + step;
+              const uint64_t db = (term == 1 ? b_lo : b_hi) + step;
+              const uint32_t accf = first ? 0u : 1u;
+              first = false;
+              asm volatile(
+                  "{\n\t.reg .pred p;\n\t"
+                  "setp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(acc_addr), "l"(da), "l"(db), "r"(idesc),
+                  "r"(accf)
+                  : "memory");
+            }
           }
         }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[b]))
+                     : "memory");
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&mma_done[s]))
-                   : "memory");
     }
-    __syncwarp();
-    if (t >= 1) select_tile(t - 1);
+  } else {
+    for (int t = 0; t < n_tiles; ++t) select_tile(t);
   }
-  select_tile(n_tiles - 1);
 
   // ---- final: every list down to at most N keys, then the two lists of a row merged, sorted and written
   __syncwarp();
-  {
+  if (warp < NT / 32) {
     unsigned need = __ballot_sync(0xffffffffu, cnt > N);
     while (need) {
       const int src = __ffs(need) - 1;
@@ -427,9 +427,9 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
       compact_row(src);
     }
   }
-  cnt_sh[half][rowl] = cnt;
+  if (warp < NT / 32) cnt_sh[half][rowl] = cnt;
   __syncthreads();                                    // both halves' lists (global, st.cg) and counts are visible
-  for (int src = half; src < 32; src += 2) {          // the two warps of a lane quarter share its 32 rows
+  for (int src = half; src < 32 && warp < NT / 32; src += 2) {   // the two warps of a lane quarter share its 32 rows
     const int r = wq * 32 + src;
     const int ur = __shfl_sync(0xffffffffu, u, src);
     if (ur < 0) continue;
@@ -450,7 +450,7 @@ score_topn_tc_kernel(const float* __restrict__ U, const uint8_t* __restrict__ it
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(2 * TN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(NBUF * TN));
   }
 }
 
@@ -471,7 +471,7 @@ int launch_tc(const float* U, const float* V, int d, int n_items, const int* use
   QREC_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&ws), list_bytes + block_bytes, st));
   uint8_t* const blocks = ws + list_bytes;                                            // (list_bytes is a multiple of 640 KB)
   split_items_kernel<KB><<<n_tiles, 128, 0, st>>>(V, d, n_items, blocks);
-  score_topn_tc_kernel<KB><<<grid, NT, SMEM, st>>>(U, blocks, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
+  score_topn_tc_kernel<KB><<<grid, NT + 32, SMEM, st>>>(U, blocks, d, n_items, user_ids, n_rows, rowptr, cols, rated_value, N, out_ids,
                                                     out_scores, reinterpret_cast<unsigned long long*>(ws));
   const cudaError_t launch_err = cudaGetLastError();
   QREC_CUDA(cudaFreeAsync(ws, st));
