@@ -419,7 +419,7 @@ def table_gather_merge_p2p(peer_S_ptrs, Q, B, D):
           'qrec_table_gather_merge_p2p_f32')
 
 
-SCORE_TOPN_TENSOR_CORES = False      # default of score_topn(tensor_cores=None); QREC_TOPN_TC=0/1 overrides
+SCORE_TOPN_TENSOR_CORES = True       # default of score_topn(tensor_cores=None) for d <= 64; QREC_TOPN_TC=0/1 overrides
 
 
 def score_topn(U, V, user_ids, rated_rowptr, rated_cols, N, rated_value=0.0, out_ids=None, out_scores=None, tensor_cores=None):
