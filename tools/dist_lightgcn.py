@@ -73,7 +73,7 @@ def main():
         def matmul(self, X, out, acc=None, acc_scale=0.0):
             return E.spmm_csr(rp, co, va, X, out, acc=acc, acc_scale=acc_scale)
     ref = Shell()
-    ref.num_users, ref.num_items, ref.emb_size, ref.n_layers, ref.lRate, ref.regU, ref.device = U, I, D, args.layers, 0.001, 0.001, dev
+    ref.num_users, ref.num_items, ref.emb_size, ref.emb_pad, ref.n_layers, ref.lRate, ref.regU, ref.device = U, I, D, D, args.layers, 0.001, 0.001, dev
     ref.norm_adj, ref.ego = Adj(), ego.clone()
     N = U + I
     ref._buf = [torch.empty(N, D, device=dev) for _ in range(2)]

@@ -62,9 +62,23 @@ def main():
     m = build(Sharded, hi - lo, I, D, dev).shard(lo)
     for k, v in ref.params.items():
         m.params[k].copy_(v[lo:hi] if k in ('PG', 'PM') else v)
+    def resync():
+        """The sharded replica takes the reference's parameters and Adam slots (its shard of the user tables): every
+        step is then compared at IDENTICAL parameters -- Adam's first steps turn a gradient that rounds to the other
+        side of zero into a step of the other sign, and the next step's TF32 products / ReLU masks would inherit it."""
+        cut = lambda k, v: v[lo:hi] if k in ('PG', 'PM') else v         # noqa: E731
+        for k, v in ref.params.items():
+            m.params[k].copy_(cut(k, v))
+        for md in (0, 1, 2):
+            m.opt_step[md] = ref.opt_step[md]
+            for k, (mm, vv) in ref.opt_state[md].items():
+                m.opt_state[md][k][0].copy_(cut(k, mm))
+                m.opt_state[md][k][1].copy_(cut(k, vv))
+
     for mode in (0, 1, 2):
         for step in range(3):
             u, i, r = batch(U, I, 2560)
+            resync()
             l_ref = float(ref.train_step(mode, u, i, r).item())
             l = float(m.train_step(mode, u, i, r).item())
             assert abs(l - l_ref) <= 1e-4 * abs(l_ref), (mode, step, l, l_ref)
@@ -76,18 +90,17 @@ def main():
                 assert float((m.grads[k] - gr).abs().max()) <= 2e-3 * float(ref.grads[k].abs().max()) + 1e-7, (k, mode, step)
             for k, v in ref.params.items():
                 mine = v[lo:hi] if k in ('PG', 'PM') else v
-                # (the sign noise accumulates over the steps taken so far in all phases)
-                taken = 3 * mode + step + 1
-                assert float((m.params[k] - mine).abs().max()) <= 2.1 * ref.lRate * taken, (k, mode, step, 'max')
-                assert float((m.params[k] - mine).abs().mean()) <= 0.1 * ref.lRate * taken, (k, mode, step, 'mean')
+                # (one step from identical parameters: at most one sign flip per entry)
+                assert float((m.params[k] - mine).abs().max()) <= 2.1 * ref.lRate, (k, mode, step, 'max')
+                assert float((m.params[k] - mine).abs().mean()) <= 0.1 * ref.lRate, (k, mode, step, 'mean')
     if world > 1:                                          # replicated parameters stay bit-identical across ranks
         for k in ('QG', 'W1', 'h_mlp'):
             parts = [torch.empty_like(m.params[k]) for _ in range(world)]
             dist.all_gather(parts, m.params[k])
             assert all(torch.equal(parts[0], t) for t in parts), k
     if rank == 0:
-        print(json.dumps({'parity': 'UserShardedNeuMF == single-GPU NeuMF over 3 phases x 3 steps (losses 1e-4, reduced gradients 2e-3 of max, '
-                                    'parameters within Adam sign noise; replicas bit-identical)', 'world': world, 'problem': [U, I]}))
+        print(json.dumps({'parity': 'UserShardedNeuMF == single-GPU NeuMF over 3 phases x 3 steps, each from identical parameters and Adam slots (losses 1e-4, '
+                                    'reduced gradients 2e-3 of max, parameters within one Adam sign flip; replicas bit-identical)', 'world': world, 'problem': [U, I]}))
     del ref, m
     torch.cuda.empty_cache()
 
