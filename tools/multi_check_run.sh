@@ -11,6 +11,7 @@ port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_neumf.py --step
 [ "${SKIP_DIST_LGCN:-0}" = 1 ] || { port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 > "$out/dist_lightgcn.log" 2>&1; echo "dist_lightgcn: exit $? -- $(grep -h '^{' "$out/dist_lightgcn.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn.log" | head -3; }
 [ "${SKIP_DIST_LGCN:-0}" = 1 ] || { port=$((port+1)); timeout 600 $TR --master-port $port tools/dist_lightgcn.py --steps 10 --scheme cols > "$out/dist_lightgcn_cols.log" 2>&1; echo "dist_lightgcn cols: exit $? -- $(grep -h '^{' "$out/dist_lightgcn_cols.log" | cut -c1-400)"; grep -E "AssertionError|Error" "$out/dist_lightgcn_cols.log" | head -3; }
 [ "${SKIP_DIST_SIMGCL:-0}" = 1 ] || { port=$((port+1)); timeout 900 $TR --master-port $port tools/dist_simgcl.py --steps 5 > "$out/dist_simgcl.log" 2>&1; echo "dist_simgcl: exit $? -- $(grep -h '^{' "$out/dist_simgcl.log" | cut -c1-600)"; grep -E "AssertionError|Error" "$out/dist_simgcl.log" | head -3; }
+[ "${SKIP_BENCH:-0}" = 1 ] && exit 0
 for w in ${WAVES:-1 2}; do
 port=$((port+1)); timeout 600 $TR --master-port $port bench.py --gpus $N --steps 20 --warmup 5 --q-syncs $w > "$out/bench_w$w.json" 2> "$out/bench_w$w.err"
 python - <<PY
