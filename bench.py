@@ -547,29 +547,38 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
                 allb = torch.cat(parts, dim=1)
                 bu, bi, bj = allb[0].contiguous(), allb[1].contiguous(), allb[2].contiguous()
             batches.append((bu, bi, bj))
-        for t in range(warmup):
-            m.train_step(*batches[t])
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for t in range(steps):
-            m.train_step(*batches[warmup + t])
-        b.record()
-        torch.cuda.synchronize()
-        tms = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        def timed(step_fn, first):
+            for t in range(warmup):
+                step_fn(*batches[(first + t) % len(batches)])
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for t in range(steps):
+                step_fn(*batches[(first + warmup + t) % len(batches)])
+            b.record()
+            torch.cuda.synchronize()
+            tms = torch.tensor([a.elapsed_time(b) / steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            return float(tms.item())
+        ms_eager = timed(m.train_step, 0)
+        # the same steps replayed from a CUDA graph (parallel.UserShardedLightGCN.train_step_graphed: one capture per batch
+        # size, three small device copies + one replay per minibatch); a failed capture falls back to the eager step
+        graphed = hasattr(m, 'train_step_graphed') and os.environ.get('QREC_LGCN_GRAPH', '1') != '0'
+        ms = timed(m.train_step_graphed, 0) if graphed else ms_eager
+        graph_used = bool(graphed and getattr(m, 'graph_error', None) is None)
         n_steps = -(-U * DEGREE // B)
         full_products = 2 * layers - (2 if (B <= 8192 and layers > 1) else 0)       # whole-graph SpMMs actually executed
         rest_bytes = (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
         executed_bytes = full_products * spmm_algo + rest_bytes
         step_bytes = 2 * layers * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
         res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
-                               'epoch_extrapolated_from_steps': steps, 'algorithmic_GB_per_step': step_bytes / 1e9,
+                               'epoch_extrapolated_from_steps': steps, 'ms_per_step_eager_launches': ms_eager,
+                               'cuda_graph': graph_used, 'graph_error': getattr(m, 'graph_error', None),
+                               'algorithmic_GB_per_step': step_bytes / 1e9,
                                'whole_graph_products_per_step': full_products, 'executed_GB_per_step': executed_bytes / 1e9,
                                'frac_of_hbm_peak_executed': executed_bytes / ms / 1e6 / (peak * world),
                                'frac_of_hbm_peak_whole_job': step_bytes / ms / 1e6 / (peak * world), 'loss': float(m.loss.item())}

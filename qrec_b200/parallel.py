@@ -637,6 +637,8 @@ class UserShardedLightGCN(object):
         self._scatter_add = scatter_add or (lambda G, idx, src, s: E.scatter_add_rows(G, idx, src, scale=s))
         self._gather = gather or (None if spmm is not None else (lambda T, idx, out: E.gather_rows(T, idx, out)))
         self._need = {}
+        self._graphs, self._capturing, self.graph_error = {}, False, None
+        self._lr_t = torch.zeros(1, dtype=torch.float32, device=dev)
 
     def _need_buf(self, n, slot=0):
         if (n, slot) not in self._need:
@@ -743,8 +745,59 @@ class UserShardedLightGCN(object):
         self._allreduce(self.loss)
         self._propagate(self.gu, self.gi, self.tot_u, self.tot_i, nz_u=rows_u, nz_i=rows_i)
         self.step += 1
-        self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
-        self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
+        if self._capturing:
+            # inside a CUDA-graph capture the step number cannot be a launch argument: Adam reads its step factor
+            # lr * sqrt(1 - b2^t) / (1 - b1^t) from device memory, refreshed before every replay
+            from . import engine as E
+            E.adam_dense_tf1_devstep(self.Eu, self.mu, self.vu, self.tot_u, self._lr_t)
+            E.adam_dense_tf1_devstep(self.Ei, self.mi, self.vi, self.tot_i, self._lr_t)
+        else:
+            self._adam(self.Eu, self.mu, self.vu, self.tot_u, self.step)
+            self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
+        return self.loss
+
+    # ---- the same step replayed from a CUDA graph ---------------------------------------------------------------
+    # At N = 8 a rank's share of a step is ~1 ms of device work issued through ~80 launches (kernels, the sort / where
+    # ops of the row lists, the NCCL calls): the host could not issue them that fast and the 8-GPU step was bound by
+    # the CPU (2.3 ms).  The step has no host read-back and a fixed launch sequence for a given batch size, so it is
+    # captured once -- kernels on torch's capture stream, the all-reduces on NCCL's stream with the captured event
+    # dependencies, so the overlap of an exchange with the neighbouring products survives -- and replayed per minibatch
+    # after three small device copies into the graph's input buffers.
+    def train_step_graphed(self, u, i, j):
+        """train_step(u, i, j) with the launch sequence replayed from a CUDA graph (one graph per batch size).  The first
+        call for a batch size runs eagerly (NCCL communicators, lazily sized buffers), the second captures and replays,
+        later ones replay.  Falls back to the eager step -- for good, the reason kept in `graph_error` -- if the capture
+        fails, and when the tensors are not on a GPU or stand-in kernels are injected (the gloo / CPU tests)."""
+        if self.graph_error is not None or u.device.type != 'cuda' or self._scatter is None or self.peer is not None:
+            return self.train_step(u, i, j)
+        from . import engine as E
+        key = int(u.shape[0])
+        st = self._graphs.get(key)
+        if st is None:                                          # first sight of this batch size: eager
+            self._graphs[key] = {'graph': None, 'in': [torch.empty_like(u), torch.empty_like(i), torch.empty_like(j)]}
+            return self.train_step(u, i, j)
+        for dst, src in zip(st['in'], (u, i, j)):
+            dst.copy_(src, non_blocking=True)
+        self._lr_t.fill_(E.adam_lr_t(self.lr, self.step + 1))
+        if st['graph'] is None:
+            try:
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                step0 = self.step
+                self._capturing = True
+                try:
+                    with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                        self.train_step(*st['in'])
+                finally:
+                    self._capturing = False
+                    self.step = step0                           # a capture launches nothing
+                st['graph'] = graph
+            except Exception as exc:                            # noqa: BLE001
+                self.graph_error = '%s: %s' % (type(exc).__name__, str(exc)[:300])
+                torch.cuda.synchronize()
+                return self.train_step(u, i, j)
+        st['graph'].replay()
+        self.step += 1
         return self.loss
 
 

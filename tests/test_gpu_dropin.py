@@ -225,6 +225,40 @@ def test_user_sharded_lightgcn_world1_equals_dropin_step(golden_graph, tmp_path)
         torch.testing.assert_close(torch.cat([m.Eu, m.Ei]), ref.ego, rtol=2e-3, atol=2e-4)
 
 
+def test_user_sharded_lightgcn_graph_replay_equals_dropin_step(golden_graph, tmp_path):
+    """train_step_graphed (the step replayed from a CUDA graph: first call eager, second captures and replays, later
+    ones replay; Adam's step factor read from device memory) against the drop-in class over five different
+    minibatches -- the replayed launch sequence must consume the NEW minibatch and the NEW Adam step each time."""
+    import torch
+    from qrec_b200 import parallel
+    from qrec_b200.util.config import ModelConf
+    from qrec_b200.model.ranking.LightGCN import LightGCN
+    g = golden_graph
+    os.chdir(tmp_path)
+    train = [[u, i, 1.0] for u, i in zip(g['train_users'].tolist(), g['train_items'].tolist())]
+    ref = LightGCN(ModelConf.from_string(str(g['conf'])), train, [])
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref.readConfiguration()
+        ref.initModel()
+    U, I = ref.num_users, ref.num_items
+    adj = ref.norm_adj
+    A_ui, A_iu, _ = parallel.shard_bipartite_by_user(adj.rowptr, adj.cols, adj.vals, U, I, 0, 1)
+    m = parallel.UserShardedLightGCN(A_ui, A_iu, ref.ego[:U].clone(), ref.ego[U:].clone(), ref.n_layers, ref.lRate, ref.regU, 0)
+    su, si, sj = g['shuffled_u'], g['shuffled_i'], g['pair_all_j']
+    for step in range(5):
+        sl = slice(step * 2048, (step + 1) * 2048)
+        b = [torch.from_numpy(np.ascontiguousarray(x[sl])).cuda() for x in (su, si, sj)]
+        l_ref = ref.train_step(*b).item()
+        l = m.train_step_graphed(*b).item()
+        assert m.graph_error is None, m.graph_error
+        assert abs(l - l_ref) <= 1e-5 * abs(l_ref)
+        gref = ref._total
+        gtot = torch.cat([m.tot_u, m.tot_i])
+        assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max())
+        torch.testing.assert_close(torch.cat([m.Eu, m.Ei]), ref.ego, rtol=2e-3, atol=2e-4)
+    assert m.step == 5 and m._graphs[2048]['graph'] is not None
+
+
 def test_scale_bpr_from_interaction_table(golden_bpr, tmp_path):
     """f-3 end to end: InteractionTable -> ScaleBPR (fused user-major epochs, device negatives) trains
     FilmTrust to the quality band of the drop-in class, follows the reference's lr schedule rules, and

@@ -23,6 +23,7 @@ def main():
                     help='user: users partitioned + items replicated (all-reduce of the item block per layer); '
                          'rows: all rows partitioned (all-gather of the whole table per layer); '
                          'cols: embedding columns partitioned, adjacency replicated (one [B] all-reduce per step)')
+    ap.add_argument('--graph', action='store_true', help='scheme user: replay the step from a CUDA graph (train_step_graphed)')
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -86,7 +87,7 @@ def main():
         bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
         bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, step)
         l_ref = ref.train_step(bu, bi, bj).item()
-        l = m.train_step(bu, bi, bj).item()
+        l = (m.train_step_graphed if args.graph else m.train_step)(bu, bi, bj).item()     # graph: eager, capture + replay, replay
         assert abs(l - l_ref) <= 1e-5 * abs(l_ref), (l, l_ref)
         if args.scheme == 'cols':
             lo_c = rank * (D // world)
@@ -100,8 +101,11 @@ def main():
         # difference wherever |g| ~ eps, so the tables get a looser absolute tolerance)
         assert float((gtot - gref).abs().max()) <= 2e-3 * float(gref.abs().max()), 'gradient mismatch'
         torch.testing.assert_close(got, eref, rtol=2e-3, atol=2e-4)
+    if args.graph:
+        assert m.graph_error is None and any(st['graph'] is not None for st in m._graphs.values()), m.graph_error
     if rank == 0:
-        print(json.dumps({'parity': 'sharded (%s) == single-GPU LightGCN step' % args.scheme, 'world': world, 'graph': [U, I, U * DEG]}))
+        print(json.dumps({'parity': 'sharded (%s%s) == single-GPU LightGCN step' % (args.scheme, ', CUDA graph' if args.graph else ''),
+                          'world': world, 'graph': [U, I, U * DEG]}))
     del data, rp, co, va, ego, m, ref
     torch.cuda.empty_cache()
 
@@ -114,15 +118,16 @@ def main():
     idx = torch.randint(0, U * DEG, (args.batch,), device=dev, generator=g)
     bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
     bj = E.sample_neg_philox(bu, data['sorted_rowptr'], data['sorted_cols'], I, 1, 0)
+    step_fn = m.train_step_graphed if args.graph else m.train_step
     for _ in range(2):
-        m.train_step(bu, bi, bj)
+        step_fn(bu, bi, bj)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(args.steps):
-        m.train_step(bu, bi, bj)
+        step_fn(bu, bi, bj)
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
@@ -132,6 +137,8 @@ def main():
         ms = float(t.item())
         print(json.dumps({'lightgcn_sharded_step_ms': ms, 'world': world, 'layers': args.layers, 'batch': args.batch,
                           'epoch_s_at_batch': ms * (-(-U * DEG // args.batch)) / 1e3, 'scheme': args.scheme,
+                          'cuda_graph': bool(args.graph and getattr(m, 'graph_error', None) is None),
+                          'graph_error': getattr(m, 'graph_error', None),
                           'local_nnz': int(m.cols.numel()) if args.scheme == 'rows' else m.local_nnz}))
     if world > 1:
         dist.destroy_process_group()
