@@ -568,8 +568,12 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
         # the same steps replayed from a CUDA graph (parallel.UserShardedLightGCN.train_step_graphed: one capture per batch
         # size, three small device copies + one replay per minibatch); a failed capture falls back to the eager step
         graphed = hasattr(m, 'train_step_graphed') and os.environ.get('QREC_LGCN_GRAPH', '1') != '0'
-        ms = timed(m.train_step_graphed, 0) if graphed else ms_eager
-        graph_used = bool(graphed and getattr(m, 'graph_error', None) is None)
+        ms_graph = timed(m.train_step_graphed, 0) if graphed else None
+        graph_ok = bool(graphed and getattr(m, 'graph_error', None) is None)
+        # the step API is chosen by measurement: the replayed graph wins where the host cannot issue ~80 launches per step
+        # fast enough (N > 1, a rank's share of a step is ~1 ms of device work); at N = 1 the step is device-bound either way
+        graph_used = bool(graph_ok and ms_graph <= ms_eager)
+        ms = ms_graph if graph_used else ms_eager
         n_steps = -(-U * DEGREE // B)
         full_products = 2 * layers - (2 if (B <= 8192 and layers > 1) else 0)       # whole-graph SpMMs actually executed
         rest_bytes = (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
@@ -577,6 +581,7 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
         step_bytes = 2 * layers * spmm_algo + (layers + 2) * N * D * 8 + B * (3 * 4 * D * 2 + 12) + 7 * N * D * 4
         res['batch_%d' % B] = {'ms_per_step': ms, 'steps_per_epoch': n_steps, 'epoch_s': ms * n_steps / 1e3,
                                'epoch_extrapolated_from_steps': steps, 'ms_per_step_eager_launches': ms_eager,
+                               'ms_per_step_graph_replay': ms_graph if graph_ok else None,
                                'cuda_graph': graph_used, 'graph_error': getattr(m, 'graph_error', None),
                                'algorithmic_GB_per_step': step_bytes / 1e9,
                                'whole_graph_products_per_step': full_products, 'executed_GB_per_step': executed_bytes / 1e9,
