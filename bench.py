@@ -605,6 +605,25 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
         res['spmm'] = {'kernel': 'spmm_csr_kernel<16,1>', 'ms': ms, 'algorithmic_GB': spmm_algo / 1e9,
                        'achieved_GBs': spmm_algo / ms / 1e6, 'frac_of_hbm_peak': spmm_algo / ms / 1e6 / peak}
         del rowptr, cols, vals, X, Y
+        # K2 as the step runs it: the two bipartite halves, one launch each.  Their bound is the rate at which the SMs can
+        # gather 256-byte rows out of the L2 (main() relates them to roofline.row_op_peak's measured gather rate): cutting the
+        # item side into column blocks of users that fit the L2 changes nothing (profiles/r2/s2/bench_spmm_blocks.jsonl)
+        Yu, Yi = torch.empty_like(Eu), torch.empty_like(Ei)
+        halves = {}
+        for name, A, X_, Y_ in (('user_side_A_ui_E_i', A_ui, Ei, Yu), ('item_side_A_iu_E_u', A_iu, Eu, Yi)):
+            for _ in range(warmup):
+                E.spmm_csr(A[0], A[1], A[2], X_, Y_, rowsplit=True)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                E.spmm_csr(A[0], A[1], A[2], X_, Y_, rowsplit=True)
+            b.record()
+            torch.cuda.synchronize()
+            hms = a.elapsed_time(b) / steps
+            halves[name] = {'ms': hms, 'gathered_rows': int(A[1].numel()), 'gathers_per_s': int(A[1].numel()) / (hms * 1e-3)}
+        res['spmm_halves'] = halves
+        del Yu, Yi
         if rank == 0:
             res['cpu_baseline'] = lightgcn_cpu_baseline(torch, synthetic, dev, layers, res['batch_2048']['steps_per_epoch'])
             res['cpu_baseline']['gpu_speedup_epoch_batch_2048'] = res['cpu_baseline']['epoch_s_batch_2048_best'] / res['batch_2048']['epoch_s']
@@ -1011,6 +1030,13 @@ def run_ours(args):
         if hbm_cfg is not None:
             out['roofline']['hbm_bound_config'] = hbm_cfg
         if lightgcn is not None:
+            if 'spmm_halves' in lightgcn and roofs is not None and 'error' not in roofs:
+                g_peak = roofs['item_table_100K_rows_25.6MB_L2_resident']['gather']['ops_per_s']
+                for h in lightgcn['spmm_halves'].values():
+                    h['frac_of_measured_l2_gather_rate'] = h['gathers_per_s'] / g_peak
+                both = sum(h['gathered_rows'] for h in lightgcn['spmm_halves'].values()) / sum(h['ms'] for h in lightgcn['spmm_halves'].values()) * 1e3
+                lightgcn['spmm_halves']['both'] = {'gathers_per_s': both, 'frac_of_measured_l2_gather_rate': both / g_peak,
+                                                   'l2_gather_peak_rows_per_s': g_peak}
             out['lightgcn'] = lightgcn
         if neumf is not None:
             out['neumf'] = neumf

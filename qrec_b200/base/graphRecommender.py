@@ -23,13 +23,27 @@ class DeviceCSR(object):
         self._finish(mat.shape, torch.from_numpy(mat.indptr.astype(np.int64)).to(device),
                      torch.from_numpy(mat.indices.astype(np.int32)).to(device),
                      torch.from_numpy(mat.data.astype(np.float32)).to(device))
+        self.split_row = None
 
     @classmethod
-    def from_tensors(cls, shape, rowptr, cols, vals):
-        """Wraps CSR arrays that already live on the device (graph_build.norm_adjacency_csr)."""
+    def from_tensors(cls, shape, rowptr, cols, vals, split_row=None):
+        """Wraps CSR arrays that already live on the device (graph_build.norm_adjacency_csr).  `split_row`: see
+        set_split_row."""
         self = cls.__new__(cls)
         self._finish(tuple(shape), rowptr, cols, vals)
+        self.set_split_row(split_row)
         return self
+
+    def set_split_row(self, row):
+        """The joint adjacency of a bipartite graph is two very different halves: `row` = num_users short user rows that
+        gather item rows (a table that lives in the L2) and long item rows that gather user rows.  One launch over all of
+        them measured 2.03-2.11 ms on the 1M x 100K x 50M-edge benchmark graph, the two halves launched one after the
+        other 0.78 + 0.92 ms (profiles/r2/s2/bench_spmm_blocks.jsonl): lane groups working on 50-entry and on 500-entry
+        rows at the same time keep neither table's rows in the L2.  With a split row `matmul` issues the row-split
+        kernel once per half; rows, arithmetic and results are those of the single launch."""
+        import os
+        n = self.shape[0]
+        self.split_row = int(row) if (row is not None and 0 < int(row) < n and os.environ.get('QREC_SPMM_SPLIT', '1') != '0') else None
 
     def _finish(self, shape, rowptr, cols, vals):
         self.shape = shape
@@ -52,6 +66,13 @@ class DeviceCSR(object):
 
     def matmul(self, X, out, acc=None, acc_scale=0.0):
         from .. import engine
+        r = getattr(self, 'split_row', None)
+        if r is not None and self.rowsplit:
+            # a row range of a CSR is a CSR over the same cols / vals arrays: rowptr keeps its absolute offsets
+            for a, b in ((0, r), (r, self.shape[0])):
+                engine.spmm_csr(self.rowptr[a:b + 1], self.cols, self.vals, X, out[a:b],
+                                acc=None if acc is None else acc[a:b], acc_scale=acc_scale, rowsplit=True)
+            return out
         return engine.spmm_csr(self.rowptr, self.cols, self.vals, X, out, acc=acc, acc_scale=acc_scale,
                                rowsplit=self.rowsplit)
 
@@ -83,7 +104,7 @@ class GraphRecommender(DeepRecommender):
         rowptr, cols, vals = norm_adjacency_csr(torch.from_numpy(u), torch.from_numpy(i), self.num_users,
                                                 self.num_items, device=dev)
         n = self.num_users + self.num_items
-        return DeviceCSR.from_tensors((n, n), rowptr, cols, vals)
+        return DeviceCSR.from_tensors((n, n), rowptr, cols, vals, split_row=self.num_users)
 
     def create_sparse_rating_matrix(self):
         """(U x I) COO float32, entry = 1/|items rated by the user| (graphRecommender.py:41-51)."""

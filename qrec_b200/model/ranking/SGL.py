@@ -46,7 +46,7 @@ class SGL(GraphRecommender):
         self.joint = JointAdjacency(torch.from_numpy(u), torch.from_numpy(i), self.num_users, self.num_items, device=dev)
         self._lines_u = torch.from_numpy(u).to(dev).long()
         self._lines_i = torch.from_numpy(i).to(dev).long()
-        self.norm_adj = DeviceCSR.from_tensors((n, n), *self.joint.full())
+        self.norm_adj = DeviceCSR.from_tensors((n, n), *self.joint.full(), split_row=self.num_users)
         self.ego = torch.cat([self.user_embeddings, self.item_embeddings], dim=0).contiguous()
         self.user_embeddings = self.ego[:self.num_users]
         self.item_embeddings = self.ego[self.num_users:]
@@ -80,7 +80,7 @@ class SGL(GraphRecommender):
                     csr = self.joint.edge_dropout(self.drop_rate, self.aug_seed, tag, epoch, keep=keep)
                 else:
                     csr = self.joint.edge_dropout(self.drop_rate, self.aug_seed, tag, epoch)
-                mats.append(DeviceCSR.from_tensors((n, n), *csr))
+                mats.append(DeviceCSR.from_tensors((n, n), *csr, split_row=self.num_users))
             views.append(mats * self.n_layers if len(mats) == 1 else mats)
         self.views = views
         return views

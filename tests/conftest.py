@@ -112,7 +112,10 @@ def row_list_kernel_stand_ins(monkeypatch):
     calls = []
 
     def dense(rowptr, cols, vals, n_cols):
-        return sp.csr_matrix((vals.numpy(), cols.numpy(), rowptr.numpy()), shape=(rowptr.numel() - 1, n_cols))
+        # a row range of a CSR is passed as a slice of rowptr over the whole cols / vals arrays (absolute offsets)
+        rp = rowptr.numpy()
+        a, b = int(rp[0]), int(rp[-1])
+        return sp.csr_matrix((vals.numpy()[a:b], cols.numpy()[a:b], rp - a), shape=(rowptr.numel() - 1, n_cols))
 
     def listed(rows):
         got = rows[rows >= 0].long()

@@ -19,7 +19,10 @@ def _stub(monkeypatch, calls):
     from qrec_b200.base.iterativeRecommender import IterativeRecommender
 
     def dense(rowptr, cols, vals, n_cols):
-        return sp.csr_matrix((vals.numpy(), cols.numpy(), rowptr.numpy()), shape=(rowptr.numel() - 1, n_cols))
+        # a row range of a CSR is passed as a slice of rowptr over the whole cols / vals arrays (absolute offsets)
+        rp = rowptr.numpy()
+        a, b = int(rp[0]), int(rp[-1])
+        return sp.csr_matrix((vals.numpy()[a:b], cols.numpy()[a:b], rp - a), shape=(rowptr.numel() - 1, n_cols))
 
     def spmm(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
         calls.append('spmm')
@@ -105,9 +108,10 @@ def test_lightgcn_step_equals_oracle_restatement(golden_graph, graph_ids, monkey
         np.testing.assert_allclose(m.ego[U_:, :50].numpy(), Vr, rtol=2e-3, atol=2e-5)
         assert float(m.ego[:, 50:].abs().sum()) == 0.0                     # padding columns never move
     # per step: (n - 1) forward SpMMs + the last layer on the batch's rows only; one sparse-source product
-    # + (n - 1) SpMMs backward
+    # + (n - 1) SpMMs backward; every whole-graph SpMM is two launches, one per bipartite half (DeviceCSR.set_split_row)
     n = m.n_layers
-    assert calls == (['spmm'] * (n - 1) + ['rows', 'scatter_rows'] + ['spmm'] * (n - 1)) * 3
+    assert m.norm_adj.split_row == U_
+    assert calls == (['spmm'] * 2 * (n - 1) + ['rows', 'scatter_rows'] + ['spmm'] * 2 * (n - 1)) * 3
     Ue, Ve = m.propagate()
     fu, fv, _ = O.lightgcn_forward(adj, Ur, Vr, n)
     np.testing.assert_allclose(Ue[:, :50].numpy(), fu, rtol=2e-3, atol=2e-5)

@@ -22,7 +22,9 @@ def _stub(monkeypatch):
     adjacency_kernel_stand_ins(monkeypatch)
 
     def spmm(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
-        A = sp.csr_matrix((vals.numpy(), cols.numpy(), rowptr.numpy()), shape=(rowptr.numel() - 1, X.shape[0]))
+        rp = rowptr.numpy()                     # possibly a row range: absolute offsets into cols / vals
+        a, b = int(rp[0]), int(rp[-1])
+        A = sp.csr_matrix((vals.numpy()[a:b], cols.numpy()[a:b], rp - a), shape=(rowptr.numel() - 1, X.shape[0]))
         Y.copy_(torch.from_numpy(A @ X.numpy()))
         if acc is not None:
             acc.add_(Y, alpha=acc_scale)

@@ -50,8 +50,8 @@ def main():
 
     from qrec_b200.base.graphRecommender import DeviceCSR
 
-    def Adj():                       # the operand class the drop-in models build in initModel (matmul + the row-list products)
-        return DeviceCSR.from_tensors((U + I, U + I), rp, co, va)
+    def Adj(split=True):             # the operand class the drop-in models build in initModel (matmul + the row-list products)
+        return DeviceCSR.from_tensors((U + I, U + I), rp, co, va, split_row=U if split else None)
     g = torch.Generator(device=dev); g.manual_seed(0)
     idx = torch.randperm(U * DEG, device=dev, generator=g)[:2048]
     bu, bi = data['u'][idx].contiguous(), data['i'][idx].contiguous()
@@ -69,6 +69,16 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / args.steps
     steps_per_epoch = -(-U * DEG // 2048)
+    # ---- LightGCN drop-in class (3 layers): one launch over the joint operator vs one launch per bipartite half
+    from qrec_b200.model.ranking.LightGCN import LightGCN
+    for split in (False, True):
+        m = shell(LightGCN, U, I, D, dev, Adj(split), n_layers=3)
+        m.initModel()
+        ms = timed(lambda: m.train_step(bu, bi, bj))
+        print(json.dumps({'model': 'LightGCN', 'n_layers': 3, 'batch': 2048, 'spmm_launch_per_half': split, 'step_ms': ms,
+                          'epoch_s': ms * steps_per_epoch / 1e3, 'loss': float(m._loss.item())}), flush=True)
+        del m
+        torch.cuda.empty_cache()
     # ---- SimGCL (n_layer 2: 3 whole-graph + 3 row-list products forward, 1 scatter + 1 whole-graph backward, noise,
     #      InfoNCE on the batch's unique rows)
     m = shell(SimGCL, U, I, D, dev, Adj(), cl_rate=0.5, eps=0.1, n_layers=2)
