@@ -23,6 +23,8 @@ def main():
                     help='user: users partitioned + items replicated (all-reduce of the item block per layer); '
                          'rows: all rows partitioned (all-gather of the whole table per layer); '
                          'cols: embedding columns partitioned, adjacency replicated (one [B] all-reduce per step)')
+    ap.add_argument('--skip-parity', action='store_true', help='timing part only')
+    ap.add_argument('--profile-range', action='store_true', help='cudaProfilerStart/Stop around the timed steps (ncu --profile-from-start off)')
     ap.add_argument('--graph', action='store_true', help='scheme user: replay the step from a CUDA graph (train_step_graphed)')
     args = ap.parse_args()
     import torch
@@ -61,6 +63,14 @@ def main():
             m.local_nnz = int(A_ui[1].numel()) * 2
         return data, (rp, co, va), ego, part, mine, m
 
+    if not args.skip_parity:
+        parity(args, build, rank, world, dev, D, DEG, E, torch)
+    timing(args, build, rank, world, dev, D, DEG, E, torch, dist)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def parity(args, build, rank, world, dev, D, DEG, E, torch):
     # ---------------- parity on a small graph (every rank also runs the 1-GPU step)
     U, I = 16000, 1600
     data, (rp, co, va), ego, part, mine, m = build(U, I)
@@ -109,8 +119,11 @@ def main():
     del data, rp, co, va, ego, m, ref
     torch.cuda.empty_cache()
 
+
+def timing(args, build, rank, world, dev, D, DEG, E, torch, dist):
     # ---------------- timing at the benchmark scale
     U, I = 1_000_000, 100_000
+    g = torch.Generator(device=dev)
     data, (rp, co, va), ego, part, mine, m = build(U, I)
     del rp, co, va, ego
     torch.cuda.empty_cache()
@@ -125,11 +138,15 @@ def main():
     if world > 1:
         dist.barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profile_range:
+        torch.cuda.profiler.start()
     a.record()
     for _ in range(args.steps):
         step_fn(bu, bi, bj)
     b.record()
     torch.cuda.synchronize()
+    if args.profile_range:
+        torch.cuda.profiler.stop()
     t = torch.tensor([a.elapsed_time(b) / args.steps], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -140,8 +157,6 @@ def main():
                           'cuda_graph': bool(args.graph and getattr(m, 'graph_error', None) is None),
                           'graph_error': getattr(m, 'graph_error', None),
                           'local_nnz': int(m.cols.numel()) if args.scheme == 'rows' else m.local_nnz}))
-    if world > 1:
-        dist.destroy_process_group()
 
 
 if __name__ == '__main__':
