@@ -408,6 +408,15 @@ int qrec_bpr_grad_scatter_f32(const float* dev_U, const float* dev_V, int32_t d,
                               float eps, float reg, float* dev_gU, float* dev_gV,
                               double* dev_loss, void* stream);
 
+/* K3 with a per-sample score scale c_k: the term is -ln(sigmoid(c_k y_k) + eps), dL/dy = -c s(1-s)/(s+eps) with
+ * s = sigmoid(c_k y_k).  Replaces the first term of SBPR's minibatch loss, model/ranking/SBPR.py:110-113
+ * (y_ik / (weights + 1): c_k = 1 / (S_uk + 1), the number of friends who consumed the social item k); the second term
+ * (y_kj) is qrec_bpr_grad_scatter_f32 on (u, k, j).  dev_y_scale: float[n]. */
+int qrec_bpr_grad_scatter_scaled_f32(const float* dev_U, const float* dev_V, int32_t d, int64_t n,
+                                     const int32_t* dev_u, const int32_t* dev_i, const int32_t* dev_j,
+                                     const float* dev_y_scale, float eps, float reg, float* dev_gU, float* dev_gV,
+                                     double* dev_loss, void* stream);
+
 /* The same step for ranks that each hold a COLUMN block of the tables (feature-parallel LightGCN: the propagation
  * A X is independent per column, so d/world columns of every row live on each rank and the only exchange of a
  * minibatch step is the sum of these partial scores).  d = the LOCAL width.

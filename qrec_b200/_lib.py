@@ -117,6 +117,8 @@ SIGNATURES = {
     'qrec_spmm_csr_rows_f32': (C.c_int, [C.c_int32, vp, vp, vp, vp, vp, vp, C.c_int32, C.c_int32, vp, C.c_float, vp]),
     'qrec_bpr_grad_scatter_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float,
                                             C.c_float, vp, vp, vp, vp]),
+    'qrec_bpr_grad_scatter_scaled_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp, C.c_float,
+                                                   C.c_float, vp, vp, vp, vp]),
     'qrec_bpr_partial_scores_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, C.c_float, vp, vp, vp]),
     'qrec_bpr_grad_from_scores_f32': (C.c_int, [vp, vp, C.c_int32, C.c_int64, vp, vp, vp, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]),
     'qrec_adam_dense_tf1_f32': (C.c_int, [vp, vp, vp, vp, C.c_int64, C.c_float, C.c_float,

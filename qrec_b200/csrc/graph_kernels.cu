@@ -378,7 +378,7 @@ bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V
                         long long n, const int* __restrict__ u, const int* __restrict__ i,
                         const int* __restrict__ j, float eps, float reg, float* __restrict__ gU,
                         float* __restrict__ gV, double* loss, float* __restrict__ y_buf = nullptr,
-                        float log_weight = 1.f) {
+                        float log_weight = 1.f, const float* __restrict__ y_scale = nullptr) {
   constexpr int TPW = 32 / LPR;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LPR, l = lane % LPR;
@@ -438,9 +438,16 @@ bpr_grad_scatter_kernel(const float* __restrict__ U, const float* __restrict__ V
           const int t = s0 + r * TPW + sub;
           y = (t < cnt) ? __ldg(y_buf + base + t) : 0.f;  // the full score (sum of the ranks' partial scores)
         }
+        // optional per-sample score scale c_k: the term is -ln(sigmoid(c_k y) + eps) (SBPR.py:112-113, c = 1/(weight+1))
+        float c = 1.f;
+        if (MODE == 0 && y_scale != nullptr) {
+          const int t = s0 + r * TPW + sub;
+          c = (t < cnt) ? __ldg(y_scale + base + t) : 1.f;
+          y *= c;
+        }
         const float s = 1.0f / (1.0f + expf(-y));
-        // d/dy of -ln(s+eps) = -s(1-s)/(s+eps)      
-        const float gy = -s * (1.0f - s) / (s + eps);
+        // d/dy of -ln(s+eps) = -s(1-s)/(s+eps)      (SURVEY A5); chain rule through the score scale
+        const float gy = -s * (1.0f - s) / (s + eps) * c;
         if (ok[r]) {
           if (l == 0) lsum += (MODE == 2) ? log_weight * -logf(s + eps) : (-logf(s + eps) + reg * 0.5f * sq);
 #pragma unroll
@@ -688,6 +695,33 @@ int qrec_bpr_grad_scatter_f32(const float* U, const float* V, int32_t d, int64_t
   else if (nvec <= 32) QREC_K3(32, 1, 4);
   else QREC_K3(32, 2, 2);
 #undef QREC_K3
+  QREC_LAUNCH_CHECK();
+  return QREC_OK;
+}
+
+int qrec_bpr_grad_scatter_scaled_f32(const float* U, const float* V, int32_t d, int64_t n,
+                                     const int32_t* u, const int32_t* i, const int32_t* j, const float* y_scale,
+                                     float eps, float reg, float* gU, float* gV, double* loss, void* stream) {
+  QREC_REQUIRE(d >= 4 && d <= 256 && d % 4 == 0, "qrec_bpr_grad_scatter_scaled_f32: d=%d unsupported", d);
+  QREC_REQUIRE(n >= 0, "qrec_bpr_grad_scatter_scaled_f32: n < 0");
+  if (n == 0) return QREC_OK;
+  QREC_REQUIRE(U && V && u && i && j && y_scale && gU && gV && loss, "qrec_bpr_grad_scatter_scaled_f32: null pointer");
+  QREC_REQUIRE(aligned16(U) && aligned16(V) && aligned16(gU) && aligned16(gV),
+               "qrec_bpr_grad_scatter_scaled_f32: tables must be 16-byte aligned");
+  const int nvec = d / 4;
+  const long long blocks_needed = ((n + 31) / 32 + 7) / 8;
+  const long long cap = (long long)sm_count() * 8;
+  const int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define QREC_K3S(LPR, VPL, UN)                                                                      \
+  bpr_grad_scatter_kernel<LPR, VPL, UN><<<grid, 256, 0, st>>>(U, V, nvec, n, u, i, j, eps, reg, gU, \
+                                                              gV, loss, nullptr, 1.f, y_scale)
+  if (nvec <= 4) QREC_K3S(4, 1, 2);
+  else if (nvec <= 8) QREC_K3S(8, 1, 4);
+  else if (nvec <= 16) QREC_K3S(16, 1, 4);
+  else if (nvec <= 32) QREC_K3S(32, 1, 4);
+  else QREC_K3S(32, 2, 2);
+#undef QREC_K3S
   QREC_LAUNCH_CHECK();
   return QREC_OK;
 }

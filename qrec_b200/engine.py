@@ -683,6 +683,22 @@ def bpr_grad_scatter(U, V, u, i, j, eps, reg, gU, gV, loss):
     return loss
 
 
+def bpr_grad_scatter_scaled(U, V, u, i, j, y_scale, eps, reg, gU, gV, loss):
+    """bpr_grad_scatter with the per-sample score scale of SBPR's first loss term (SBPR.py:110-113):
+    -ln(sigmoid(y_scale[k] * y_k) + eps)."""
+    torch = _torch()
+    if y_scale.shape[0] != u.shape[0]:
+        raise QRecError('bpr_grad_scatter_scaled: y_scale has %d entries for %d samples' % (y_scale.shape[0], u.shape[0]))
+    check(lib.qrec_bpr_grad_scatter_scaled_f32(_dev(U, torch.float32, 'U'), _dev(V, torch.float32, 'V'),
+                                               U.shape[1], u.shape[0], _dev(u, torch.int32, 'u'),
+                                               _dev(i, torch.int32, 'i'), _dev(j, torch.int32, 'j'),
+                                               _dev(y_scale, torch.float32, 'y_scale'),
+                                               float(eps), float(reg), _dev(gU, torch.float32, 'gU'),
+                                               _dev(gV, torch.float32, 'gV'), _dev(loss, torch.float64, 'loss'),
+                                               _stream()), 'qrec_bpr_grad_scatter_scaled_f32')
+    return loss
+
+
 def adam_dense_tf1(var, m, v, g, lr, t, beta1=0.9, beta2=0.999, eps=1e-8):
     torch = _torch()
     check(lib.qrec_adam_dense_tf1_f32(_dev(var, torch.float32, 'var'), _dev(m, torch.float32, 'm'),
