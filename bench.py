@@ -1060,8 +1060,11 @@ def run_ours(args):
             except Exception as exc:                     # noqa: BLE001
                 out['cpu_baseline'] = {'value': None, 'unit': 'triples/s', 'cores': 1, 'kind': 'port',
                                        'sample': 'failed: %s: %s' % (type(exc).__name__, exc)}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        from qrec_b200 import parallel
+        if parallel.captured_graphs():
+            parallel.finish_process(0)      # a live CUDA graph with NCCL work inside blocks the communicator teardown
         dist.destroy_process_group()
 
 

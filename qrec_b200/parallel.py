@@ -792,6 +792,7 @@ class UserShardedLightGCN(object):
                     self._capturing = False
                     self.step = step0                           # a capture launches nothing
                 st['graph'] = graph
+                _CAPTURED_GRAPHS[0] += 1
             except Exception as exc:                            # noqa: BLE001
                 self.graph_error = '%s: %s' % (type(exc).__name__, str(exc)[:300])
                 torch.cuda.synchronize()
@@ -799,6 +800,34 @@ class UserShardedLightGCN(object):
         st['graph'].replay()
         self.step += 1
         return self.loss
+
+
+_CAPTURED_GRAPHS = [0]
+
+
+def captured_graphs():
+    """How many CUDA graphs with NCCL collectives inside this process has captured.  Measured on 2 GPUs
+    (profiles/r2/s2): while such a graph (or its executable) is alive, tearing the NCCL communicator down --
+    dist.destroy_process_group(), or the interpreter's own shutdown -- does not return.  A program that used
+    train_step_graphed under NCCL therefore ends with `finish_process()` instead of destroy_process_group()."""
+    return _CAPTURED_GRAPHS[0]
+
+
+def finish_process(code=0):
+    """Orderly end of a rank that holds captured NCCL work: everything the job produced is flushed, the ranks meet at a
+    barrier (no collective is in flight afterwards), and the process leaves without the communicator teardown that
+    would block (see captured_graphs)."""
+    import os
+    import sys
+    if dist.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        dist.barrier()
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
 
 
 # =============================================================================================
