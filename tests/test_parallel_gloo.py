@@ -335,7 +335,9 @@ def _user_sharded_worker(rank, world, port, out, blocks=1, row_lists=False):
             u = rng.integers(0, U, 7).astype(np.int32); i = rng.integers(0, I, 7).astype(np.int32)
             j = rng.integers(0, I, 7).astype(np.int32)
             ref_loss = O.lightgcn_step(A, Ur, Vr, mU, vU, mV, vV, u, i, j, L, lr, reg, step + 1)
-            loss = m.train_step(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            # the graph-replay API on tensors that are not on a GPU is the eager step (nothing to capture)
+            loss = (m.train_step_graphed if step == 2 else m.train_step)(torch.from_numpy(u), torch.from_numpy(i), torch.from_numpy(j))
+            assert m.graph_error is None and parallel.captured_graphs() == 0 and m.step == step + 1
             assert abs(float(loss) - ref_loss) < 1e-4 * abs(ref_loss) + 1e-6
             assert np.allclose(m.Eu.numpy(), Ur[lo:hi], rtol=1e-3, atol=1e-6), (rank, step)
             assert np.allclose(m.Ei.numpy(), Vr, rtol=1e-3, atol=1e-6), (rank, step)
