@@ -1063,7 +1063,7 @@ def run_ours(args):
         print(json.dumps(out), flush=True)
     if world > 1:
         from qrec_b200 import parallel
-        if parallel.captured_graphs():
+        if parallel.any_rank_captured_graphs():
             parallel.finish_process(0)      # a live CUDA graph with NCCL work inside blocks the communicator teardown
         dist.destroy_process_group()
 

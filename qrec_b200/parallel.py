@@ -813,6 +813,18 @@ def captured_graphs():
     return _CAPTURED_GRAPHS[0]
 
 
+def any_rank_captured_graphs(group=None):
+    """captured_graphs() > 0 on ANY rank (one small all-reduce): the ranks must take the same way out, and a rank whose
+    capture failed (it fell back to the eager step) has none of its own."""
+    n = captured_graphs()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dev = torch.device('cuda', torch.cuda.current_device()) if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+        t = torch.tensor([n], dtype=torch.int64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+        n = int(t.item())
+    return n > 0
+
+
 def finish_process(code=0):
     """Orderly end of a rank that holds captured NCCL work: everything the job produced is flushed, the ranks meet at a
     barrier (no collective is in flight afterwards), and the process leaves without the communicator teardown that

@@ -412,6 +412,31 @@ def test_column_sharded_lightgcn_matches_single_process_world2():
     assert dict(out) == {0: 1, 1: 1}
 
 
+def _exit_decision_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        assert parallel.any_rank_captured_graphs() is False
+        if rank == 1:
+            parallel._CAPTURED_GRAPHS[0] = 2          # as if only this rank's capture had succeeded
+        assert parallel.any_rank_captured_graphs() is True      # ... every rank must still take the same way out
+        parallel._CAPTURED_GRAPHS[0] = 0
+        out[rank] = 1
+    finally:
+        dist.destroy_process_group()
+
+
+def test_exit_decision_after_graph_capture_is_collective_world2():
+    """bench.py / the tools end through parallel.finish_process() when ANY rank holds a captured NCCL graph: a rank
+    deciding on its own would leave the others in the barrier."""
+    port = 36300 + os.getpid() % 2000
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exit_decision_worker, args=(2, port, out), nprocs=2, join=True)
+    assert dict(out) == {0: 1, 1: 1}
+    assert parallel.any_rank_captured_graphs() is False          # no process group: this process's own count
+
+
 def test_user_sharded_lightgcn_row_restricted_layers_world2():
     """The row-restricted layers of the sharded step (last forward layer evaluated on the batch's rows only, with
     the ranks' [rows, d] partial blocks all-reduced instead of the whole item block; first backward layer

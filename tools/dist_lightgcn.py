@@ -67,7 +67,7 @@ def main():
         parity(args, build, rank, world, dev, D, DEG, E, torch)
     timing(args, build, rank, world, dev, D, DEG, E, torch, dist)
     if world > 1:
-        if parallel.captured_graphs():
+        if parallel.any_rank_captured_graphs():
             parallel.finish_process(0)      # a live CUDA graph with NCCL work inside blocks the communicator teardown
         dist.destroy_process_group()
 
