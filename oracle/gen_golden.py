@@ -17,12 +17,13 @@ What is exercised (reference file:line):
   * BasicMF / PMF / SVD .trainModel   model/rating/BasicMF.py:9-25, PMF.py:9-28, SVD.py:9-36
     (pointwise sequential SGD; §8 f-4), with the per-epoch shuffle of isConverged and the
     MAE / RMSE of evalRatings (base/recommender.py:95-125, util/measure.py)
+  * SBPR.initModel / next_batch   model/ranking/SBPR.py:12-29, 69-101 (social-feedback sets, minibatch sampler)
 
 `tensorflow` and `mkl` are absent from this image; both are stubbed with empty
 modules because the reference imports them at module level (model/ranking/BPR.py:7,
 QRec.py:6).  The numpy path never calls into either.
 
-Usage:  python oracle/gen_golden.py [bpr] [mf]   (default: all sections; writes tests/golden/*.npz)
+Usage:  python oracle/gen_golden.py [bpr] [mf] [sbpr]   (default: all sections; writes tests/golden/*.npz)
 """
 import os
 import sys
@@ -332,13 +333,71 @@ def gen_mf():
             **init, **extra)
 
 
+CONF_SBPR = """ratings=./dataset/FilmTrust/ratings.txt
+social=./dataset/FilmTrust/trust.txt
+ratings.setup=-columns 0 1 2
+social.setup=-columns 0 1
+model.name=SBPR
+evaluation.setup=-testSet ./dataset/FilmTrust/testset.txt -b 1.0 -tf
+item.ranking=on -topN 10
+num.factors=16
+num.max.epoch=2
+batch_size=512
+learnRate=-init 0.005 -max 0.1
+reg.lambda=-u 0.01 -i 0.01 -b 0.01 -s 0.2
+output.setup=off -dir ./results/
+"""
+
+
+def gen_sbpr():
+    """model/ranking/SBPR.py:12-29 (PositiveSet / FPSet from FilmTrust's trust network) and :69-101 (next_batch): the
+    social-feedback sets and the first minibatches of the UNMODIFIED reference class on the training split recorded in
+    bpr_filmtrust_seed0.npz.  Only dicts are involved (no sets), so the stream does not depend on the hash seed."""
+    from util.config import ModelConf
+    from util.io import FileIO
+    from model.ranking.SBPR import SBPR
+    g = np.load(os.path.join(OUT, 'bpr_filmtrust_seed0.npz'), allow_pickle=True)
+    train = [[u, i, float(r)] for u, i, r in zip(g['train_users'].tolist(), g['train_items'].tolist(), g['train_rating'].tolist())]
+    with open('SBPR_ft.conf', 'w') as f:
+        f.write(CONF_SBPR)
+    conf = ModelConf('SBPR_ft.conf')
+    relation = FileIO.loadRelationship(conf, conf['social'])
+    np.random.seed(0)
+    random.seed(0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = SBPR(conf, [list(r) for r in train], [], [list(r) for r in relation])
+        m.readConfiguration()
+        m.initModel()
+    m.batch_size = 512
+    users = list(m.data.user.keys())
+    fp_sizes = np.array([len(m.FPSet[u]) if u in m.FPSet else 0 for u in users], dtype=np.int64)
+    fp_sums = np.array([sum(m.FPSet[u].values()) if u in m.FPSet else 0 for u in users], dtype=np.int64)
+    fp_first = np.array([(next(iter(m.FPSet[u])) if (u in m.FPSet and len(m.FPSet[u])) else '') for u in users])
+    random.seed(77)
+    batches = []
+    for n, b in enumerate(m.next_batch()):
+        batches.append(np.array(b, dtype=np.int64))                  # [5, batch]: u, i, k, j, S_uk
+        if n == 7:
+            break
+    state = _state_to_array(random.getstate())
+    np.savez_compressed(
+        os.path.join(OUT, 'sbpr_filmtrust_seed77.npz'),
+        relation_from=np.array([r[0] for r in relation]), relation_to=np.array([r[1] for r in relation]),
+        relation_w=np.array([float(r[2]) for r in relation]),
+        fp_sizes=fp_sizes, fp_sums=fp_sums, fp_first=fp_first,
+        batches=np.stack(batches), mt_state_after_8_batches=state, conf=np.array(CONF_SBPR))
+    print('sbpr: %d relations, %d users with social feedback, 8 batches of 512' % (len(relation), int((fp_sizes > 0).sum())))
+
+
 def main():
-    what = set(sys.argv[1:]) or {'bpr', 'mf'}
+    what = set(sys.argv[1:]) or {'bpr', 'mf', 'sbpr'}
     _enter_workdir()
     if 'bpr' in what:
         gen_bpr()
     if 'mf' in what:
         gen_mf()
+    if 'sbpr' in what:
+        gen_sbpr()
 
 
 if __name__ == '__main__':

@@ -3,6 +3,8 @@
 (1) the item sets and the minibatch sampler against the UNMODIFIED reference class in the same process (TensorFlow
     stubbed: `initModel` and `next_batch` never touch it): same PositiveSet / FPSet, same (u, i, k, j, S_uk) batches
     from the same `random` state, same generator state afterwards;
+    and (portable: no reference checkout needed) against the golden record oracle/gen_golden.py made from the unmodified
+    reference class on FilmTrust with its real trust network (tests/golden/sbpr_filmtrust_seed77.npz);
 (2) the numpy path stops where the reference's does (SBPR.py:47, TypeError);
 (3) trainModel_tf, with the kernels replaced by stand-ins that follow include/qrec.h, against float64 autograd of the
     loss SBPR.py:110-114 states plus the oracle's TF1 Adam (TensorFlow is absent: parity unpinned for this part)."""
@@ -175,3 +177,35 @@ def test_sbpr_trainModel_tf_composition_equals_autograd_restatement(golden_bpr, 
     np.testing.assert_allclose(m.P, U, rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(m.Q, V, rtol=1e-3, atol=1e-5)
     assert float(np.abs(m.P).max()) > 0.01
+
+
+def test_sbpr_sets_and_sampler_equal_golden_reference_record(golden_bpr, monkeypatch, tmp_path):
+    """FilmTrust + its trust network: FPSet (sizes, count sums, first key = insertion order) and the first eight
+    512-sample minibatches (u, i, k, j, S_uk) from random.seed(77), and the generator state after them, equal what the
+    unmodified reference class produced (oracle/gen_golden.py gen_sbpr)."""
+    from qrec_b200.model.ranking.SBPR import SBPR
+    calls = []
+    _stub_engine(monkeypatch, calls)
+    monkeypatch.chdir(tmp_path)
+    gs = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'sbpr_filmtrust_seed77.npz'), allow_pickle=False)
+    g = golden_bpr
+    train = [[u, i, float(r)] for u, i, r in zip(g['train_users'].tolist(), g['train_items'].tolist(), g['train_rating'].tolist())]
+    rel = [[a, b, w] for a, b, w in zip(gs['relation_from'].tolist(), gs['relation_to'].tolist(), gs['relation_w'].tolist())]
+    conf = str(gs['conf']).replace('./dataset/FilmTrust/ratings.txt', 'x').replace('./dataset/FilmTrust/trust.txt', 'x') \
+                          .replace('./dataset/FilmTrust/testset.txt', 'x')
+    np.random.seed(0); random.seed(0)
+    m = SBPR(ModelConf.from_string(conf), train, [], rel)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m.readConfiguration()
+        m.initModel()
+    users = list(m.data.user.keys())
+    assert np.array_equal(np.array([len(m.FPSet[u]) for u in users]), gs['fp_sizes'])
+    assert np.array_equal(np.array([sum(m.FPSet[u].values()) for u in users]), gs['fp_sums'])
+    assert [next(iter(m.FPSet[u])) if len(m.FPSet[u]) else '' for u in users] == gs['fp_first'].tolist()
+    m.batch_size = 512
+    random.seed(77)
+    for n, b in enumerate(m.next_batch()):
+        assert np.array_equal(np.array(b, dtype=np.int64), gs['batches'][n]), 'batch %d' % n
+        if n == 7:
+            break
+    assert np.array_equal(np.array(random.getstate()[1], dtype=np.uint32), gs['mt_state_after_8_batches'])
