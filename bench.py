@@ -622,6 +622,17 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
             torch.cuda.synchronize()
             hms = a.elapsed_time(b) / steps
             halves[name] = {'ms': hms, 'gathered_rows': int(A[1].numel()), 'gathers_per_s': int(A[1].numel()) / (hms * 1e-3)}
+        try:                                               # DRAM bytes per launch from the committed ncu --set full capture
+            with open(os.path.join(ROOT, 'profiles', 'k2_traffic.json')) as f:
+                k2t = json.load(f)
+            for name in halves:
+                t = k2t.get(name)
+                if t:
+                    halves[name]['traffic'] = t['dram_bytes_read'] + t['dram_bytes_write']
+                    halves[name]['algorithmic_bytes'] = k2t['algorithmic_bytes_per_half']
+                    halves[name]['traffic_source'] = k2t['source']
+        except Exception:                                  # noqa: BLE001
+            pass
         res['spmm_halves'] = halves
         del Yu, Yi
         if rank == 0:

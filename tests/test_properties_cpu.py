@@ -208,3 +208,49 @@ def test_native_rated_csr_large_threaded_and_errors():
         E.RatedCSR(3, 4, np.array([0, 1]), np.array([1, -1]))         # negative item id
     with pytest.raises(E.QRecError):
         E.RatedCSR(3, 4, np.array([0, 1]), np.array([1]))
+
+
+def test_device_csr_split_row_issues_one_launch_per_half_with_the_same_result(monkeypatch):
+    """DeviceCSR.set_split_row: matmul over the joint adjacency = the row-split product over rows [0, split) and over
+    rows [split, n), each a row range of the same CSR (rowptr slice with absolute offsets into cols / vals)."""
+    import scipy.sparse as sp
+    import torch
+    from qrec_b200 import engine as E
+    from qrec_b200.base.graphRecommender import DeviceCSR
+    rng = np.random.default_rng(4)
+    nu, ni, d = 23, 9, 8
+    R = (rng.random((nu, ni)) < 0.3).astype(np.float32)
+    A = sp.bmat([[None, sp.csr_matrix(R)], [sp.csr_matrix(R.T), None]], format='csr').astype(np.float32)
+    A.data[:] = rng.random(A.nnz).astype(np.float32)
+    calls = []
+
+    def spmm(rowptr, cols, vals, X, Y, acc=None, acc_scale=0.0, rowsplit=False):
+        rp = rowptr.numpy()
+        a, b = int(rp[0]), int(rp[-1])
+        calls.append((rowptr.numel() - 1, a, b, rowsplit))
+        M = sp.csr_matrix((vals.numpy()[a:b], cols.numpy()[a:b], rp - a), shape=(rowptr.numel() - 1, X.shape[0]))
+        Y.copy_(torch.from_numpy(M @ X.numpy()))
+        if acc is not None:
+            acc.add_(Y, alpha=acc_scale)
+        return Y
+    monkeypatch.setattr(E, 'spmm_csr', spmm)
+    X = torch.from_numpy(rng.standard_normal((nu + ni, d)).astype(np.float32))
+    ref = torch.from_numpy(A @ X.numpy())
+    whole = DeviceCSR(A, 'cpu')
+    assert whole.split_row is None
+    Y0, acc0 = torch.empty_like(X), torch.ones_like(X)
+    whole.matmul(X, Y0, acc=acc0, acc_scale=0.5)
+    assert len(calls) == 1 and calls[0][0] == nu + ni
+    split = DeviceCSR.from_tensors(A.shape, whole.rowptr, whole.cols, whole.vals, split_row=nu)
+    assert split.split_row == nu
+    calls.clear()
+    Y1, acc1 = torch.full_like(X, 7.0), torch.ones_like(X)
+    split.matmul(X, Y1, acc=acc1, acc_scale=0.5)
+    nnz_u = int(whole.rowptr[nu])
+    assert calls == [(nu, 0, nnz_u, True), (ni, nnz_u, A.nnz, True)]
+    assert torch.allclose(Y0, ref, atol=1e-6) and torch.equal(Y1, Y0) and torch.equal(acc1, acc0)
+    # out-of-range split rows and the experiment switch leave the single launch
+    assert DeviceCSR.from_tensors(A.shape, whole.rowptr, whole.cols, whole.vals, split_row=0).split_row is None
+    assert DeviceCSR.from_tensors(A.shape, whole.rowptr, whole.cols, whole.vals, split_row=nu + ni).split_row is None
+    monkeypatch.setenv('QREC_SPMM_SPLIT', '0')
+    assert DeviceCSR.from_tensors(A.shape, whole.rowptr, whole.cols, whole.vals, split_row=nu).split_row is None
