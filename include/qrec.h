@@ -88,6 +88,16 @@ int qrec_sample_pairwise(qrec_mt19937* st, int64_t n, int32_t num_items, const i
                          const int64_t* sorted_rowptr, const int32_t* sorted_cols,
                          int32_t* out_j);
 
+/* SBPR minibatch rows, model/ranking/SBPR.py:84-100 (host): per row the social item k = choice(list(FPSet[user].keys()))
+ * with its friend count S_uk (no social feedback: choice(item_list), weight 0), then the negative j = choice(item_list)
+ * until j is neither rated by the user nor in FPSet[user] -- the same draws from the same MT19937 stream.
+ * fp_items / fp_counts: every user's FPSet in dict (insertion) order, CSR over user ids; fp_sorted: the same sets
+ * ascending (membership test); rated_*: all rated items per user, ascending. */
+int qrec_sample_sbpr_batch(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,
+                           const int64_t* rated_rowptr, const int32_t* rated_cols, const int64_t* fp_rowptr,
+                           const int32_t* fp_items, const int32_t* fp_counts, const int32_t* fp_sorted,
+                           int32_t* out_k, int32_t* out_j, int32_t* out_w);
+
 /* base/deepRecommender.py:65-76: per interaction emit (u,i,1) then 4 x (u, randint(0,I-1)
  * until unrated, 0).  Outputs have 5*n entries. */
 int qrec_sample_pointwise(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,

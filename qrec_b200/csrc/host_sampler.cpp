@@ -187,6 +187,40 @@ int qrec_sample_pairwise(qrec_mt19937* st, int64_t n, int32_t num_items, const i
   return QREC_OK;
 }
 
+// SBPR's minibatch rows (model/ranking/SBPR.py:84-100): per row one social item k = choice(list(FPSet[user].keys()))
+// with its friend count S_uk (a user without social feedback draws choice(item_list) and weight 0), then a negative
+// j = choice(item_list) until j is neither rated by the user nor in FPSet[user].  choice(seq) = seq[_randbelow(len(seq))];
+// item_list is in id order.  fp_items / fp_counts: the users' FPSet in dict (insertion) order; fp_sorted: the same sets
+// ascending, for the membership test.
+int qrec_sample_sbpr_batch(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,
+                           const int64_t* rated_rowptr, const int32_t* rated_cols, const int64_t* fp_rowptr,
+                           const int32_t* fp_items, const int32_t* fp_counts, const int32_t* fp_sorted,
+                           int32_t* out_k, int32_t* out_j, int32_t* out_w) {
+  QREC_REQUIRE(st && rated_rowptr && fp_rowptr && (n == 0 || (u && out_k && out_j && out_w)),
+               "qrec_sample_sbpr_batch: null pointer");
+  QREC_REQUIRE(num_items >= 1, "qrec_sample_sbpr_batch: num_items < 1");
+  for (int64_t r = 0; r < n; ++r) {
+    const int32_t uu = u[r];
+    const int64_t f0 = fp_rowptr[uu], nf = fp_rowptr[uu + 1] - f0;
+    if (nf == 0) {
+      out_k[r] = (int32_t)randbelow(st, (uint32_t)num_items);
+      out_w[r] = 0;
+    } else {
+      QREC_REQUIRE(fp_items && fp_counts && fp_sorted, "qrec_sample_sbpr_batch: null social-feedback arrays");
+      const uint32_t t = randbelow(st, (uint32_t)nf);
+      out_k[r] = fp_items[f0 + t];
+      out_w[r] = fp_counts[f0 + t];
+    }
+    QREC_REQUIRE((rated_rowptr[uu + 1] - rated_rowptr[uu]) + nf < num_items,
+                 "qrec_sample_sbpr_batch: user %d leaves no item to draw a negative from", uu);
+    uint32_t j = randbelow(st, (uint32_t)num_items);
+    while (row_contains(rated_rowptr, rated_cols, uu, (int32_t)j) || (nf > 0 && row_contains(fp_rowptr, fp_sorted, uu, (int32_t)j)))
+      j = randbelow(st, (uint32_t)num_items);
+    out_j[r] = (int32_t)j;
+  }
+  return QREC_OK;
+}
+
 int qrec_sample_pointwise(qrec_mt19937* st, int64_t n, int32_t num_items, const int32_t* u,
                           const int32_t* i, const int64_t* sorted_rowptr,
                           const int32_t* sorted_cols, int32_t* out_u, int32_t* out_i,

@@ -155,6 +155,16 @@ class MT19937(object):
               'qrec_sample_pairwise')
         return j
 
+    def sample_sbpr_batch(self, csr, fp_rowptr, fp_items, fp_counts, fp_sorted, u):
+        """Social item, its friend count and the negative for a batch of users: model/ranking/SBPR.py:84-100."""
+        u = np.ascontiguousarray(u, dtype=np.int32)
+        k, j, w = (np.empty(u.shape[0], np.int32) for _ in range(3))
+        check(lib.qrec_sample_sbpr_batch(C.byref(self._st), u.shape[0], csr.num_items, _i32p(u),
+                                         _i64p(csr.sorted_rowptr), _i32p(csr.sorted_cols), _i64p(fp_rowptr),
+                                         _i32p(fp_items), _i32p(fp_counts), _i32p(fp_sorted), _i32p(k), _i32p(j), _i32p(w)),
+              'qrec_sample_sbpr_batch')
+        return k, j, w
+
     def sample_pointwise(self, csr, u, i):
         """1 positive + 4 negatives per interaction: base/deepRecommender.py:65-76."""
         u = np.ascontiguousarray(u, dtype=np.int32)

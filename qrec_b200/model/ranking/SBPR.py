@@ -66,7 +66,42 @@ class SBPR(SocialRecommender):
                         'carries untrained item biases (SBPR.py:56-65) -- not built; use evaluation.setup -tf (config/SBPR.conf)')
 
     # ------------------------------------------------------------------ minibatch sampler (SBPR.py:69-101)
+    def _social_csr(self):
+        """FPSet as arrays over user ids: items in dict (insertion) order -- `choice(list(keys))` indexes that order --,
+        their friend counts, and the same sets ascending for the membership test of the negative's rejection loop."""
+        if getattr(self, '_fp_arrays', None) is None:
+            item_id = self.data.item
+            rowptr = np.zeros(self.num_users + 1, dtype=np.int64)
+            items, counts, ordered = [], [], []
+            for uid in range(self.num_users):
+                social = self.FPSet[self.data.id2user[uid]]
+                ids = [item_id[k] for k in social]
+                items.extend(ids); counts.extend(social.values()); ordered.extend(sorted(ids))
+                rowptr[uid + 1] = len(items)
+            self._fp_arrays = (rowptr, np.asarray(items, dtype=np.int32), np.asarray(counts, dtype=np.int32),
+                               np.asarray(ordered, dtype=np.int32))
+        return self._fp_arrays
+
     def next_batch(self):
+        """SBPR.py:69-101 with the per-row draws made by the native clone of CPython's generator
+        (qrec_sample_sbpr_batch): Python's `random` state goes in before a batch and comes back after it, so the stream
+        the interpreter sees is the reference's, draw for draw (`_next_batch_python` is the same loop in Python;
+        tests/test_sbpr_cpu.py holds the two and the unmodified reference class against each other)."""
+        import random
+        from ...engine import MT19937
+        csr = self.data.rated_csr()
+        fp_rowptr, fp_items, fp_counts, fp_sorted = self._social_csr()
+        u_all, i_all, _ = self.data.training_ids()
+        for b in range(0, self.train_size, self.batch_size):
+            u = np.ascontiguousarray(u_all[b:b + self.batch_size], dtype=np.int32)
+            i = np.ascontiguousarray(i_all[b:b + self.batch_size], dtype=np.int32)
+            mt = MT19937()
+            mt.setstate(random.getstate())
+            k, j, w = mt.sample_sbpr_batch(csr, fp_rowptr, fp_items, fp_counts, fp_sorted, u)
+            random.setstate(mt.getstate())
+            yield u, i, k, j, w
+
+    def _next_batch_python(self):
         data, item_id, user_id = self.data.trainingData, self.data.item, self.data.user
         item_list = list(item_id.keys())
         batch_id = 0
@@ -115,7 +150,7 @@ class SBPR(SocialRecommender):
         for epoch in range(self.maxEpoch):
             for n, (u, i, k, j, w) in enumerate(self.next_batch()):
                 t += 1
-                du, di, dk, dj = ids(u), ids(i), ids(k), ids(j)
+                du, di, dk, dj = ids(u), ids(i), ids(k), ids(j)                 # int32 arrays from the native sampler
                 scale = torch.from_numpy(1.0 / (np.asarray(w, dtype=np.float32) + np.float32(1.0))).to(dev)
                 gU.zero_(); gV.zero_(); loss.zero_()
                 E.bpr_grad_scatter_scaled(U, V, du, di, dk, scale, 1e-6, 0.0, gU, gV, loss)      # y_ik / (S_uk + 1)

@@ -69,6 +69,13 @@ def test_sbpr_item_sets_and_numpy_path_error(golden_bpr, monkeypatch, tmp_path):
     m.batch_size = 700
     batches = list(m.next_batch())
     assert [len(b[0]) for b in batches] == [700, 700, 700, 700, 200]
+    # the native sampler (qrec_sample_sbpr_batch) and the same loop in Python: same rows, same generator state afterwards
+    native_state = random.getstate()
+    random.seed(3)
+    python_batches = list(m._next_batch_python())
+    assert random.getstate() == native_state
+    for a, b in zip(batches, python_batches):
+        assert all(np.array_equal(np.asarray(x), np.asarray(y)) for x, y in zip(a, b))
     flat_u = [x for b in batches for x in b[0]]
     assert flat_u == [m.data.user[r[0]] for r in m.data.trainingData]
     id2item = {v: k for k, v in m.data.item.items()}
