@@ -88,6 +88,19 @@ int qrec_sample_pairwise(qrec_mt19937* st, int64_t n, int32_t num_items, const i
                          const int64_t* sorted_rowptr, const int32_t* sorted_cols,
                          int32_t* out_j);
 
+/* TBPR epoch of preference chains, model/ranking/TBPR.py:131-160 (host): for every listed user and every positive item
+ * (insertion order) the chain  i > joint > weak > strong > unobserved  of the levels that exist for the user -- one
+ * choice(list) per non-empty level in that order, then choice(item_list) until it is not one of the user's positives --
+ * written as the chain's consecutive (u, a, b) steps; the same draws from the same MT19937 stream.  Pools: CSR over
+ * user ids, items in list order.  out_u/a/b: capacity 4 * positives of the listed users; out_per_user[k]: steps of
+ * order[k]; *out_n: steps written. */
+int qrec_sample_tbpr_epoch(qrec_mt19937* st, int32_t n_order, const int32_t* order, int32_t num_items,
+                           const int64_t* pos_rowptr, const int32_t* pos_cols, const int64_t* possorted_rowptr,
+                           const int32_t* possorted_cols, const int64_t* joint_rowptr, const int32_t* joint_items,
+                           const int64_t* weak_rowptr, const int32_t* weak_items, const int64_t* strong_rowptr,
+                           const int32_t* strong_items, int32_t* out_u, int32_t* out_a, int32_t* out_b,
+                           int64_t* out_per_user, int64_t* out_n);
+
 /* SBPR minibatch rows, model/ranking/SBPR.py:84-100 (host): per row the social item k = choice(list(FPSet[user].keys()))
  * with its friend count S_uk (no social feedback: choice(item_list), weight 0), then the negative j = choice(item_list)
  * until j is neither rated by the user nor in FPSet[user] -- the same draws from the same MT19937 stream.

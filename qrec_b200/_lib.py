@@ -42,6 +42,8 @@ SIGNATURES = {
     'qrec_sample_bpr_epoch': (C.c_int, [MTp, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i64p, c_i32p,
                                         c_i32p, c_i32p, c_i32p]),
     'qrec_sample_pairwise': (C.c_int, [MTp, C.c_int64, C.c_int32, c_i32p, c_i64p, c_i32p, c_i32p]),
+    'qrec_sample_tbpr_epoch': (C.c_int, [MTp, C.c_int32, c_i32p, C.c_int32, c_i64p, c_i32p, c_i64p, c_i32p, c_i64p, c_i32p,
+                                         c_i64p, c_i32p, c_i64p, c_i32p, c_i32p, c_i32p, c_i32p, c_i64p, c_i64p]),
     'qrec_sample_sbpr_batch': (C.c_int, [MTp, C.c_int64, C.c_int32, c_i32p, c_i64p, c_i32p, c_i64p, c_i32p, c_i32p, c_i32p,
                                          c_i32p, c_i32p, c_i32p]),
     'qrec_sample_pointwise': (C.c_int, [MTp, C.c_int64, C.c_int32, c_i32p, c_i32p, c_i64p, c_i32p,

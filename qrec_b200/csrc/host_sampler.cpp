@@ -187,6 +187,50 @@ int qrec_sample_pairwise(qrec_mt19937* st, int64_t n, int32_t num_items, const i
   return QREC_OK;
 }
 
+// TBPR's epoch of preference chains (model/ranking/TBPR.py:131-160): for every user of positiveSet (ids in `order`), for
+// every positive item i (insertion order) a chain  i > joint > weak > strong > unobserved  of the levels that exist for
+// the user -- one choice(list) per non-empty level in that order, then choice(item_list) until the item is not one of the
+// user's positives -- emitted as the consecutive (u, a, b) steps of the chain.  Pools: CSR over user ids, items in list
+// order.  out_*: capacity 4 * (number of positives of the listed users); out_per_user[k] = steps of order[k].
+int qrec_sample_tbpr_epoch(qrec_mt19937* st, int32_t n_order, const int32_t* order, int32_t num_items,
+                           const int64_t* pos_rowptr, const int32_t* pos_cols, const int64_t* possorted_rowptr,
+                           const int32_t* possorted_cols, const int64_t* joint_rowptr, const int32_t* joint_items,
+                           const int64_t* weak_rowptr, const int32_t* weak_items, const int64_t* strong_rowptr,
+                           const int32_t* strong_items, int32_t* out_u, int32_t* out_a, int32_t* out_b,
+                           int64_t* out_per_user, int64_t* out_n) {
+  QREC_REQUIRE(st && pos_rowptr && possorted_rowptr && joint_rowptr && weak_rowptr && strong_rowptr && out_per_user && out_n &&
+                   (n_order == 0 || order),
+               "qrec_sample_tbpr_epoch: null pointer");
+  QREC_REQUIRE(num_items >= 1, "qrec_sample_tbpr_epoch: num_items < 1");
+  const int64_t* lrp[3] = {joint_rowptr, weak_rowptr, strong_rowptr};
+  const int32_t* lit[3] = {joint_items, weak_items, strong_items};
+  int64_t o = 0;
+  for (int32_t k = 0; k < n_order; ++k) {
+    const int32_t uu = order[k];
+    const int64_t start = o;
+    QREC_REQUIRE(possorted_rowptr[uu + 1] - possorted_rowptr[uu] < num_items,
+                 "qrec_sample_tbpr_epoch: every item is a positive of user %d", uu);
+    for (int64_t e = pos_rowptr[uu]; e < pos_rowptr[uu + 1]; ++e) {
+      int32_t chain[5];
+      int len = 0;
+      chain[len++] = pos_cols[e];
+      for (int l = 0; l < 3; ++l) {
+        const int64_t a = lrp[l][uu], m = lrp[l][uu + 1] - a;
+        if (m > 0) chain[len++] = lit[l][a + randbelow(st, (uint32_t)m)];
+      }
+      uint32_t j = randbelow(st, (uint32_t)num_items);
+      while (row_contains(possorted_rowptr, possorted_cols, uu, (int32_t)j)) j = randbelow(st, (uint32_t)num_items);
+      chain[len++] = (int32_t)j;
+      for (int t = 0; t + 1 < len; ++t) {
+        out_u[o] = uu; out_a[o] = chain[t]; out_b[o] = chain[t + 1]; ++o;
+      }
+    }
+    out_per_user[k] = o - start;
+  }
+  *out_n = o;
+  return QREC_OK;
+}
+
 // SBPR's minibatch rows (model/ranking/SBPR.py:84-100): per row one social item k = choice(list(FPSet[user].keys()))
 // with its friend count S_uk (a user without social feedback draws choice(item_list) and weight 0), then a negative
 // j = choice(item_list) until j is neither rated by the user nor in FPSet[user].  choice(seq) = seq[_randbelow(len(seq))];

@@ -155,6 +155,29 @@ class MT19937(object):
               'qrec_sample_pairwise')
         return j
 
+    def sample_tbpr_epoch(self, csr, order, joint, weak, strong):
+        """One epoch of TBPR's preference chains (model/ranking/TBPR.py:131-160) for the users `order` (ids, in the
+        order positiveSet lists them); joint / weak / strong: (rowptr int64 [U+1], items int32) pools in list order.
+        -> (u, a, b) int32 steps and the number of steps per listed user (int64)."""
+        order = np.ascontiguousarray(order, dtype=np.int32)
+        cap = 4 * int((csr.pos_rowptr[order.astype(np.int64) + 1] - csr.pos_rowptr[order.astype(np.int64)]).sum()) if order.size else 0
+        u, a, b = (np.empty(max(cap, 1), np.int32) for _ in range(3))
+        per_user = np.zeros(max(order.shape[0], 1), np.int64)
+        n = C.c_int64(0)
+        arrs = [(np.ascontiguousarray(rp, dtype=np.int64), np.ascontiguousarray(items, dtype=np.int32))
+                for rp, items in (joint, weak, strong)]               # kept alive until the call returns
+        for rp, _ in arrs:
+            if rp.shape[0] != csr.num_users + 1:
+                raise QRecError('sample_tbpr_epoch: a pool rowptr has %d entries for %d users' % (rp.shape[0], csr.num_users))
+        pools = [p for rp, items in arrs for p in (_i64p(rp), _i32p(items))]
+        check(lib.qrec_sample_tbpr_epoch(C.byref(self._st), order.shape[0], _i32p(order), csr.num_items,
+                                         _i64p(csr.pos_rowptr), _i32p(csr.pos_cols), _i64p(csr.possorted_rowptr),
+                                         _i32p(csr.possorted_cols), *pools, _i32p(u), _i32p(a), _i32p(b),
+                                         _i64p(per_user), C.byref(n)), 'qrec_sample_tbpr_epoch')
+        del arrs
+        k = int(n.value)
+        return u[:k].copy(), a[:k].copy(), b[:k].copy(), per_user[:order.shape[0]].copy()
+
     def sample_sbpr_batch(self, csr, fp_rowptr, fp_items, fp_counts, fp_sorted, u):
         """Social item, its friend count and the negative for a batch of users: model/ranking/SBPR.py:84-100."""
         u = np.ascontiguousarray(u, dtype=np.int32)

@@ -113,8 +113,33 @@ class TBPR(SocialRecommender):
                 self.weakSet[u1] = {k: 1 for k in self.weakSet[u1] if k not in joint}
 
     def _sample_epoch(self):
-        """The epoch's chain steps as int32 arrays (u, a, b) plus the number of steps of every user of positiveSet,
-        drawing from Python's global `random` exactly as TBPR.py:131-160 does."""
+        """The epoch's chain steps as int32 arrays (u, a, b) plus the number of steps of every user of positiveSet --
+        TBPR.py:131-160 with the draws made by the native clone of CPython's generator (qrec_sample_tbpr_epoch): the
+        interpreter's `random` state goes in and comes back, so the stream is the reference's draw for draw
+        (`_sample_epoch_python` is the same loop in Python; tests/test_tbpr_cpu.py holds the two against each other and
+        against the unmodified reference class)."""
+        from ...engine import MT19937
+        item_id, user_id = self.data.item, self.data.user
+        csr = self.data.rated_csr()
+        order = np.fromiter((user_id[x] for x in self.positiveSet), np.int32, len(self.positiveSet))
+        # positiveSet[user] must be the positives RatedCSR lists (rating >= 1, insertion order)
+        pools = []
+        for level in (self.jointSet, self.weakSet, self.strongSet):
+            rowptr = np.zeros(self.num_users + 1, np.int64)
+            items = []
+            for uid in range(self.num_users):
+                keys = level.get(self.data.id2user[uid])
+                if keys:
+                    items.extend(item_id[k] for k in keys)
+                rowptr[uid + 1] = len(items)
+            pools.append((rowptr, np.asarray(items, dtype=np.int32)))
+        mt = MT19937()
+        mt.setstate(random.getstate())
+        out = mt.sample_tbpr_epoch(csr, order, *pools)
+        random.setstate(mt.getstate())
+        return out
+
+    def _sample_epoch_python(self):
         item_id, user_id = self.data.item, self.data.user
         item_list = list(item_id.keys())
         us, ia, ib, per_user = [], [], [], []

@@ -94,6 +94,14 @@ def test_tbpr_host_logic_self_consistency(golden_bpr, monkeypatch, tmp_path):
     assert len(losses) == 3 and losses[0][0] > losses[-1][0] > 0           # the loss falls
     assert losses[0][1] == 0.01 and losses[2][1] == pytest.approx(0.01 * 1.05)     # epoch 1 never changes lr; epoch 2 raised it
     assert measure[0].startswith('Top 10')
+    # the native epoch sampler (qrec_sample_tbpr_epoch) and the same loop in Python: same steps, same generator state
+    random.seed(99)
+    nat = m._sample_epoch()
+    nat_state = random.getstate()
+    random.seed(99)
+    py = m._sample_epoch_python()
+    assert random.getstate() == nat_state
+    assert all(np.array_equal(x, y) for x, y in zip(nat, py)) and nat[0].dtype == np.int32 and len(nat[3]) == len(m.positiveSet)
     # same seeds -> same run (the draw order from `random` is deterministic inside one process)
     m2, losses2, _ = _run(TBPR, train, test, rel, CONF)
     assert losses2 == losses and np.array_equal(m.P, m2.P) and np.array_equal(m.Q, m2.Q)
