@@ -149,3 +149,25 @@ def sgl_loss_and_grad(adj_main, views, ego, num_users, u, i, j, n_layers, ssl_re
     ssl = -torch.log(pos / ttl).sum()
     (rec + ssl_reg * ssl).backward()
     return float(rec), float(ssl_reg * ssl), E0.grad.numpy()
+
+
+def sbpr_loss_and_grad(U, V, u, i, k, j, weights):
+    """model/ranking/SBPR.py:103-115 (trainModel_tf): the minibatch loss over the two embedding tables,
+
+        y_ik = (u.i - u.k) / (weights + 1)                               SBPR.py:110-111
+        y_kj = u.k - u.j                                                  SBPR.py:112-113
+        loss = -sum( ln(sigmoid(y_ik) + 1e-6) + ln(sigmoid(y_kj) + 1e-6) )   SBPR.py:114
+
+    The `+ self.regU * (l2_loss(U) + l2_loss(V))` on SBPR.py:115 is an expression statement of its own (the previous
+    line is complete), so the regulariser never reaches `loss`; it is absent here.  Returns (loss, dL/dU, dL/dV) with
+    the gradients dense (TF's IndexedSlices of the three lookups, summed per row)."""
+    Ut = torch.tensor(np.asarray(U), dtype=torch.float64, requires_grad=True)
+    Vt = torch.tensor(np.asarray(V), dtype=torch.float64, requires_grad=True)
+    ul, il, kl, jl = (torch.as_tensor(np.asarray(x, dtype=np.int64)) for x in (u, i, k, j))
+    wt = torch.as_tensor(np.asarray(weights, dtype=np.float64))
+    ue = Ut[ul]
+    y_ik = ((ue * Vt[il]).sum(1) - (ue * Vt[kl]).sum(1)) / (wt + 1)
+    y_kj = (ue * Vt[kl]).sum(1) - (ue * Vt[jl]).sum(1)
+    loss = -(torch.log(torch.sigmoid(y_ik) + 1e-6) + torch.log(torch.sigmoid(y_kj) + 1e-6)).sum()
+    loss.backward()
+    return float(loss.detach()), Ut.grad.numpy(), Vt.grad.numpy()

@@ -131,7 +131,7 @@ def test_sbpr_sampler_equals_unmodified_reference_class(golden_bpr, monkeypatch,
 
 def test_sbpr_trainModel_tf_composition_equals_autograd_restatement(golden_bpr, monkeypatch, tmp_path):
     import torch
-    from oracle import bpr_oracle as O
+    from oracle import bpr_oracle as O, tf_models as T
     from qrec_b200 import engine as E
     calls = []
     _stub_engine(monkeypatch, calls)
@@ -171,16 +171,9 @@ def test_sbpr_trainModel_tf_composition_equals_autograd_restatement(golden_bpr, 
     for epoch in range(2):
         for u, i, k, j, w in m.next_batch():
             t += 1
-            Ut = torch.tensor(U, dtype=torch.float64, requires_grad=True)
-            Vt = torch.tensor(V, dtype=torch.float64, requires_grad=True)
-            ul, il, kl, jl = (torch.tensor(x, dtype=torch.int64) for x in (u, i, k, j))
-            wt = torch.tensor(w, dtype=torch.float64)
-            y_ik = ((Ut[ul] * Vt[il]).sum(1) - (Ut[ul] * Vt[kl]).sum(1)) / (wt + 1)
-            y_kj = (Ut[ul] * Vt[kl]).sum(1) - (Ut[ul] * Vt[jl]).sum(1)
-            loss = -(torch.log(torch.sigmoid(y_ik) + 1e-6) + torch.log(torch.sigmoid(y_kj) + 1e-6)).sum()
-            loss.backward()
-            O.adam_tf1(U, mU, vU, Ut.grad.numpy().astype(np.float32), m.lRate, t)
-            O.adam_tf1(V, mV, vV, Vt.grad.numpy().astype(np.float32), m.lRate, t)
+            _, gU, gV = T.sbpr_loss_and_grad(U, V, u, i, k, j, w)           # oracle/tf_models.py (SBPR.py:103-115)
+            O.adam_tf1(U, mU, vU, gU.astype(np.float32), m.lRate, t)
+            O.adam_tf1(V, mV, vV, gV.astype(np.float32), m.lRate, t)
     np.testing.assert_allclose(m.P, U, rtol=1e-3, atol=1e-5)
     np.testing.assert_allclose(m.Q, V, rtol=1e-3, atol=1e-5)
     assert float(np.abs(m.P).max()) > 0.01
