@@ -1137,6 +1137,11 @@ class UserShardedSimGCL(UserShardedLightGCN):
         self._adam(self.Ei, self.mi, self.vi, self.tot_i, self.step)
         return self.losses_dev
 
+    def train_step_graphed(self, u, i, j):
+        """Not capturable: the step compacts the rank's own triples and takes tf.unique of the batch (data-dependent
+        shapes, hence host read-backs), and the noise is keyed by the step number -- the eager step."""
+        return self.train_step(u, i, j)
+
     def losses(self):
         l = self.losses_dev.cpu().numpy()
         rec, cl = float(l[0]), self.cl_rate * float(l[1])
