@@ -567,7 +567,10 @@ def lightgcn_section(torch, dist, E, synthetic, data, dev, peak, rank, world, la
         ms_eager = timed(m.train_step, 0)
         # the same steps replayed from a CUDA graph (parallel.UserShardedLightGCN.train_step_graphed: one capture per batch
         # size, three small device copies + one replay per minibatch); a failed capture falls back to the eager step
-        graphed = hasattr(m, 'train_step_graphed') and os.environ.get('QREC_LGCN_GRAPH', '1') != '0'
+        # run on hardware at N = 1, 2 and 4 (profiles/r2/s2); beyond that it is opt-in (QREC_LGCN_GRAPH=1): a capture that
+        # goes wrong at an untested size must not cost the whole line
+        g_env = os.environ.get('QREC_LGCN_GRAPH', 'auto')
+        graphed = hasattr(m, 'train_step_graphed') and g_env != '0' and (world <= 4 or g_env == '1')
         ms_graph = timed(m.train_step_graphed, 0) if graphed else None
         graph_ok = bool(graphed and getattr(m, 'graph_error', None) is None)
         # the step API is chosen by measurement: the replayed graph wins where the host cannot issue ~80 launches per step
