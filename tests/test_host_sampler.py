@@ -165,3 +165,77 @@ def test_bpr_epoch_with_non_binarised_ratings_uses_positive_set_only():
     u, i, j = m.sample_bpr_epoch(d.rated_csr())
     assert np.array_equal(np.stack([u, i, j], 1), np.array(ref)) and m.getstate() == state
     assert any(v < 1 for row in d.trainSet_u.values() for v in row.values())      # the filter mattered
+
+
+def test_sbpr_and_tbpr_native_samplers_equal_python_random_on_random_structures():
+    """qrec_sample_sbpr_batch / qrec_sample_tbpr_epoch against the same loops written with random.Random (the calls
+    model/ranking/SBPR.py:84-100 and TBPR.py:131-160 make), on small random structures that hit the corners: users
+    without social feedback, one-element pools, missing chain levels, users without positives."""
+    import random
+    from qrec_b200 import engine as E
+    rng = np.random.default_rng(12)
+    for trial in range(25):
+        nu, ni = int(rng.integers(3, 12)), int(rng.integers(8, 40))
+        rated = [sorted(rng.choice(ni, int(rng.integers(0, min(5, ni - 3))), replace=False).tolist()) for _ in range(nu)]
+        u_ids = np.array([u for u in range(nu) for _ in rated[u]], np.int32)
+        i_ids = np.array([x for u in range(nu) for x in rated[u]], np.int32)
+        csr = E.RatedCSR(nu, ni, u_ids, i_ids)
+
+        def pool(p_empty):
+            out = []
+            for u in range(nu):
+                free = [x for x in range(ni) if x not in rated[u]]
+                k = 0 if rng.random() < p_empty else int(rng.integers(1, max(2, min(4, len(free) - 2))))
+                out.append([int(x) for x in rng.permutation(free)[:k]])
+            return out
+
+        def as_csr(lists):
+            rp = np.zeros(nu + 1, np.int64)
+            rp[1:] = np.cumsum([len(x) for x in lists])
+            return rp, np.array([x for row in lists for x in row], np.int32)
+        # ---- SBPR rows
+        fp = pool(0.4)
+        counts = [[int(rng.integers(1, 4)) for _ in row] for row in fp]
+        fp_rp, fp_items = as_csr(fp)
+        fp_counts = np.array([c for row in counts for c in row], np.int32)
+        fp_sorted = np.array([x for row in fp for x in sorted(row)], np.int32)
+        rows = rng.integers(0, nu, 60).astype(np.int32)
+        seed = int(rng.integers(0, 2 ** 31))
+        mt = E.MT19937(seed)
+        k, j, w = mt.sample_sbpr_batch(csr, fp_rp, fp_items, fp_counts, fp_sorted, rows)
+        ref = random.Random(seed)
+        item_list = list(range(ni))
+        for r, u in enumerate(rows.tolist()):
+            if len(fp[u]) == 0:
+                f, wt = ref.choice(item_list), 0
+            else:
+                f = ref.choice(fp[u]); wt = counts[u][fp[u].index(f)]
+            neg = ref.choice(item_list)
+            while neg in rated[u] or neg in fp[u]:
+                neg = ref.choice(item_list)
+            assert (int(k[r]), int(j[r]), int(w[r])) == (f, neg, wt), (trial, r)
+        assert mt.getstate() == ref.getstate()
+        # ---- TBPR chains (positives = rated: every rating is 1)
+        joint, weak, strong = pool(0.5), pool(0.5), pool(0.5)
+        order = np.array([u for u in range(nu) if rated[u]], np.int32)
+        mt = E.MT19937(seed + 1)
+        su, sa, sb, per_user = mt.sample_tbpr_epoch(csr, order, as_csr(joint), as_csr(weak), as_csr(strong))
+        ref = random.Random(seed + 1)
+        eu, ea, eb, ecount = [], [], [], []
+        pos_order = {u: csr.pos_cols[csr.pos_rowptr[u]:csr.pos_rowptr[u + 1]].tolist() for u in range(nu)}
+        for u in order.tolist():
+            start = len(eu)
+            for item in pos_order[u]:
+                chain = [item]
+                for level in (joint[u], weak[u], strong[u]):
+                    if level:
+                        chain.append(ref.choice(level))
+                neg = ref.choice(item_list)
+                while neg in rated[u]:
+                    neg = ref.choice(item_list)
+                chain.append(neg)
+                for a, b in zip(chain[:-1], chain[1:]):
+                    eu.append(u); ea.append(a); eb.append(b)
+            ecount.append(len(eu) - start)
+        assert su.tolist() == eu and sa.tolist() == ea and sb.tolist() == eb and per_user.tolist() == ecount, trial
+        assert mt.getstate() == ref.getstate()
